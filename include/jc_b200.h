@@ -1,0 +1,232 @@
+/*
+ * jc_b200.h -- C ABI of the B200-native angular-power-spectrum path.
+ *
+ * This is the drop-in boundary for jax_cosmo's `angular_cl` / `gaussian_cl_covariance_and_mean`
+ * hot path.  The reference has NO native interface for this path (pure Python on JAX; SURVEY.md
+ * section 8b) -- its boundary is the Python call
+ *     jax_cosmo/angular_cl.py:49   angular_cl(cosmo, ell, probes, transfer_fn, nonlinear_fn)
+ *     jax_cosmo/angular_cl.py:101  noise_cl(ell, probes)
+ *     jax_cosmo/angular_cl.py:120  gaussian_cl_covariance(ell, probes, cl_signal, cl_noise, f_sky, sparse)
+ *     jax_cosmo/angular_cl.py:166  gaussian_cl_covariance_and_mean(...)
+ * so the entry points below are what an XLA-FFI custom call (`jax.ffi`) or a ctypes stub for those
+ * four functions binds (INTEGRATION.md shows both bindings).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types, no exceptions across the boundary;
+ *   - every function returns JC_OK (0) or a negative jc_status; nothing is launched on error;
+ *   - `*_dev` pointers are DEVICE pointers owned by the caller; `*_host` are host pointers;
+ *   - device entry points are stream-ordered and asynchronous (`stream` is a cudaStream_t passed
+ *     as void*), never allocate or free device memory, and keep no mutable global state, so they
+ *     are re-entrant and CUDA-graph capturable;
+ *   - all floating point is IEEE binary64 ("jax_enable_x64" semantics of the reference).
+ *
+ * Layouts (row-major, last index fastest)
+ *   cosmo  [B, 8]      Omega_c, Omega_b, h, n_s, sigma8, Omega_k, w0, wa
+ *                      (= Cosmology.tree_flatten order, jax_cosmo/core.py:99-108)
+ *   ell    [L]
+ *   cl     [B, P, L]   P = T(T+1)/2 tracer pairs (i<=j), row-major upper triangle
+ *                      (jax_cosmo/angular_cl.py:15-25); one [P, L] slab == the reference's output
+ *   cov    [P, P, L]   jax_cosmo.sparse block layout (jax_cosmo/angular_cl.py:156-157)
+ */
+#ifndef JC_B200_H
+#define JC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JC_ABI_VERSION 1
+#define JC_MAX_TRACERS 32
+#define JC_MAX_SHIFTS 4
+#define JC_N_COSMO_PARAMS 8
+#define JC_N_LIMBER_NODES 513 /* simps(..., 512) in a, jax_cosmo/angular_cl.py:96 */
+
+typedef enum jc_status {
+  JC_OK = 0,
+  JC_ERR_INVALID = -1,     /* malformed argument (NULL, n<=0, bad enum, ...)                  */
+  JC_ERR_UNSUPPORTED = -2, /* valid in the reference but outside this path (raise, no fallback) */
+  JC_ERR_WORKSPACE = -3,   /* workspace smaller than jc_workspace_bytes(plan, 1)              */
+  JC_ERR_CUDA = -4,        /* a CUDA runtime call failed; see jc_last_cuda_error()            */
+  JC_ERR_NO_DEVICE = -5    /* no CUDA device / not an sm_100 device                           */
+} jc_status;
+
+/* n(z) families: jax_cosmo/redshift.py */
+enum { JC_NZ_SMAIL = 1 /* redshift.py:61-77: z^a exp(-(z/z0)^b), params = {a, b, z0} */ };
+/* bias families: jax_cosmo/bias.py */
+enum {
+  JC_BIAS_NONE = 0,
+  JC_BIAS_CONSTANT = 1,       /* bias.py:10-22  params = {b}          */
+  JC_BIAS_INVERSE_GROWTH = 2, /* bias.py:25-39  params = {b}  b/D(a)  */
+  JC_BIAS_DES_Y1_IA = 3       /* bias.py:42-57  params = {A, eta, z0} */
+};
+enum {
+  JC_TRACER_WEAK_LENSING = 1, /* probes.py:132-223 */
+  JC_TRACER_NUMBER_COUNTS = 2 /* probes.py:226-281 */
+};
+enum {
+  JC_PK_LINEAR = 0,               /* power.py:81-83   nonlinear_fn=power.linear  */
+  JC_PK_HALOFIT_TAKAHASHI2012 = 1 /* power.py:144-262 nonlinear_fn=power.halofit */
+};
+enum { JC_TF_EISENSTEIN_HU_OSC = 1 /* transfer.py:10-156, type="eisenhu_osc" */ };
+
+/* One redshift bin.  `shifts` is the chain of systematic_shift wrappers (redshift.py:159-171),
+ * outermost first: pz_fn(z) = parent.pz_fn(clip(z - shift, 0)).  `zmax` is the n(z)'s own
+ * normalisation range (redshift.py:16,29-30). */
+typedef struct jc_nz {
+  int32_t family;
+  int32_t n_shifts;
+  double params[4];
+  double shifts[JC_MAX_SHIFTS];
+  double gals_per_arcmin2;
+  double zmax;
+} jc_nz;
+
+typedef struct jc_bias {
+  int32_t family;
+  int32_t reserved;
+  double params[3];
+} jc_bias;
+
+/* One tracer = one redshift bin of one probe, in probe-list order then bin order. */
+typedef struct jc_tracer {
+  int32_t kind;       /* JC_TRACER_*                                                        */
+  int32_t ia_enabled; /* WL only: add the NLA kernel (probes.py:201-203) with `bias` as b_IA */
+  jc_nz nz;
+  jc_bias bias;      /* NC: galaxy bias; WL: IA bias when ia_enabled                        */
+  double m_bias;     /* WL multiplicative bias m: kernel *= (1+m), probes.py:205-207        */
+  double sigma_e;    /* WL shape noise, probes.py:210-223                                   */
+  double probe_zmax; /* max zmax over the bins of the owning probe (probes.py:24,179-186)   */
+} jc_tracer;
+
+typedef struct jc_problem {
+  int32_t abi_version; /* must be JC_ABI_VERSION */
+  int32_t n_tracers;
+  int32_t transfer;  /* JC_TF_*  */
+  int32_t nonlinear; /* JC_PK_*  */
+  jc_tracer tracers[JC_MAX_TRACERS];
+} jc_problem;
+
+/* Offsets (in doubles) of the per-stage tables inside a workspace for n_cosmo cosmologies
+ * processed as ONE chunk.  Exposed so that tests can check every stage against the oracle. */
+typedef struct jc_ws_layout {
+  int64_t chunk;       /* cosmologies per pass for the given workspace size                  */
+  int64_t node_stride; /* padded length of a per-node array (>= 513)                         */
+  int64_t ell_stride;  /* padded n_ell of a V row                                            */
+  int64_t chitab;      /* [chunk, 256]  chi(a) table, background.py:223-236                  */
+  int64_t gtab;        /* [chunk, 128]  D(a)/D(1) table, background.py:461-481               */
+  int64_t scal;        /* [chunk, 32]   per-cosmology scalars (EH constants, pknorm, ...)    */
+  int64_t stab;        /* [chunk, 256]  halofit S(R) table (sigma^2(R, a) = D(a)^2 S(R))     */
+  int64_t node;        /* [chunk, JC_NODE_FIELDS, node_stride] per-Limber-node arrays        */
+  int64_t rker;        /* [chunk, T, node_stride]  ell-independent radial kernels R_i(a_n)   */
+  int64_t vtab;        /* [chunk, 513, ell_stride] V[n, l] = w_n P(k_ln, a_n) dchi/da/chi^2/c^2 */
+  int64_t total;       /* doubles                                                            */
+} jc_ws_layout;
+
+/* fields of the per-node table (index into ws.node) */
+enum {
+  JC_NODE_CHI = 0,    /* chi(a_n) >= 0                                  */
+  JC_NODE_INVCHIC,    /* 1 / max(chi, 1)                                */
+  JC_NODE_LNCHIC,     /* ln max(chi, 1)                                 */
+  JC_NODE_GEOM,       /* w_n dchi/da / max(chi^2, 1) / c^2              */
+  JC_NODE_GROWTH,     /* D(a_n) in [0, 1]                               */
+  JC_NODE_HUBBLE,     /* H(a_n) = 100 sqrt(E^2)                         */
+  JC_NODE_AMP,        /* D^2 pknorm / (2 pi^2)                          */
+  JC_NODE_RNL,        /* 1 / k_nl                                       */
+  JC_NODE_LNKNL,      /* ln k_nl                                        */
+  JC_NODE_NEFF,       /* n_eff                                          */
+  JC_NODE_CURV,       /* C                                              */
+  JC_NODE_AN,         /* a_n                                            */
+  JC_NODE_BN,         /* b_n                                            */
+  JC_NODE_LNCF,       /* ln(c_n f3)                                     */
+  JC_NODE_P3,         /* 3 - gamma_n                                    */
+  JC_NODE_ALPHA,      /* alpha_n                                        */
+  JC_NODE_BETA,       /* beta_n                                         */
+  JC_NODE_NU,         /* nu_n                                           */
+  JC_NODE_E1,         /* 3 f1                                           */
+  JC_NODE_E2,         /* f2                                             */
+  JC_NODE_FIELDS
+};
+/* fields of the per-cosmology scalar block (index into ws.scal) */
+enum {
+  JC_SCAL_LN13KEQ = 0, /* ln(13.41 k_eq)      transfer.py:116   */
+  JC_SCAL_INV13KEQ,    /* 1 / (13.41 k_eq)                      */
+  JC_SCAL_BETA_C,      /* transfer.py:110-111                   */
+  JC_SCAL_C14_ALPHA_C, /* 14.2 / alpha_c      transfer.py:118   */
+  JC_SCAL_SH_D,        /* sound horizon       transfer.py:72-77 */
+  JC_SCAL_LNKSILK,     /* ln k_silk           transfer.py:79-85 */
+  JC_SCAL_ALPHA_B,     /* transfer.py:131                       */
+  JC_SCAL_BETA_B,      /* transfer.py:136                       */
+  JC_SCAL_BETA_NODE,   /* transfer.py:133                       */
+  JC_SCAL_FB,
+  JC_SCAL_FC,
+  JC_SCAL_NS,
+  JC_SCAL_PKNORM,      /* sigma8^2 / sigmasqr(8)  power.py:47   */
+  JC_SCAL_SIGMASQR8,   /* raw sigmasqr(cosmo, 8)  power.py:56-78 */
+  JC_SCAL_OMEGA_M,
+  JC_SCAL_FIELDS = 32
+};
+
+typedef struct jc_plan jc_plan; /* opaque: cosmology-independent device tables for one problem */
+
+/* Build the plan for (problem, ell) on CUDA device `device`: validates the problem, uploads the
+ * quadrature grids / interpolation brackets / Romberg weights and runs the one-time n(z) kernels.
+ * Synchronous; allocates device memory owned by the plan. */
+int jc_plan_create(const jc_problem* problem, const double* ell_host, int32_t n_ell,
+                   int32_t device, jc_plan** plan_out);
+void jc_plan_destroy(jc_plan* plan);
+
+int32_t jc_plan_n_tracers(const jc_plan* plan);
+int32_t jc_plan_n_cls(const jc_plan* plan); /* P = T(T+1)/2 */
+int32_t jc_plan_n_ell(const jc_plan* plan);
+
+/* Workspace: recommended size for n_cosmo cosmologies (processed in chunks of at most
+ * JC_MAX_CHUNK) and the table offsets for a given size.  Any ws_bytes >= jc_workspace_bytes(plan,
+ * 1, ..) is accepted by jc_angular_cl_f64; smaller chunks just mean more passes. */
+int jc_workspace_bytes(const jc_plan* plan, int64_t n_cosmo, size_t* bytes_out);
+int jc_workspace_layout(const jc_plan* plan, size_t ws_bytes, jc_ws_layout* layout_out);
+
+/* angular_cl for a batch of cosmologies (replaces jax_cosmo/angular_cl.py:49-98; B == 1 is the
+ * reference call).  cosmo_dev [B,8], cl_dev [B,P,L], ws_dev scratch.  Asynchronous on `stream`. */
+int jc_angular_cl_f64(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo,
+                      double* cl_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
+/* Same call with HOST buffers: copies cosmo in, runs, copies cl out, synchronises.  Uses a
+ * device arena owned by the plan (grown on first use).  This is what the Python drop-in calls. */
+int jc_angular_cl_host_f64(jc_plan* plan, const double* cosmo_host, int64_t n_cosmo,
+                           double* cl_host);
+
+/* Per-tracer noise (replaces probes.py:210-223,274-281 / angular_cl.py:101-117): noise_host[T];
+ * the [P,L] noise_cl has noise[i] on auto pairs (i,i) and 0 elsewhere. */
+int jc_noise_f64(const jc_plan* plan, double* noise_host);
+
+/* Gaussian covariance in the sparse block layout (replaces angular_cl.py:120-163, sparse=True):
+ * cov[(ij),(mn),l] = (C_im C_jn + C_in C_jm) / ((2l+1) gradient(l) f_sky),  C = signal + noise.
+ * cl_dev [B,P,L] signal, noise_dev [T], cov_dev [B,P,P,L].  Uses the plan's ell. */
+int jc_gaussian_cov_f64(const jc_plan* plan, const double* cl_dev, const double* noise_dev,
+                        int64_t n_cosmo, double f_sky, double* cov_dev, void* stream);
+
+/* Per-stage device timing (CUDA events recorded on the launch stream between the stages of
+ * jc_angular_cl_f64).  Stages: 0 setup, 1 lensing efficiency, 2 tracer finish, 3 power, 4 pair
+ * contraction.  While enabled the plan is not re-entrant.  jc_profile_read synchronises the
+ * recorded events, returns the summed milliseconds and kernel-launch counts per stage since the
+ * last read, and resets the counters. */
+#define JC_N_STAGES 5
+int jc_profile_enable(jc_plan* plan, int32_t enable);
+int jc_profile_read(jc_plan* plan, double* stage_ms, int64_t* stage_launches);
+
+/* FP64 roofline probe: runs an FMA-only kernel (mode 0: DFMA chains, mode 1: DMMA m8n8k4) on the
+ * current device for ~`seconds` and returns TFLOP/s.  Used by bench.py for the roofline
+ * denominator, which MEASURED_PEAKS.json does not hold for FP64. */
+int jc_fp64_peak_tflops(int32_t mode, double seconds, double* tflops_out);
+
+const char* jc_status_string(int status);
+const char* jc_last_cuda_error(void);
+int32_t jc_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JC_B200_H */

@@ -1,0 +1,364 @@
+"""ctypes binding of libjc_b200.so (include/jc_b200.h) + flattening of the reference-style probe
+objects into the POD `jc_problem`.
+
+PyTorch is used only for device memory and streams.  There is NO CPU fallback: a missing library
+or a missing CUDA device raises.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libjc_b200.so")
+
+JC_ABI_VERSION = 1
+JC_MAX_TRACERS = 32
+JC_MAX_SHIFTS = 4
+JC_OK, JC_ERR_INVALID, JC_ERR_UNSUPPORTED, JC_ERR_WORKSPACE, JC_ERR_CUDA, JC_ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5
+JC_NZ_SMAIL = 1
+JC_BIAS = {"constant": 1, "inverse_growth": 2, "des_y1_ia": 3}
+JC_TRACER_WL, JC_TRACER_NC = 1, 2
+JC_PK_LINEAR, JC_PK_HALOFIT = 0, 1
+JC_TF_EH_OSC = 1
+
+NODE_FIELDS = ["CHI", "INVCHIC", "LNCHIC", "GEOM", "GROWTH", "HUBBLE", "AMP", "RNL", "LNKNL", "NEFF",
+               "CURV", "AN", "BN", "LNCF", "P3", "ALPHA", "BETA", "NU", "E1", "E2"]
+SCAL_FIELDS = ["LN13KEQ", "INV13KEQ", "BETA_C", "C14_ALPHA_C", "SH_D", "LNKSILK", "ALPHA_B", "BETA_B",
+               "BETA_NODE", "FB", "FC", "NS", "PKNORM", "SIGMASQR8", "OMEGA_M"]
+
+# every symbol include/jc_b200.h declares
+EXPORTS = ["jc_plan_create", "jc_plan_destroy", "jc_plan_n_tracers", "jc_plan_n_cls", "jc_plan_n_ell",
+           "jc_workspace_bytes", "jc_workspace_layout", "jc_angular_cl_f64", "jc_angular_cl_host_f64",
+           "jc_noise_f64", "jc_gaussian_cov_f64", "jc_profile_enable", "jc_profile_read",
+           "jc_fp64_peak_tflops", "jc_status_string",
+           "jc_last_cuda_error", "jc_abi_version"]
+
+
+class jc_nz(C.Structure):
+    _fields_ = [("family", C.c_int32), ("n_shifts", C.c_int32), ("params", C.c_double * 4),
+                ("shifts", C.c_double * JC_MAX_SHIFTS), ("gals_per_arcmin2", C.c_double),
+                ("zmax", C.c_double)]
+
+
+class jc_bias(C.Structure):
+    _fields_ = [("family", C.c_int32), ("reserved", C.c_int32), ("params", C.c_double * 3)]
+
+
+class jc_tracer(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("ia_enabled", C.c_int32), ("nz", jc_nz), ("bias", jc_bias),
+                ("m_bias", C.c_double), ("sigma_e", C.c_double), ("probe_zmax", C.c_double)]
+
+
+class jc_problem(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("n_tracers", C.c_int32), ("transfer", C.c_int32),
+                ("nonlinear", C.c_int32), ("tracers", jc_tracer * JC_MAX_TRACERS)]
+
+
+class jc_ws_layout(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("chunk", "node_stride", "ell_stride", "chitab", "gtab", "scal",
+                                         "stab", "node", "rker", "vtab", "total")]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load_library():
+    """Load libjc_b200.so; raise loudly when it has not been built (no fallback path exists)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "jax_cosmo_b200: %s not found. Build it with jax_cosmo_b200/csrc/build.sh "
+                "(or __graft_entry__.build()); there is no CPU fallback." % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        vp, i32, i64, dp = C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_double)
+        lib.jc_plan_create.argtypes = [C.POINTER(jc_problem), dp, i32, i32, C.POINTER(vp)]
+        lib.jc_plan_create.restype = C.c_int
+        lib.jc_plan_destroy.argtypes = [vp]
+        lib.jc_plan_destroy.restype = None
+        for f in ("jc_plan_n_tracers", "jc_plan_n_cls", "jc_plan_n_ell"):
+            getattr(lib, f).argtypes = [vp]
+            getattr(lib, f).restype = i32
+        lib.jc_workspace_bytes.argtypes = [vp, i64, C.POINTER(C.c_size_t)]
+        lib.jc_workspace_bytes.restype = C.c_int
+        lib.jc_workspace_layout.argtypes = [vp, C.c_size_t, C.POINTER(jc_ws_layout)]
+        lib.jc_workspace_layout.restype = C.c_int
+        lib.jc_angular_cl_f64.argtypes = [vp, vp, i64, vp, vp, C.c_size_t, vp]
+        lib.jc_angular_cl_f64.restype = C.c_int
+        lib.jc_angular_cl_host_f64.argtypes = [vp, vp, i64, vp]
+        lib.jc_angular_cl_host_f64.restype = C.c_int
+        lib.jc_noise_f64.argtypes = [vp, dp]
+        lib.jc_noise_f64.restype = C.c_int
+        lib.jc_gaussian_cov_f64.argtypes = [vp, vp, vp, i64, C.c_double, vp, vp]
+        lib.jc_gaussian_cov_f64.restype = C.c_int
+        lib.jc_profile_enable.argtypes = [vp, i32]
+        lib.jc_profile_enable.restype = C.c_int
+        lib.jc_profile_read.argtypes = [vp, dp, C.POINTER(C.c_int64)]
+        lib.jc_profile_read.restype = C.c_int
+        lib.jc_fp64_peak_tflops.argtypes = [i32, C.c_double, dp]
+        lib.jc_fp64_peak_tflops.restype = C.c_int
+        lib.jc_status_string.argtypes = [C.c_int]
+        lib.jc_status_string.restype = C.c_char_p
+        lib.jc_last_cuda_error.argtypes = []
+        lib.jc_last_cuda_error.restype = C.c_char_p
+        lib.jc_abi_version.argtypes = []
+        lib.jc_abi_version.restype = i32
+        if lib.jc_abi_version() != JC_ABI_VERSION:
+            raise ImportError("libjc_b200.so ABI version mismatch")
+        _lib = lib
+        return lib
+
+
+class JcError(RuntimeError):
+    pass
+
+
+def check(status, what=""):
+    if status == JC_OK:
+        return
+    lib = load_library()
+    msg = lib.jc_status_string(status).decode()
+    if status == JC_ERR_CUDA:
+        msg += ": " + lib.jc_last_cuda_error().decode()
+    if status == JC_ERR_UNSUPPORTED:
+        raise NotImplementedError("%s: %s" % (what, msg))
+    if status == JC_ERR_INVALID:
+        raise ValueError("%s: %s" % (what, msg))
+    raise JcError("%s: %s" % (what, msg))
+
+
+# ------------------------------------------------------------------------------------------------
+# reference-style objects -> jc_problem
+# ------------------------------------------------------------------------------------------------
+def _per_bin(value, i, n, what):
+    if isinstance(value, (list, tuple)):
+        if len(value) != n:
+            raise ValueError("%s: expected %d entries, got %d" % (what, n, len(value)))
+        return value[i]
+    return value
+
+
+def _fill_bias(dst, b):
+    fam = getattr(b, "_family", None)
+    if fam not in JC_BIAS:
+        raise NotImplementedError("bias %r is not supported by the B200 path" % type(b).__name__)
+    dst.family = JC_BIAS[fam]
+    for k, v in enumerate(b.params[:3]):
+        dst.params[k] = float(v)
+
+
+def build_problem(probes, transfer_fn=None, nonlinear_fn=None):
+    """Flatten a list of WeakLensing / NumberCounts probes (reference objects of this package)
+    into the C descriptor.  Tracer order = probe order, then bin order (angular_cl.py:15-25)."""
+    from jax_cosmo_b200 import power as _power
+    from jax_cosmo_b200 import transfer as _transfer
+    from jax_cosmo_b200.probes import NumberCounts, WeakLensing
+
+    if transfer_fn is None:
+        transfer_fn = _transfer.Eisenstein_Hu
+    if nonlinear_fn is None:
+        nonlinear_fn = _power.halofit
+    if transfer_fn is not _transfer.Eisenstein_Hu:
+        raise NotImplementedError("transfer_fn: only jax_cosmo_b200.transfer.Eisenstein_Hu is on the B200 path")
+    if nonlinear_fn is _power.halofit:
+        nl = JC_PK_HALOFIT
+    elif nonlinear_fn is _power.linear:
+        nl = JC_PK_LINEAR
+    else:
+        raise NotImplementedError("nonlinear_fn: only power.halofit (takahashi2012) and power.linear are on the B200 path")
+
+    pb = jc_problem()
+    pb.abi_version = JC_ABI_VERSION
+    pb.transfer = JC_TF_EH_OSC
+    pb.nonlinear = nl
+    t = 0
+    for probe in probes:
+        if isinstance(probe, WeakLensing):
+            kind = JC_TRACER_WL
+        elif isinstance(probe, NumberCounts):
+            kind = JC_TRACER_NC
+        else:
+            raise NotImplementedError("probe %r is not supported by the B200 path" % type(probe).__name__)
+        pzs = probe.params[0]
+        nb = len(pzs)
+        pzmax = float(probe.zmax)
+        for i, pz in enumerate(pzs):
+            if t >= JC_MAX_TRACERS:
+                raise NotImplementedError("more than %d tracers" % JC_MAX_TRACERS)
+            tr = pb.tracers[t]
+            tr.kind = kind
+            fam, p, shifts = pz._describe()
+            if fam != "smail":
+                raise NotImplementedError("n(z) family %s" % fam)
+            if len(shifts) > JC_MAX_SHIFTS:
+                raise NotImplementedError("more than %d nested systematic_shift" % JC_MAX_SHIFTS)
+            tr.nz.family = JC_NZ_SMAIL
+            for k, v in enumerate(p):
+                tr.nz.params[k] = v
+            tr.nz.n_shifts = len(shifts)
+            for k, v in enumerate(shifts):
+                tr.nz.shifts[k] = v
+            tr.nz.gals_per_arcmin2 = float(pz.gals_per_arcmin2)
+            tr.nz.zmax = float(pz.zmax)
+            tr.probe_zmax = pzmax
+            if kind == JC_TRACER_WL:
+                m = probe.params[1]
+                tr.m_bias = float(_per_bin(m, i, nb, "multiplicative_bias"))
+                tr.sigma_e = float(_per_bin(probe.config["sigma_e"], i, nb, "sigma_e"))
+                if probe.config["ia_enabled"]:
+                    tr.ia_enabled = 1
+                    _fill_bias(tr.bias, _per_bin(probe.params[2], i, nb, "ia_bias"))
+            else:
+                _fill_bias(tr.bias, _per_bin(probe.params[1], i, nb, "bias"))
+            t += 1
+    if t == 0:
+        raise ValueError("no tracers")
+    pb.n_tracers = t
+    return pb
+
+
+class Plan:
+    """Owns a jc_plan (cosmology-independent device tables for one (probes, ell) problem)."""
+
+    def __init__(self, problem, ell, device=None):
+        import torch
+
+        lib = load_library()
+        if not torch.cuda.is_available():
+            raise JcError("jax_cosmo_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.ell = np.ascontiguousarray(np.atleast_1d(np.asarray(ell, dtype=np.float64)))
+        self.problem = problem
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            st = lib.jc_plan_create(C.byref(problem), self.ell.ctypes.data_as(C.POINTER(C.c_double)),
+                                    len(self.ell), self.device, C.byref(handle))
+        check(st, "jc_plan_create")
+        self._h = handle
+        self.T = lib.jc_plan_n_tracers(handle)
+        self.P = lib.jc_plan_n_cls(handle)
+        self.L = lib.jc_plan_n_ell(handle)
+        self._ws = None
+        self._noise_dev = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                load_library().jc_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # -- sizes -----------------------------------------------------------------------------------
+    def workspace_bytes(self, n_cosmo):
+        out = C.c_size_t()
+        check(load_library().jc_workspace_bytes(self._h, int(n_cosmo), C.byref(out)), "jc_workspace_bytes")
+        return out.value
+
+    def workspace_layout(self, ws_bytes):
+        lo = jc_ws_layout()
+        check(load_library().jc_workspace_layout(self._h, int(ws_bytes), C.byref(lo)), "jc_workspace_layout")
+        return lo
+
+    def workspace(self, n_cosmo):
+        import torch
+
+        need = self.workspace_bytes(n_cosmo)
+        if self._ws is None or self._ws.numel() * 8 < need:
+            self._ws = torch.empty(need // 8, dtype=torch.float64, device="cuda:%d" % self.device)
+        return self._ws
+
+    # -- calls -----------------------------------------------------------------------------------
+    def angular_cl_device(self, cosmo_dev, out=None, workspace=None):
+        """cosmo_dev: CUDA float64 tensor [B,8] -> CUDA tensor [B,P,L]; async on torch's current stream."""
+        import torch
+
+        assert cosmo_dev.is_cuda and cosmo_dev.dtype == torch.float64 and cosmo_dev.is_contiguous()
+        B = cosmo_dev.shape[0]
+        if out is None:
+            out = torch.empty((B, self.P, self.L), dtype=torch.float64, device=cosmo_dev.device)
+        ws = self.workspace(B) if workspace is None else workspace
+        stream = torch.cuda.current_stream(cosmo_dev.device).cuda_stream
+        st = load_library().jc_angular_cl_f64(self._h, cosmo_dev.data_ptr(), B, out.data_ptr(), ws.data_ptr(),
+                                              ws.numel() * 8, stream)
+        check(st, "jc_angular_cl_f64")
+        return out
+
+    def angular_cl_host(self, cosmo_rows, out=None):
+        """cosmo_rows: host float64 [B,8] (numpy or CPU tensor) -> host [B,P,L] (same kind)."""
+        import torch
+
+        is_t = isinstance(cosmo_rows, torch.Tensor)
+        rows = cosmo_rows if is_t else np.ascontiguousarray(cosmo_rows, dtype=np.float64)
+        B = rows.shape[0]
+        if out is None:
+            out = (torch.empty((B, self.P, self.L), dtype=torch.float64, pin_memory=True) if is_t
+                   else np.empty((B, self.P, self.L), dtype=np.float64))
+        src = rows.data_ptr() if is_t else rows.ctypes.data
+        dst = out.data_ptr() if isinstance(out, torch.Tensor) else out.ctypes.data
+        with torch.cuda.device(self.device):
+            st = load_library().jc_angular_cl_host_f64(self._h, src, B, dst)
+        check(st, "jc_angular_cl_host_f64")
+        return out
+
+    STAGES = ["setup", "lens", "finish", "power", "contract"]
+
+    def profile_enable(self, on=True):
+        check(load_library().jc_profile_enable(self._h, 1 if on else 0), "jc_profile_enable")
+
+    def profile_read(self):
+        """-> ({stage: ms}, {stage: kernel launches}) summed since the last read."""
+        ms = (C.c_double * 5)()
+        nl = (C.c_int64 * 5)()
+        check(load_library().jc_profile_read(self._h, ms, nl), "jc_profile_read")
+        return dict(zip(self.STAGES, list(ms))), dict(zip(self.STAGES, list(nl)))
+
+    def noise(self):
+        out = np.zeros(self.T, dtype=np.float64)
+        check(load_library().jc_noise_f64(self._h, out.ctypes.data_as(C.POINTER(C.c_double))), "jc_noise_f64")
+        return out
+
+    def gaussian_cov_device(self, cl_dev, f_sky=0.25, noise=None):
+        """cl_dev CUDA [B,P,L] (signal) -> CUDA [B,P,P,L] sparse-block covariance."""
+        import torch
+
+        B = cl_dev.shape[0]
+        nv = self.noise() if noise is None else np.asarray(noise, dtype=np.float64)
+        noise_dev = torch.as_tensor(nv, device=cl_dev.device)
+        cov = torch.empty((B, self.P, self.P, self.L), dtype=torch.float64, device=cl_dev.device)
+        stream = torch.cuda.current_stream(cl_dev.device).cuda_stream
+        st = load_library().jc_gaussian_cov_f64(self._h, cl_dev.data_ptr(), noise_dev.data_ptr(), B, float(f_sky),
+                                                cov.data_ptr(), stream)
+        check(st, "jc_gaussian_cov_f64")
+        return cov
+
+
+_plan_cache = {}
+
+
+def get_plan(probes, ell, transfer_fn=None, nonlinear_fn=None, device=None):
+    """Plans are cached per (problem bytes, ell bytes, device)."""
+    import torch
+
+    pb = build_problem(probes, transfer_fn, nonlinear_fn)
+    ell = np.ascontiguousarray(np.atleast_1d(np.asarray(ell, dtype=np.float64)))
+    dev = (torch.cuda.current_device() if torch.cuda.is_available() else -1) if device is None else int(device)
+    key = (bytes(pb), ell.tobytes(), dev)
+    plan = _plan_cache.get(key)
+    if plan is None:
+        if len(_plan_cache) >= 8:
+            _plan_cache.pop(next(iter(_plan_cache)))
+        plan = Plan(pb, ell, device=None if dev < 0 else dev)
+        _plan_cache[key] = plan
+    return plan
+
+
+def fp64_peak_tflops(mode=0, seconds=0.5):
+    out = C.c_double()
+    check(load_library().jc_fp64_peak_tflops(int(mode), float(seconds), C.byref(out)), "jc_fp64_peak_tflops")
+    return out.value

@@ -1,0 +1,248 @@
+// jc_api.cu -- remaining C-ABI entry points: host-buffer call, Gaussian covariance, FP64 roofline
+// probe, status strings.
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+
+#include "jc_internal.cuh"
+
+static thread_local char g_cuda_err[512] = "";
+
+void jc_set_cuda_error(cudaError_t e, const char* where) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+extern "C" const char* jc_last_cuda_error(void) { return g_cuda_err; }
+extern "C" int32_t jc_abi_version(void) { return JC_ABI_VERSION; }
+
+extern "C" const char* jc_status_string(int status) {
+  switch (status) {
+    case JC_OK: return "ok";
+    case JC_ERR_INVALID: return "invalid argument";
+    case JC_ERR_UNSUPPORTED: return "configuration not supported by the B200 path (no fallback)";
+    case JC_ERR_WORKSPACE: return "workspace too small";
+    case JC_ERR_CUDA: return "CUDA runtime error";
+    case JC_ERR_NO_DEVICE: return "no CUDA device";
+    default: return "unknown status";
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-buffer entry: H2D cosmologies, chunked compute on one stream, D2H of each finished chunk on
+// a second stream (double-buffered), so PCIe traffic overlaps the FP64 kernels when the host
+// buffers are pinned.
+// ---------------------------------------------------------------------------------------------
+#define JC_HOST_CHUNK 1024
+
+static int ensure(void** p, size_t* have, size_t need) {
+  if (*have >= need) return JC_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *have = 0;
+  JC_CUDA_TRY(cudaMalloc(p, need));
+  *have = need;
+  return JC_OK;
+}
+
+extern "C" int jc_angular_cl_host_f64(jc_plan* plan, const double* cosmo_host, int64_t n_cosmo,
+                                      double* cl_host) {
+  if (!plan || !cosmo_host || !cl_host || n_cosmo < 1) return JC_ERR_INVALID;
+  JC_CUDA_TRY(cudaSetDevice(plan->device));
+  if (!plan->s_compute) {
+    JC_CUDA_TRY(cudaStreamCreateWithFlags(&plan->s_compute, cudaStreamNonBlocking));
+    JC_CUDA_TRY(cudaStreamCreateWithFlags(&plan->s_copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      JC_CUDA_TRY(cudaEventCreateWithFlags(&plan->ev_done[i], cudaEventDisableTiming));
+      JC_CUDA_TRY(cudaEventCreateWithFlags(&plan->ev_copied[i], cudaEventDisableTiming));
+    }
+  }
+  const int64_t chunk = n_cosmo < JC_HOST_CHUNK ? n_cosmo : JC_HOST_CHUNK;
+  const size_t pl_elems = (size_t)plan->d.P * plan->d.L;
+  size_t ws_need = 0;
+  int st = jc_workspace_bytes(plan, chunk, &ws_need);
+  if (st != JC_OK) return st;
+  if ((st = ensure(&plan->arena_ws, &plan->arena_ws_bytes, ws_need)) != JC_OK) return st;
+  if ((st = ensure((void**)&plan->arena_cosmo, &plan->arena_cosmo_bytes,
+                   (size_t)n_cosmo * JC_N_COSMO_PARAMS * sizeof(double))) != JC_OK) return st;
+  size_t cl_need = (size_t)chunk * pl_elems * sizeof(double);
+  if (plan->arena_cl_bytes < cl_need) {
+    for (int i = 0; i < 2; ++i) {
+      if (plan->arena_cl[i]) cudaFree(plan->arena_cl[i]);
+      plan->arena_cl[i] = nullptr;
+    }
+    plan->arena_cl_bytes = 0;
+    for (int i = 0; i < 2; ++i) JC_CUDA_TRY(cudaMalloc((void**)&plan->arena_cl[i], cl_need));
+    plan->arena_cl_bytes = cl_need;
+  }
+  JC_CUDA_TRY(cudaMemcpyAsync(plan->arena_cosmo, cosmo_host, (size_t)n_cosmo * JC_N_COSMO_PARAMS * sizeof(double),
+                              cudaMemcpyHostToDevice, plan->s_compute));
+  int k = 0;
+  for (int64_t c0 = 0; c0 < n_cosmo; c0 += chunk, ++k) {
+    const int b = k & 1;
+    const int64_t nc = (n_cosmo - c0) < chunk ? (n_cosmo - c0) : chunk;
+    if (k >= 2) JC_CUDA_TRY(cudaStreamWaitEvent(plan->s_compute, plan->ev_copied[b], 0));
+    st = jc_angular_cl_f64(plan, plan->arena_cosmo + c0 * JC_N_COSMO_PARAMS, nc, plan->arena_cl[b],
+                           plan->arena_ws, plan->arena_ws_bytes, plan->s_compute);
+    if (st != JC_OK) return st;
+    JC_CUDA_TRY(cudaEventRecord(plan->ev_done[b], plan->s_compute));
+    JC_CUDA_TRY(cudaStreamWaitEvent(plan->s_copy, plan->ev_done[b], 0));
+    JC_CUDA_TRY(cudaMemcpyAsync(cl_host + (size_t)c0 * pl_elems, plan->arena_cl[b], (size_t)nc * pl_elems * sizeof(double),
+                                cudaMemcpyDeviceToHost, plan->s_copy));
+    JC_CUDA_TRY(cudaEventRecord(plan->ev_copied[b], plan->s_copy));
+  }
+  JC_CUDA_TRY(cudaStreamSynchronize(plan->s_compute));
+  JC_CUDA_TRY(cudaStreamSynchronize(plan->s_copy));
+  return JC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gaussian covariance, sparse block layout [P,P,L] (angular_cl.py:120-163); HBM-write bound.
+// One thread per output element, ell fastest (coalesced 8-byte stores; the four C_l reads per
+// element hit L1/L2: the [P,L] signal of one cosmology is 168 KB at P=210, L=100).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pair_index(int i, int j, int T) {  // angular_cl.py:34-38
+  if (i > j) { int t = i; i = j; j = t; }
+  return i * T - (i * (i - 1)) / 2 + (j - i);
+}
+
+__global__ void __launch_bounds__(256) jc_cov_kernel(JcDevPlan pl, const double* __restrict__ cl,
+                                                     const double* __restrict__ noise, double f_sky,
+                                                     double* __restrict__ cov, size_t total) {
+  size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int L = pl.L, P = pl.P, T = pl.T;
+  int l = (int)(idx % L);
+  size_t r = idx / L;
+  int q = (int)(r % P); r /= P;
+  int p = (int)(r % P);
+  size_t c = r / P;
+  int i = pl.pair_i[p], j = pl.pair_j[p], m = pl.pair_i[q], n = pl.pair_j[q];
+  const double* C = cl + c * (size_t)P * L + l;
+  // cl_obs = cl_signal + cl_noise (noise on auto pairs only, angular_cl.py:112-115,135)
+  double A = C[(size_t)pair_index(i, m, T) * L] + (i == m ? noise[i] : 0.0);
+  double B = C[(size_t)pair_index(j, n, T) * L] + (j == n ? noise[j] : 0.0);
+  double Cc = C[(size_t)pair_index(i, n, T) * L] + (i == n ? noise[i] : 0.0);
+  double D = C[(size_t)pair_index(j, m, T) * L] + (j == m ? noise[j] : 0.0);
+  cov[idx] = (A * B + Cc * D) / (pl.covnorm[l] * f_sky);  // angular_cl.py:139,146-147
+}
+
+extern "C" int jc_gaussian_cov_f64(const jc_plan* plan, const double* cl_dev, const double* noise_dev,
+                                   int64_t n_cosmo, double f_sky, double* cov_dev, void* stream) {
+  if (!plan || !cl_dev || !noise_dev || !cov_dev || n_cosmo < 1) return JC_ERR_INVALID;
+  if (plan->d.L < 2) return JC_ERR_INVALID;  // np.gradient needs >= 2 points
+  size_t total = (size_t)n_cosmo * plan->d.P * plan->d.P * plan->d.L;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 0x7fffffffu) return JC_ERR_INVALID;
+  jc_cov_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(plan->d, cl_dev, noise_dev, f_sky, cov_dev, total);
+  JC_CUDA_TRY(cudaGetLastError());
+  return JC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-stage profiling
+// ---------------------------------------------------------------------------------------------
+extern "C" int jc_profile_enable(jc_plan* plan, int32_t enable) {
+  if (!plan) return JC_ERR_INVALID;
+  JC_CUDA_TRY(cudaSetDevice(plan->device));
+  if (enable && !plan->prof) {
+    plan->prof = new JcProf();
+    memset(plan->prof, 0, sizeof(JcProf));
+    for (int i = 0; i < JC_PROF_SLOTS; ++i)
+      for (int j = 0; j <= JC_N_STAGES; ++j) JC_CUDA_TRY(cudaEventCreate(&plan->prof->ev[i][j]));
+  }
+  if (plan->prof) { plan->prof->enabled = enable ? 1 : 0; plan->prof->used = 0; }
+  return JC_OK;
+}
+
+extern "C" int jc_profile_read(jc_plan* plan, double* stage_ms, int64_t* stage_launches) {
+  if (!plan || !plan->prof || !stage_ms || !stage_launches) return JC_ERR_INVALID;
+  JcProf* p = plan->prof;
+  for (int j = 0; j < JC_N_STAGES; ++j) { stage_ms[j] = 0.0; stage_launches[j] = 0; }
+  for (int i = 0; i < p->used; ++i) {
+    JC_CUDA_TRY(cudaEventSynchronize(p->ev[i][JC_N_STAGES]));
+    for (int j = 0; j < JC_N_STAGES; ++j) {
+      float ms = 0.f;
+      JC_CUDA_TRY(cudaEventElapsedTime(&ms, p->ev[i][j], p->ev[i][j + 1]));
+      stage_ms[j] += ms;
+      stage_launches[j] += p->launches[i][j];
+    }
+  }
+  p->used = 0;
+  return JC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 roofline probe
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) jc_dfma_probe_kernel(double* out, int iters, double seed) {
+  double a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = seed + threadIdx.x * 1e-9 + i;
+  const double m = 1.0000000001, b = 1e-12;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = fma(a[i], m, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i];
+  if (s == 12345.678) out[0] = s;  // keep the chain alive
+}
+
+__global__ void __launch_bounds__(256) jc_dmma_probe_kernel(double* out, int iters, double seed) {
+  double c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0};
+  double a = seed + threadIdx.x * 1e-9, b = 1.0 + threadIdx.x * 1e-12;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                     : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s += c0[i] + c1[i];
+  if (s == 12345.678) out[0] = s;
+}
+
+extern "C" int jc_fp64_peak_tflops(int32_t mode, double seconds, double* tflops_out) {
+  if (!tflops_out || (mode != 0 && mode != 1)) return JC_ERR_INVALID;
+  int dev = 0, sms = 0;
+  JC_CUDA_TRY(cudaGetDevice(&dev));
+  JC_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  double* d_out = nullptr;
+  JC_CUDA_TRY(cudaMalloc(&d_out, 8));
+  cudaEvent_t e0, e1;
+  JC_CUDA_TRY(cudaEventCreate(&e0));
+  JC_CUDA_TRY(cudaEventCreate(&e1));
+  const int blocks = sms * 8, threads = 256, iters = 4096;
+  // flops per launch
+  double flops = mode == 0 ? (double)blocks * threads * iters * 64.0 * 2.0
+                           : (double)blocks * (threads / 32) * iters * 16.0 * (8 * 8 * 4 * 2.0);
+  auto launch = [&]() {
+    if (mode == 0) jc_dfma_probe_kernel<<<blocks, threads>>>(d_out, iters, 1.0);
+    else jc_dmma_probe_kernel<<<blocks, threads>>>(d_out, iters, 1.0);
+  };
+  launch();  // warm-up
+  JC_CUDA_TRY(cudaDeviceSynchronize());
+  auto t0 = std::chrono::steady_clock::now();
+  double total_ms = 0.0, total_flops = 0.0;
+  do {
+    JC_CUDA_TRY(cudaEventRecord(e0));
+    for (int i = 0; i < 4; ++i) launch();
+    JC_CUDA_TRY(cudaEventRecord(e1));
+    JC_CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    JC_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    total_ms += ms;
+    total_flops += 4.0 * flops;
+  } while (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() < seconds);
+  *tflops_out = total_flops / (total_ms * 1e-3) / 1e12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  return JC_OK;
+}

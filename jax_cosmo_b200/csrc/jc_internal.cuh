@@ -1,0 +1,198 @@
+// jc_internal.cuh -- shared definitions of the sm_100a angular-C_ell pipeline (not part of the ABI).
+//
+// Pipeline per chunk of cosmologies (all FP64, one stream, no host sync):
+//   K1 jc_setup_kernel    per-cosmology tables: chi(a) [256], D(a) [128], EH scalars, sigma8 norm,
+//                         halofit S(R) [256], k_nl/n_eff/C and Takahashi coefficients at the 513
+//                         Limber nodes                                  (one CTA per cosmology)
+//   K2 jc_tracer_kernel   radial kernels R_i(a_n): lensing efficiency on the [257 x 512] z' grid
+//                         against cosmology-independent n(z') tables, NC / NLA / m-bias
+//   K3 jc_power_kernel    V[n,l] = w_n P(k=(l+1/2)/chi_n, a_n) dchi/da / chi_n^2 / c^2
+//                         (Eisenstein-Hu + halofit, fully in registers)
+//   K4 jc_contract_kernel C[(i,j),l] = e_i(l) e_j(l) sum_n R_i[n] R_j[n] V[n,l]
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/jc_b200.h"
+
+#define JC_NA 513        // Limber nodes (angular_cl.py:96)
+#define JC_NA_PAD 520    // padded per-node stride (64-byte multiple)
+#define JC_NCHI 256      // chi table (background.py:199)
+#define JC_NGROW 128     // growth table (background.py:443)
+#define JC_NLENS 257     // z' nodes of the lensing-efficiency Simpson rule (probes.py:51)
+#define JC_NLENS_COLS 512  // Limber nodes with chi>0 (node 512 is a=1: kernel == 0)
+#define JC_NHFK 257      // halofit ln k nodes (power.py:111)
+#define JC_NHFR 256      // halofit ln R nodes (power.py:93)
+#define JC_NROMB 129     // Romberg nodes, divmax=7 (power.py:77)
+#define JC_MAX_CHUNK 4096
+
+#define JC_C_LIGHT 299792.458      // constants.py:9
+#define JC_RH 2997.92458           // constants.py:15
+#define JC_H0 100.0                // constants.py:21
+#define JC_TCMB 2.726              // constants.py:12
+#define JC_C1_RHOCRIT (5.0 * 1e-14 * (2.7750 * 1e11))  // constants.py:24,27 ; probes.py:121
+#define JC_STERADIAN_TO_ARCMIN2 11818102.86004228      // redshift.py:10
+#define JC_TWO_PI_SQ 19.739208802178716                // 2 pi^2
+
+// Device-side view of the plan: cosmology-independent tables (all device pointers).
+struct JcDevPlan {
+  int T, P, L, Lpad, nonlinear;
+  int n_src;                 // number of weak-lensing tracers
+  double zmax;               // Limber zmax (max over probes), angular_cl.py:63
+  double lens_zmax;          // zmax of the WL probe(s), probes.py:24
+  // chi table quadrature: points p = 2i (node i), 2i+1 (midpoint of interval i)
+  const double* chi_pt_a;    // [511]
+  const double* chi_pt_lna;  // [511]
+  const double* chi_h6;      // [255]  h_i / 6
+  // growth table quadrature: points p = 2i (node), 2i+1 (a_i + h_i/2)
+  const double* gr_pt_a;     // [255]
+  const double* gr_pt_lna;   // [255]
+  const double* gr_h;        // [127]
+  // Limber nodes
+  const double* limb_a;      // [513]
+  const double* limb_lna;    // [513]
+  const double* limb_z;      // [513]
+  const double* limb_w;      // [513] Simpson weights * dx/3
+  const double* limb_chi_t;  // [513] interpolation weight in the chi table
+  const double* limb_gr_t;   // [513] interpolation weight in the growth table
+  const uint16_t* limb_chi_ix;  // [513] i0 | i1<<8
+  const uint16_t* limb_gr_ix;   // [513]
+  // sigma8 Romberg functional
+  const double* romb_k;      // [129]
+  const double* romb_lnk;    // [129]
+  const double* romb_f;      // [129] w_i (b-a) k (k W(8k))^2 / (2 pi^2)
+  // halofit grids
+  const double* hf_k;        // [257]
+  const double* hf_lnk;      // [257]
+  const double* hf_wk;       // [257] Simpson weights * dx/3
+  const double* hf_r;        // [256]
+  const double* hf_logr;     // [256]
+  // lensing-efficiency grid, [257][512] (row m = z' node, column n = Limber node)
+  const double* lens_t;      // interpolation weight of a'=1/(1+z') in the chi table
+  const uint16_t* lens_ix;   // i0 | i1<<8
+  const double* lens_nw;     // [n_src][257][512]  simpson_w[m]/(3*256) * n_s(z'(m,n))
+  // tracers
+  const double* nz_node;     // [T][513] normalised n_i(z_n)
+  const double* bias_node;   // [T][513] cosmology-independent part of b_i(z_n) (NC) / b_IA (WL)
+  const int* tr_kind;        // [T]
+  const int* tr_inv_growth;  // [T] bias multiplies 1/D(a)
+  const int* tr_ia;          // [T]
+  const int* tr_src;         // [T] index into lens_nw or -1
+  const int* src_tracer;     // [n_src] tracer index of each lensing source
+  const double* tr_m1;       // [T] 1 + m
+  // ell
+  const double* ell;         // [L]
+  const double* ellp5;       // [L] ell + 0.5
+  const double* lnellp5;     // [L]
+  const double* ellfac;      // [L] WL ell factor (probes.py:73)
+  const double* covnorm;     // [L] (2l+1) gradient(l)   (angular_cl.py:139, without f_sky)
+  // pairs
+  const uint8_t* pair_i;     // [P]
+  const uint8_t* pair_j;     // [P]
+};
+
+#define JC_PROF_SLOTS 2048
+struct JcProf {
+  int enabled;
+  int used;                                   // chunk passes recorded
+  cudaEvent_t ev[JC_PROF_SLOTS][JC_N_STAGES + 1];
+  int launches[JC_PROF_SLOTS][JC_N_STAGES];
+};
+
+struct jc_plan {
+  int device;
+  JcProf* prof;
+  jc_problem problem;
+  JcDevPlan d;
+  void* dev_blob;       // single allocation holding every table
+  size_t dev_blob_bytes;
+  double noise[JC_MAX_TRACERS];
+  // arena for the host entry point
+  void* arena_ws;
+  size_t arena_ws_bytes;
+  double* arena_cosmo;
+  size_t arena_cosmo_bytes;
+  double* arena_cl[2];
+  size_t arena_cl_bytes;
+  cudaStream_t s_compute, s_copy;
+  cudaEvent_t ev_done[2], ev_copied[2];
+};
+
+void jc_set_cuda_error(cudaError_t e, const char* where);
+int jc_pipeline_init();  // one-time function attributes (dynamic shared memory opt-in)
+
+#define JC_CUDA_TRY(expr)                          \
+  do {                                             \
+    cudaError_t _e = (expr);                       \
+    if (_e != cudaSuccess) {                       \
+      jc_set_cuda_error(_e, #expr);                \
+      return JC_ERR_CUDA;                          \
+    }                                              \
+  } while (0)
+
+// ---- device math helpers ------------------------------------------------------------------
+__device__ __forceinline__ double jc_fde(double w0, double wa, double a, double lna) {
+  return -3.0 * (1.0 + w0 + wa) * lna + 3.0 * wa * (a - 1.0);  // background.py:90
+}
+
+struct JcBg {
+  double Om, Ok, Ode, w0, wa;
+};
+
+// E^2(a), background.py:122-126.  Returns also the dark-energy term.
+__device__ __forceinline__ double jc_esqr(const JcBg& c, double a, double lna, double* de_term) {
+  double ia = 1.0 / a;
+  double ia2 = ia * ia;
+  double de = c.Ode * exp(jc_fde(c.w0, c.wa, a, lna));
+  *de_term = de;
+  return c.Om * (ia2 * ia) + c.Ok * ia2 + de;
+}
+
+// Eisenstein-Hu per-cosmology constants (transfer.py:47-136), computed once per cosmology.
+struct JcEH {
+  double ln13keq, inv13keq, beta_c, c14_alpha_c, sh_d, lnksilk, alpha_b, beta_b, beta_node, fb, fc;
+};
+
+__device__ __forceinline__ void jc_eh_load(JcEH& e, const double* __restrict__ s) {
+  e.ln13keq = s[JC_SCAL_LN13KEQ];
+  e.inv13keq = s[JC_SCAL_INV13KEQ];
+  e.beta_c = s[JC_SCAL_BETA_C];
+  e.c14_alpha_c = s[JC_SCAL_C14_ALPHA_C];
+  e.sh_d = s[JC_SCAL_SH_D];
+  e.lnksilk = s[JC_SCAL_LNKSILK];
+  e.alpha_b = s[JC_SCAL_ALPHA_B];
+  e.beta_b = s[JC_SCAL_BETA_B];
+  e.beta_node = s[JC_SCAL_BETA_NODE];
+  e.fb = s[JC_SCAL_FB];
+  e.fc = s[JC_SCAL_FC];
+}
+
+// T(k) of transfer.py:113-153 ("eisenhu_osc") given k and ln k.
+__device__ __forceinline__ double jc_eh_transfer(const JcEH& e, double k, double lnk) {
+  const double E1 = 2.718281828459045;  // np.exp(1.0)
+  double q = k * e.inv13keq;
+  double q2 = q * q;
+  double q108 = exp(1.08 * (lnk - e.ln13keq));  // np.power(q, 1.08)
+  double c386 = 386.0 / (1.0 + 69.9 * q108);
+  double L1 = log(E1 + 1.8 * e.beta_c * q);
+  double L2 = log(E1 + 1.8 * q);
+  double C1 = 14.2 + c386;            // alpha = 1
+  double C2 = e.c14_alpha_c + c386;   // alpha = alpha_c
+  double T1 = L1 / (L1 + C1 * q2);    // T_tilde(k, 1, beta_c)
+  double T2 = L1 / (L1 + C2 * q2);    // T_tilde(k, alpha_c, beta_c)
+  double T3 = L2 / (L2 + C1 * q2);    // T_tilde(k, 1, 1)
+  double ks = k * e.sh_d;
+  double x54 = ks / 5.4;
+  double x54_2 = x54 * x54;
+  double f = 1.0 / (1.0 + x54_2 * x54_2);
+  double Tc = f * T1 + (1.0 - f) * T2;
+  double bn = e.beta_node / ks;
+  double st = e.sh_d / cbrt(1.0 + bn * bn * bn);
+  double x52 = ks / 5.2;
+  double bb = e.beta_b / ks;
+  double silk = exp(-exp(1.4 * (lnk - e.lnksilk)));  // exp(-(k/k_silk)^1.4)
+  double arg = k * st;
+  double sinc = sin(arg) / arg;  // np.sinc(k s~/pi); k > 0 on this path
+  double Tb = (T3 / (1.0 + x52 * x52) + e.alpha_b / (1.0 + bb * bb * bb) * silk) * sinc;
+  return e.fb * Tb + e.fc * Tc;
+}

@@ -1,0 +1,445 @@
+// jc_plan.cu -- plan creation: validation of the problem, cosmology-independent quadrature grids
+// and interpolation brackets (host, C++), one-time n(z) kernels (device).
+//
+// The grids restate the reference's discretisation exactly:
+//   chi table    logspace(-3,0,256) in a, RK4 in ln a            background.py:223-236
+//   growth table logspace(-3,0,128), RK4 in a                    background.py:461-481
+//   Limber       simps over linspace(1/(1+zmax), 1, 513)         angular_cl.py:96
+//   lensing      simps over linspace(z_n, zmax, 257) per node    probes.py:51
+//   sigma8       Romberg divmax=7 over x in [-4,3], k = e^x      power.py:70-78
+//   halofit      ln k in linspace(ln1e-4, ln1e4, 257), ln R in linspace(ln1e-4, ln10, 256)
+//                                                                power.py:93,111
+//   interp       nearest node + neighbour by sign                scipy/interpolate.py:25-37
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "jc_internal.cuh"
+
+namespace {
+
+// numpy.linspace(start, stop, num) for float64 (i*step + start, last = stop)
+std::vector<double> linspace(double start, double stop, int num) {
+  std::vector<double> y(num);
+  int div = num - 1;
+  double delta = stop - start;
+  double step = delta / div;
+  for (int i = 0; i < num; ++i) {
+    volatile double p = (double)i * step;  // no FMA contraction
+    y[i] = p + start;
+  }
+  if (num > 1) y[num - 1] = stop;
+  return y;
+}
+
+// Composite Simpson weights (1,4,2,...,4,1) * dx/3, scipy/integrate.py:193-199
+std::vector<double> simpson_weights(int N, double dx) {
+  std::vector<double> w(N + 1, 1.0);
+  for (int i = 1; i < N; ++i) w[i] = (i & 1) ? 4.0 : 2.0;
+  for (auto& v : w) v *= dx / 3.0;
+  return w;
+}
+
+// Romberg (scipy/integrate.py:134-159) as weights over 2^divmax+1 equispaced nodes, unit interval
+std::vector<double> romberg_weights(int divmax) {
+  int n = (1 << divmax) + 1;
+  std::vector<std::vector<double>> R;
+  for (int i = 0; i <= divmax; ++i) {
+    int step = 1 << (divmax - i);
+    std::vector<double> w(n, 0.0);
+    for (int j = 0; j < n; j += step) w[j] = 1.0;
+    w[0] = w[n - 1] = 0.5;
+    for (auto& v : w) v /= (double)(1 << i);
+    R.push_back(w);
+  }
+  for (int k = 1; k <= divmax; ++k) {
+    double f = std::pow(4.0, k);
+    std::vector<std::vector<double>> Rn;
+    for (size_t j = 0; j + 1 < R.size(); ++j) {
+      std::vector<double> w(n);
+      for (int t = 0; t < n; ++t) w[t] = (f * R[j + 1][t] - R[j][t]) / (f - 1.0);
+      Rn.push_back(w);
+    }
+    R.swap(Rn);
+  }
+  return R[0];
+}
+
+// The (ind, ind+d) pair chosen by scipy/interpolate.py:25-37 for an increasing table, and the
+// weight t such that interp(x) = fp[i0] + (fp[i1]-fp[i0]) * t.
+void bracket(double x, const std::vector<double>& xp, int* i0, int* i1, double* t) {
+  int n = (int)xp.size();
+  // searchsorted (left)
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) / 2;
+    if (xp[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  int j = lo < 1 ? 1 : (lo > n - 1 ? n - 1 : lo);
+  double dl = (x - xp[j - 1]) * (x - xp[j - 1]);
+  double dr = (x - xp[j]) * (x - xp[j]);
+  int ind = (dl <= dr) ? j - 1 : j;  // argmin returns the first minimum
+  if (ind < 1) ind = 1;
+  if (ind > n - 2) ind = n - 2;
+  double xc = x < xp[1] ? xp[1] : (x > xp[n - 2] ? xp[n - 2] : x);
+  int d = (xc - xp[ind] >= 0.0) ? 1 : -1;
+  *i0 = ind;
+  *i1 = ind + d;
+  *t = (x - xp[ind]) / (xp[ind + d] - xp[ind]);
+}
+
+struct Blob {
+  std::vector<unsigned char> host;
+  size_t add(const void* p, size_t bytes) {
+    size_t off = (host.size() + 255) & ~(size_t)255;
+    host.resize(off + bytes);
+    if (p) memcpy(host.data() + off, p, bytes);
+    return off;
+  }
+  template <class T>
+  size_t add(const std::vector<T>& v) { return add(v.data(), v.size() * sizeof(T)); }
+  size_t reserve(size_t bytes) { return add(nullptr, bytes); }
+};
+
+// ---- one-time device kernels ----------------------------------------------------------------
+struct NzDev {
+  int family, n_shifts;
+  double p[4];
+  double shifts[JC_MAX_SHIFTS];
+  double zmax;
+};
+struct NzDevAll { NzDev nz[JC_MAX_TRACERS]; };
+
+__device__ __forceinline__ double pz_fn(const NzDev& nz, double z) {
+  // systematic_shift chain (redshift.py:169-171), then smail (redshift.py:75-77)
+  for (int s = 0; s < nz.n_shifts; ++s) z = fmax(z - nz.shifts[s], 0.0);
+  return pow(z, nz.p[0]) * exp(-pow(z / nz.p[2], nz.p[1]));
+}
+
+// norm[t] = simps(pz_fn, 0, zmax, 256)  (redshift.py:29-30); one block of 256+ threads per tracer
+__global__ void jc_nz_norm_kernel(NzDevAll all, double* __restrict__ norm) {
+  __shared__ double red[288];
+  const NzDev& nz = all.nz[blockIdx.x];
+  int i = threadIdx.x;
+  double v = 0.0;
+  if (i <= 256) {
+    double dx = nz.zmax / 256.0;
+    double z = (i == 256) ? nz.zmax : (double)i * dx;  // linspace(0, zmax, 257)
+    double w = (i == 0 || i == 256) ? 1.0 : ((i & 1) ? 4.0 : 2.0);
+    v = w * pz_fn(nz, z);
+  }
+  red[i] = v;
+  __syncthreads();
+  if (i == 0) {
+    double s = 0.0;
+    for (int j = 0; j <= 256; ++j) s += red[j];
+    norm[blockIdx.x] = nz.zmax / 256.0 / 3.0 * s;
+  }
+}
+
+// nz_node[t][n] = pz_t(z_n)/norm_t on the 513 Limber nodes
+__global__ void jc_nz_node_kernel(NzDevAll all, const double* __restrict__ norm,
+                                  const double* __restrict__ limb_z, double* __restrict__ out) {
+  int t = blockIdx.y;
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < JC_NA) out[(size_t)t * JC_NA_PAD + n] = pz_fn(all.nz[t], limb_z[n]) / norm[t];
+}
+
+// lens_nw[s][m][n] = simpson_w[m]/(3*256) * pz_s(z'(m,n))/norm_s ; z' = linspace(z_n, zmax, 257)[m]
+__global__ void jc_nz_lens_kernel(NzDevAll all, const int* __restrict__ src_tracer,
+                                  const double* __restrict__ norm,
+                                  const double* __restrict__ lens_z, double* __restrict__ out) {
+  int s = blockIdx.z;
+  int m = blockIdx.y;
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= JC_NLENS_COLS) return;
+  int t = src_tracer[s];
+  double w = (m == 0 || m == 256) ? 1.0 : ((m & 1) ? 4.0 : 2.0);
+  size_t o = (size_t)m * JC_NLENS_COLS + n;
+  out[(size_t)s * JC_NLENS * JC_NLENS_COLS + o] =
+      (w / 3.0 / 256.0) * (pz_fn(all.nz[t], lens_z[o]) / norm[t]);
+}
+
+int validate(const jc_problem* pb, int n_ell) {
+  if (!pb) return JC_ERR_INVALID;
+  if (pb->abi_version != JC_ABI_VERSION) return JC_ERR_INVALID;
+  if (pb->n_tracers < 1 || pb->n_tracers > JC_MAX_TRACERS) return JC_ERR_INVALID;
+  if (n_ell < 1) return JC_ERR_INVALID;
+  if (pb->transfer != JC_TF_EISENSTEIN_HU_OSC) return JC_ERR_UNSUPPORTED;
+  if (pb->nonlinear != JC_PK_LINEAR && pb->nonlinear != JC_PK_HALOFIT_TAKAHASHI2012)
+    return JC_ERR_UNSUPPORTED;
+  double lens_zmax = -1.0;
+  for (int t = 0; t < pb->n_tracers; ++t) {
+    const jc_tracer& tr = pb->tracers[t];
+    if (tr.kind != JC_TRACER_WEAK_LENSING && tr.kind != JC_TRACER_NUMBER_COUNTS)
+      return JC_ERR_INVALID;
+    if (tr.nz.family != JC_NZ_SMAIL) return JC_ERR_UNSUPPORTED;
+    if (tr.nz.n_shifts < 0 || tr.nz.n_shifts > JC_MAX_SHIFTS) return JC_ERR_UNSUPPORTED;
+    if (!(tr.nz.zmax > 0.0) || !(tr.probe_zmax > 0.0)) return JC_ERR_INVALID;
+    if (!(tr.nz.gals_per_arcmin2 > 0.0)) return JC_ERR_INVALID;
+    bool needs_bias = tr.kind == JC_TRACER_NUMBER_COUNTS || tr.ia_enabled;
+    if (needs_bias) {
+      if (tr.bias.family < JC_BIAS_CONSTANT || tr.bias.family > JC_BIAS_DES_Y1_IA)
+        return JC_ERR_INVALID;
+    }
+    if (tr.kind == JC_TRACER_WEAK_LENSING) {
+      // one z' grid per plan: all WL probes must share their zmax (true for the default zmax=10)
+      if (lens_zmax < 0.0) lens_zmax = tr.probe_zmax;
+      else if (lens_zmax != tr.probe_zmax) return JC_ERR_UNSUPPORTED;
+    }
+  }
+  return JC_OK;
+}
+
+}  // namespace
+
+extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int32_t n_ell,
+                              int32_t device, jc_plan** plan_out) {
+  if (!plan_out || !ell_host) return JC_ERR_INVALID;
+  *plan_out = nullptr;
+  int st = validate(pb, n_ell);
+  if (st != JC_OK) return st;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return JC_ERR_NO_DEVICE;
+  if (device < 0 || device >= ndev) return JC_ERR_INVALID;
+  JC_CUDA_TRY(cudaSetDevice(device));
+  st = jc_pipeline_init();
+  if (st != JC_OK) return st;
+
+  const int T = pb->n_tracers, L = n_ell;
+  const int P = T * (T + 1) / 2;
+  double zmax = 0.0, lens_zmax = 0.0;
+  int n_src = 0;
+  std::vector<int> tr_kind(T), tr_inv(T, 0), tr_ia(T, 0), tr_src(T, -1), src_tracer;
+  std::vector<double> tr_m1(T, 1.0);
+  for (int t = 0; t < T; ++t) {
+    const jc_tracer& tr = pb->tracers[t];
+    if (tr.probe_zmax > zmax) zmax = tr.probe_zmax;  // angular_cl.py:63
+    tr_kind[t] = tr.kind;
+    bool needs_bias = tr.kind == JC_TRACER_NUMBER_COUNTS || tr.ia_enabled;
+    tr_inv[t] = needs_bias && tr.bias.family == JC_BIAS_INVERSE_GROWTH;
+    if (tr.kind == JC_TRACER_WEAK_LENSING) {
+      tr_ia[t] = tr.ia_enabled ? 1 : 0;
+      tr_src[t] = n_src++;
+      src_tracer.push_back(t);
+      tr_m1[t] = 1.0 + tr.m_bias;
+      lens_zmax = tr.probe_zmax;
+    }
+  }
+  if (src_tracer.empty()) src_tracer.push_back(0);
+
+  Blob B;
+  JcDevPlan d;
+  memset(&d, 0, sizeof(d));
+  d.T = T; d.P = P; d.L = L; d.Lpad = (L + 3) & ~3; d.nonlinear = pb->nonlinear;
+  d.n_src = n_src; d.zmax = zmax; d.lens_zmax = lens_zmax;
+
+  // ---- chi table grid -----------------------------------------------------------------------
+  std::vector<double> e256 = linspace(-3.0, 0.0, JC_NCHI), atab(JC_NCHI), xtab(JC_NCHI);
+  for (int i = 0; i < JC_NCHI; ++i) { atab[i] = std::pow(10.0, e256[i]); xtab[i] = std::log(atab[i]); }
+  std::vector<double> chi_pt_a(511), chi_pt_lna(511), chi_h6(255);
+  for (int i = 0; i < JC_NCHI; ++i) { chi_pt_a[2 * i] = atab[i]; chi_pt_lna[2 * i] = xtab[i]; }
+  for (int i = 0; i < JC_NCHI - 1; ++i) {
+    double h = xtab[i + 1] - xtab[i];
+    double xm = xtab[i] + h / 2;
+    chi_pt_lna[2 * i + 1] = xm;
+    chi_pt_a[2 * i + 1] = std::exp(xm);
+    chi_h6[i] = 1.0 / 6.0 * h;
+  }
+  // ---- growth table grid ----------------------------------------------------------------------
+  std::vector<double> e128 = linspace(-3.0, 0.0, JC_NGROW), ag(JC_NGROW);
+  for (int i = 0; i < JC_NGROW; ++i) ag[i] = std::pow(10.0, e128[i]);
+  std::vector<double> gr_pt_a(255), gr_pt_lna(255), gr_h(127);
+  for (int i = 0; i < JC_NGROW; ++i) gr_pt_a[2 * i] = ag[i];
+  for (int i = 0; i < JC_NGROW - 1; ++i) {
+    gr_h[i] = ag[i + 1] - ag[i];
+    gr_pt_a[2 * i + 1] = ag[i] + gr_h[i] / 2;
+  }
+  for (int i = 0; i < 255; ++i) gr_pt_lna[i] = std::log(gr_pt_a[i]);
+  // ---- Limber nodes ---------------------------------------------------------------------------
+  double amin = 1.0 / (1.0 + zmax);  // z2a(zmax), utils.py:2-4
+  std::vector<double> la = linspace(amin, 1.0, JC_NA), llna(JC_NA), lz(JC_NA);
+  std::vector<double> lw = simpson_weights(512, (1.0 - amin) / 512);
+  std::vector<double> lct(JC_NA), lgt(JC_NA);
+  std::vector<uint16_t> lcix(JC_NA), lgix(JC_NA);
+  for (int n = 0; n < JC_NA; ++n) {
+    llna[n] = std::log(la[n]);
+    lz[n] = 1.0 / la[n] - 1.0;  // a2z, utils.py:7-9
+    int i0, i1; double t;
+    bracket(la[n], atab, &i0, &i1, &t);
+    lcix[n] = (uint16_t)(i0 | (i1 << 8)); lct[n] = t;
+    bracket(la[n], ag, &i0, &i1, &t);
+    lgix[n] = (uint16_t)(i0 | (i1 << 8)); lgt[n] = t;
+  }
+  // ---- sigma8 Romberg functional ----------------------------------------------------------------
+  std::vector<double> rw = romberg_weights(7), rk(JC_NROMB), rlnk(JC_NROMB), rf(JC_NROMB);
+  {
+    double lo = std::log10(0.0001), hi = std::log10(1000.0);
+    std::vector<double> x = linspace(lo, hi, JC_NROMB);
+    for (int i = 0; i < JC_NROMB; ++i) {
+      double k = std::exp(x[i]);  // quirk A.9-2: log10 limits, natural exp
+      double xr = k * 8.0;
+      double w = 3.0 * (std::sin(xr) - xr * std::cos(xr)) / (xr * xr * xr);
+      rk[i] = k; rlnk[i] = x[i];
+      rf[i] = rw[i] * (hi - lo) * (k * (k * w) * (k * w)) / (2.0 * M_PI * M_PI);
+    }
+  }
+  // ---- halofit grids ------------------------------------------------------------------------------
+  std::vector<double> hlnk = linspace(std::log(1e-4), std::log(1e4), JC_NHFK), hk(JC_NHFK);
+  for (int i = 0; i < JC_NHFK; ++i) hk[i] = std::exp(hlnk[i]);
+  std::vector<double> hwk = simpson_weights(256, (std::log(1e4) - std::log(1e-4)) / 256);
+  std::vector<double> hlogr = linspace(std::log(1e-4), std::log(1e1), JC_NHFR), hr(JC_NHFR);
+  for (int i = 0; i < JC_NHFR; ++i) hr[i] = std::exp(hlogr[i]);
+  // ---- lensing-efficiency grid ----------------------------------------------------------------------
+  size_t nl = (size_t)JC_NLENS * JC_NLENS_COLS;
+  std::vector<double> lens_t(n_src ? nl : 1), lens_z(n_src ? nl : 1);
+  std::vector<uint16_t> lens_ix(n_src ? nl : 1);
+  if (n_src) {
+    for (int n = 0; n < JC_NLENS_COLS; ++n) {
+      double delta = lens_zmax - lz[n];
+      double step = delta / 256;
+      for (int m = 0; m < JC_NLENS; ++m) {
+        volatile double p = (double)m * step;
+        double zp = (m == 256) ? lens_zmax : p + lz[n];
+        double ap = 1.0 / (1.0 + zp);
+        int i0, i1; double t;
+        bracket(ap, atab, &i0, &i1, &t);
+        size_t o = (size_t)m * JC_NLENS_COLS + n;
+        lens_z[o] = zp; lens_t[o] = t; lens_ix[o] = (uint16_t)(i0 | (i1 << 8));
+      }
+    }
+  }
+  // ---- ell ----------------------------------------------------------------------------------------------
+  std::vector<double> ell(ell_host, ell_host + L), ellp5(L), lnellp5(L), ellfac(L), covnorm(L);
+  for (int l = 0; l < L; ++l) {
+    double e = ell[l];
+    ellp5[l] = e + 0.5;
+    lnellp5[l] = std::log(e + 0.5);
+    ellfac[l] = std::sqrt((e - 1) * e * (e + 1) * (e + 2)) / ((e + 0.5) * (e + 0.5));  // probes.py:73
+    double g;  // np.gradient(ell), unit spacing (angular_cl.py:139)
+    if (L == 1) g = 0.0;
+    else if (l == 0) g = ell[1] - ell[0];
+    else if (l == L - 1) g = ell[L - 1] - ell[L - 2];
+    else g = (ell[l + 1] - ell[l - 1]) / 2.0;
+    covnorm[l] = (2 * e + 1) * g;
+  }
+  // ---- pairs, bias tables, noise ---------------------------------------------------------------------------
+  std::vector<uint8_t> pi(P), pj(P);
+  { int p = 0; for (int i = 0; i < T; ++i) for (int j = i; j < T; ++j) { pi[p] = i; pj[p] = j; ++p; } }
+  std::vector<double> bias_node((size_t)T * JC_NA_PAD, 0.0);
+  for (int t = 0; t < T; ++t) {
+    const jc_tracer& tr = pb->tracers[t];
+    bool needs_bias = tr.kind == JC_TRACER_NUMBER_COUNTS || tr.ia_enabled;
+    for (int n = 0; n < JC_NA && needs_bias; ++n) {
+      double b = tr.bias.params[0];  // constant / inverse_growth: b (bias.py:20-22,37-39)
+      if (tr.bias.family == JC_BIAS_DES_Y1_IA)  // bias.py:55-57
+        b = tr.bias.params[0] * std::pow((1.0 + lz[n]) / (1.0 + tr.bias.params[2]), tr.bias.params[1]);
+      bias_node[(size_t)t * JC_NA_PAD + n] = b;
+    }
+  }
+
+  jc_plan* plan = new jc_plan();
+  memset(plan, 0, sizeof(*plan));
+  plan->device = device;
+  plan->problem = *pb;
+  for (int t = 0; t < T; ++t) {
+    const jc_tracer& tr = pb->tracers[t];
+    double ng = tr.nz.gals_per_arcmin2 * JC_STERADIAN_TO_ARCMIN2;  // redshift.py:49-51
+    plan->noise[t] = tr.kind == JC_TRACER_WEAK_LENSING ? tr.sigma_e * tr.sigma_e / ng : 1.0 / ng;
+  }
+
+  size_t o_chi_pt_a = B.add(chi_pt_a), o_chi_pt_lna = B.add(chi_pt_lna), o_chi_h6 = B.add(chi_h6);
+  size_t o_gr_pt_a = B.add(gr_pt_a), o_gr_pt_lna = B.add(gr_pt_lna), o_gr_h = B.add(gr_h);
+  size_t o_la = B.add(la), o_llna = B.add(llna), o_lz = B.add(lz), o_lw = B.add(lw);
+  size_t o_lct = B.add(lct), o_lgt = B.add(lgt), o_lcix = B.add(lcix), o_lgix = B.add(lgix);
+  size_t o_rk = B.add(rk), o_rlnk = B.add(rlnk), o_rf = B.add(rf);
+  size_t o_hk = B.add(hk), o_hlnk = B.add(hlnk), o_hwk = B.add(hwk), o_hr = B.add(hr), o_hlogr = B.add(hlogr);
+  size_t o_lens_t = B.add(lens_t), o_lens_ix = B.add(lens_ix), o_lens_z = B.add(lens_z);
+  size_t o_lens_nw = B.reserve((size_t)(n_src ? n_src : 1) * nl * sizeof(double));
+  size_t o_nz_node = B.reserve((size_t)T * JC_NA_PAD * sizeof(double));
+  size_t o_bias_node = B.add(bias_node);
+  size_t o_kind = B.add(tr_kind), o_inv = B.add(tr_inv), o_ia = B.add(tr_ia), o_src = B.add(tr_src);
+  size_t o_m1 = B.add(tr_m1), o_srct = B.add(src_tracer);
+  size_t o_ell = B.add(ell), o_ellp5 = B.add(ellp5), o_lnellp5 = B.add(lnellp5);
+  size_t o_ellfac = B.add(ellfac), o_covnorm = B.add(covnorm);
+  size_t o_pi = B.add(pi), o_pj = B.add(pj);
+  size_t o_norm = B.reserve(JC_MAX_TRACERS * sizeof(double));
+
+  unsigned char* base = nullptr;
+  cudaError_t ce = cudaMalloc(&base, B.host.size());
+  if (ce != cudaSuccess) { jc_set_cuda_error(ce, "cudaMalloc(plan)"); delete plan; return JC_ERR_CUDA; }
+  ce = cudaMemcpy(base, B.host.data(), B.host.size(), cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) { jc_set_cuda_error(ce, "cudaMemcpy(plan)"); cudaFree(base); delete plan; return JC_ERR_CUDA; }
+  plan->dev_blob = base; plan->dev_blob_bytes = B.host.size();
+#define DP(T_, off) ((const T_*)(base + (off)))
+  d.chi_pt_a = DP(double, o_chi_pt_a); d.chi_pt_lna = DP(double, o_chi_pt_lna); d.chi_h6 = DP(double, o_chi_h6);
+  d.gr_pt_a = DP(double, o_gr_pt_a); d.gr_pt_lna = DP(double, o_gr_pt_lna); d.gr_h = DP(double, o_gr_h);
+  d.limb_a = DP(double, o_la); d.limb_lna = DP(double, o_llna); d.limb_z = DP(double, o_lz); d.limb_w = DP(double, o_lw);
+  d.limb_chi_t = DP(double, o_lct); d.limb_gr_t = DP(double, o_lgt);
+  d.limb_chi_ix = DP(uint16_t, o_lcix); d.limb_gr_ix = DP(uint16_t, o_lgix);
+  d.romb_k = DP(double, o_rk); d.romb_lnk = DP(double, o_rlnk); d.romb_f = DP(double, o_rf);
+  d.hf_k = DP(double, o_hk); d.hf_lnk = DP(double, o_hlnk); d.hf_wk = DP(double, o_hwk);
+  d.hf_r = DP(double, o_hr); d.hf_logr = DP(double, o_hlogr);
+  d.lens_t = DP(double, o_lens_t); d.lens_ix = DP(uint16_t, o_lens_ix); d.lens_nw = DP(double, o_lens_nw);
+  d.nz_node = DP(double, o_nz_node); d.bias_node = DP(double, o_bias_node);
+  d.tr_kind = DP(int, o_kind); d.tr_inv_growth = DP(int, o_inv); d.tr_ia = DP(int, o_ia); d.tr_src = DP(int, o_src);
+  d.tr_m1 = DP(double, o_m1); d.src_tracer = DP(int, o_srct);
+  d.ell = DP(double, o_ell); d.ellp5 = DP(double, o_ellp5); d.lnellp5 = DP(double, o_lnellp5);
+  d.ellfac = DP(double, o_ellfac); d.covnorm = DP(double, o_covnorm);
+  d.pair_i = DP(uint8_t, o_pi); d.pair_j = DP(uint8_t, o_pj);
+  plan->d = d;
+
+  // ---- one-time n(z) kernels ---------------------------------------------------------------------------------
+  NzDevAll all;
+  memset(&all, 0, sizeof(all));
+  for (int t = 0; t < T; ++t) {
+    const jc_nz& nz = pb->tracers[t].nz;
+    all.nz[t].family = nz.family; all.nz[t].n_shifts = nz.n_shifts; all.nz[t].zmax = nz.zmax;
+    for (int i = 0; i < 4; ++i) all.nz[t].p[i] = nz.params[i];
+    for (int i = 0; i < JC_MAX_SHIFTS; ++i) all.nz[t].shifts[i] = nz.shifts[i];
+  }
+  double* norm = (double*)(base + o_norm);
+  jc_nz_norm_kernel<<<T, 288>>>(all, norm);
+  jc_nz_node_kernel<<<dim3((JC_NA + 127) / 128, T), 128>>>(all, norm, d.limb_z, (double*)(base + o_nz_node));
+  if (n_src)
+    jc_nz_lens_kernel<<<dim3(JC_NLENS_COLS / 128, JC_NLENS, n_src), 128>>>(
+        all, (const int*)(base + o_srct), norm, (const double*)(base + o_lens_z), (double*)(base + o_lens_nw));
+  ce = cudaDeviceSynchronize();
+  if (ce == cudaSuccess) ce = cudaGetLastError();
+  if (ce != cudaSuccess) { jc_set_cuda_error(ce, "plan n(z) kernels"); cudaFree(base); delete plan; return JC_ERR_CUDA; }
+#undef DP
+  *plan_out = plan;
+  return JC_OK;
+}
+
+extern "C" void jc_plan_destroy(jc_plan* plan) {
+  if (!plan) return;
+  cudaSetDevice(plan->device);
+  if (plan->prof) {
+    for (int i = 0; i < JC_PROF_SLOTS; ++i)
+      for (int j = 0; j <= JC_N_STAGES; ++j) if (plan->prof->ev[i][j]) cudaEventDestroy(plan->prof->ev[i][j]);
+    delete plan->prof;
+  }
+  if (plan->dev_blob) cudaFree(plan->dev_blob);
+  if (plan->arena_ws) cudaFree(plan->arena_ws);
+  if (plan->arena_cosmo) cudaFree(plan->arena_cosmo);
+  for (int i = 0; i < 2; ++i) {
+    if (plan->arena_cl[i]) cudaFree(plan->arena_cl[i]);
+    if (plan->ev_done[i]) cudaEventDestroy(plan->ev_done[i]);
+    if (plan->ev_copied[i]) cudaEventDestroy(plan->ev_copied[i]);
+  }
+  if (plan->s_compute) cudaStreamDestroy(plan->s_compute);
+  if (plan->s_copy) cudaStreamDestroy(plan->s_copy);
+  delete plan;
+}
+
+extern "C" int32_t jc_plan_n_tracers(const jc_plan* plan) { return plan ? plan->d.T : 0; }
+extern "C" int32_t jc_plan_n_cls(const jc_plan* plan) { return plan ? plan->d.P : 0; }
+extern "C" int32_t jc_plan_n_ell(const jc_plan* plan) { return plan ? plan->d.L : 0; }
+
+extern "C" int jc_noise_f64(const jc_plan* plan, double* noise_host) {
+  if (!plan || !noise_host) return JC_ERR_INVALID;
+  for (int t = 0; t < plan->d.T; ++t) noise_host[t] = plan->noise[t];
+  return JC_OK;
+}

@@ -1,0 +1,242 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every check goes through the C ABI
+(include/jc_b200.h) via jax_cosmo_b200._native and compares with the CPU oracle on identical
+inputs.  Bar: rtol 1e-6 (BASELINE.json north_star, FP64 kernels); the assertions use 1e-9, the
+observed error is recorded in the assertion messages."""
+import os
+
+import numpy as np
+import pytest
+from conftest import golden_cl_files, load_golden, relerr
+
+from oracle import cl_oracle as o
+from oracle import scenarios as sc
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9  # asserted; project bar is 1e-6
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+def _plan(jc, scn, ell=None):
+    from jax_cosmo_b200 import _native
+    probes = sc.build_probes(scn, jc)
+    tf, nl = sc.build_fns(scn, jc)
+    return _native.get_plan(probes, scn["ell"] if ell is None else ell, tf, nl), probes
+
+
+def full_ell(scn):
+    """The full ell vector of the BASELINE config the golden subset was drawn from."""
+    n = scn["name"]
+    if n.startswith("cfg1"):
+        return sc.ELL_CFG1
+    if n.startswith("cfg2") or n.startswith("cfg5"):
+        return sc.ELL_CFG2
+    if n.startswith("reftest"):
+        return np.logspace(0.1, 4, 50)
+    return np.array(scn["ell"])
+
+
+@pytest.mark.parametrize("path", golden_cl_files(), ids=lambda p: os.path.basename(p)[3:-4])
+def test_cl_vs_golden_and_oracle(jc, torch_cuda, path):
+    """angular_cl / noise_cl / gaussian_cl_covariance(_and_mean) through the drop-in API against
+    (a) the reference-source golden vectors and (b) the oracle on the full ell vector."""
+    scn, g = load_golden(path)
+    probes = sc.build_probes(scn, jc)
+    tf, nl = sc.build_fns(scn, jc)
+    cosmo = sc.build_cosmo(scn, jc)
+    cl = jc.cl.angular_cl(cosmo, g["ell"], probes, transfer_fn=tf, nonlinear_fn=nl)
+    assert cl.shape == g["cl"].shape
+    e = relerr(cl, g["cl"])
+    assert e < RTOL, "C_ell vs reference golden: %.3e" % e
+    noise = jc.cl.noise_cl(g["ell"], probes)
+    assert np.array_equal(noise, g["noise"])
+    cov = jc.cl.gaussian_cl_covariance(g["ell"], probes, cl, noise, f_sky=scn["f_sky"], sparse=True)
+    e = relerr(cov, g["cov_sparse"])
+    assert e < RTOL, "sparse cov vs golden: %.3e" % e
+    if "cov_dense" in g:
+        dense = jc.cl.gaussian_cl_covariance(g["ell"], probes, cl, noise, f_sky=scn["f_sky"], sparse=False)
+        assert dense.shape == g["cov_dense"].shape
+        assert np.allclose(dense, g["cov_dense"], rtol=RTOL, atol=0)
+        assert np.array_equal(jc.sparse.to_dense(cov), dense)  # tests/test_angular_cl.py:201-213
+        mu, cov2 = jc.cl.gaussian_cl_covariance_and_mean(cosmo, g["ell"], probes, transfer_fn=tf,
+                                                          nonlinear_fn=nl, f_sky=scn["f_sky"], sparse=True)
+        assert mu.shape == (cl.size,) and relerr(mu, g["cl"].flatten()) < RTOL
+        assert relerr(cov2, g["cov_sparse"]) < RTOL
+    # full ell vector against the oracle
+    ell = full_ell(scn)
+    cl_full = jc.cl.angular_cl(cosmo, ell, probes, transfer_fn=tf, nonlinear_fn=nl)
+    ref = o.angular_cl(sc.cosmo_row(scn["cosmo"]), ell, sc.flatten_spec(scn))
+    e = relerr(cl_full, ref)
+    assert e < RTOL, "C_ell vs oracle (full ell): %.3e" % e
+
+
+@pytest.mark.parametrize("name", ["cfg2_3x2pt_5p5", "cfg2_extended_wcdm", "cfg1_wl4_linear"])
+def test_stage_tables(jc, torch_cuda, name):
+    """Every intermediate table of the CUDA pipeline (read back from the workspace through
+    jc_workspace_layout) against the oracle's stage values."""
+    torch = torch_cuda
+    from jax_cosmo_b200 import _native
+    scn = [s for s in sc.golden_scenarios() if s["name"] == name][0]
+    ell = full_ell(scn)
+    plan, probes = _plan(jc, scn, ell)
+    rows = np.stack([sc.cosmo_row(scn["cosmo"]), sc.config5_cosmologies(3)[2]])
+    cos = torch.as_tensor(rows, device="cuda")
+    ws = torch.zeros(plan.workspace_bytes(len(rows)) // 8, dtype=torch.float64, device="cuda")
+    cl = plan.angular_cl_device(cos, workspace=ws)
+    torch.cuda.synchronize()
+    lo = plan.workspace_layout(ws.numel() * 8)
+    assert lo.chunk == len(rows)
+    w = ws.cpu().numpy()
+    NS, LS, T, NF = lo.node_stride, lo.ell_stride, plan.T, len(_native.NODE_FIELDS)
+    prob = sc.flatten_spec(scn)
+    for c, row in enumerate(rows):
+        st = {}
+        ref_cl = o.angular_cl(row, ell, prob, stages=st)
+        chitab = w[lo.chitab + c * 256: lo.chitab + (c + 1) * 256]
+        gtab = w[lo.gtab + c * 128: lo.gtab + (c + 1) * 128]
+        scal = dict(zip(_native.SCAL_FIELDS, w[lo.scal + c * 32: lo.scal + c * 32 + len(_native.SCAL_FIELDS)]))
+        node = w[lo.node + c * NF * NS: lo.node + (c + 1) * NF * NS].reshape(NF, NS)[:, :513]
+        node = dict(zip(_native.NODE_FIELDS, node))
+        R = w[lo.rker + c * T * NS: lo.rker + (c + 1) * T * NS].reshape(T, NS)[:, :513]
+        V = w[lo.vtab + c * 513 * LS: lo.vtab + (c + 1) * 513 * LS].reshape(513, LS)[:, :len(ell)]
+        errs = {}
+        errs["chitab"] = relerr(chitab[:-1], st["chitab"][:-1])
+        assert chitab[-1] == 0.0
+        errs["gtab"] = relerr(gtab, st["gtab"])
+        errs["chi"] = relerr(node["CHI"][:-1], st["chi"][:-1])
+        assert abs(node["CHI"][-1]) < 1e-9
+        errs["growth"] = relerr(node["GROWTH"], st["growth"])
+        errs["hubble"] = relerr(node["HUBBLE"], st["hubble"])
+        errs["geom"] = relerr(node["GEOM"], st["geom"])
+        errs["sigmasqr8"] = relerr(scal["SIGMASQR8"], st["sigmasqr8"])
+        errs["pknorm"] = relerr(scal["PKNORM"], st["pknorm"])
+        if prob["nonlinear"]:
+            stab = w[lo.stab + c * 256: lo.stab + (c + 1) * 256]
+            errs["S(R)"] = relerr(stab, st["S_tab"])
+            errs["k_nl"] = relerr(1.0 / node["RNL"], st["k_nl"])
+            errs["n_eff"] = relerr(node["NEFF"], st["n_eff"])
+            errs["C"] = relerr(node["CURV"], st["C_hf"], floor=1e-3)
+            errs["a_n"] = relerr(node["AN"], st["a_n"])
+            errs["b_n"] = relerr(node["BN"], st["b_n"])
+            errs["c_n*f3"] = relerr(np.exp(node["LNCF"]), st["c_n"] * st["f3"])
+            errs["3-gamma"] = relerr(node["P3"], 3.0 - st["gamma_n"])
+            errs["alpha"] = relerr(node["ALPHA"], st["alpha_n"], floor=1e-3)
+            errs["beta"] = relerr(node["BETA"], st["beta_n"], floor=1e-3)
+            errs["nu"] = relerr(node["NU"], st["nu_n"])
+            errs["3f1"] = relerr(node["E1"], 3 * st["f1"])
+            errs["f2"] = relerr(node["E2"], st["f2"])
+        scale = np.abs(st["R"]).max(axis=1, keepdims=True)
+        errs["R"] = float(np.max(np.abs(R - st["R"]) / scale))
+        errs["V"] = relerr(V, st["V"].T)
+        errs["cl"] = relerr(cl[c].cpu().numpy(), ref_cl)
+        print(name, "cosmo", c, " ".join("%s=%.1e" % kv for kv in errs.items()))
+        bad = {k: v for k, v in errs.items() if not v < RTOL}
+        assert not bad, bad
+
+
+def test_batch_config5_subset(jc, torch_cuda):
+    """Config 5 (10+10 bins, 100 ell, halofit): the first 48 + 16 strided rows of the seeded
+    65,536-cosmology box against the oracle (SURVEY 8d parity subset, sized for the CPU oracle)."""
+    scn = sc.scenario("cfg5", sc.PLANCK15, sc.ELL_CFG2, [sc.sources(10, 1.0), sc.lenses(10, 1.0)])
+    probes = sc.build_probes(scn, jc)
+    box = sc.config5_cosmologies(65536)
+    assert np.allclose(box[0], [0.22006637, 0.04818603, 0.69582672, 0.98829804, 0.82877877, 0.0, -1.23299074, 0.02711681], atol=5e-9)
+    idx = np.concatenate([np.arange(48), np.arange(4095, 65536, 4096)])
+    rows = box[idx]
+    cl = jc.cl.angular_cl_batch(rows, scn["ell"], probes)
+    assert cl.shape == (len(rows), 210, 100) and np.isfinite(cl).all()
+    prob = sc.flatten_spec(scn)
+    worst = 0.0
+    for i, row in enumerate(rows):
+        worst = max(worst, relerr(cl[i], o.angular_cl(row, scn["ell"], prob)))
+    print("config5 subset worst rel err %.3e over %d cosmologies" % (worst, len(rows)))
+    assert worst < RTOL, worst
+
+
+def test_batch_properties_full_size(jc, torch_cuda):
+    """Size-independent properties on a large batch (8192 cosmologies x 210 x 100):
+    chunking invariance (bitwise), batch == single-row calls (bitwise), device == host entry,
+    finiteness and positive auto-spectra."""
+    torch = torch_cuda
+    scn = sc.scenario("cfg5", sc.PLANCK15, sc.ELL_CFG2, [sc.sources(10, 1.0), sc.lenses(10, 1.0)])
+    plan, probes = _plan(jc, scn)
+    B = 8192
+    rows = sc.config5_cosmologies(65536)[:B]
+    cos = torch.as_tensor(rows, device="cuda")
+    cl = plan.angular_cl_device(cos)
+    torch.cuda.synchronize()
+    assert torch.isfinite(cl).all()
+    autos = [o.pair_index(i, i, 20) for i in range(20)]
+    assert (cl[:, autos, :] > 0).all()
+    # a workspace for 7 cosmologies forces ragged chunks: results must be bitwise identical
+    small = torch.empty(plan.workspace_bytes(7) // 8, dtype=torch.float64, device="cuda")
+    sub = slice(100, 100 + 45)
+    cl_small = plan.angular_cl_device(cos[sub].contiguous(), workspace=small)
+    assert torch.equal(cl_small, cl[sub])
+    for i in (0, 4097, B - 1):
+        one = plan.angular_cl_device(cos[i:i + 1].contiguous())
+        assert torch.equal(one[0], cl[i])
+    host = plan.angular_cl_host(rows[:2100])  # > 2 host chunks, double-buffered D2H
+    assert np.array_equal(host, cl[:2100].cpu().numpy())
+
+
+def test_linear_sigma8_scaling(jc, torch_cuda):
+    """Linear P(k): C_ell is exactly proportional to sigma8^2 (power.py:47)."""
+    scn = sc.scenario("lin", sc.PLANCK15, sc.ELL_CFG1, [sc.sources(4, 6.5)], "linear")
+    probes = sc.build_probes(scn, jc)
+    rows = np.repeat(sc.cosmo_row(sc.PLANCK15)[None], 3, axis=0)
+    rows[:, 4] = [0.8159, 0.8159 * 2, 0.4]
+    cl = jc.cl.angular_cl_batch(rows, scn["ell"], probes, nonlinear_fn=jc.power.linear)
+    assert relerr(cl[1], 4.0 * cl[0]) < 1e-13
+    assert relerr(cl[2], (0.4 / 0.8159) ** 2 * cl[0]) < 1e-13
+
+
+def test_covariance_batch_and_symmetry(jc, torch_cuda):
+    torch = torch_cuda
+    scn = sc.scenario("c3", sc.PLANCK15, sc.ELL_CFG2, [sc.sources(10, 1.0), sc.lenses(10, 1.0)])
+    plan, probes = _plan(jc, scn)
+    rows = sc.config5_cosmologies(4)
+    cl = plan.angular_cl_device(torch.as_tensor(rows, device="cuda"))
+    cov = plan.gaussian_cov_device(cl, f_sky=0.25)
+    assert cov.shape == (4, 210, 210, 100)
+    assert torch.equal(cov, cov.transpose(1, 2))  # block symmetry
+    prob = sc.flatten_spec(scn)
+    clh = cl.cpu().numpy()
+    ref = o.gaussian_cl_covariance(scn["ell"], 20, clh[3], o.noise_cl(scn["ell"], prob), 0.25, True)
+    assert relerr(cov[3].cpu().numpy(), ref) < 1e-13
+    assert np.allclose(plan.noise(), o.noise_vector(prob), rtol=1e-15)
+
+
+def test_edge_cases(jc, torch_cuda):
+    """Single ell, single tracer, ragged (non-multiple-of-32) ell counts, extreme cosmologies."""
+    nz = jc.redshift.smail_nz(1.0, 2.0, 1.0)
+    prob1 = sc.flatten_spec(sc.scenario("e", sc.PLANCK15, [50.0], [sc.wl([sc.smail(1.0, 2.0, 1.0)])]))
+    for ell in ([50.0], np.logspace(1, 3, 33), np.logspace(0.5, 3.9, 7)):
+        cl = jc.cl.angular_cl(jc.Planck15(), ell, [jc.probes.WeakLensing([nz])])
+        assert cl.shape == (1, len(ell))
+        assert relerr(cl, o.angular_cl(sc.cosmo_row(sc.PLANCK15), ell, prob1)) < RTOL
+    # corners of the config-5 prior box
+    lo = [0.20, 0.04, 0.60, 0.92, 0.70, 0.0, -1.3, -0.5]
+    hi = [0.35, 0.06, 0.80, 1.00, 0.90, 0.0, -0.7, 0.5]
+    scn = sc.scenario("c", sc.PLANCK15, sc.ELL_CFG2[::9], [sc.sources(5, 2.0), sc.lenses(5, 2.0)])
+    probes = sc.build_probes(scn, jc)
+    rows = np.array([lo, hi, lo[:6] + hi[6:], hi[:6] + lo[6:]])
+    cl = jc.cl.angular_cl_batch(rows, scn["ell"], probes)
+    for i, row in enumerate(rows):
+        assert relerr(cl[i], o.angular_cl(row, scn["ell"], sc.flatten_spec(scn))) < RTOL
+    with pytest.raises(ValueError):
+        jc.cl.angular_cl_batch(np.zeros((2, 7)), [10.0, 20.0], probes)
+
+
+def test_fp64_peak_probe(torch_cuda):
+    from jax_cosmo_b200 import _native
+    dfma = _native.fp64_peak_tflops(0, 0.2)
+    dmma = _native.fp64_peak_tflops(1, 0.2)
+    print("FP64 peak probe: DFMA %.1f TFLOP/s, DMMA %.1f TFLOP/s" % (dfma, dmma))
+    assert 5.0 < dfma < 100.0 and 1.0 < dmma < 200.0

@@ -1,0 +1,127 @@
+"""Host-side logic that needs no GPU: the C-ABI library loads and exports every declared symbol,
+reference-style objects flatten into the POD descriptor, unsupported options raise (no fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+from conftest import ROOT
+
+from oracle import scenarios as sc
+
+
+def test_library_exports_every_declared_symbol():
+    from jax_cosmo_b200 import _native
+    lib = _native.load_library()
+    header = open(os.path.join(ROOT, "include", "jc_b200.h")).read()
+    declared = set(re.findall(r"\b(jc_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_native.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.jc_abi_version() == _native.JC_ABI_VERSION
+    assert lib.jc_status_string(-2).decode().startswith("configuration not supported")
+
+
+def test_struct_sizes_match_header():
+    """ctypes mirrors of the POD structs have the C layout (8-byte aligned doubles)."""
+    import ctypes as C
+
+    from jax_cosmo_b200 import _native
+    assert C.sizeof(_native.jc_nz) == 8 + 8 * (4 + 4 + 2)
+    assert C.sizeof(_native.jc_bias) == 8 + 24
+    assert C.sizeof(_native.jc_tracer) == 8 + C.sizeof(_native.jc_nz) + C.sizeof(_native.jc_bias) + 24
+    assert C.sizeof(_native.jc_problem) == 16 + 32 * C.sizeof(_native.jc_tracer)
+    assert C.sizeof(_native.jc_ws_layout) == 11 * 8
+
+
+def test_problem_flattening(jc):
+    from jax_cosmo_b200 import _native
+    scn = [s for s in sc.golden_scenarios() if s["name"] == "cfg2_extended_wcdm"][0]
+    probes = sc.build_probes(scn, jc)
+    pb = _native.build_problem(probes, *sc.build_fns(scn, jc))
+    flat = sc.flatten_spec(scn)
+    assert pb.n_tracers == len(flat["tracers"]) == 10
+    assert pb.nonlinear == _native.JC_PK_HALOFIT
+    for t, ref in enumerate(flat["tracers"]):
+        tr = pb.tracers[t]
+        assert tr.kind == (_native.JC_TRACER_WL if ref["kind"] == "wl" else _native.JC_TRACER_NC)
+        assert list(tr.nz.params)[:3] == ref["nz"]["params"]
+        assert list(tr.nz.shifts)[:tr.nz.n_shifts] == ref["nz"]["shifts"]
+        assert tr.nz.gals_per_arcmin2 == ref["nz"]["gals_per_arcmin2"]  # shift drops n_gal (redshift.py:16)
+        assert tr.nz.zmax == ref["nz"]["zmax"] and tr.probe_zmax == ref["probe_zmax"]
+        if ref["kind"] == "wl":
+            assert tr.m_bias == ref["m"] and tr.sigma_e == ref["sigma_e"] and tr.ia_enabled == 1
+            assert tr.bias.family == _native.JC_BIAS["des_y1_ia"]
+        else:
+            assert tr.bias.family == _native.JC_BIAS["inverse_growth"]
+            assert tr.bias.params[0] == ref["bias"]["params"][0]
+
+
+def test_orderings_and_noise(jc):
+    import jax_cosmo_b200.angular_cl as acl
+    from oracle import cl_oracle as o
+    scn = sc.golden_scenarios()[0]
+    probes = sc.build_probes(scn, jc)
+    assert acl._get_cl_ordering(probes) == o.cl_ordering(4)
+    blocks = acl._get_cov_blocks_ordering(probes)
+    pairs = o.cl_ordering(4)
+
+    def find(a, b):
+        return pairs.index((a, b)) if (a, b) in pairs else pairs.index((b, a))
+
+    want = [(find(i, m), find(j, n), find(i, n), find(j, m)) for i, j in pairs for m, n in pairs]
+    assert blocks == want
+    # noise_cl is host-only bookkeeping (probes.py:210-223,274-281 / angular_cl.py:101-117)
+    assert np.array_equal(jc.cl.noise_cl(scn["ell"], probes), o.noise_cl(scn["ell"], sc.flatten_spec(scn)))
+
+
+def test_unsupported_options_raise(jc):
+    from jax_cosmo_b200 import _native
+    nz = jc.redshift.smail_nz(1.0, 2.0, 1.0)
+    wl = jc.probes.WeakLensing([nz])
+    with pytest.raises(NotImplementedError):
+        _native.build_problem([wl], transfer_fn=lambda *a: None)
+    with pytest.raises(NotImplementedError):
+        _native.build_problem([wl], nonlinear_fn=lambda *a: None)
+    with pytest.raises(NotImplementedError):
+        _native.build_problem([jc.probes.WeakLensing([jc.redshift.delta_nz(1.0)])])
+    with pytest.raises(NotImplementedError):
+        jc.Cosmology(0.3, 0.05, 0.7, 0.96, 0.8, 0.0, -1.0, 0.0, gamma=0.55).to_row()
+    with pytest.raises(NotImplementedError):
+        jc.power.halofit(None, None, None, None)
+    with pytest.raises(ValueError):
+        _native.build_problem([jc.probes.WeakLensing([nz, nz], multiplicative_bias=[0.1])])
+
+
+def test_no_cpu_fallback(jc):
+    """Without a CUDA device the product path raises; it never routes through the oracle."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    nz = jc.redshift.smail_nz(1.0, 2.0, 1.0)
+    with pytest.raises(RuntimeError):
+        jc.cl.angular_cl(jc.Planck15(), [10.0, 100.0], [jc.probes.WeakLensing([nz])])
+    import jax_cosmo_b200
+    pkg = os.path.dirname(jax_cosmo_b200.__file__)
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            assert "oracle" not in open(os.path.join(pkg, fn)).read().replace("no CPU fallback", ""), fn
+
+
+def test_cosmology_mirror(jc):
+    c = jc.Planck15(Omega_c=0.3)
+    assert np.allclose(c.to_row(), [0.3, 0.0486, 0.6774, 0.9667, 0.8159, 0.0, -1.0, 0.0])
+    assert c.Omega_m == 0.3 + 0.0486 and c.Omega_de == 1.0 - c.Omega_m
+    params, flags = c.tree_flatten()
+    assert len(params) == 8 and flags == {"gamma_growth": False}
+    assert np.array_equal(type(c).tree_unflatten(flags, params).to_row(), c.to_row())
+
+
+def test_sparse_to_dense(jc):
+    rng = np.random.default_rng(0)
+    s = rng.random((3, 2, 4))
+    d = jc.sparse.to_dense(s)
+    assert d.shape == (12, 8)
+    for i in range(3):
+        for j in range(2):
+            assert np.array_equal(d[i * 4:(i + 1) * 4, j * 4:(j + 1) * 4], np.diag(s[i, j]))

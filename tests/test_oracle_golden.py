@@ -1,0 +1,115 @@
+"""The oracle (oracle/cl_oracle.py) against the golden vectors produced by executing the
+reference source itself (oracle/make_golden.py).  CPU only.  Tolerance: rtol 1e-12 (observed
+<= 1e-14); the project parity bar for the CUDA path is rtol 1e-6 (BASELINE.json north_star)."""
+import os
+
+import numpy as np
+import pytest
+from conftest import GOLDEN, golden_cl_files, load_golden, relerr
+
+from oracle import cl_oracle as o
+from oracle import scenarios as sc
+
+RTOL = 1e-12
+
+
+@pytest.mark.parametrize("path", golden_cl_files(), ids=lambda p: os.path.basename(p)[3:-4])
+def test_cl_noise_cov(path):
+    scn, g = load_golden(path)
+    prob = sc.flatten_spec(scn)
+    T = len(prob["tracers"])
+    cl = o.angular_cl(sc.cosmo_row(scn["cosmo"]), g["ell"], prob)
+    assert cl.shape == g["cl"].shape == (T * (T + 1) // 2, len(g["ell"]))
+    assert relerr(cl, g["cl"]) < RTOL
+    nl = o.noise_cl(g["ell"], prob)
+    assert np.array_equal(nl, g["noise"])
+    cov = o.gaussian_cl_covariance(g["ell"], T, cl, nl, scn["f_sky"], True)
+    assert relerr(cov, g["cov_sparse"]) < RTOL
+    if "cov_dense" in g:
+        dense = o.gaussian_cl_covariance(g["ell"], T, cl, nl, scn["f_sky"], False)
+        assert dense.shape == g["cov_dense"].shape
+        assert np.allclose(dense, g["cov_dense"], rtol=RTOL, atol=0)
+        mean, cov2 = o.gaussian_cl_covariance_and_mean(sc.cosmo_row(scn["cosmo"]), g["ell"], prob,
+                                                        scn["f_sky"], sparse=True)
+        assert np.array_equal(mean, cl.flatten()) and np.array_equal(cov2, cov)
+
+
+@pytest.mark.parametrize("name", ["planck15", "testcosmo", "wcdm", "cfg5row0"])
+def test_stages(name):
+    g = np.load(os.path.join(GOLDEN, "stages_%s.npz" % name))
+    c = o.Cosmo(g["cosmo"])
+    bg = o.Background(c)
+    pw = o.Power(bg)
+    a, k = g["a"], g["k"]
+    assert relerr(bg.chitab[:-1], g["chitab"][:-1]) < RTOL and bg.chitab[-1] == 0.0
+    assert relerr(bg.gtab, g["gtab"]) < RTOL
+    for fast in (True, False):  # searchsorted bracket == brute-force argmin (scipy/interpolate.py:25)
+        assert relerr(bg.chi(a, fast)[:-1], g["chi"][:-1]) < RTOL
+        assert relerr(bg.growth(a, fast), g["growth"]) < RTOL
+    assert relerr(o.dchioverda(c, a), g["dchioverda"]) < RTOL
+    assert relerr(o.Esqr(c, a), g["Esqr"]) < RTOL
+    assert relerr(o.eisenstein_hu(c, k), g["T_eh"]) < RTOL
+    assert relerr(o.sigmasqr_raw(c), g["sigmasqr8"]) < RTOL
+    pl = np.stack([pw.linear(k, ai) for ai in a])
+    assert relerr(pl, g["plin"]) < RTOL
+    knl, neff, C, _ = pw.halofit_parameters(a)
+    assert relerr(knl, g["k_nl"]) < RTOL and relerr(neff, g["n_eff"]) < RTOL and relerr(C, g["C_hf"]) < 1e-11
+    pn = np.stack([pw.halofit(k, np.full_like(k, ai)) for ai in a])
+    assert relerr(pn, g["pnl"]) < 1e-11
+    z = g["z"]
+    for ext, tag in [(False, ""), (True, "_ext")]:
+        scn = sc.scenario("x", dict(zip(sc.COSMO_KEYS, g["cosmo"])), [100.0],
+                          [sc.sources(5, 2.0, ext), sc.lenses(5, 2.0, ext)])
+        prob = sc.flatten_spec(scn)
+        R, is_wl = o.radial_kernels(bg, prob["tracers"], z)
+        mine = R * np.where(is_wl, o.wl_ell_factor(100.0), 1.0)[:, None]
+        ref = np.concatenate([g["kernel_wl" + tag], g["kernel_nc" + tag]])
+        nzm = np.abs(ref) > 0
+        assert relerr(mine[nzm], ref[nzm]) < RTOL
+        assert np.all(mine[~nzm] == 0)
+
+
+def test_survey_appendix_b_values():
+    """SURVEY.md Appendix B spot values (reference source on the shim, recorded by the survey)."""
+    scn, g = load_golden(os.path.join(GOLDEN, "cl_appB_halofit.npz"))
+    cl = o.angular_cl(sc.cosmo_row(scn["cosmo"]), [10.0, 100.0, 1000.0], sc.flatten_spec(scn))
+    assert np.allclose(cl[0], [2.8420570643e-08, 5.0021960512e-09, 2.7575923124e-10], rtol=1e-10)
+    assert np.allclose(cl[9], [1.3200119784e-05, 2.1836638472e-06, 1.2375248633e-07], rtol=1e-10)
+    c = o.Cosmo(sc.cosmo_row(sc.PLANCK15))
+    bg = o.Background(c)
+    assert np.allclose(bg.chi(np.array([0.1, 0.5, 0.9])), [6390.801429332794, 2302.727432573115, 324.56217948725], rtol=1e-12)
+    assert np.isclose(o.sigmasqr_raw(c), 2.1317114706320716e-07, rtol=1e-12)
+
+
+def test_quirks():
+    """the quirks that move results by >> 1e-6 are present in the oracle."""
+    c = o.Cosmo(sc.cosmo_row(sc.PLANCK15))
+    bg = o.Background(c)
+    pw = o.Power(bg)
+    a = np.linspace(1 / 11.0, 1, 33)
+    knl, _, _, ind = pw.halofit_parameters(a)
+    k, wk, d2, logr, S = pw._hf_tables()
+    g2 = bg.growth(a) ** 2
+    # (1) root is extrapolated from segment [ind-1, ind] even when sigma^2=1 lies in [ind, ind+1]
+    sig = g2[:, None] * S[None, :]
+    rows = np.arange(len(a))
+    right = sig[rows, ind] > 1.0  # nearest node left of the root: proper bracket would be [ind, ind+1]
+    assert right.any()
+    proper = logr[ind] + (1.0 - sig[rows, ind]) * (logr[ind + 1] - logr[ind]) / (sig[rows, ind + 1] - sig[rows, ind])
+    assert np.max(np.abs(1.0 / np.exp(proper[right]) / knl[right] - 1.0)) > 1e-5
+    # (2) sigma8 integral: log10 limits, natural exp
+    assert np.isclose(o.sigmasqr_raw(c), 2.1317114706320716e-07, rtol=1e-12)
+    # (10) noise only on auto pairs
+    scn = sc.golden_scenarios()[0]
+    nl = o.noise_cl(scn["ell"], sc.flatten_spec(scn))
+    pairs = o.cl_ordering(4)
+    assert all((nl[p] != 0).all() == (i == j) for p, (i, j) in enumerate(pairs))
+
+
+def test_pair_index_matches_list_search():
+    for T in (1, 2, 5, 20):
+        pairs = o.cl_ordering(T)
+        for i in range(T):
+            for j in range(T):
+                want = pairs.index((i, j)) if (i, j) in pairs else pairs.index((j, i))
+                assert o.pair_index(i, j, T) == want
