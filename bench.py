@@ -58,7 +58,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.h = None
         try:
             import pynvml
@@ -72,7 +72,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
                  0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 if self.h is not None:
                     self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
@@ -94,10 +94,10 @@ class ClockSampler(threading.Thread):
                             self.reasons.add(nm)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._halt.wait(0.05)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
