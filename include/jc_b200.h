@@ -115,12 +115,13 @@ typedef struct jc_ws_layout {
   int64_t chunk;       /* cosmologies per pass for the given workspace size                  */
   int64_t node_stride; /* padded length of a per-node array (>= 513)                         */
   int64_t ell_stride;  /* padded n_ell of a V row                                            */
+  int64_t tracer_stride; /* padded T of an R row                                             */
   int64_t chitab;      /* [chunk, 256]  chi(a) table, background.py:223-236                  */
   int64_t gtab;        /* [chunk, 128]  D(a)/D(1) table, background.py:461-481               */
   int64_t scal;        /* [chunk, 32]   per-cosmology scalars (EH constants, pknorm, ...)    */
   int64_t stab;        /* [chunk, 256]  halofit S(R) table (sigma^2(R, a) = D(a)^2 S(R))     */
   int64_t node;        /* [chunk, JC_NODE_FIELDS, node_stride] per-Limber-node arrays        */
-  int64_t rker;        /* [chunk, T, node_stride]  ell-independent radial kernels R_i(a_n)   */
+  int64_t rker;        /* [chunk, node_stride, tracer_stride] radial kernels R_i(a_n), node-major */
   int64_t vtab;        /* [chunk, 513, ell_stride] V[n, l] = w_n P(k_ln, a_n) dchi/da/chi^2/c^2 */
   int64_t total;       /* doubles                                                            */
 } jc_ws_layout;

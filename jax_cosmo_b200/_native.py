@@ -57,8 +57,8 @@ class jc_problem(C.Structure):
 
 
 class jc_ws_layout(C.Structure):
-    _fields_ = [(n, C.c_int64) for n in ("chunk", "node_stride", "ell_stride", "chitab", "gtab", "scal",
-                                         "stab", "node", "rker", "vtab", "total")]
+    _fields_ = [(n, C.c_int64) for n in ("chunk", "node_stride", "ell_stride", "tracer_stride", "chitab",
+                                         "gtab", "scal", "stab", "node", "rker", "vtab", "total")]
 
 
 _lib = None

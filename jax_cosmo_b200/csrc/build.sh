@@ -4,7 +4,15 @@ set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
 OUT="$HERE/../libjc_b200.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-"$NVCC" -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
-  -Xcompiler -fPIC,-O2,-ffp-contract=off -shared \
-  -o "$OUT" "$HERE/jc_plan.cu" "$HERE/jc_pipeline.cu" "$HERE/jc_api.cu" -lcudart "$@"
+SRCS="jc_plan.cu jc_setup.cu jc_tracers.cu jc_power.cu jc_contract.cu jc_pipeline.cu jc_api.cu"
+mkdir -p "$HERE/build"
+pids=()
+for f in $SRCS; do
+  "$NVCC" -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
+    -Xcompiler -fPIC,-O2,-ffp-contract=off -c "$HERE/$f" -o "$HERE/build/${f%.cu}.o" "$@" &
+  pids+=($!)
+done
+for p in "${pids[@]}"; do wait "$p"; done
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" \
+  $(for f in $SRCS; do echo "$HERE/build/${f%.cu}.o"; done) -lcudart
 echo "built $OUT"

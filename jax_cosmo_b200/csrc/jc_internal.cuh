@@ -37,6 +37,7 @@
 // Device-side view of the plan: cosmology-independent tables (all device pointers).
 struct JcDevPlan {
   int T, P, L, Lpad, nonlinear;
+  int TS;                    // tracer stride of the node-major R table (>= T, TS mod 16 in {4,12})
   int n_src;                 // number of weak-lensing tracers
   double zmax;               // Limber zmax (max over probes), angular_cl.py:63
   double lens_zmax;          // zmax of the WL probe(s), probes.py:24
@@ -120,6 +121,40 @@ struct jc_plan {
 
 void jc_set_cuda_error(cudaError_t e, const char* where);
 int jc_pipeline_init();  // one-time function attributes (dynamic shared memory opt-in)
+
+struct Ws {  // resolved workspace pointers for one chunk of cosmologies
+  double* chitab;  // [chunk][256]
+  double* gtab;    // [chunk][128]
+  double* scal;    // [chunk][32]
+  double* stab;    // [chunk][256]
+  double* node;    // [chunk][JC_NODE_FIELDS][JC_NA_PAD]
+  double* rker;    // [chunk][JC_NA_PAD][TS]   node-major radial kernels R_i(a_n)
+  double* vtab;    // [chunk][513][Lpad]
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ double* node_ptr(const Ws& ws, int c, int field) {
+  return ws.node + ((size_t)c * JC_NODE_FIELDS + field) * JC_NA_PAD;
+}
+// 1/x for finite positive normal x: MUFU.RCP64H seed + 2 Newton steps (<= ~1.5 ulp), no special cases.
+__device__ __forceinline__ double jc_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+#endif
+
+// per-stage launchers (one translation unit per kernel)
+void jc_launch_setup(const JcDevPlan& pl, const double* cosmo, const Ws& ws, int chunk, cudaStream_t s);
+int jc_launch_tracers(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s);  // lensing; returns #launches
+void jc_launch_finish(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s);
+void jc_launch_power(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s);
+void jc_launch_contract(const JcDevPlan& pl, const Ws& ws, double* cl, int chunk, cudaStream_t s);
+int jc_contract_init();
 
 #define JC_CUDA_TRY(expr)                          \
   do {                                             \

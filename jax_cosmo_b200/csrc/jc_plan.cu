@@ -233,6 +233,8 @@ extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int3
   JcDevPlan d;
   memset(&d, 0, sizeof(d));
   d.T = T; d.P = P; d.L = L; d.Lpad = (L + 3) & ~3; d.nonlinear = pb->nonlinear;
+  d.TS = T;  // bank-conflict-free A-fragment gathers in the contraction kernel need TS = 4 or 12 (mod 16)
+  while (d.TS % 16 != 4 && d.TS % 16 != 12) ++d.TS;
   d.n_src = n_src; d.zmax = zmax; d.lens_zmax = lens_zmax;
 
   // ---- chi table grid -----------------------------------------------------------------------

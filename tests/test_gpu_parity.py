@@ -103,7 +103,8 @@ def test_stage_tables(jc, torch_cuda, name):
         scal = dict(zip(_native.SCAL_FIELDS, w[lo.scal + c * 32: lo.scal + c * 32 + len(_native.SCAL_FIELDS)]))
         node = w[lo.node + c * NF * NS: lo.node + (c + 1) * NF * NS].reshape(NF, NS)[:, :513]
         node = dict(zip(_native.NODE_FIELDS, node))
-        R = w[lo.rker + c * T * NS: lo.rker + (c + 1) * T * NS].reshape(T, NS)[:, :513]
+        TS = lo.tracer_stride
+        R = w[lo.rker + c * NS * TS: lo.rker + (c + 1) * NS * TS].reshape(NS, TS)[:513, :T].T
         V = w[lo.vtab + c * 513 * LS: lo.vtab + (c + 1) * 513 * LS].reshape(513, LS)[:, :len(ell)]
         errs = {}
         errs["chitab"] = relerr(chitab[:-1], st["chitab"][:-1])
