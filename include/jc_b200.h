@@ -123,6 +123,7 @@ typedef struct jc_ws_layout {
   int64_t node;        /* [chunk, JC_NODE_FIELDS, node_stride] per-Limber-node arrays        */
   int64_t rker;        /* [chunk, node_stride, tracer_stride] radial kernels R_i(a_n), node-major */
   int64_t vtab;        /* [chunk, 513, ell_stride] V[n, l] = w_n P(k_ln, a_n) dchi/da/chi^2/c^2 */
+  int64_t ellpow;      /* [chunk, ell_stride]  (l+1/2)^(3+n_s)                                */
   int64_t total;       /* doubles                                                            */
 } jc_ws_layout;
 
@@ -148,6 +149,10 @@ enum {
   JC_NODE_NU,         /* nu_n                                           */
   JC_NODE_E1,         /* 3 f1                                           */
   JC_NODE_E2,         /* f2                                             */
+  JC_NODE_NQ108,      /* (13.41 k_eq max(chi,1))^-1.08 : q^1.08 = (l+1/2)^1.08 * this   */
+  JC_NODE_NSILK,      /* (k_silk max(chi,1))^-1.4      : (k/k_silk)^1.4 = (l+1/2)^1.4 * this */
+  JC_NODE_NAMP,       /* max(chi,1)^-(3+n_s) D^2 pknorm/(2 pi^2) : Delta^2_L = (l+1/2)^(3+n_s) T^2 * this */
+  JC_NODE_GK,         /* GEOM * 2 pi^2 max(chi,1)^3    : V = Delta^2 (l+1/2)^-3 * this */
   JC_NODE_FIELDS
 };
 /* fields of the per-cosmology scalar block (index into ws.scal) */

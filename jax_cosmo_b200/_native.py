@@ -24,7 +24,7 @@ JC_PK_LINEAR, JC_PK_HALOFIT = 0, 1
 JC_TF_EH_OSC = 1
 
 NODE_FIELDS = ["CHI", "INVCHIC", "LNCHIC", "GEOM", "GROWTH", "HUBBLE", "AMP", "RNL", "LNKNL", "NEFF",
-               "CURV", "AN", "BN", "LNCF", "P3", "ALPHA", "BETA", "NU", "E1", "E2"]
+               "CURV", "AN", "BN", "LNCF", "P3", "ALPHA", "BETA", "NU", "E1", "E2", "NQ108", "NSILK", "NAMP", "GK"]
 SCAL_FIELDS = ["LN13KEQ", "INV13KEQ", "BETA_C", "C14_ALPHA_C", "SH_D", "LNKSILK", "ALPHA_B", "BETA_B",
                "BETA_NODE", "FB", "FC", "NS", "PKNORM", "SIGMASQR8", "OMEGA_M"]
 
@@ -58,7 +58,7 @@ class jc_problem(C.Structure):
 
 class jc_ws_layout(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("chunk", "node_stride", "ell_stride", "tracer_stride", "chitab",
-                                         "gtab", "scal", "stab", "node", "rker", "vtab", "total")]
+                                         "gtab", "scal", "stab", "node", "rker", "vtab", "ellpow", "total")]
 
 
 _lib = None

@@ -86,6 +86,9 @@ struct JcDevPlan {
   const double* ellp5;       // [L] ell + 0.5
   const double* lnellp5;     // [L]
   const double* ellfac;      // [L] WL ell factor (probes.py:73)
+  const double* ell108;      // [L] (l+1/2)^1.08
+  const double* ell14;       // [L] (l+1/2)^1.4
+  const double* ellm3;       // [L] (l+1/2)^-3
   const double* covnorm;     // [L] (2l+1) gradient(l)   (angular_cl.py:139, without f_sky)
   // pairs
   const uint8_t* pair_i;     // [P]
@@ -130,6 +133,7 @@ struct Ws {  // resolved workspace pointers for one chunk of cosmologies
   double* node;    // [chunk][JC_NODE_FIELDS][JC_NA_PAD]
   double* rker;    // [chunk][JC_NA_PAD][TS]   node-major radial kernels R_i(a_n)
   double* vtab;    // [chunk][513][Lpad]
+  double* ellpow;  // [chunk][Lpad]  (l+1/2)^(3+n_s)
 };
 
 #ifdef __CUDACC__

@@ -6,7 +6,7 @@ namespace {
 
 size_t per_cosmo_doubles(const JcDevPlan& pl) {
   return (size_t)JC_NCHI + JC_NGROW + JC_SCAL_FIELDS + JC_NHFR + (size_t)JC_NODE_FIELDS * JC_NA_PAD +
-         (size_t)JC_NA_PAD * pl.TS + (size_t)JC_NA * pl.Lpad;
+         (size_t)JC_NA_PAD * pl.TS + (size_t)JC_NA * pl.Lpad + (size_t)pl.Lpad;
 }
 
 void layout_for(const JcDevPlan& pl, int64_t chunk, jc_ws_layout* lo) {
@@ -22,6 +22,7 @@ void layout_for(const JcDevPlan& pl, int64_t chunk, jc_ws_layout* lo) {
   lo->node = o; o += chunk * (int64_t)JC_NODE_FIELDS * JC_NA_PAD;
   lo->rker = o; o += chunk * (int64_t)JC_NA_PAD * pl.TS;
   lo->vtab = o; o += chunk * (int64_t)JC_NA * pl.Lpad;
+  lo->ellpow = o; o += chunk * (int64_t)pl.Lpad;
   lo->total = o;
 }
 
@@ -58,6 +59,7 @@ extern "C" int jc_angular_cl_f64(const jc_plan* plan, const double* cosmo_dev, i
   Ws ws;
   ws.chitab = base + lo.chitab; ws.gtab = base + lo.gtab; ws.scal = base + lo.scal;
   ws.stab = base + lo.stab; ws.node = base + lo.node; ws.rker = base + lo.rker; ws.vtab = base + lo.vtab;
+  ws.ellpow = base + lo.ellpow;
 
   JcProf* prof = (plan->prof && plan->prof->enabled) ? plan->prof : nullptr;
   for (int64_t c0 = 0; c0 < n_cosmo; c0 += lo.chunk) {

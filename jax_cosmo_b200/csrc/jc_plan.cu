@@ -313,11 +313,14 @@ extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int3
     }
   }
   // ---- ell ----------------------------------------------------------------------------------------------
-  std::vector<double> ell(ell_host, ell_host + L), ellp5(L), lnellp5(L), ellfac(L), covnorm(L);
+  std::vector<double> ell(ell_host, ell_host + L), ellp5(L), lnellp5(L), ellfac(L), covnorm(L), ell108(L), ell14(L), ellm3(L);
   for (int l = 0; l < L; ++l) {
     double e = ell[l];
     ellp5[l] = e + 0.5;
     lnellp5[l] = std::log(e + 0.5);
+    ell108[l] = std::pow(e + 0.5, 1.08);
+    ell14[l] = std::pow(e + 0.5, 1.4);
+    ellm3[l] = 1.0 / ((e + 0.5) * (e + 0.5) * (e + 0.5));
     ellfac[l] = std::sqrt((e - 1) * e * (e + 1) * (e + 2)) / ((e + 0.5) * (e + 0.5));  // probes.py:73
     double g;  // np.gradient(ell), unit spacing (angular_cl.py:139)
     if (L == 1) g = 0.0;
@@ -365,6 +368,7 @@ extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int3
   size_t o_m1 = B.add(tr_m1), o_srct = B.add(src_tracer);
   size_t o_ell = B.add(ell), o_ellp5 = B.add(ellp5), o_lnellp5 = B.add(lnellp5);
   size_t o_ellfac = B.add(ellfac), o_covnorm = B.add(covnorm);
+  size_t o_ell108 = B.add(ell108), o_ell14 = B.add(ell14), o_ellm3 = B.add(ellm3);
   size_t o_pi = B.add(pi), o_pj = B.add(pj);
   size_t o_norm = B.reserve(JC_MAX_TRACERS * sizeof(double));
 
@@ -389,6 +393,7 @@ extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int3
   d.tr_m1 = DP(double, o_m1); d.src_tracer = DP(int, o_srct);
   d.ell = DP(double, o_ell); d.ellp5 = DP(double, o_ellp5); d.lnellp5 = DP(double, o_lnellp5);
   d.ellfac = DP(double, o_ellfac); d.covnorm = DP(double, o_covnorm);
+  d.ell108 = DP(double, o_ell108); d.ell14 = DP(double, o_ell14); d.ellm3 = DP(double, o_ellm3);
   d.pair_i = DP(uint8_t, o_pi); d.pair_j = DP(uint8_t, o_pj);
   plan->d = d;
 

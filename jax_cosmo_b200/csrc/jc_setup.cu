@@ -177,9 +177,12 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
     double ia = 1.0 / a;
     node_ptr(ws, c, JC_NODE_CHI)[n] = chi;
     node_ptr(ws, c, JC_NODE_INVCHIC)[n] = 1.0 / chic;
-    node_ptr(ws, c, JC_NODE_LNCHIC)[n] = log(chic);
-    node_ptr(ws, c, JC_NODE_GEOM)[n] =
-        pl.limb_w[n] * dchida / fmax(chi * chi, 1.0) / (JC_C_LIGHT * JC_C_LIGHT);  // angular_cl.py:91,96
+    const double lnchic = log(chic);
+    const double geom = pl.limb_w[n] * dchida / fmax(chi * chi, 1.0) / (JC_C_LIGHT * JC_C_LIGHT);  // angular_cl.py:91,96
+    node_ptr(ws, c, JC_NODE_LNCHIC)[n] = lnchic;
+    node_ptr(ws, c, JC_NODE_GEOM)[n] = geom;
+    node_ptr(ws, c, JC_NODE_GK)[n] = geom * JC_TWO_PI_SQ * (chic * chic * chic);
+    s_rnl[n] = lnchic;  // scratch until the halofit root phase
     node_ptr(ws, c, JC_NODE_GROWTH)[n] = D;
     node_ptr(ws, c, JC_NODE_HUBBLE)[n] = JC_H0 * se;               // background.py:143
     s_D2[n] = D * D;
@@ -211,9 +214,20 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
   }
   const double pknorm = s_sc[JC_SCAL_PKNORM];
   if (tid < JC_SCAL_FIELDS) ws.scal[(size_t)c * JC_SCAL_FIELDS + tid] = s_sc[tid];
-  for (int n = tid; n < JC_NA; n += 256)
-    node_ptr(ws, c, JC_NODE_AMP)[n] = s_D2[n] * pknorm / JC_TWO_PI_SQ;
+  // separable power laws of k = (l+1/2)/chi_c: the node-side factors (the ell-side factors are plan
+  // tables, and (l+1/2)^(3+n_s) goes to ws.ellpow)
+  for (int n = tid; n < JC_NA; n += 256) {
+    const double amp = s_D2[n] * pknorm / JC_TWO_PI_SQ;
+    const double lc = s_rnl[n];
+    node_ptr(ws, c, JC_NODE_AMP)[n] = amp;
+    node_ptr(ws, c, JC_NODE_NQ108)[n] = exp(-1.08 * (lc + s_sc[JC_SCAL_LN13KEQ]));
+    node_ptr(ws, c, JC_NODE_NSILK)[n] = exp(-1.4 * (lc + s_sc[JC_SCAL_LNKSILK]));
+    node_ptr(ws, c, JC_NODE_NAMP)[n] = exp(-(3.0 + ns) * lc) * amp;
+  }
+  for (int l = tid; l < pl.L; l += 256)
+    ws.ellpow[(size_t)c * pl.Lpad + l] = exp((3.0 + ns) * pl.lnellp5[l]);
   if (!pl.nonlinear) return;
+  __syncthreads();  // s_rnl is reused below
 
   // ---- halofit tables ---------------------------------------------------------------------------
   // d2w[i] = w_i * Delta^2_L(k_i, a=1) ; linear_matter_power(cosmo, k) uses growth_factor(1.0)

@@ -31,7 +31,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_native.jc_bias) == 8 + 24
     assert C.sizeof(_native.jc_tracer) == 8 + C.sizeof(_native.jc_nz) + C.sizeof(_native.jc_bias) + 24
     assert C.sizeof(_native.jc_problem) == 16 + 32 * C.sizeof(_native.jc_tracer)
-    assert C.sizeof(_native.jc_ws_layout) == 12 * 8
+    assert C.sizeof(_native.jc_ws_layout) == 13 * 8
 
 
 def test_problem_flattening(jc):
