@@ -228,6 +228,10 @@ int jc_profile_read(jc_plan* plan, double* stage_ms, int64_t* stage_launches);
  * denominator, which MEASURED_PEAKS.json does not hold for FP64. */
 int jc_fp64_peak_tflops(int32_t mode, double seconds, double* tflops_out);
 
+/* Self-test hook for the kernels' own FP64 elementary functions (csrc/jc_math.cuh):
+ * y[i] = fn(x[i]) on device arrays; fn: 0 exp, 1 log, 2 sin, 3 x^(-1/3), 4 1/x. */
+int jc_debug_math_f64(int32_t fn, const double* x_dev, double* y_dev, int64_t n, void* stream);
+
 const char* jc_status_string(int status);
 const char* jc_last_cuda_error(void);
 int32_t jc_abi_version(void);

@@ -32,7 +32,7 @@ SCAL_FIELDS = ["LN13KEQ", "INV13KEQ", "BETA_C", "C14_ALPHA_C", "SH_D", "LNKSILK"
 EXPORTS = ["jc_plan_create", "jc_plan_destroy", "jc_plan_n_tracers", "jc_plan_n_cls", "jc_plan_n_ell",
            "jc_workspace_bytes", "jc_workspace_layout", "jc_angular_cl_f64", "jc_angular_cl_host_f64",
            "jc_noise_f64", "jc_gaussian_cov_f64", "jc_profile_enable", "jc_profile_read",
-           "jc_fp64_peak_tflops", "jc_status_string",
+           "jc_fp64_peak_tflops", "jc_debug_math_f64", "jc_status_string",
            "jc_last_cuda_error", "jc_abi_version"]
 
 
@@ -102,6 +102,8 @@ def load_library():
         lib.jc_profile_read.restype = C.c_int
         lib.jc_fp64_peak_tflops.argtypes = [i32, C.c_double, dp]
         lib.jc_fp64_peak_tflops.restype = C.c_int
+        lib.jc_debug_math_f64.argtypes = [i32, vp, vp, i64, vp]
+        lib.jc_debug_math_f64.restype = C.c_int
         lib.jc_status_string.argtypes = [C.c_int]
         lib.jc_status_string.restype = C.c_char_p
         lib.jc_last_cuda_error.argtypes = []
@@ -356,6 +358,20 @@ def get_plan(probes, ell, transfer_fn=None, nonlinear_fn=None, device=None):
         plan = Plan(pb, ell, device=None if dev < 0 else dev)
         _plan_cache[key] = plan
     return plan
+
+
+def debug_math(fn, x):
+    """Evaluate the kernels' own device math (csrc/jc_math.cuh) on a CUDA float64 tensor.
+    fn in {"exp", "log", "sin", "rcbrt", "rcp"}."""
+    import torch
+
+    code = {"exp": 0, "log": 1, "sin": 2, "rcbrt": 3, "rcp": 4}[fn]
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    st = load_library().jc_debug_math_f64(code, x.data_ptr(), y.data_ptr(), x.numel(),
+                                          torch.cuda.current_stream(x.device).cuda_stream)
+    check(st, "jc_debug_math_f64")
+    return y
 
 
 def fp64_peak_tflops(mode=0, seconds=0.5):

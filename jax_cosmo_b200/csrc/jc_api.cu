@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "jc_internal.cuh"
+#include "jc_math.cuh"
 
 static thread_local char g_cuda_err[512] = "";
 
@@ -133,6 +134,31 @@ extern "C" int jc_gaussian_cov_f64(const jc_plan* plan, const double* cl_dev, co
   size_t blocks = (total + 255) / 256;
   if (blocks > 0x7fffffffu) return JC_ERR_INVALID;
   jc_cov_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(plan->d, cl_dev, noise_dev, f_sky, cov_dev, total);
+  JC_CUDA_TRY(cudaGetLastError());
+  return JC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-math self test
+// ---------------------------------------------------------------------------------------------
+__global__ void jc_debug_math_kernel(int fn, const double* __restrict__ x, double* __restrict__ y, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = x[i];
+  double r;
+  switch (fn) {
+    case 0: r = jcm_exp(v); break;
+    case 1: r = jcm_log(v); break;
+    case 2: r = jcm_sin(v); break;
+    case 3: r = jcm_rcbrt(v); break;
+    default: r = jcm_rcp(v); break;
+  }
+  y[i] = r;
+}
+
+extern "C" int jc_debug_math_f64(int32_t fn, const double* x_dev, double* y_dev, int64_t n, void* stream) {
+  if (!x_dev || !y_dev || n < 1 || fn < 0 || fn > 4) return JC_ERR_INVALID;
+  jc_debug_math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(fn, x_dev, y_dev, n);
   JC_CUDA_TRY(cudaGetLastError());
   return JC_OK;
 }

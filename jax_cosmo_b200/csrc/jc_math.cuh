@@ -1,0 +1,116 @@
+// jc_math.cuh -- FP64 elementary functions for the hot kernels (sm_100a).
+//
+// Why not CUDA libm: ncu's source page for jc_power_kernel showed 731 warp-instructions per point of
+// which only 290 were FP64 -- ~240 were UMOV / IMAD.MOV pairs materialising the 64-bit polynomial
+// coefficients of exp/log/sin as immediates (profiles/r01_power_sass_mix.md).  Here every coefficient
+// lives in __constant__ memory, so it is a c[bank][offset] operand of the DFMA itself, and the
+// special-case paths (NaN/Inf/denormal/huge-argument) that this path never reaches are dropped.
+// Accuracy (tests/test_gpu_parity.py::test_device_math): <= 2 ulp on the argument ranges documented
+// per function; the project parity bar is rtol 1e-6 on C_ell.
+#pragma once
+#include <cuda_runtime.h>
+
+struct JcMathK {
+  double log2e, magic, ln2_hi, ln2_lo;
+  double ec[13];  // 1/n!, n = 0..12
+  double lg[7];   // fdlibm e_log.c Lg1..Lg7
+  double invpio2, pio2_1, pio2_2, pio2_2t;
+  double sc[12];  // [0..5] = S1..S6 (k_sin.c), [6..11] = C1..C6 (k_cos.c)
+  double third, half, one, two, exp_lo;
+};
+
+static __constant__ JcMathK JCK = {
+    1.4426950408889634074, 6755399441055744.0, 6.93147180369123816490e-01, 1.90821492927058770002e-10,
+    {1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
+     1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600},
+    {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,
+     1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01},
+    6.36619772367581382433e-01, 1.57079632673412561417e+00, 6.07710050630396597660e-11,
+    2.02226624879595063154e-21,
+    {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+     2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,
+     4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+     -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11},
+    1.0 / 3.0, 0.5, 1.0, 2.0, -708.0};
+
+// 1/x for finite positive normal x: MUFU.RCP64H seed + 2 Newton steps, no special cases.
+__device__ __forceinline__ double jcm_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, JCK.one);
+  r = fma(r, e, r);
+  e = fma(-x, r, JCK.one);
+  r = fma(r, e, r);
+  return r;
+}
+
+// exp(x) for x <= 709.  x < -708 is clamped (returns ~3e-308 instead of a denormal / 0).
+__device__ __forceinline__ double jcm_exp(double x) {
+  x = fmax(x, JCK.exp_lo);
+  const double kd = fma(x, JCK.log2e, JCK.magic);
+  const int k = __double2loint(kd);
+  const double kf = kd - JCK.magic;
+  double r = fma(kf, -JCK.ln2_hi, x);
+  r = fma(kf, -JCK.ln2_lo, r);
+  double p = JCK.ec[12];
+#pragma unroll
+  for (int i = 11; i >= 0; --i) p = fma(p, r, JCK.ec[i]);
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+// log(x) for finite positive normal x (fdlibm e_log.c without the special cases).
+__device__ __forceinline__ double jcm_log(double x) {
+  int hx = __double2hiint(x);
+  int k = (hx >> 20) - 1023;
+  hx &= 0x000fffff;
+  const int i = (hx + 0x95f64) & 0x100000;  // mantissa > sqrt(2): halve, k += 1
+  k += i >> 20;
+  const double m = __hiloint2double(hx | (i ^ 0x3ff00000), __double2loint(x));
+  const double f = m - JCK.one;
+  const double s = f * jcm_rcp(JCK.two + f);
+  const double z = s * s;
+  double R = JCK.lg[6];
+#pragma unroll
+  for (int j = 5; j >= 0; --j) R = fma(R, z, JCK.lg[j]);
+  R *= z;
+  const double hfsq = JCK.half * f * f;
+  const double dk = (double)k;
+  // dk*ln2_hi - ((hfsq - (s*(hfsq+R) + dk*ln2_lo)) - f)
+  const double t = fma(s, hfsq + R, dk * JCK.ln2_lo);
+  return fma(dk, JCK.ln2_hi, f - (hfsq - t));
+}
+
+// sin(x) for 0 <= x < ~1e6 (3-term Cody-Waite reduction; error grows linearly with x beyond 2^20*pi/2,
+// where this path's integrand is already suppressed by > 1e-12).
+__device__ __forceinline__ double jcm_sin(double x) {
+  const double nd = fma(x, JCK.invpio2, JCK.magic);
+  const int n = __double2loint(nd);
+  const double nf = nd - JCK.magic;
+  double r = fma(nf, -JCK.pio2_1, x);
+  r = fma(nf, -JCK.pio2_2, r);
+  r = fma(nf, -JCK.pio2_2t, r);
+  const double z = r * r;
+  const bool odd = n & 1;  // odd quadrant: cosine polynomial
+  const double* c = JCK.sc + (odd ? 6 : 0);
+  double p = c[5];
+#pragma unroll
+  for (int j = 4; j >= 0; --j) p = fma(p, z, c[j]);
+  const double head = odd ? fma(z, -JCK.half, JCK.one) : r;
+  const double mult = odd ? z * z : r * z;
+  const double v = fma(mult, p, head);
+  return (n & 2) ? -v : v;
+}
+
+// x^(-1/3) for positive x within float range: MUFU.LG2/EX2 seed (rel. err ~1e-6) + 2 Newton steps.
+__device__ __forceinline__ double jcm_rcbrt(double x) {
+  float lf, yf;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lf) : "f"((float)x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"(-0.333333333f * lf));
+  double y = (double)yf;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const double e = fma(-x, y * y * y, JCK.one);  // 1 - x y^3
+    y = fma(y * JCK.third, e, y);
+  }
+  return y;
+}

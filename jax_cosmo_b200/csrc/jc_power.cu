@@ -7,76 +7,90 @@
 //   * every fixed-exponent power law of k = (l+1/2)/chi_c is separable: k^p = (l+1/2)^p * chi_c^-p,
 //     so q^1.08, (k/k_silk)^1.4, k^(3+n_s) and k^-3 are one multiply of a per-ell (plan / ws.ellpow)
 //     and a per-node (setup kernel) table entry -- 6 exp, 3 log, 1 rcbrt, 1 sin remain per point;
-//   * the ~14 divisions of T(k) and of Delta^2_Q + Delta^2_H are merged into two reciprocals.
+//   * the ~14 divisions of T(k) and of Delta^2_Q + Delta^2_H are merged into two reciprocals;
+//   * exp/log/sin/rcbrt come from jc_math.cuh (coefficients as constant-bank DFMA operands).
 #include "jc_internal.cuh"
+#include "jc_math.cuh"
 
 namespace {
 
-__global__ void __launch_bounds__(256) jc_power_kernel(JcDevPlan pl, Ws ws) {
-  const int c = blockIdx.y;
-  const int idx = blockIdx.x * 256 + threadIdx.x;
-  if (idx >= JC_NA * pl.L) return;
-  const int n = idx / pl.L, l = idx - n * pl.L;
-  const double* sc = ws.scal + (size_t)c * JC_SCAL_FIELDS;
-  const double E1 = 2.718281828459045;  // np.exp(1.0)
+struct PowerK {
+  double e1, c699, c142, c386, c18, inv54, inv52, eighth, quarter;
+};
+static __constant__ PowerK PK = {2.718281828459045 /* np.exp(1.0) */, 69.9, 14.2, 386.0, 1.8,
+                                 1.0 / 5.4, 1.0 / 5.2, 0.125, 0.25};
 
-  const double lnk = pl.lnellp5[l] - node_ptr(ws, c, JC_NODE_LNCHIC)[n];
-  const double k = pl.ellp5[l] * node_ptr(ws, c, JC_NODE_INVCHIC)[n];  // angular_cl.py:73
+__global__ void __launch_bounds__(256) jc_power_kernel(JcDevPlan pl, Ws ws, unsigned inv_L) {
+  const int c = blockIdx.y;
+  const unsigned idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= (unsigned)(JC_NA * pl.L)) return;
+  // idx / L: multiply-high by inv_L = ceil(2^32 / L) is exact while 513 L^2 < 2^32 (inv_L = 0 otherwise)
+  const int n = inv_L ? (int)__umulhi(idx, inv_L) : (int)(idx / (unsigned)pl.L);
+  const int l = (int)idx - n * pl.L;
+  const double* sc = ws.scal + (size_t)c * JC_SCAL_FIELDS;
+  const double* nd = ws.node + (size_t)c * JC_NODE_FIELDS * JC_NA_PAD + n;
+#define NODE(f) nd[(f)*JC_NA_PAD]
+
+  const double lnk = pl.lnellp5[l] - NODE(JC_NODE_LNCHIC);
+  const double k = pl.ellp5[l] * NODE(JC_NODE_INVCHIC);  // angular_cl.py:73
   // ---- Eisenstein & Hu (transfer.py:113-153) ----------------------------------------------------
   const double q = k * sc[JC_SCAL_INV13KEQ];
   const double q2 = q * q;
-  const double W = fma(69.9, pl.ell108[l] * node_ptr(ws, c, JC_NODE_NQ108)[n], 1.0);  // 1 + 69.9 q^1.08
-  const double U1 = fma(14.2, W, 386.0);                      // C(alpha=1) W
-  const double U2 = fma(sc[JC_SCAL_C14_ALPHA_C], W, 386.0);   // C(alpha_c) W
-  const double L1 = log(fma(1.8 * sc[JC_SCAL_BETA_C], q, E1));
-  const double L2 = log(fma(1.8, q, E1));
+  const double W = fma(PK.c699, pl.ell108[l] * NODE(JC_NODE_NQ108), JCK.one);  // 1 + 69.9 q^1.08
+  const double U1 = fma(PK.c142, W, PK.c386);                    // C(alpha=1) W
+  const double U2 = fma(sc[JC_SCAL_C14_ALPHA_C], W, PK.c386);    // C(alpha_c) W
+  const double L1 = jcm_log(fma(PK.c18 * sc[JC_SCAL_BETA_C], q, PK.e1));
+  const double L2 = jcm_log(fma(PK.c18, q, PK.e1));
   const double L1W = L1 * W, L2W = L2 * W;
   const double N1 = fma(U1, q2, L1W);  // T~(k,1,beta_c)       = L1W / N1
   const double N2 = fma(U2, q2, L1W);  // T~(k,alpha_c,beta_c) = L1W / N2
   const double N3 = fma(U1, q2, L2W);  // T~(k,1,1)            = L2W / N3
   const double ks = k * sc[JC_SCAL_SH_D];
-  const double x54 = ks * (1.0 / 5.4);
+  const double x54 = ks * PK.inv54;
   const double x54_2 = x54 * x54;
   const double Fm1 = x54_2 * x54_2;  // f = 1/(1+Fm1)
   // Tc = f T1 + (1-f) T2 = L1W (N2 + Fm1 N1) / ((1+Fm1) N1 N2)
   const double numC = L1W * fma(Fm1, N1, N2);
-  const double denC = (1.0 + Fm1) * (N1 * N2);
+  const double denC = (JCK.one + Fm1) * (N1 * N2);
   const double ks2 = ks * ks, ks3 = ks2 * ks;
   const double bnode = sc[JC_SCAL_BETA_NODE], bb = sc[JC_SCAL_BETA_B];
-  const double arg = ks2 * rcbrt(fma(bnode * bnode, bnode, ks3));  // k s~ = ks^2 / cbrt(ks^3 + beta_node^3)
-  const double x52 = ks * (1.0 / 5.2);
-  const double X52 = fma(x52, x52, 1.0);
+  const double arg = ks2 * jcm_rcbrt(fma(bnode * bnode, bnode, ks3));  // k s~ = ks^2 / cbrt(ks^3 + beta_node^3)
+  const double x52 = ks * PK.inv52;
+  const double X52 = fma(x52, x52, JCK.one);
   const double BB = fma(bb * bb, bb, ks3);  // 1/(1+(beta_b/ks)^3) = ks^3 / BB
-  const double silk = exp(-(pl.ell14[l] * node_ptr(ws, c, JC_NODE_NSILK)[n]));  // exp(-(k/k_silk)^1.4)
+  const double silk = jcm_exp(-(pl.ell14[l] * NODE(JC_NODE_NSILK)));  // exp(-(k/k_silk)^1.4)
   // Tb = [T3/X52 + alpha_b ks^3/BB silk] sin(arg)/arg
   const double N3X = N3 * X52;
-  const double numB = fma(L2W, BB, sc[JC_SCAL_ALPHA_B] * ks3 * silk * N3X) * sin(arg);
+  const double numB = fma(L2W, BB, sc[JC_SCAL_ALPHA_B] * ks3 * silk * N3X) * jcm_sin(arg);
   const double denB = N3X * BB * arg;
-  const double Tk = fma(sc[JC_SCAL_FB] * numB, denC, sc[JC_SCAL_FC] * numC * denB) * jc_rcp(denB * denC);
+  const double Tk = fma(sc[JC_SCAL_FB] * numB, denC, sc[JC_SCAL_FC] * numC * denB) * jcm_rcp(denB * denC);
   // ---- Delta^2_L = k^3 P_lin / (2 pi^2)  (power.py:49-52, :250) ---------------------------------------
-  const double d2l = ws.ellpow[(size_t)c * pl.Lpad + l] * node_ptr(ws, c, JC_NODE_NAMP)[n] * (Tk * Tk);
+  const double d2l = ws.ellpow[(size_t)c * pl.Lpad + l] * NODE(JC_NODE_NAMP) * (Tk * Tk);
   double d2;
   if (pl.nonlinear) {  // halofit, takahashi2012 (power.py:246-262)
-    const double y = k * node_ptr(ws, c, JC_NODE_RNL)[n];
-    const double lny = lnk - node_ptr(ws, c, JC_NODE_LNKNL)[n];
+    const double y = k * NODE(JC_NODE_RNL);
+    const double lny = lnk - NODE(JC_NODE_LNKNL);
     const double y2 = y * y;
-    const double Nq = d2l * exp(node_ptr(ws, c, JC_NODE_BETA)[n] * log(1.0 + d2l)) * exp(-fma(y2, 0.125, 0.25 * y));
-    const double Dq = fma(node_ptr(ws, c, JC_NODE_ALPHA)[n], d2l, 1.0);
-    const double ye1 = exp(node_ptr(ws, c, JC_NODE_E1)[n] * lny);
-    const double ye2 = exp(node_ptr(ws, c, JC_NODE_E2)[n] * lny);
-    const double cfy = exp(node_ptr(ws, c, JC_NODE_P3)[n] * (node_ptr(ws, c, JC_NODE_LNCF)[n] + lny));
-    const double Nh = node_ptr(ws, c, JC_NODE_AN)[n] * ye1 * y2;
-    const double Dh = (fma(node_ptr(ws, c, JC_NODE_BN)[n], ye2, 1.0) + cfy) * (y2 + node_ptr(ws, c, JC_NODE_NU)[n]);
-    d2 = fma(Nq, Dh, Nh * Dq) * jc_rcp(Dq * Dh);  // Delta^2_Q + Delta^2_H
+    const double Nq = d2l * jcm_exp(NODE(JC_NODE_BETA) * jcm_log(JCK.one + d2l)) *
+                      jcm_exp(-fma(y2, PK.eighth, PK.quarter * y));
+    const double Dq = fma(NODE(JC_NODE_ALPHA), d2l, JCK.one);
+    const double ye1 = jcm_exp(NODE(JC_NODE_E1) * lny);
+    const double ye2 = jcm_exp(NODE(JC_NODE_E2) * lny);
+    const double cfy = jcm_exp(NODE(JC_NODE_P3) * (NODE(JC_NODE_LNCF) + lny));
+    const double Nh = NODE(JC_NODE_AN) * ye1 * y2;
+    const double Dh = (fma(NODE(JC_NODE_BN), ye2, JCK.one) + cfy) * (y2 + NODE(JC_NODE_NU));
+    d2 = fma(Nq, Dh, Nh * Dq) * jcm_rcp(Dq * Dh);  // Delta^2_Q + Delta^2_H
   } else {
     d2 = d2l;
   }
+#undef NODE
   // P = 2 pi^2 / k^3 * Delta^2 ;  V = P * geom = Delta^2 (l+1/2)^-3 * [geom 2 pi^2 chi_c^3]
-  ws.vtab[((size_t)c * JC_NA + n) * pl.Lpad + l] = d2 * pl.ellm3[l] * node_ptr(ws, c, JC_NODE_GK)[n];
+  ws.vtab[((size_t)c * JC_NA + n) * pl.Lpad + l] = d2 * pl.ellm3[l] * nd[JC_NODE_GK * JC_NA_PAD];
 }
 
 }  // namespace
 
 void jc_launch_power(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s) {
-  jc_power_kernel<<<dim3((JC_NA * pl.L + 255) / 256, chunk), 256, 0, s>>>(pl, ws);
+  const unsigned inv_L = (pl.L >= 2 && pl.L <= 2048) ? (unsigned)((0x100000000ull + pl.L - 1) / pl.L) : 0u;
+  jc_power_kernel<<<dim3((JC_NA * pl.L + 255) / 256, chunk), 256, 0, s>>>(pl, ws, inv_L);
 }

@@ -235,6 +235,33 @@ def test_edge_cases(jc, torch_cuda):
         jc.cl.angular_cl_batch(np.zeros((2, 7)), [10.0, 20.0], probes)
 
 
+def test_device_math(torch_cuda):
+    """The kernels' own exp/log/sin/rcbrt/rcp (csrc/jc_math.cuh) against NumPy on the argument
+    ranges the pipeline produces.  Stated bound: 4 ulp-ish relative (2e-15); sin: absolute."""
+    torch = torch_cuda
+    from jax_cosmo_b200 import _native
+    rng = np.random.default_rng(1)
+
+    def run(fn, x):
+        return _native.debug_math(fn, torch.as_tensor(x, device="cuda")).cpu().numpy()
+
+    x = np.concatenate([rng.uniform(-700, 700, 200000), rng.uniform(-2, 2, 200000), [0.0, -708.0, 709.0, 1e-300]])
+    e = relerr(run("exp", x), np.exp(x))
+    assert e < 2e-15, e
+    assert np.all(run("exp", np.array([-800.0, -1e9])) < 1e-300)
+    x = np.concatenate([np.exp(rng.uniform(-600, 600, 200000)), rng.uniform(0.5, 2.0, 200000), [1.0, 2.718281828459045]])
+    ref = np.log(x)
+    err = np.abs(run("log", x) - ref) / np.maximum(np.abs(ref), 1e-3)
+    assert err.max() < 2e-15, err.max()
+    x = np.concatenate([rng.uniform(0, 50, 200000), np.exp(rng.uniform(-30, 13.8, 200000)), [0.0]])
+    err = np.abs(run("sin", x) - np.sin(x))
+    assert err.max() < 2e-15, err.max()
+    x = np.exp(rng.uniform(-60, 80, 200000))
+    assert relerr(run("rcbrt", x), 1.0 / np.cbrt(x)) < 2e-15
+    x = np.exp(rng.uniform(-300, 300, 200000))
+    assert relerr(run("rcp", x), 1.0 / x) < 2e-15
+
+
 def test_fp64_peak_probe(torch_cuda):
     from jax_cosmo_b200 import _native
     dfma = _native.fp64_peak_tflops(0, 0.2)
