@@ -223,7 +223,8 @@ int jc_gaussian_cov_f64(const jc_plan* plan, const double* cl_dev, const double*
 int jc_profile_enable(jc_plan* plan, int32_t enable);
 int jc_profile_read(jc_plan* plan, double* stage_ms, int64_t* stage_launches);
 
-/* FP64 roofline probe: runs an FMA-only kernel (mode 0: DFMA chains, mode 1: DMMA m8n8k4) on the
+/* FP64 roofline probe: runs an FMA-only kernel (mode 0: DFMA chains, mode 1: DMMA m8n8k4,
+ * mode 2: both interleaved in every warp -- tells whether they share a datapath) on the
  * current device for ~`seconds` and returns TFLOP/s.  Used by bench.py for the roofline
  * denominator, which MEASURED_PEAKS.json does not hold for FP64. */
 int jc_fp64_peak_tflops(int32_t mode, double seconds, double* tflops_out);

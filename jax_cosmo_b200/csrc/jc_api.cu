@@ -234,8 +234,37 @@ __global__ void __launch_bounds__(256) jc_dmma_probe_kernel(double* out, int ite
   if (s == 12345.678) out[0] = s;
 }
 
+// mode 2: every warp interleaves 16 DFMA with 4 DMMA per iteration (128 FMA-lanes each side):
+// if the two share one datapath the rate stays at the single-pipe peak, otherwise it adds up.
+__global__ void __launch_bounds__(256) jc_mixed_probe_kernel(double* out, int iters, double seed) {
+  double c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0};
+  double f[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = seed + threadIdx.x * 1e-9 + i;
+  double a = seed + threadIdx.x * 1e-9, b = 1.0 + threadIdx.x * 1e-12;
+  const double m = 1.0000000001, bb = 1e-12;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                     : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fma(f[j], m, bb);
+      }
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s += c0[i] + c1[i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += f[i];
+  if (s == 12345.678) out[0] = s;
+}
+
 extern "C" int jc_fp64_peak_tflops(int32_t mode, double seconds, double* tflops_out) {
-  if (!tflops_out || (mode != 0 && mode != 1)) return JC_ERR_INVALID;
+  if (!tflops_out || mode < 0 || mode > 2) return JC_ERR_INVALID;
   int dev = 0, sms = 0;
   JC_CUDA_TRY(cudaGetDevice(&dev));
   JC_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -246,11 +275,14 @@ extern "C" int jc_fp64_peak_tflops(int32_t mode, double seconds, double* tflops_
   JC_CUDA_TRY(cudaEventCreate(&e1));
   const int blocks = sms * 8, threads = 256, iters = 4096;
   // flops per launch
-  double flops = mode == 0 ? (double)blocks * threads * iters * 64.0 * 2.0
-                           : (double)blocks * (threads / 32) * iters * 16.0 * (8 * 8 * 4 * 2.0);
+  const double f_dfma = (double)blocks * threads * iters * 64.0 * 2.0;
+  const double f_dmma = (double)blocks * (threads / 32) * iters * 16.0 * (8 * 8 * 4 * 2.0);
+  // mode 2: per iteration and warp 16 DMMA (16*512 flop) + 128 DFMA instructions (128*64 flop)
+  double flops = mode == 0 ? f_dfma : (mode == 1 ? f_dmma : f_dmma + (double)blocks * threads * iters * 128.0 * 2.0);
   auto launch = [&]() {
     if (mode == 0) jc_dfma_probe_kernel<<<blocks, threads>>>(d_out, iters, 1.0);
-    else jc_dmma_probe_kernel<<<blocks, threads>>>(d_out, iters, 1.0);
+    else if (mode == 1) jc_dmma_probe_kernel<<<blocks, threads>>>(d_out, iters, 1.0);
+    else jc_mixed_probe_kernel<<<blocks, threads>>>(d_out, iters, 1.0);
   };
   launch();  // warm-up
   JC_CUDA_TRY(cudaDeviceSynchronize());

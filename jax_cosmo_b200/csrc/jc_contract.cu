@@ -5,24 +5,26 @@
 // is a dense GEMM  C[P x L] = KK[P x 513] . V[513 x L]  per cosmology (210 x 513 x 100 at 10+10 bins),
 // where KK[p, n] = R_i(p)[n] R_j(p)[n] is never materialised: each A fragment element is one product
 // of two shared-memory loads.  mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4) runs at the DFMA peak rate on
-// B200 (measured: jc_fp64_peak_tflops) but needs 1/16 of the issue slots and pads P,L only to
-// multiples of 8 (216 x 104) instead of the 4x4-block x 32-lane tiling of a scalar kernel (240 x 128).
+// B200 and shares its datapath (measured: jc_fp64_peak_tflops modes 0/1/2 = 36.5/37.2/34.1 TFLOP/s),
+// but needs 1/16 of the issue slots and pads P, L only to multiples of 8 (216 x 104) instead of the
+// 4x4-block x 32-lane tiling of a scalar kernel (240 x 128).
 //
-// CTA = (cosmology, group of <= 7 ell-tiles); warp = 2 pair-tiles (16 pairs) x 7 ell-tiles, 28 FP64
-// accumulators per lane.  R and V stream through a 4-stage cp.async pipeline of 12 Limber nodes per
-// stage (43 stages = 516 nodes, the 3 padding nodes are zero rows).  Row strides TS and 60 are
-// 4 or 12 (mod 16) so every fragment load is bank-conflict free.
+// CTA = (cosmology, group of <= 7 ell-tiles), 16 warps.  The pair tiles (8 pairs each) are dealt to the
+// warps 2-or-1 each so that the four SMSPs (warp % 4) carry 7/7/7/6 of the 27 tiles at P=210; a warp
+// holds <= 2 x 7 accumulator tiles (28 FP64 accumulators per lane).  R and V stream through a 4-stage
+// cp.async pipeline of 12 Limber nodes per stage (43 stages = 516 nodes; the 3 padding nodes are zero
+// rows); every thread owns fixed copy slots, and issues the next stage's copies after its MMA burst.
+// Row strides TS and 60 are 4 or 12 (mod 16) so every fragment load is bank-conflict free.
+#include <cstdlib>
+
 #include "jc_internal.cuh"
 
 namespace {
 
-constexpr int KC = 12;       // Limber nodes per pipeline stage (3 k-steps of 4)
 constexpr int STAGES = 4;
 constexpr int NTW = 7;       // ell-tiles (of 8) per warp
 constexpr int NCOLS = NTW * 8;
 constexpr int LSV = 60;      // shared-memory row stride of a V stage (>= 56, = 12 mod 16)
-constexpr int NKC = (JC_NA + KC - 1) / KC;  // 43
-constexpr int MAX_WARPS = 16;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -33,12 +35,53 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(MAX_WARPS * 32)
+// One pipeline stage (KC/4 k-steps) of a warp's CNT x NT accumulator tiles; branch-free so that the
+// fragment loads of a k-step are issued ahead of its MMAs.
+template <int KC, int CNT, int NT>
+__device__ __forceinline__ void mma_stage(const double* __restrict__ Rs, const double* __restrict__ Vs,
+                                          int TS, int g, int tig, const int (&ti)[2], const int (&tj)[2],
+                                          double (&acc)[2][NTW][2]) {
+#pragma unroll
+  for (int ks = 0; ks < KC / 4; ++ks) {
+    const double* rr = Rs + (ks * 4 + tig) * TS;
+    const double* vr = Vs + (ks * 4 + tig) * LSV + g;
+    double a[CNT], b[NT];
+#pragma unroll
+    for (int mt = 0; mt < CNT; ++mt) a[mt] = rr[ti[mt]] * rr[tj[mt]];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) b[nt] = vr[nt * 8];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int mt = 0; mt < CNT; ++mt) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+  }
+}
+
+template <int KC, int CNT>
+__device__ __forceinline__ void mma_stage_nt(int ntw, const double* Rs, const double* Vs, int TS, int g, int tig,
+                                             const int (&ti)[2], const int (&tj)[2], double (&acc)[2][NTW][2]) {
+  switch (ntw) {  // warp-uniform
+    case 7: mma_stage<KC, CNT, 7>(Rs, Vs, TS, g, tig, ti, tj, acc); break;
+    case 6: mma_stage<KC, CNT, 6>(Rs, Vs, TS, g, tig, ti, tj, acc); break;
+    case 5: mma_stage<KC, CNT, 5>(Rs, Vs, TS, g, tig, ti, tj, acc); break;
+    case 4: mma_stage<KC, CNT, 4>(Rs, Vs, TS, g, tig, ti, tj, acc); break;
+    case 3: mma_stage<KC, CNT, 3>(Rs, Vs, TS, g, tig, ti, tj, acc); break;
+    case 2: mma_stage<KC, CNT, 2>(Rs, Vs, TS, g, tig, ti, tj, acc); break;
+    default: mma_stage<KC, CNT, 1>(Rs, Vs, TS, g, tig, ti, tj, acc); break;
+  }
+}
+
+// KC: Limber nodes per pipeline stage (KC/4 k-steps); WARPS per CTA; MINB CTAs per SM; the pair tiles
+// are split over gridDim.z CTAs.
+template <int KC, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 jc_contract_kernel(JcDevPlan pl, Ws ws, double* __restrict__ cl) {
+  constexpr int NKC = (JC_NA + KC - 1) / KC;
+  constexpr int MAX_SLOTS = (KC * (18 + NCOLS / 2) + WARPS * 32 - 1) / (WARPS * 32);  // TS <= 36
   extern __shared__ __align__(16) double smem[];
   const int c = blockIdx.y;
   const int l0 = blockIdx.x * NCOLS;
@@ -48,41 +91,58 @@ jc_contract_kernel(JcDevPlan pl, Ws ws, double* __restrict__ cl) {
   const int stage_doubles = KC * (TS + LSV);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int g = lane >> 2, tig = lane & 3;
-  const int mtiles = (pl.P + 7) >> 3;
-  const int ntask = (mtiles + 1) >> 1;
+  const int mtiles_all = (pl.P + 7) >> 3;
+  const int m_per_cta = (mtiles_all + gridDim.z - 1) / gridDim.z;
+  const int m_lo = blockIdx.z * m_per_cta;
+  const int mtiles = min(mtiles_all, m_lo + m_per_cta);  // this CTA owns pair tiles [m_lo, mtiles)
   const double* Rg = ws.rker + (size_t)c * JC_NA_PAD * TS;
   const double* Vg = ws.vtab + (size_t)c * JC_NA * pl.Lpad + l0;
 
-  auto load_stage = [&](int kc) {
-    double* Rs = smem + (size_t)(kc % STAGES) * stage_doubles;
-    double* Vs = Rs + KC * TS;
-    const int n0 = kc * KC;
-    const int rp = TS >> 1;  // 16-byte pieces per R row
-    for (int q = threadIdx.x; q < KC * rp; q += blockDim.x) {
-      const int r = q / rp, p2 = q - r * rp;
-      double* dst = Rs + r * TS + 2 * p2;
-      if (n0 + r < JC_NA) cp_async16(dst, Rg + (size_t)(n0 + r) * TS + 2 * p2);
-      else *reinterpret_cast<double2*>(dst) = make_double2(0.0, 0.0);
+  // fixed copy slots of this thread: piece q = tid + j*blockDim of the [R | V] stage image
+  const double* slot_src[MAX_SLOTS];
+  int slot_dst[MAX_SLOTS], slot_row[MAX_SLOTS], slot_step[MAX_SLOTS];
+  {
+    const int rp = TS >> 1, vp = ncols >> 1;
+    const int nR = KC * rp, nV = KC * vp;
+#pragma unroll
+    for (int j = 0; j < MAX_SLOTS; ++j) {
+      const int q = threadIdx.x + j * blockDim.x;
+      if (q < nR) {
+        const int r = q / rp, p2 = q - r * rp;
+        slot_src[j] = Rg + r * TS + 2 * p2; slot_dst[j] = r * TS + 2 * p2; slot_row[j] = r; slot_step[j] = KC * TS;
+      } else if (q < nR + nV) {
+        const int qv = q - nR;
+        const int r = qv / vp, p2 = qv - r * vp;
+        slot_src[j] = Vg + (size_t)r * pl.Lpad + 2 * p2; slot_dst[j] = KC * TS + r * LSV + 2 * p2;
+        slot_row[j] = r; slot_step[j] = KC * pl.Lpad;
+      } else {
+        slot_src[j] = nullptr; slot_dst[j] = 0; slot_row[j] = 0; slot_step[j] = 0;
+      }
     }
-    const int vp = ncols >> 1;
-    for (int q = threadIdx.x; q < KC * vp; q += blockDim.x) {
-      const int r = q / vp, p2 = q - r * vp;
-      double* dst = Vs + r * LSV + 2 * p2;
-      if (n0 + r < JC_NA) cp_async16(dst, Vg + (size_t)(n0 + r) * pl.Lpad + 2 * p2);
-      else *reinterpret_cast<double2*>(dst) = make_double2(0.0, 0.0);
+  }
+  auto load_stage = [&](int kc) {
+    double* st = smem + (size_t)(kc % STAGES) * stage_doubles;
+#pragma unroll
+    for (int j = 0; j < MAX_SLOTS; ++j) {
+      if (slot_src[j]) {
+        if (kc * KC + slot_row[j] < JC_NA) cp_async16(st + slot_dst[j], slot_src[j] + (size_t)kc * slot_step[j]);
+        else *reinterpret_cast<double2*>(st + slot_dst[j]) = make_double2(0.0, 0.0);
+      }
     }
   };
 
-  for (int round = 0; round * nwarps < ntask; ++round) {
-    const int task = round * nwarps + warp;
-    const bool active = task < ntask;
-    // this lane's pair rows in the two m-tiles -> tracer indices (clamped rows are never stored)
+  for (int m_base = m_lo; m_base < mtiles; m_base += 2 * nwarps) {
+    // deal the round's pair tiles to the warps: base or base+1 each, the extras to the lowest warps
+    const int m_round = min(2 * nwarps, mtiles - m_base);
+    const int base = m_round / nwarps, extra = m_round - base * nwarps;
+    const int cnt = base + (warp < extra ? 1 : 0);
+    const int m_first = m_base + warp * base + min(warp, extra);
     int ti[2], tj[2];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
-      const int p = min((2 * task + mt) * 8 + g, pl.P - 1);
-      ti[mt] = active ? pl.pair_i[p] : 0;
-      tj[mt] = active ? pl.pair_j[p] : 0;
+      const int p = min((m_first + mt) * 8 + g, pl.P - 1);  // clamped rows are never stored
+      ti[mt] = pl.pair_i[p];
+      tj[mt] = pl.pair_j[p];
     }
     double acc[2][NTW][2];
 #pragma unroll
@@ -90,7 +150,7 @@ jc_contract_kernel(JcDevPlan pl, Ws ws, double* __restrict__ cl) {
 #pragma unroll
       for (int nt = 0; nt < NTW; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
-    __syncthreads();  // previous round's stages are no longer read
+    __syncthreads();  // the previous round's stages are no longer read
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
       load_stage(s);
@@ -98,66 +158,74 @@ jc_contract_kernel(JcDevPlan pl, Ws ws, double* __restrict__ cl) {
     }
     for (int kc = 0; kc < NKC; ++kc) {
       cp_async_wait<STAGES - 2>();
-      __syncthreads();
+      __syncthreads();  // stage kc landed; stage kc-1 (refilled below) is no longer read by anyone
+      const double* Rs = smem + (size_t)(kc % STAGES) * stage_doubles;
+      const double* Vs = Rs + KC * TS;
+      if (cnt == 2) mma_stage_nt<KC, 2>(ntw, Rs, Vs, TS, g, tig, ti, tj, acc);
+      else if (cnt == 1) mma_stage_nt<KC, 1>(ntw, Rs, Vs, TS, g, tig, ti, tj, acc);
       if (kc + STAGES - 1 < NKC) load_stage(kc + STAGES - 1);
       cp_async_commit();
-      if (active) {
-        const double* Rs = smem + (size_t)(kc % STAGES) * stage_doubles;
-        const double* Vs = Rs + KC * TS;
-#pragma unroll
-        for (int ks = 0; ks < KC / 4; ++ks) {
-          const double* rr = Rs + (ks * 4 + tig) * TS;
-          const double a0 = rr[ti[0]] * rr[tj[0]];
-          const double a1 = rr[ti[1]] * rr[tj[1]];
-          const double* vr = Vs + (ks * 4 + tig) * LSV + g;
-#pragma unroll
-          for (int nt = 0; nt < NTW; ++nt) {
-            if (nt < ntw) {
-              const double b = vr[nt * 8];
-              dmma(acc[0][nt][0], acc[0][nt][1], a0, b);
-              dmma(acc[1][nt][0], acc[1][nt][1], a1, b);
-            }
-          }
-        }
-      }
     }
     cp_async_wait<0>();
-    if (active) {
+
+    const bool vec2 = (pl.L & 1) == 0;
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        const int p = (2 * task + mt) * 8 + g;
-        if (p >= pl.P) continue;
-        const bool wi = pl.tr_kind[ti[mt]] == JC_TRACER_WEAK_LENSING;
-        const bool wj = pl.tr_kind[tj[mt]] == JC_TRACER_WEAK_LENSING;
-        double* out = cl + ((size_t)c * pl.P + p) * pl.L;
+    for (int mt = 0; mt < 2; ++mt) {
+      const int p = (m_first + mt) * 8 + g;
+      if (mt >= cnt || p >= pl.P) continue;
+      const bool wi = pl.tr_kind[ti[mt]] == JC_TRACER_WEAK_LENSING;
+      const bool wj = pl.tr_kind[tj[mt]] == JC_TRACER_WEAK_LENSING;
+      double* out = cl + ((size_t)c * pl.P + p) * pl.L;
 #pragma unroll
-        for (int nt = 0; nt < NTW; ++nt) {
+      for (int nt = 0; nt < NTW; ++nt) {
+        const int l = l0 + nt * 8 + 2 * tig;
+        double v[2];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int l = l0 + nt * 8 + 2 * tig + h;
-            if (l < pl.L) {
-              const double ef = pl.ellfac[l];
-              out[l] = acc[mt][nt][h] * ((wi ? ef : 1.0) * (wj ? ef : 1.0));  // probes.py:73
-            }
-          }
+        for (int h = 0; h < 2; ++h) {
+          const double ef = (l + h < pl.L) ? pl.ellfac[l + h] : 1.0;
+          v[h] = acc[mt][nt][h] * ((wi ? ef : 1.0) * (wj ? ef : 1.0));  // probes.py:73
+        }
+        if (vec2 && l + 1 < pl.L) {
+          *reinterpret_cast<double2*>(out + l) = make_double2(v[0], v[1]);
+        } else {
+          if (l < pl.L) out[l] = v[0];
+          if (l + 1 < pl.L) out[l + 1] = v[1];
         }
       }
     }
   }
 }
 
+template <int KC, int WARPS, int MINB>
+void launch_cfg(const JcDevPlan& pl, const Ws& ws, double* cl, int chunk, int msplit, cudaStream_t s) {
+  const int ngroups = (pl.L + NCOLS - 1) / NCOLS;
+  const size_t smem = (size_t)STAGES * KC * (pl.TS + LSV) * sizeof(double);
+  static bool attr_done = false;  // idempotent attribute; racing writers set the same value
+  if (!attr_done) {
+    cudaFuncSetAttribute(jc_contract_kernel<KC, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr_done = true;
+  }
+  jc_contract_kernel<KC, WARPS, MINB><<<dim3(ngroups, chunk, msplit), WARPS * 32, smem, s>>>(pl, ws, cl);
+}
+
+int g_contract_cfg = -1;
+
 }  // namespace
 
 int jc_contract_init() {
-  JC_CUDA_TRY(cudaFuncSetAttribute(jc_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  if (g_contract_cfg < 0) {
+    const char* e = getenv("JC_CONTRACT_CFG");  // tuning knob (profiles/r01_tuning.md)
+    g_contract_cfg = e ? atoi(e) : 0;
+  }
   return JC_OK;
 }
 
 void jc_launch_contract(const JcDevPlan& pl, const Ws& ws, double* cl, int chunk, cudaStream_t s) {
   const int mtiles = (pl.P + 7) / 8;
-  const int ntask = (mtiles + 1) / 2;
-  const int warps = ntask < MAX_WARPS ? ntask : MAX_WARPS;
-  const int ngroups = (pl.L + NCOLS - 1) / NCOLS;
-  const size_t smem = (size_t)STAGES * KC * (pl.TS + LSV) * sizeof(double);
-  jc_contract_kernel<<<dim3(ngroups, chunk), warps * 32, smem, s>>>(pl, ws, cl);
+  switch (g_contract_cfg) {
+    case 1: launch_cfg<12, 16, 1>(pl, ws, cl, chunk, 1, s); break;
+    case 2: launch_cfg<24, 16, 1>(pl, ws, cl, chunk, 1, s); break;
+    case 3: launch_cfg<24, 8, 2>(pl, ws, cl, chunk, mtiles > 16 ? 2 : 1, s); break;
+    default: launch_cfg<12, 8, 2>(pl, ws, cl, chunk, mtiles > 16 ? 2 : 1, s); break;  // fastest (profiles/r01_tuning.md)
+  }
 }
