@@ -169,6 +169,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--peak-tflops", type=float, default=0.0,
+                    help="use this FP64 peak instead of probing (for runs under ncu)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -211,9 +213,15 @@ def main():
     ws_bytes = ws.numel() * 8
 
     # FP64 roofline denominator (not in MEASURED_PEAKS.json): DFMA probe, burst and sustained
-    peak_burst = _native.fp64_peak_tflops(0, 0.3)
-    peak_sustained = _native.fp64_peak_tflops(0, 2.0)
-    peak_dmma = _native.fp64_peak_tflops(1, 0.3)
+    if args.peak_tflops > 0:  # profiler runs: skip the probe launches
+        peak_burst = peak_sustained = peak_dmma = args.peak_tflops
+        peak_src = "--peak-tflops (earlier jc_fp64_peak_tflops measurement on this pool's B200)"
+    else:
+        peak_burst = _native.fp64_peak_tflops(0, 0.3)
+        peak_sustained = _native.fp64_peak_tflops(0, 2.0)
+        peak_dmma = _native.fp64_peak_tflops(1, 0.3)
+        peak_src = ("measured live: jc_fp64_peak_tflops DFMA probe, 2 s sustained "
+                    "(MEASURED_PEAKS.json holds no FP64 figure)")
 
     for _ in range(max(args.warmup, 3)):
         plan.angular_cl_device(cos, out=out, workspace=ws)
@@ -266,24 +274,39 @@ def main():
         return
 
     slots = v0_slots(N_ELL, N_SRC, P)
-    steps_chunks = args.steps
-    power_ms = stage_ms["power"] / max(stage_n["power"], 1)  # average launch duration
     lo = plan.workspace_layout(ws_bytes)
     chunk = min(int(lo.chunk), B)
-    n_launch_power = max(stage_n["power"], 1)
-    cosmo_per_power_launch = B * args.steps / n_launch_power
-    flops_power = 2.0 * slots["power"] * cosmo_per_power_launch
-    achieved = flops_power / (power_ms * 1e-3) / 1e12
+    kernels = {"setup": "jc_setup_kernel", "lens": "jc_lens_kernel", "finish": "jc_tracer_finish_kernel",
+               "power": "jc_power_kernel", "contract": "jc_contract_kernel"}
+    dom = max(("power", "contract", "setup", "lens"), key=lambda k: stage_ms[k])  # dominant kernel of the step
+    n_launch = max(stage_n[dom], 1)
+    launch_ms = stage_ms[dom] / n_launch              # average launch duration (CUDA events on the launch stream)
+    cosmo_per_launch = B * args.steps / n_launch
+    achieved = 2.0 * slots[dom] * cosmo_per_launch / (launch_ms * 1e-3) / 1e12
+    # FP64 work the compiled kernels actually execute (ncu, profiles/r01_ncu_summary.md): FP64-pipe warp
+    # instructions per (ell, node) point x 64 flop for K3; DMMA m8n8k4 count x 512 flop for K4
+    sass_flops = {"power": 264.0 * 2 * N_ELL * A, "contract": 45279.0 * 512}
+    # DRAM bytes per launch of `chunk` cosmologies, scaled from the ncu --set full capture at 592 cosmologies
+    ncu_dram_per_cosmo = {"power": (42.63e6 + 186.98e6) / 592, "contract": (291.70e6 + 79.22e6) / 592}
     step_tflops = 2.0 * slots["total"] * B * args.steps / (ms * 1e-3) / 1e12
-    roofline = {"bound": "fp64", "kernel": "jc_power_kernel", "achieved": achieved, "peak": peak_sustained,
-                "unit": "TFLOP/s", "frac": achieved / peak_sustained, "traffic": None,
-                "peak_source": "measured live: jc_fp64_peak_tflops DFMA probe, 2 s sustained (MEASURED_PEAKS.json has no FP64 figure)",
-                "peak_burst": peak_burst, "peak_dmma": peak_dmma,
-                "flops_convention": "SURVEY 8(d) v0: 2 x slots; power kernel = L*513*500 slots per cosmology",
+    roofline = {"bound": "fp64", "kernel": kernels[dom], "achieved": achieved, "peak": peak_sustained,
+                "unit": "TFLOP/s", "frac": achieved / peak_sustained,
+                "traffic": ncu_dram_per_cosmo[dom] * cosmo_per_launch if dom in ncu_dram_per_cosmo else None,
+                "traffic_note": "dram__bytes_read+write per launch from profiles/r01_ncu_summary.md, scaled to the launch size; "
+                                "algorithmic bytes per launch: %.3e" % (
+                                    (8.0 * A * N_ELL if dom == "power" else 8.0 * (A * N_ELL + A * T + P * N_ELL)) * cosmo_per_launch),
+                "bound_note": "FP64 arithmetic pipe (DFMA and DMMA share one datapath: jc_fp64_peak_tflops mode 2); "
+                              "~550 flop/B, HBM and bf16 tensor peaks of MEASURED_PEAKS.json do not bound this path",
+                "peak_source": peak_src, "peak_burst": peak_burst, "peak_dmma": peak_dmma,
+                "flops_convention": "SURVEY 8(d) v0 (2 x issue slots): power 500 slots/point, contraction 1 slot/(ell,node,pair)",
+                "achieved_sass": (sass_flops[dom] * cosmo_per_launch / (launch_ms * 1e-3) / 1e12) if dom in sass_flops else None,
+                "launch_ms": launch_ms, "cosmologies_per_launch": cosmo_per_launch,
                 "step": {"achieved": step_tflops, "frac": step_tflops / peak_sustained,
                          "slots_per_cosmology": slots["total"]},
                 "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
-                "stage_share": {k: v / max(sum(stage_ms.values()), 1e-9) for k, v in stage_ms.items()}}
+                "stage_share": {k: v / max(sum(stage_ms.values()), 1e-9) for k, v in stage_ms.items()},
+                "stage_v0_frac": {k: (2.0 * slots[k] * B * args.steps / (stage_ms[k] * 1e-3) / 1e12 / peak_sustained)
+                                  for k in ("setup", "lens", "power", "contract")}}
     cpu = None
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
