@@ -230,7 +230,8 @@ int jc_profile_read(jc_plan* plan, double* stage_ms, int64_t* stage_launches);
 int jc_fp64_peak_tflops(int32_t mode, double seconds, double* tflops_out);
 
 /* Self-test hook for the kernels' own FP64 elementary functions (csrc/jc_math.cuh):
- * y[i] = fn(x[i]) on device arrays; fn: 0 exp, 1 log, 2 sin, 3 x^(-1/3), 4 1/x. */
+ * y[i] = fn(x[i]) on device arrays; fn: 0 exp, 1 log, 2 sin, 3 x^(-1/3), 4 1/x, 5 table-driven exp,
+ * 6 table-driven log (x >= 1).  Synchronises the stream. */
 int jc_debug_math_f64(int32_t fn, const double* x_dev, double* y_dev, int64_t n, void* stream);
 
 const char* jc_status_string(int status);

@@ -365,7 +365,7 @@ def debug_math(fn, x):
     fn in {"exp", "log", "sin", "rcbrt", "rcp"}."""
     import torch
 
-    code = {"exp": 0, "log": 1, "sin": 2, "rcbrt": 3, "rcp": 4}[fn]
+    code = {"exp": 0, "log": 1, "sin": 2, "rcbrt": 3, "rcp": 4, "exp_t": 5, "log_t": 6}[fn]
     x = x.contiguous()
     y = torch.empty_like(x)
     st = load_library().jc_debug_math_f64(code, x.data_ptr(), y.data_ptr(), x.numel(),

@@ -141,7 +141,11 @@ extern "C" int jc_gaussian_cov_f64(const jc_plan* plan, const double* cl_dev, co
 // ---------------------------------------------------------------------------------------------
 // device-math self test
 // ---------------------------------------------------------------------------------------------
-__global__ void jc_debug_math_kernel(int fn, const double* __restrict__ x, double* __restrict__ y, int64_t n) {
+__global__ void jc_debug_math_kernel(int fn, const double* __restrict__ x, double* __restrict__ y, int64_t n,
+                                     const double* __restrict__ tab_g) {
+  __shared__ __align__(16) double tab[JCM_TAB_DOUBLES];
+  for (int i = threadIdx.x; i < JCM_TAB_DOUBLES; i += blockDim.x) tab[i] = tab_g[i];
+  __syncthreads();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double v = x[i];
@@ -151,15 +155,24 @@ __global__ void jc_debug_math_kernel(int fn, const double* __restrict__ x, doubl
     case 1: r = jcm_log(v); break;
     case 2: r = jcm_sin(v); break;
     case 3: r = jcm_rcbrt(v); break;
-    default: r = jcm_rcp(v); break;
+    case 4: r = jcm_rcp(v); break;
+    case 5: r = jcm_exp_t(v, tab); break;
+    default: r = jcm_log_t(v, tab); break;
   }
   y[i] = r;
 }
 
 extern "C" int jc_debug_math_f64(int32_t fn, const double* x_dev, double* y_dev, int64_t n, void* stream) {
-  if (!x_dev || !y_dev || n < 1 || fn < 0 || fn > 4) return JC_ERR_INVALID;
-  jc_debug_math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(fn, x_dev, y_dev, n);
-  JC_CUDA_TRY(cudaGetLastError());
+  if (!x_dev || !y_dev || n < 1 || fn < 0 || fn > 6) return JC_ERR_INVALID;
+  double tab_h[JCM_TAB_DOUBLES];
+  jc_math_table(tab_h);
+  double* tab_d = nullptr;
+  JC_CUDA_TRY(cudaMalloc(&tab_d, sizeof(tab_h)));
+  JC_CUDA_TRY(cudaMemcpy(tab_d, tab_h, sizeof(tab_h), cudaMemcpyHostToDevice));
+  jc_debug_math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(fn, x_dev, y_dev, n, tab_d);
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(tab_d);
+  if (e != cudaSuccess) { jc_set_cuda_error(e, "jc_debug_math_kernel"); return JC_ERR_CUDA; }
   return JC_OK;
 }
 

@@ -73,8 +73,8 @@ struct JcDevPlan {
   const uint16_t* lens_ix;   // i0 | i1<<8
   const double* lens_nw;     // [n_src][257][512]  simpson_w[m]/(3*256) * n_s(z'(m,n))
   // tracers
-  const double* nz_node;     // [T][513] normalised n_i(z_n)
-  const double* bias_node;   // [T][513] cosmology-independent part of b_i(z_n) (NC) / b_IA (WL)
+  const double* nz_node;     // [520][TS] normalised n_i(z_n), node-major
+  const double* bias_node;   // [520][TS] cosmology-independent part of b_i(z_n) (NC) / b_IA (WL)
   const int* tr_kind;        // [T]
   const int* tr_inv_growth;  // [T] bias multiplies 1/D(a)
   const int* tr_ia;          // [T]
@@ -90,6 +90,7 @@ struct JcDevPlan {
   const double* ell14;       // [L] (l+1/2)^1.4
   const double* ellm3;       // [L] (l+1/2)^-3
   const double* covnorm;     // [L] (2l+1) gradient(l)   (angular_cl.py:139, without f_sky)
+  const double* math_tab;    // [288] exp2 / log tables of jc_math.cuh (JCM_TAB_*)
   // pairs
   const uint8_t* pair_i;     // [P]
   const uint8_t* pair_j;     // [P]
@@ -123,6 +124,7 @@ struct jc_plan {
 };
 
 void jc_set_cuda_error(cudaError_t e, const char* where);
+void jc_math_table(double* out288);  // host: tables of the table-driven exp / log (jc_math.cuh)
 int jc_pipeline_init();  // one-time function attributes (dynamic shared memory opt-in)
 
 struct Ws {  // resolved workspace pointers for one chunk of cosmologies

@@ -80,6 +80,59 @@ __device__ __forceinline__ double jcm_log(double x) {
   return fma(dk, JCK.ln2_hi, f - (hfsq - t));
 }
 
+// ---- table-driven variants (tables: plan.math_tab, staged in shared memory by the caller) -------------
+// layout of the table: [0,32) 2^(j/32);  [32, 32+256) pairs {c_j, -ln c_j}, j = top 7 mantissa bits,
+// c_j = 1/(1 + (j+1/2)/128) (c_0 = 1 so that log stays relatively accurate next to 1).
+#define JCM_TAB_EXP 0
+#define JCM_TAB_LOG 32
+#define JCM_TAB_DOUBLES (32 + 256)
+
+struct JcMathT {
+  double k32, magic, l32_hi, l32_lo;  // 32/ln2, 1.5*2^52, ln2/32 split
+  double e[5];                        // 1/2, 1/6, 1/24, 1/120, 1/720
+  double l[6];                        // -1/2, 1/3, -1/4, 1/5, -1/6, 1/7
+};
+static __constant__ JcMathT JCT = {
+    46.166241308446828384, 6755399441055744.0, 6.93147180369123816490e-01 / 32, 1.90821492927058770002e-10 / 32,
+    {0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720},
+    {-0.5, 1.0 / 3, -0.25, 0.2, -1.0 / 6, 1.0 / 7}};
+
+// exp(x), x <= 709 (x < -708 clamped): 2^n * T[j] * p(r), |r| <= ln2/64, degree-6 Taylor (3.5e-18).
+__device__ __forceinline__ double jcm_exp_t(double x, const double* __restrict__ tab) {
+  x = fmax(x, JCK.exp_lo);
+  const double kd = fma(x, JCT.k32, JCT.magic);
+  const int k = __double2loint(kd);
+  const double kf = kd - JCT.magic;
+  double r = fma(kf, -JCT.l32_hi, x);
+  r = fma(kf, -JCT.l32_lo, r);
+  double p = fma(JCT.e[4], r, JCT.e[3]);
+  p = fma(p, r, JCT.e[2]);
+  p = fma(p, r, JCT.e[1]);
+  p = fma(p, r, JCT.e[0]);
+  p = fma(p, r, JCK.one);
+  p = fma(p, r, JCK.one);
+  p *= tab[JCM_TAB_EXP + (k & 31)];
+  return __hiloint2double(__double2hiint(p) + ((k >> 5) << 20), __double2loint(p));
+}
+
+// log(x) for finite normal x >= 1 (absolute error ~1e-16 max(1, |log x|); relative next to x = 1).
+__device__ __forceinline__ double jcm_log_t(double x, const double* __restrict__ tab) {
+  const int hx = __double2hiint(x);
+  const int e = (hx >> 20) - 1023;
+  const int j = (hx >> 13) & 127;
+  const double m = __hiloint2double((hx & 0x000fffff) | 0x3ff00000, __double2loint(x));
+  const double2 cl = *reinterpret_cast<const double2*>(tab + JCM_TAB_LOG + 2 * j);
+  const double r = fma(m, cl.x, -JCK.one);
+  double p = fma(JCT.l[5], r, JCT.l[4]);
+  p = fma(p, r, JCT.l[3]);
+  p = fma(p, r, JCT.l[2]);
+  p = fma(p, r, JCT.l[1]);
+  p = fma(p, r, JCT.l[0]);
+  p = fma(p * r, r, r);  // r - r^2/2 + ...
+  const double de = (double)e;
+  return fma(de, JCK.ln2_hi, cl.y) + fma(de, JCK.ln2_lo, p);
+}
+
 // sin(x) for 0 <= x < ~1e6 (3-term Cody-Waite reduction; error grows linearly with x beyond 2^20*pi/2,
 // where this path's integrand is already suppressed by > 1e-12).
 __device__ __forceinline__ double jcm_sin(double x) {

@@ -138,12 +138,12 @@ __global__ void jc_nz_norm_kernel(NzDevAll all, double* __restrict__ norm) {
   }
 }
 
-// nz_node[t][n] = pz_t(z_n)/norm_t on the 513 Limber nodes
+// nz_node[n][t] = pz_t(z_n)/norm_t on the 513 Limber nodes (node-major, stride TS, like ws.rker)
 __global__ void jc_nz_node_kernel(NzDevAll all, const double* __restrict__ norm,
-                                  const double* __restrict__ limb_z, double* __restrict__ out) {
+                                  const double* __restrict__ limb_z, double* __restrict__ out, int TS) {
   int t = blockIdx.y;
   int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < JC_NA) out[(size_t)t * JC_NA_PAD + n] = pz_fn(all.nz[t], limb_z[n]) / norm[t];
+  if (n < JC_NA) out[(size_t)n * TS + t] = pz_fn(all.nz[t], limb_z[n]) / norm[t];
 }
 
 // lens_nw[s][m][n] = simpson_w[m]/(3*256) * pz_s(z'(m,n))/norm_s ; z' = linspace(z_n, zmax, 257)[m]
@@ -193,6 +193,15 @@ int validate(const jc_problem* pb, int n_ell) {
 }
 
 }  // namespace
+
+void jc_math_table(double* out) {
+  for (int j = 0; j < 32; ++j) out[j] = std::exp2(j / 32.0);
+  for (int j = 0; j < 128; ++j) {
+    const double cj = j == 0 ? 1.0 : 1.0 / (1.0 + (j + 0.5) / 128.0);
+    out[32 + 2 * j] = cj;
+    out[32 + 2 * j + 1] = j == 0 ? 0.0 : -std::log(cj);
+  }
+}
 
 extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int32_t n_ell,
                               int32_t device, jc_plan** plan_out) {
@@ -332,7 +341,7 @@ extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int3
   // ---- pairs, bias tables, noise ---------------------------------------------------------------------------
   std::vector<uint8_t> pi(P), pj(P);
   { int p = 0; for (int i = 0; i < T; ++i) for (int j = i; j < T; ++j) { pi[p] = i; pj[p] = j; ++p; } }
-  std::vector<double> bias_node((size_t)T * JC_NA_PAD, 0.0);
+  std::vector<double> bias_node((size_t)JC_NA_PAD * d.TS, 0.0);  // node-major [n][TS]
   for (int t = 0; t < T; ++t) {
     const jc_tracer& tr = pb->tracers[t];
     bool needs_bias = tr.kind == JC_TRACER_NUMBER_COUNTS || tr.ia_enabled;
@@ -340,7 +349,7 @@ extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int3
       double b = tr.bias.params[0];  // constant / inverse_growth: b (bias.py:20-22,37-39)
       if (tr.bias.family == JC_BIAS_DES_Y1_IA)  // bias.py:55-57
         b = tr.bias.params[0] * std::pow((1.0 + lz[n]) / (1.0 + tr.bias.params[2]), tr.bias.params[1]);
-      bias_node[(size_t)t * JC_NA_PAD + n] = b;
+      bias_node[(size_t)n * d.TS + t] = b;
     }
   }
 
@@ -362,7 +371,7 @@ extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int3
   size_t o_hk = B.add(hk), o_hlnk = B.add(hlnk), o_hwk = B.add(hwk), o_hr = B.add(hr), o_hlogr = B.add(hlogr);
   size_t o_lens_t = B.add(lens_t), o_lens_ix = B.add(lens_ix), o_lens_z = B.add(lens_z);
   size_t o_lens_nw = B.reserve((size_t)(n_src ? n_src : 1) * nl * sizeof(double));
-  size_t o_nz_node = B.reserve((size_t)T * JC_NA_PAD * sizeof(double));
+  size_t o_nz_node = B.reserve((size_t)JC_NA_PAD * d.TS * sizeof(double));
   size_t o_bias_node = B.add(bias_node);
   size_t o_kind = B.add(tr_kind), o_inv = B.add(tr_inv), o_ia = B.add(tr_ia), o_src = B.add(tr_src);
   size_t o_m1 = B.add(tr_m1), o_srct = B.add(src_tracer);
@@ -370,6 +379,10 @@ extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int3
   size_t o_ellfac = B.add(ellfac), o_covnorm = B.add(covnorm);
   size_t o_ell108 = B.add(ell108), o_ell14 = B.add(ell14), o_ellm3 = B.add(ellm3);
   size_t o_pi = B.add(pi), o_pj = B.add(pj);
+  // tables of the kernels' table-driven exp / log (jc_math.cuh): 2^(j/32); {c_j, -ln c_j}
+  std::vector<double> math_tab(32 + 256);
+  jc_math_table(math_tab.data());
+  size_t o_math = B.add(math_tab);
   size_t o_norm = B.reserve(JC_MAX_TRACERS * sizeof(double));
 
   unsigned char* base = nullptr;
@@ -395,6 +408,7 @@ extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int3
   d.ellfac = DP(double, o_ellfac); d.covnorm = DP(double, o_covnorm);
   d.ell108 = DP(double, o_ell108); d.ell14 = DP(double, o_ell14); d.ellm3 = DP(double, o_ellm3);
   d.pair_i = DP(uint8_t, o_pi); d.pair_j = DP(uint8_t, o_pj);
+  d.math_tab = DP(double, o_math);
   plan->d = d;
 
   // ---- one-time n(z) kernels ---------------------------------------------------------------------------------
@@ -408,7 +422,7 @@ extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int3
   }
   double* norm = (double*)(base + o_norm);
   jc_nz_norm_kernel<<<T, 288>>>(all, norm);
-  jc_nz_node_kernel<<<dim3((JC_NA + 127) / 128, T), 128>>>(all, norm, d.limb_z, (double*)(base + o_nz_node));
+  jc_nz_node_kernel<<<dim3((JC_NA + 127) / 128, T), 128>>>(all, norm, d.limb_z, (double*)(base + o_nz_node), d.TS);
   if (n_src)
     jc_nz_lens_kernel<<<dim3(JC_NLENS_COLS / 128, JC_NLENS, n_src), 128>>>(
         all, (const int*)(base + o_srct), norm, (const double*)(base + o_lens_z), (double*)(base + o_lens_nw));

@@ -27,16 +27,24 @@ static __constant__ PowerK PK = {2.718281828459045 /* np.exp(1.0) */, 69.9, 14.2
                                  1.0 / 5.4, 1.0 / 5.2, 0.125, 0.25};
 
 // NPT: Limber nodes per thread; MINB: CTAs per SM the register allocation must allow.
-template <int NPT, int MINB>
+// TAB: table-driven exp / log (tables staged in shared memory once per CTA; the CTA then strides over
+// the (node group, ell) index space of its cosmology so that the staging is amortised).
+template <int NPT, int MINB, bool TAB>
 __global__ void __launch_bounds__(256, MINB) jc_power_kernel(JcDevPlan pl, Ws ws, unsigned inv_L) {
   constexpr int NGRP = (JC_NA + NPT - 1) / NPT;
+  __shared__ __align__(16) double s_tab[TAB ? JCM_TAB_DOUBLES : 2];
+  if (TAB) {
+    for (int i = threadIdx.x; i < JCM_TAB_DOUBLES; i += 256) s_tab[i] = pl.math_tab[i];
+    __syncthreads();
+  }
+#define EXPF(x) (TAB ? jcm_exp_t((x), s_tab) : jcm_exp(x))
+#define LOGF(x) (TAB ? jcm_log_t((x), s_tab) : jcm_log(x))
   const int c = blockIdx.y;
-  const unsigned idx = blockIdx.x * 256 + threadIdx.x;
-  if (idx >= (unsigned)(NGRP * pl.L)) return;
+  const double* sc = ws.scal + (size_t)c * JC_SCAL_FIELDS;
+  for (unsigned idx = blockIdx.x * 256 + threadIdx.x; idx < (unsigned)(NGRP * pl.L); idx += gridDim.x * 256) {
   // idx / L: multiply-high by inv_L = ceil(2^32 / L) is exact while 513 L^2 < 2^32 (inv_L = 0 otherwise)
   const int grp = inv_L ? (int)__umulhi(idx, inv_L) : (int)(idx / (unsigned)pl.L);
   const int l = (int)idx - grp * pl.L;
-  const double* sc = ws.scal + (size_t)c * JC_SCAL_FIELDS;
   // ell side
   const double lnl = pl.lnellp5[l], lp5 = pl.ellp5[l], l108 = pl.ell108[l], l14 = pl.ell14[l];
   const double lm3 = pl.ellm3[l], lpns = ws.ellpow[(size_t)c * pl.Lpad + l];
@@ -61,8 +69,8 @@ __global__ void __launch_bounds__(256, MINB) jc_power_kernel(JcDevPlan pl, Ws ws
     const double W = fma(PK.c699, l108 * NODE(JC_NODE_NQ108), JCK.one);  // 1 + 69.9 q^1.08
     const double U1 = fma(PK.c142, W, PK.c386);                          // C(alpha=1) W
     const double U2 = fma(c14ac, W, PK.c386);                            // C(alpha_c) W
-    const double L1 = jcm_log(fma(b18, q, PK.e1));
-    const double L2 = jcm_log(fma(PK.c18, q, PK.e1));
+    const double L1 = LOGF(fma(b18, q, PK.e1));
+    const double L2 = LOGF(fma(PK.c18, q, PK.e1));
     const double L1W = L1 * W, L2W = L2 * W;
     const double N1 = fma(U1, q2, L1W);  // T~(k,1,beta_c)       = L1W / N1
     const double N2 = fma(U2, q2, L1W);  // T~(k,alpha_c,beta_c) = L1W / N2
@@ -79,7 +87,7 @@ __global__ void __launch_bounds__(256, MINB) jc_power_kernel(JcDevPlan pl, Ws ws
     const double x52 = ks * PK.inv52;
     const double X52 = fma(x52, x52, JCK.one);
     const double BB = ks3 + bb3;  // 1/(1+(beta_b/ks)^3) = ks^3 / BB
-    const double silk = jcm_exp(-(l14 * NODE(JC_NODE_NSILK)));  // exp(-(k/k_silk)^1.4)
+    const double silk = EXPF(-(l14 * NODE(JC_NODE_NSILK)));  // exp(-(k/k_silk)^1.4)
     // Tb = [T3/X52 + alpha_b ks^3/BB silk] sin(arg)/arg
     const double N3X = N3 * X52;
     const double numB = fma(L2W, BB, alpha_b * ks3 * silk * N3X) * jcm_sin(arg);
@@ -93,11 +101,11 @@ __global__ void __launch_bounds__(256, MINB) jc_power_kernel(JcDevPlan pl, Ws ws
       const double lny = lnk - NODE(JC_NODE_LNKNL);
       const double y2 = y * y;
       // Delta^2_Q = D2L (1+D2L)^beta / (1 + alpha D2L) exp(-(y/4 + y^2/8))
-      const double Nq = d2l * jcm_exp(fma(NODE(JC_NODE_BETA), jcm_log(JCK.one + d2l), -fma(y2, PK.eighth, PK.quarter * y)));
+      const double Nq = d2l * EXPF(fma(NODE(JC_NODE_BETA), LOGF(JCK.one + d2l), -fma(y2, PK.eighth, PK.quarter * y)));
       const double Dq = fma(NODE(JC_NODE_ALPHA), d2l, JCK.one);
-      const double ye1 = jcm_exp(NODE(JC_NODE_E1) * lny);
-      const double ye2 = jcm_exp(NODE(JC_NODE_E2) * lny);
-      const double cfy = jcm_exp(NODE(JC_NODE_P3) * (NODE(JC_NODE_LNCF) + lny));
+      const double ye1 = EXPF(NODE(JC_NODE_E1) * lny);
+      const double ye2 = EXPF(NODE(JC_NODE_E2) * lny);
+      const double cfy = EXPF(NODE(JC_NODE_P3) * (NODE(JC_NODE_LNCF) + lny));
       const double Nh = NODE(JC_NODE_AN) * ye1 * y2;
       const double Dh = (fma(NODE(JC_NODE_BN), ye2, JCK.one) + cfy) * (y2 + NODE(JC_NODE_NU));
       d2 = fma(Nq, Dh, Nh * Dq) * jcm_rcp(Dq * Dh);  // Delta^2_Q + Delta^2_H
@@ -107,14 +115,20 @@ __global__ void __launch_bounds__(256, MINB) jc_power_kernel(JcDevPlan pl, Ws ws
     // P = 2 pi^2 / k^3 * Delta^2 ;  V = P * geom = Delta^2 (l+1/2)^-3 * [geom 2 pi^2 chi_c^3]
     vout[(size_t)n * pl.Lpad] = d2 * lm3 * NODE(JC_NODE_GK);
   }
+  }  // idx
 #undef NODE
+#undef EXPF
+#undef LOGF
 }
 
-template <int NPT, int MINB>
-void launch_power_cfg(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s) {
+// split: CTAs per cosmology (each strides over the index space); 0 = one CTA per 256 indices
+template <int NPT, int MINB, bool TAB>
+void launch_power_cfg(const JcDevPlan& pl, const Ws& ws, int chunk, int split, cudaStream_t s) {
   constexpr int NGRP = (JC_NA + NPT - 1) / NPT;
   const unsigned inv_L = (pl.L >= 2 && pl.L <= 2048) ? (unsigned)((0x100000000ull + pl.L - 1) / pl.L) : 0u;
-  jc_power_kernel<NPT, MINB><<<dim3((NGRP * pl.L + 255) / 256, chunk), 256, 0, s>>>(pl, ws, inv_L);
+  const int full = (NGRP * pl.L + 255) / 256;
+  const int gx = split > 0 && split < full ? split : full;
+  jc_power_kernel<NPT, MINB, TAB><<<dim3(gx, chunk), 256, 0, s>>>(pl, ws, inv_L);
 }
 
 }  // namespace
@@ -123,8 +137,13 @@ void jc_launch_power(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t 
   static int cfg = -1;
   if (cfg < 0) { const char* e = getenv("JC_POWER_CFG"); cfg = e ? atoi(e) : 0; }  // tuning knob
   switch (cfg) {
-    case 1: launch_power_cfg<4, 4>(pl, ws, chunk, s); break;  // 64 registers
-    case 2: launch_power_cfg<1, 6>(pl, ws, chunk, s); break;  // 40 registers, one node per thread
-    default: launch_power_cfg<4, 1>(pl, ws, chunk, s); break; // 116 registers: fastest (profiles/r01_tuning.md)
+    case 1: launch_power_cfg<4, 1, false>(pl, ws, chunk, 0, s); break;  // polynomial exp/log, 1 CTA / 256 indices
+    case 2: launch_power_cfg<4, 1, true>(pl, ws, chunk, 4, s); break;
+    case 3: launch_power_cfg<4, 1, true>(pl, ws, chunk, 16, s); break;
+    case 4: launch_power_cfg<4, 1, true>(pl, ws, chunk, 8, s); break;   // unconstrained registers
+    case 5: launch_power_cfg<2, 1, true>(pl, ws, chunk, 8, s); break;
+    case 6: launch_power_cfg<1, 6, true>(pl, ws, chunk, 8, s); break;   // one node per thread, 40 registers
+    // fastest (profiles/r01_tuning.md): table-driven exp/log, 64 registers, 8 CTAs per cosmology
+    default: launch_power_cfg<4, 4, true>(pl, ws, chunk, 8, s); break;
   }
 }

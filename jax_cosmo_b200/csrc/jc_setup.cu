@@ -1,7 +1,10 @@
 // jc_setup.cu -- K1: per-cosmology setup kernel (background tables, EH constants, sigma8 norm, halofit).
 #include "jc_internal.cuh"
+#include "jc_math.cuh"
 
 namespace {
+
+constexpr double HF_HALF_LN_CUT = 2.1910133173369406;  // ln sqrt(80): halofit Gaussian-window truncation
 
 struct M2 { double a, b, c, d; };  // [[a b][c d]]
 __device__ __forceinline__ M2 mul(const M2& x, const M2& y) {
@@ -34,6 +37,7 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
   __shared__ double s_omm[JC_NA], s_odew[JC_NA];
   __shared__ double s_rnl[JC_NA];
   __shared__ double s_red[8];
+  double* const s_hfk = s_f;  // halofit k nodes (s_f is free once the Limber-node values exist)
 
   const int c = blockIdx.x;
   const int tid = threadIdx.x;
@@ -237,17 +241,24 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
     double Tk = jc_eh_transfer(eh, k, lnk);
     double pk = exp(ns * lnk) * (Tk * Tk) * g1sq * pknorm;  // power.py:49-52
     s_d2w[i] = pl.hf_wk[i] * (pk * (k * k * k) / JC_TWO_PI_SQ);
+    s_hfk[i] = k;
   }
   __syncthreads();
   {  // S(R_j), one R per thread (power.py:98-111 with g^2 factored out)
-    double r = pl.hf_r[tid];
-    double acc = 0.0;
-    for (int i = 0; i < JC_NHFK; ++i) {
-      double y = pl.hf_k[i] * r;
-      double y2 = y * y;
-      if (y2 > 300.0) break;  // exp(-300) ~ 5e-131: below any representable contribution
-      acc += s_d2w[i] * exp(-y2);
+    // terms with (k r)^2 > HF_CUT are < e^-80 = 2e-35 of the leading ones: the k loop stops at
+    // ln k <= ln sqrt(HF_CUT) - ln r (the ln k grid is uniform), which also makes it unrollable
+    const double r = pl.hf_r[tid];
+    const double dlnk = pl.hf_lnk[1] - pl.hf_lnk[0];
+    const int imax = min(JC_NHFK, (int)((HF_HALF_LN_CUT - pl.hf_logr[tid] - pl.hf_lnk[0]) / dlnk) + 2);
+    double acc0 = 0.0, acc1 = 0.0;
+    int i = 0;
+    for (; i + 1 < imax; i += 2) {
+      const double ya = s_hfk[i] * r, yb = s_hfk[i + 1] * r;
+      acc0 = fma(s_d2w[i], jcm_exp(-(ya * ya)), acc0);
+      acc1 = fma(s_d2w[i + 1], jcm_exp(-(yb * yb)), acc1);
     }
+    if (i < imax) { const double ya = s_hfk[i] * r; acc0 = fma(s_d2w[i], jcm_exp(-(ya * ya)), acc0); }
+    const double acc = acc0 + acc1;
     s_S[tid] = acc;
     ws.stab[(size_t)c * JC_NHFR + tid] = acc;
   }
@@ -283,16 +294,19 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
   // n_eff and C (power.py:121-141): one node per warp round, ln k nodes strided over lanes
   {
     const int warp = tid >> 5, lane = tid & 31;
+    const double dlnk = pl.hf_lnk[1] - pl.hf_lnk[0], lnk0 = pl.hf_lnk[0];
     for (int n = warp; n < JC_NA; n += 8) {
-      double rnl = s_rnl[n];
+      const double rnl = s_rnl[n];
+      // same (k R)^2 <= HF_CUT truncation as for S(R); ln R_nl = -ln k_nl was stored above
+      const int imax = min(JC_NHFK, (int)((HF_HALF_LN_CUT + node_ptr(ws, c, JC_NODE_LNKNL)[n] - lnk0) / dlnk) + 2);
       double r0 = 0.0, r1 = 0.0;
-      for (int i = lane; i < JC_NHFK; i += 32) {
-        double y = pl.hf_k[i] * rnl;
-        double y2 = y * y;
-        if (y2 > 300.0) break;
-        double res = s_d2w[i] * exp(-y2);
-        r0 += 2.0 * res * y2;
-        r1 += 4.0 * res * (y2 - y2 * y2);
+#pragma unroll 2
+      for (int i = lane; i < imax; i += 32) {
+        const double y = s_hfk[i] * rnl;
+        const double y2 = y * y;
+        const double res = s_d2w[i] * jcm_exp(-y2);
+        r0 = fma(2.0 * res, y2, r0);
+        r1 = fma(4.0 * res, y2 - y2 * y2, r1);
       }
       for (int o = 16; o > 0; o >>= 1) {
         r0 += __shfl_xor_sync(0xffffffffu, r0, o);

@@ -83,8 +83,8 @@ __global__ void __launch_bounds__(256) jc_tracer_finish_kernel(JcDevPlan pl, Ws 
   const double H = node_ptr(ws, c, JC_NODE_HUBBLE)[n];
   const double D = node_ptr(ws, c, JC_NODE_GROWTH)[n];
   double* out = ws.rker + ((size_t)c * JC_NA_PAD + n) * pl.TS + t;
-  const double nz = pl.nz_node[(size_t)t * JC_NA_PAD + n];
-  double b = pl.bias_node[(size_t)t * JC_NA_PAD + n];
+  const double nz = pl.nz_node[(size_t)n * pl.TS + t];
+  double b = pl.bias_node[(size_t)n * pl.TS + t];
   if (pl.tr_inv_growth[t]) b = b / D;  // bias.py:37-39
   double r;
   if (pl.tr_kind[t] == JC_TRACER_WEAK_LENSING) {

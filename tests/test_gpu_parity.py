@@ -303,6 +303,17 @@ def test_device_math(torch_cuda):
     x = np.concatenate([rng.uniform(0, 50, 200000), np.exp(rng.uniform(-30, 13.8, 200000)), [0.0]])
     err = np.abs(run("sin", x) - np.sin(x))
     assert err.max() < 2e-15, err.max()
+    # table-driven variants used by the power kernel (log_t: x >= 1 only)
+    x = np.concatenate([rng.uniform(-700, 700, 200000), rng.uniform(-2, 2, 200000), [0.0, -708.0, 709.0]])
+    e = relerr(run("exp_t", x), np.exp(x))
+    assert e < 2e-15, e
+    x = np.concatenate([np.exp(rng.uniform(0, 600, 200000)), rng.uniform(1.0, 2.0, 200000),
+                        1.0 + np.exp(rng.uniform(-40, 0, 100000)), [1.0, 2.718281828459045, 1.0078125, 1.0078124]])
+    ref = np.log(x)
+    err = np.abs(run("log_t", x) - ref) / np.maximum(np.abs(ref), 1.0)
+    assert err.max() < 4e-16, err.max()
+    near1 = x < 1.0078125  # first table bin: relative accuracy next to 1
+    assert relerr(run("log_t", x[near1]), np.log(x[near1]), floor=1e-300) < 2e-15
     x = np.exp(rng.uniform(-60, 80, 200000))
     assert relerr(run("rcbrt", x), 1.0 / np.cbrt(x)) < 2e-15
     x = np.exp(rng.uniform(-300, 300, 200000))
