@@ -199,6 +199,18 @@ int jc_workspace_layout(const jc_plan* plan, size_t ws_bytes, jc_ws_layout* layo
 int jc_angular_cl_f64(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo,
                       double* cl_dev, void* ws_dev, size_t ws_bytes, void* stream);
 
+/* Forward-mode derivatives in the same pipeline (BASELINE config 4; what jax.jacfwd of the reference's
+ * angular_cl returns, notebook docs/notebooks/jax-cosmo-intro.ipynb:989): for each of the n_tangents
+ * directions tangents_dev[k, 0..7] in parameter space (same order as a cosmo row), dcl[b, k] is the
+ * directional derivative of cl[b] along it -- the derivative of the discretised program with
+ * interpolation / root indices and clip branches frozen at the evaluation point.  cl_dev may be NULL.
+ * cosmo_dev [B,8], tangents_dev [K,8], cl_dev [B,P,L], dcl_dev [B,K,P,L]; the workspace holds a value
+ * plane and a tangent plane: jc_workspace_bytes_jvp() = 2 x jc_workspace_bytes(). */
+int jc_workspace_bytes_jvp(const jc_plan* plan, int64_t n_cosmo, size_t* bytes_out);
+int jc_angular_cl_jvp_f64(const jc_plan* plan, const double* cosmo_dev, const double* tangents_dev,
+                          int32_t n_tangents, int64_t n_cosmo, double* cl_dev, double* dcl_dev,
+                          void* ws_dev, size_t ws_bytes, void* stream);
+
 /* Same call with HOST buffers: copies cosmo in, runs, copies cl out, synchronises.  Uses a
  * device arena owned by the plan (grown on first use).  This is what the Python drop-in calls. */
 int jc_angular_cl_host_f64(jc_plan* plan, const double* cosmo_host, int64_t n_cosmo,

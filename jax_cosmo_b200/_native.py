@@ -31,6 +31,7 @@ SCAL_FIELDS = ["LN13KEQ", "INV13KEQ", "BETA_C", "C14_ALPHA_C", "SH_D", "LNKSILK"
 # every symbol include/jc_b200.h declares
 EXPORTS = ["jc_plan_create", "jc_plan_destroy", "jc_plan_n_tracers", "jc_plan_n_cls", "jc_plan_n_ell",
            "jc_workspace_bytes", "jc_workspace_layout", "jc_angular_cl_f64", "jc_angular_cl_host_f64",
+           "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64",
            "jc_noise_f64", "jc_gaussian_cov_f64", "jc_profile_enable", "jc_profile_read",
            "jc_fp64_peak_tflops", "jc_debug_math_f64", "jc_status_string",
            "jc_last_cuda_error", "jc_abi_version"]
@@ -90,6 +91,10 @@ def load_library():
         lib.jc_workspace_layout.restype = C.c_int
         lib.jc_angular_cl_f64.argtypes = [vp, vp, i64, vp, vp, C.c_size_t, vp]
         lib.jc_angular_cl_f64.restype = C.c_int
+        lib.jc_workspace_bytes_jvp.argtypes = [vp, i64, C.POINTER(C.c_size_t)]
+        lib.jc_workspace_bytes_jvp.restype = C.c_int
+        lib.jc_angular_cl_jvp_f64.argtypes = [vp, vp, vp, i32, i64, vp, vp, vp, C.c_size_t, vp]
+        lib.jc_angular_cl_jvp_f64.restype = C.c_int
         lib.jc_angular_cl_host_f64.argtypes = [vp, vp, i64, vp]
         lib.jc_angular_cl_host_f64.restype = C.c_int
         lib.jc_noise_f64.argtypes = [vp, dp]
@@ -290,6 +295,24 @@ class Plan:
                                               ws.numel() * 8, stream)
         check(st, "jc_angular_cl_f64")
         return out
+
+    def angular_cl_jvp_device(self, cosmo_dev, tangents_dev):
+        """cosmo_dev [B,8], tangents_dev [K,8] (CUDA float64) -> (cl [B,P,L], dcl [B,K,P,L]) on the device."""
+        import torch
+
+        assert cosmo_dev.is_cuda and cosmo_dev.dtype == torch.float64 and cosmo_dev.is_contiguous()
+        assert tangents_dev.is_cuda and tangents_dev.dtype == torch.float64 and tangents_dev.is_contiguous()
+        B, K = cosmo_dev.shape[0], tangents_dev.shape[0]
+        need = C.c_size_t()
+        check(load_library().jc_workspace_bytes_jvp(self._h, B, C.byref(need)), "jc_workspace_bytes_jvp")
+        ws = torch.empty(need.value // 8, dtype=torch.float64, device=cosmo_dev.device)
+        cl = torch.empty((B, self.P, self.L), dtype=torch.float64, device=cosmo_dev.device)
+        dcl = torch.empty((B, K, self.P, self.L), dtype=torch.float64, device=cosmo_dev.device)
+        stream = torch.cuda.current_stream(cosmo_dev.device).cuda_stream
+        st = load_library().jc_angular_cl_jvp_f64(self._h, cosmo_dev.data_ptr(), tangents_dev.data_ptr(), K, B,
+                                                  cl.data_ptr(), dcl.data_ptr(), ws.data_ptr(), ws.numel() * 8, stream)
+        check(st, "jc_angular_cl_jvp_f64")
+        return cl, dcl
 
     def angular_cl_host(self, cosmo_rows, out=None):
         """cosmo_rows: host float64 [B,8] (numpy or CPU tensor) -> host [B,P,L] (same kind)."""

@@ -19,7 +19,7 @@ from jax_cosmo_b200 import _native
 from jax_cosmo_b200 import power
 from jax_cosmo_b200 import transfer as tklib
 
-__all__ = ["angular_cl", "angular_cl_batch", "noise_cl", "gaussian_cl_covariance",
+__all__ = ["angular_cl", "angular_cl_batch", "angular_cl_jvp", "angular_cl_jacobian", "noise_cl", "gaussian_cl_covariance",
            "gaussian_cl_covariance_and_mean"]
 
 
@@ -76,6 +76,41 @@ def angular_cl_batch(cosmo_rows, ell, probes, transfer_fn=tklib.Eisenstein_Hu, n
     except ImportError:  # pragma: no cover
         pass
     return plan.angular_cl_host(_rows(cosmo_rows), out=out)
+
+
+_PARAM_INDEX = {"Omega_c": 0, "Omega_b": 1, "h": 2, "n_s": 3, "sigma8": 4, "Omega_k": 5, "w0": 6, "wa": 7}
+WCDM_PARAMS = ("Omega_c", "Omega_b", "h", "n_s", "sigma8", "w0", "wa")  # BASELINE config 4
+
+
+def angular_cl_jvp(cosmo, ell, probes, tangents, transfer_fn=tklib.Eisenstein_Hu, nonlinear_fn=power.halofit):
+    """Forward-mode derivatives of angular_cl in one call (what `jax.jvp` / `jax.jacfwd` of the
+    reference return, docs/notebooks/jax-cosmo-intro.ipynb:989): `tangents` is [K, 8] directions in
+    the cosmology-row parameter space.  Returns (cl [B, n_cls, n_ell], dcl [B, K, n_cls, n_ell]) as
+    NumPy arrays (B = 1 for a Cosmology object)."""
+    import torch
+
+    plan = _native.get_plan(probes, ell, transfer_fn, nonlinear_fn)
+    dev = "cuda:%d" % plan.device
+    rows = torch.as_tensor(_rows(cosmo), device=dev)
+    tang = np.ascontiguousarray(np.atleast_2d(np.asarray(tangents, dtype=np.float64)))
+    if tang.shape[1] != 8:
+        raise ValueError("tangents must have shape [K, 8]")
+    cl, dcl = plan.angular_cl_jvp_device(rows, torch.as_tensor(tang, device=dev))
+    return cl.cpu().numpy(), dcl.cpu().numpy()
+
+
+def angular_cl_jacobian(cosmo, ell, probes, params=WCDM_PARAMS, transfer_fn=tklib.Eisenstein_Hu,
+                        nonlinear_fn=power.halofit):
+    """(cl [n_cls, n_ell], jac [n_params, n_cls, n_ell]): d cl / d theta for the named parameters,
+    default the 7 wCDM parameters of BASELINE config 4.  `jac.reshape(n_params, -1).T` is the
+    [n_cls*n_ell, n_params] layout of `jax.jacfwd(mean_fn)` (jax-cosmo-intro.ipynb:1039)."""
+    tang = np.zeros((len(params), 8))
+    for k, name in enumerate(params):
+        if name not in _PARAM_INDEX:
+            raise ValueError("unknown parameter %r" % (name,))
+        tang[k, _PARAM_INDEX[name]] = 1.0
+    cl, dcl = angular_cl_jvp(cosmo, ell, probes, tang, transfer_fn, nonlinear_fn)
+    return cl[0], dcl[0]
 
 
 def noise_cl(ell, probes):

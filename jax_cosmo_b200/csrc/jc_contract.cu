@@ -9,12 +9,16 @@
 // but needs 1/16 of the issue slots and pads P, L only to multiples of 8 (216 x 104) instead of the
 // 4x4-block x 32-lane tiling of a scalar kernel (240 x 128).
 //
-// CTA = (cosmology, group of <= 7 ell-tiles), 16 warps.  The pair tiles (8 pairs each) are dealt to the
-// warps 2-or-1 each so that the four SMSPs (warp % 4) carry 7/7/7/6 of the 27 tiles at P=210; a warp
-// holds <= 2 x 7 accumulator tiles (28 FP64 accumulators per lane).  R and V stream through a 4-stage
-// cp.async pipeline of 12 Limber nodes per stage (43 stages = 516 nodes; the 3 padding nodes are zero
-// rows); every thread owns fixed copy slots, and issues the next stage's copies after its MMA burst.
-// Row strides TS and 60 are 4 or 12 (mod 16) so every fragment load is bank-conflict free.
+// CTA = (cosmology, group of <= 7 ell-tiles, share of the pair tiles).  The pair tiles (8 pairs each)
+// are dealt to the warps 2-or-1 each (balanced over the four SMSPs); a warp holds <= 2 x 7 accumulator
+// tiles (28 FP64 accumulators per lane).  R and V stream through a 4-stage cp.async pipeline of KC
+// Limber nodes per stage (padding nodes are zero rows); every thread owns fixed copy slots and issues
+// the next stage's copies after its MMA burst.  The stage body is branch-free (templated on the tile
+// counts) so the fragment loads of a k-step are issued ahead of its MMAs.  Row strides TS and 60 are 4
+// or 12 (mod 16): every fragment load is bank-conflict free.
+//
+// JVP mode (template flag): the tangent  dC = (dR_i R_j + R_i dR_j) . V + (R_i R_j) . dV  with the value
+// planes and the tangent planes (ws.doff) of R and V staged side by side; two MMAs per tile and k-step.
 #include <cstdlib>
 
 #include "jc_internal.cuh"
@@ -39,11 +43,11 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
       : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// One pipeline stage (KC/4 k-steps) of a warp's CNT x NT accumulator tiles; branch-free so that the
-// fragment loads of a k-step are issued ahead of its MMAs.
-template <int KC, int CNT, int NT>
+// One pipeline stage (KC/4 k-steps) of a warp's CNT x NT accumulator tiles.  `half` = doubles from the
+// value image [R | V] of a stage to its tangent image (JVP only).
+template <int KC, int CNT, int NT, bool JVP>
 __device__ __forceinline__ void mma_stage(const double* __restrict__ Rs, const double* __restrict__ Vs,
-                                          int TS, int g, int tig, const int (&ti)[2], const int (&tj)[2],
+                                          int TS, int half, int g, int tig, const int (&ti)[2], const int (&tj)[2],
                                           double (&acc)[2][NTW][2]) {
 #pragma unroll
   for (int ks = 0; ks < KC / 4; ++ks) {
@@ -54,41 +58,60 @@ __device__ __forceinline__ void mma_stage(const double* __restrict__ Rs, const d
     for (int mt = 0; mt < CNT; ++mt) a[mt] = rr[ti[mt]] * rr[tj[mt]];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) b[nt] = vr[nt * 8];
+    if (!JVP) {
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
+      for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-      for (int mt = 0; mt < CNT; ++mt) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+        for (int mt = 0; mt < CNT; ++mt) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+    } else {
+      double ad[CNT], bd[NT];
+#pragma unroll
+      for (int mt = 0; mt < CNT; ++mt)
+        ad[mt] = fma(rr[half + ti[mt]], rr[tj[mt]], rr[ti[mt]] * rr[half + tj[mt]]);  // dR_i R_j + R_i dR_j
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) bd[nt] = vr[half + nt * 8];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int mt = 0; mt < CNT; ++mt) {
+          dmma(acc[mt][nt][0], acc[mt][nt][1], ad[mt], b[nt]);
+          dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], bd[nt]);
+        }
+    }
   }
 }
 
-template <int KC, int CNT>
-__device__ __forceinline__ void mma_stage_nt(int ntw, const double* Rs, const double* Vs, int TS, int g, int tig,
-                                             const int (&ti)[2], const int (&tj)[2], double (&acc)[2][NTW][2]) {
+template <int KC, int CNT, bool JVP>
+__device__ __forceinline__ void mma_stage_nt(int ntw, const double* Rs, const double* Vs, int TS, int half, int g,
+                                             int tig, const int (&ti)[2], const int (&tj)[2],
+                                             double (&acc)[2][NTW][2]) {
   switch (ntw) {  // warp-uniform
-    case 7: mma_stage<KC, CNT, 7>(Rs, Vs, TS, g, tig, ti, tj, acc); break;
-    case 6: mma_stage<KC, CNT, 6>(Rs, Vs, TS, g, tig, ti, tj, acc); break;
-    case 5: mma_stage<KC, CNT, 5>(Rs, Vs, TS, g, tig, ti, tj, acc); break;
-    case 4: mma_stage<KC, CNT, 4>(Rs, Vs, TS, g, tig, ti, tj, acc); break;
-    case 3: mma_stage<KC, CNT, 3>(Rs, Vs, TS, g, tig, ti, tj, acc); break;
-    case 2: mma_stage<KC, CNT, 2>(Rs, Vs, TS, g, tig, ti, tj, acc); break;
-    default: mma_stage<KC, CNT, 1>(Rs, Vs, TS, g, tig, ti, tj, acc); break;
+    case 7: mma_stage<KC, CNT, 7, JVP>(Rs, Vs, TS, half, g, tig, ti, tj, acc); break;
+    case 6: mma_stage<KC, CNT, 6, JVP>(Rs, Vs, TS, half, g, tig, ti, tj, acc); break;
+    case 5: mma_stage<KC, CNT, 5, JVP>(Rs, Vs, TS, half, g, tig, ti, tj, acc); break;
+    case 4: mma_stage<KC, CNT, 4, JVP>(Rs, Vs, TS, half, g, tig, ti, tj, acc); break;
+    case 3: mma_stage<KC, CNT, 3, JVP>(Rs, Vs, TS, half, g, tig, ti, tj, acc); break;
+    case 2: mma_stage<KC, CNT, 2, JVP>(Rs, Vs, TS, half, g, tig, ti, tj, acc); break;
+    default: mma_stage<KC, CNT, 1, JVP>(Rs, Vs, TS, half, g, tig, ti, tj, acc); break;
   }
 }
 
 // KC: Limber nodes per pipeline stage (KC/4 k-steps); WARPS per CTA; MINB CTAs per SM; the pair tiles
-// are split over gridDim.z CTAs.
-template <int KC, int WARPS, int MINB>
+// are split over gridDim.z CTAs.  out_cosmo_stride: doubles between consecutive cosmologies of `out`.
+template <int KC, int WARPS, int MINB, bool JVP>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
-jc_contract_kernel(JcDevPlan pl, Ws ws, double* __restrict__ cl) {
+jc_contract_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64_t out_cosmo_stride) {
   constexpr int NKC = (JC_NA + KC - 1) / KC;
-  constexpr int MAX_SLOTS = (KC * (18 + NCOLS / 2) + WARPS * 32 - 1) / (WARPS * 32);  // TS <= 36
+  constexpr int NIMG = JVP ? 2 : 1;
+  constexpr int MAX_SLOTS = (NIMG * KC * (18 + NCOLS / 2) + WARPS * 32 - 1) / (WARPS * 32);  // TS <= 36
   extern __shared__ __align__(16) double smem[];
   const int c = blockIdx.y;
   const int l0 = blockIdx.x * NCOLS;
   const int ncols = min(NCOLS, pl.Lpad - l0);  // multiple of 4 (Lpad is)
   const int ntw = (min(pl.L - l0, NCOLS) + 7) >> 3;
   const int TS = pl.TS;
-  const int stage_doubles = KC * (TS + LSV);
+  const int half = KC * (TS + LSV);            // one [R | V] image
+  const int stage_doubles = NIMG * half;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int g = lane >> 2, tig = lane & 3;
   const int mtiles_all = (pl.P + 7) >> 3;
@@ -98,7 +121,7 @@ jc_contract_kernel(JcDevPlan pl, Ws ws, double* __restrict__ cl) {
   const double* Rg = ws.rker + (size_t)c * JC_NA_PAD * TS;
   const double* Vg = ws.vtab + (size_t)c * JC_NA * pl.Lpad + l0;
 
-  // fixed copy slots of this thread: piece q = tid + j*blockDim of the [R | V] stage image
+  // fixed copy slots of this thread: piece q = tid + j*blockDim of the stage image(s) [R | V] (| [dR | dV])
   const double* slot_src[MAX_SLOTS];
   int slot_dst[MAX_SLOTS], slot_row[MAX_SLOTS], slot_step[MAX_SLOTS];
   {
@@ -106,17 +129,21 @@ jc_contract_kernel(JcDevPlan pl, Ws ws, double* __restrict__ cl) {
     const int nR = KC * rp, nV = KC * vp;
 #pragma unroll
     for (int j = 0; j < MAX_SLOTS; ++j) {
-      const int q = threadIdx.x + j * blockDim.x;
-      if (q < nR) {
+      int q = threadIdx.x + j * blockDim.x;
+      const int img = q / (nR + nV);  // 0 value image, 1 tangent image
+      q -= img * (nR + nV);
+      const ptrdiff_t goff = img ? ws.doff : 0;
+      if (img >= NIMG) {
+        slot_src[j] = nullptr; slot_dst[j] = 0; slot_row[j] = 0; slot_step[j] = 0;
+      } else if (q < nR) {
         const int r = q / rp, p2 = q - r * rp;
-        slot_src[j] = Rg + r * TS + 2 * p2; slot_dst[j] = r * TS + 2 * p2; slot_row[j] = r; slot_step[j] = KC * TS;
-      } else if (q < nR + nV) {
+        slot_src[j] = Rg + goff + r * TS + 2 * p2; slot_dst[j] = img * half + r * TS + 2 * p2;
+        slot_row[j] = r; slot_step[j] = KC * TS;
+      } else {
         const int qv = q - nR;
         const int r = qv / vp, p2 = qv - r * vp;
-        slot_src[j] = Vg + (size_t)r * pl.Lpad + 2 * p2; slot_dst[j] = KC * TS + r * LSV + 2 * p2;
+        slot_src[j] = Vg + goff + (size_t)r * pl.Lpad + 2 * p2; slot_dst[j] = img * half + KC * TS + r * LSV + 2 * p2;
         slot_row[j] = r; slot_step[j] = KC * pl.Lpad;
-      } else {
-        slot_src[j] = nullptr; slot_dst[j] = 0; slot_row[j] = 0; slot_step[j] = 0;
       }
     }
   }
@@ -161,21 +188,21 @@ jc_contract_kernel(JcDevPlan pl, Ws ws, double* __restrict__ cl) {
       __syncthreads();  // stage kc landed; stage kc-1 (refilled below) is no longer read by anyone
       const double* Rs = smem + (size_t)(kc % STAGES) * stage_doubles;
       const double* Vs = Rs + KC * TS;
-      if (cnt == 2) mma_stage_nt<KC, 2>(ntw, Rs, Vs, TS, g, tig, ti, tj, acc);
-      else if (cnt == 1) mma_stage_nt<KC, 1>(ntw, Rs, Vs, TS, g, tig, ti, tj, acc);
+      if (cnt == 2) mma_stage_nt<KC, 2, JVP>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+      else if (cnt == 1) mma_stage_nt<KC, 1, JVP>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
       if (kc + STAGES - 1 < NKC) load_stage(kc + STAGES - 1);
       cp_async_commit();
     }
     cp_async_wait<0>();
 
-    const bool vec2 = (pl.L & 1) == 0;
+    const bool vec2 = (pl.L & 1) == 0 && (out_cosmo_stride & 1) == 0;
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
       const int p = (m_first + mt) * 8 + g;
       if (mt >= cnt || p >= pl.P) continue;
       const bool wi = pl.tr_kind[ti[mt]] == JC_TRACER_WEAK_LENSING;
       const bool wj = pl.tr_kind[tj[mt]] == JC_TRACER_WEAK_LENSING;
-      double* out = cl + ((size_t)c * pl.P + p) * pl.L;
+      double* out = out_base + (size_t)c * out_cosmo_stride + (size_t)p * pl.L;
 #pragma unroll
       for (int nt = 0; nt < NTW; ++nt) {
         const int l = l0 + nt * 8 + 2 * tig;
@@ -196,16 +223,16 @@ jc_contract_kernel(JcDevPlan pl, Ws ws, double* __restrict__ cl) {
   }
 }
 
-template <int KC, int WARPS, int MINB>
-void launch_cfg(const JcDevPlan& pl, const Ws& ws, double* cl, int chunk, int msplit, cudaStream_t s) {
+template <int KC, int WARPS, int MINB, bool JVP>
+void launch_cfg(const JcDevPlan& pl, const Ws& ws, double* out, int64_t stride, int chunk, int msplit, cudaStream_t s) {
   const int ngroups = (pl.L + NCOLS - 1) / NCOLS;
-  const size_t smem = (size_t)STAGES * KC * (pl.TS + LSV) * sizeof(double);
+  const size_t smem = (size_t)(JVP ? 2 : 1) * STAGES * KC * (pl.TS + LSV) * sizeof(double);
   static bool attr_done = false;  // idempotent attribute; racing writers set the same value
   if (!attr_done) {
-    cudaFuncSetAttribute(jc_contract_kernel<KC, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(jc_contract_kernel<KC, WARPS, MINB, JVP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     attr_done = true;
   }
-  jc_contract_kernel<KC, WARPS, MINB><<<dim3(ngroups, chunk, msplit), WARPS * 32, smem, s>>>(pl, ws, cl);
+  jc_contract_kernel<KC, WARPS, MINB, JVP><<<dim3(ngroups, chunk, msplit), WARPS * 32, smem, s>>>(pl, ws, out, stride);
 }
 
 int g_contract_cfg = -1;
@@ -222,10 +249,17 @@ int jc_contract_init() {
 
 void jc_launch_contract(const JcDevPlan& pl, const Ws& ws, double* cl, int chunk, cudaStream_t s) {
   const int mtiles = (pl.P + 7) / 8;
+  const int64_t stride = (int64_t)pl.P * pl.L;
   switch (g_contract_cfg) {
-    case 1: launch_cfg<12, 16, 1>(pl, ws, cl, chunk, 1, s); break;
-    case 2: launch_cfg<24, 16, 1>(pl, ws, cl, chunk, 1, s); break;
-    case 3: launch_cfg<24, 8, 2>(pl, ws, cl, chunk, mtiles > 16 ? 2 : 1, s); break;
-    default: launch_cfg<12, 8, 2>(pl, ws, cl, chunk, mtiles > 16 ? 2 : 1, s); break;  // fastest (profiles/r01_tuning.md)
+    case 1: launch_cfg<12, 16, 1, false>(pl, ws, cl, stride, chunk, 1, s); break;
+    case 2: launch_cfg<24, 16, 1, false>(pl, ws, cl, stride, chunk, 1, s); break;
+    // fastest (profiles/r01_tuning.md): 8 warps, 2 CTAs per SM, pair tiles split over 2 CTAs
+    default: launch_cfg<12, 8, 2, false>(pl, ws, cl, stride, chunk, mtiles > 16 ? 2 : 1, s); break;
   }
+}
+
+void jc_launch_contract_jvp(const JcDevPlan& pl, const Ws& ws, double* dcl, int64_t dcl_cosmo_stride, int chunk,
+                            cudaStream_t s) {
+  const int mtiles = (pl.P + 7) / 8;
+  launch_cfg<12, 8, 2, true>(pl, ws, dcl, dcl_cosmo_stride, chunk, mtiles > 16 ? 2 : 1, s);
 }

@@ -136,6 +136,7 @@ struct Ws {  // resolved workspace pointers for one chunk of cosmologies
   double* rker;    // [chunk][JC_NA_PAD][TS]   node-major radial kernels R_i(a_n)
   double* vtab;    // [chunk][513][Lpad]
   double* ellpow;  // [chunk][Lpad]  (l+1/2)^(3+n_s)
+  ptrdiff_t doff;  // JVP passes: offset (doubles) from a value to its tangent (second plane); 0 otherwise
 };
 
 #ifdef __CUDACC__
@@ -156,6 +157,15 @@ __device__ __forceinline__ double jc_rcp(double x) {
 
 // per-stage launchers (one translation unit per kernel)
 void jc_launch_setup(const JcDevPlan& pl, const double* cosmo, const Ws& ws, int chunk, cudaStream_t s);
+// JVP (Dual) variants: same kernels instantiated on value+tangent; `tangent` = direction [8] in parameter space
+void jc_launch_setup_jvp(const JcDevPlan& pl, const double* cosmo, const double* tangent, const Ws& ws, int chunk,
+                         cudaStream_t s);
+int jc_launch_tracers_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s);
+void jc_launch_finish_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s);
+void jc_launch_power_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s);
+void jc_launch_contract_jvp(const JcDevPlan& pl, const Ws& ws, double* dcl, int64_t dcl_cosmo_stride, int chunk,
+                            cudaStream_t s);
+int jc_setup_init();
 int jc_launch_tracers(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s);  // lensing; returns #launches
 void jc_launch_finish(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s);
 void jc_launch_power(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s);

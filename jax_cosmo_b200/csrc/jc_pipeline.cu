@@ -28,7 +28,54 @@ void layout_for(const JcDevPlan& pl, int64_t chunk, jc_ws_layout* lo) {
 
 }  // namespace
 
-int jc_pipeline_init() { return jc_contract_init(); }
+int jc_pipeline_init() {
+  int st = jc_contract_init();
+  if (st != JC_OK) return st;
+  return jc_setup_init();
+}
+
+static void resolve(const jc_ws_layout& lo, double* base, ptrdiff_t doff, Ws* ws) {
+  ws->chitab = base + lo.chitab; ws->gtab = base + lo.gtab; ws->scal = base + lo.scal;
+  ws->stab = base + lo.stab; ws->node = base + lo.node; ws->rker = base + lo.rker; ws->vtab = base + lo.vtab;
+  ws->ellpow = base + lo.ellpow;
+  ws->doff = doff;
+}
+
+extern "C" int jc_workspace_bytes_jvp(const jc_plan* plan, int64_t n_cosmo, size_t* bytes_out) {
+  int st = jc_workspace_bytes(plan, n_cosmo, bytes_out);
+  if (st == JC_OK) *bytes_out *= 2;  // value plane + tangent plane
+  return st;
+}
+
+// Forward-mode derivatives: for every tangent direction k (a row of tangents_dev [K,8] in parameter
+// space) one pass of the Dual-instantiated kernels K1..K3 and the tangent contraction.
+extern "C" int jc_angular_cl_jvp_f64(const jc_plan* plan, const double* cosmo_dev, const double* tangents_dev,
+                                     int32_t n_tangents, int64_t n_cosmo, double* cl_dev, double* dcl_dev,
+                                     void* ws_dev, size_t ws_bytes, void* stream) {
+  if (!plan || !cosmo_dev || !tangents_dev || !dcl_dev || !ws_dev || n_cosmo < 1 || n_tangents < 1)
+    return JC_ERR_INVALID;
+  jc_ws_layout lo;
+  int st = jc_workspace_layout(plan, ws_bytes / 2, &lo);
+  if (st != JC_OK) return st;
+  const JcDevPlan& pl = plan->d;
+  cudaStream_t s = (cudaStream_t)stream;
+  Ws ws;
+  resolve(lo, (double*)ws_dev, (ptrdiff_t)((lo.total + 1) & ~(int64_t)1), &ws);
+  const int64_t PL = (int64_t)pl.P * pl.L;
+  for (int64_t c0 = 0; c0 < n_cosmo; c0 += lo.chunk) {
+    const int chunk = (int)((n_cosmo - c0) < lo.chunk ? (n_cosmo - c0) : lo.chunk);
+    for (int k = 0; k < n_tangents; ++k) {
+      jc_launch_setup_jvp(pl, cosmo_dev + c0 * JC_N_COSMO_PARAMS, tangents_dev + (size_t)k * JC_N_COSMO_PARAMS, ws, chunk, s);
+      jc_launch_tracers_jvp(pl, ws, chunk, s);
+      jc_launch_finish_jvp(pl, ws, chunk, s);
+      jc_launch_power_jvp(pl, ws, chunk, s);
+      if (k == 0 && cl_dev) jc_launch_contract(pl, ws, cl_dev + (size_t)c0 * PL, chunk, s);  // value plane
+      jc_launch_contract_jvp(pl, ws, dcl_dev + ((size_t)c0 * n_tangents + k) * PL, (int64_t)n_tangents * PL, chunk, s);
+    }
+  }
+  JC_CUDA_TRY(cudaGetLastError());
+  return JC_OK;
+}
 
 extern "C" int jc_workspace_bytes(const jc_plan* plan, int64_t n_cosmo, size_t* bytes_out) {
   if (!plan || !bytes_out || n_cosmo < 1) return JC_ERR_INVALID;
@@ -57,9 +104,7 @@ extern "C" int jc_angular_cl_f64(const jc_plan* plan, const double* cosmo_dev, i
   cudaStream_t s = (cudaStream_t)stream;
   double* base = (double*)ws_dev;
   Ws ws;
-  ws.chitab = base + lo.chitab; ws.gtab = base + lo.gtab; ws.scal = base + lo.scal;
-  ws.stab = base + lo.stab; ws.node = base + lo.node; ws.rker = base + lo.rker; ws.vtab = base + lo.vtab;
-  ws.ellpow = base + lo.ellpow;
+  resolve(lo, base, 0, &ws);
 
   JcProf* prof = (plan->prof && plan->prof->enabled) ? plan->prof : nullptr;
   for (int64_t c0 = 0; c0 < n_cosmo; c0 += lo.chunk) {

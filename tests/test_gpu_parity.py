@@ -235,6 +235,61 @@ def test_edge_cases(jc, torch_cuda):
         jc.cl.angular_cl_batch(np.zeros((2, 7)), [10.0, 20.0], probes)
 
 
+@pytest.mark.parametrize("variant", ["cfg4_planck", "cfg4_extended_wcdm", "linear"])
+def test_jvp_config4(jc, torch_cuda, variant):
+    """BASELINE config 4: C_ell plus d/d(Omega_c, Omega_b, h, n_s, sigma8, w0, wa) in one call, against
+    central finite differences of the oracle with frozen halofit root indices (oracle/derivatives.py).
+    Bound: 1e-6 of the largest |dC_ell/dtheta| of each spectrum (FD itself is good to ~1e-9)."""
+    from oracle import derivatives as od
+    if variant == "cfg4_planck":
+        scn = sc.scenario("c4", sc.PLANCK15, sc.ELL_CFG2[::4], [sc.sources(5, 2.0), sc.lenses(5, 2.0)])
+    elif variant == "cfg4_extended_wcdm":
+        scn = sc.scenario("c4x", sc.WCDM, sc.ELL_CFG2[::9], [sc.sources(5, 2.0, True), sc.lenses(5, 2.0, True)])
+    else:
+        scn = sc.scenario("c4l", sc.WCDM, sc.ELL_CFG1[::5], [sc.sources(4, 6.5)], "linear")
+    probes = sc.build_probes(scn, jc)
+    tf, nl = sc.build_fns(scn, jc)
+    cosmo = sc.build_cosmo(scn, jc)
+    row = sc.cosmo_row(scn["cosmo"])
+    cl, jac = jc.cl.angular_cl_jacobian(cosmo, scn["ell"], probes, transfer_fn=tf, nonlinear_fn=nl)
+    prob = sc.flatten_spec(scn)
+    cl_ref, jac_ref, steps = od.fd_jacobian(row, scn["ell"], prob)
+    assert jac.shape == jac_ref.shape == (7,) + cl.shape
+    assert relerr(cl, cl_ref) < RTOL
+    assert relerr(cl, jc.cl.angular_cl(cosmo, scn["ell"], probes, transfer_fn=tf, nonlinear_fn=nl)) < 1e-12
+    scale = np.abs(jac_ref).max(axis=2, keepdims=True)
+    err = np.abs(jac - jac_ref) / scale
+    worst = err.reshape(7, -1).max(axis=1)
+    print(variant, "max |dC - FD| / max|dC| per parameter:", " ".join("%s=%.1e" % kv for kv in zip(od.WCDM_PARAMS, worst)))
+    assert worst.max() < 1e-6, worst
+    # a general direction is the linear combination of the columns
+    rng = np.random.default_rng(3)
+    w = rng.normal(size=7)
+    tang = np.zeros((1, 8))
+    tang[0, [0, 1, 2, 3, 4, 6, 7]] = w
+    _, d = jc.cl.angular_cl_jvp(cosmo, scn["ell"], probes, tang, transfer_fn=tf, nonlinear_fn=nl)
+    comb = np.tensordot(w, jac, axes=1)
+    assert np.max(np.abs(d[0, 0] - comb)) <= 1e-11 * np.max(np.abs(comb))
+    if variant == "linear":  # C_ell ~ sigma8^2 exactly for linear P(k) (power.py:47)
+        assert relerr(jac[4], 2.0 * cl / row[4]) < 1e-12
+
+
+def test_jvp_batch(jc, torch_cuda):
+    """JVP on a batch: every row equals its single-cosmology call; Fisher-style layout check."""
+    torch = torch_cuda
+    scn = sc.scenario("c4", sc.PLANCK15, sc.ELL_CFG2[::10], [sc.sources(5, 2.0), sc.lenses(5, 2.0)])
+    plan, probes = _plan(jc, scn)
+    rows = sc.config5_cosmologies(5)
+    tang = np.zeros((7, 8))
+    tang[np.arange(7), [0, 1, 2, 3, 4, 6, 7]] = 1.0
+    cl, dcl = plan.angular_cl_jvp_device(torch.as_tensor(rows, device="cuda"), torch.as_tensor(tang, device="cuda"))
+    assert dcl.shape == (5, 7, 55, 10) and torch.isfinite(dcl).all()
+    one_cl, one_d = plan.angular_cl_jvp_device(torch.as_tensor(rows[3:4], device="cuda"), torch.as_tensor(tang, device="cuda"))
+    assert torch.equal(one_cl[0], cl[3]) and torch.equal(one_d[0], dcl[3])
+    fwd = plan.angular_cl_device(torch.as_tensor(rows, device="cuda"))
+    assert float(((fwd - cl).abs() / fwd.abs()).max()) < 1e-12
+
+
 def _nccl_worker(rank, world, port, out_dir):
     import torch
     import torch.distributed as dist
