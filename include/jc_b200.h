@@ -226,6 +226,17 @@ int jc_noise_f64(const jc_plan* plan, double* noise_host);
 int jc_gaussian_cov_f64(const jc_plan* plan, const double* cl_dev, const double* noise_dev,
                         int64_t n_cosmo, double f_sky, double* cov_dev, void* stream);
 
+/* Gaussian log-likelihood on the sparse block covariance (replaces jax_cosmo/likelihood.py:9-61 with
+ * sparse.inv / sparse.slogdet, jax_cosmo/sparse.py:295-366; BASELINE config 3):
+ *   loglike[b] = -0.5 * (r^T C^-1 r - log det C),  r = mu[b] - data   (the reference's sign convention;
+ *   without the log-determinant term when include_logdet == 0).
+ * data_dev [N] (data_stride = 0) or [B, N] (data_stride = N), mu_dev [B, N], N = P*L in cls-major order;
+ * cov_dev [B, P, P, L] with SPD slices cov[b, :, :, l]; loglike_dev [B]; scratch_dev [B, L, 2] doubles.
+ * JC_ERR_UNSUPPORTED if a slice does not fit shared memory (P > 238). */
+int jc_gaussian_loglike_f64(const double* data_dev, int64_t data_stride, const double* mu_dev,
+                            const double* cov_dev, int64_t n_cosmo, int32_t P, int32_t L,
+                            int32_t include_logdet, double* loglike_dev, double* scratch_dev, void* stream);
+
 /* Per-stage device timing (CUDA events recorded on the launch stream between the stages of
  * jc_angular_cl_f64).  Stages: 0 setup, 1 lensing efficiency, 2 tracer finish, 3 power, 4 pair
  * contraction.  While enabled the plan is not re-entrant.  jc_profile_read synchronises the

@@ -31,7 +31,7 @@ SCAL_FIELDS = ["LN13KEQ", "INV13KEQ", "BETA_C", "C14_ALPHA_C", "SH_D", "LNKSILK"
 # every symbol include/jc_b200.h declares
 EXPORTS = ["jc_plan_create", "jc_plan_destroy", "jc_plan_n_tracers", "jc_plan_n_cls", "jc_plan_n_ell",
            "jc_workspace_bytes", "jc_workspace_layout", "jc_angular_cl_f64", "jc_angular_cl_host_f64",
-           "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64",
+           "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64", "jc_gaussian_loglike_f64",
            "jc_noise_f64", "jc_gaussian_cov_f64", "jc_profile_enable", "jc_profile_read",
            "jc_fp64_peak_tflops", "jc_debug_math_f64", "jc_status_string",
            "jc_last_cuda_error", "jc_abi_version"]
@@ -95,6 +95,8 @@ def load_library():
         lib.jc_workspace_bytes_jvp.restype = C.c_int
         lib.jc_angular_cl_jvp_f64.argtypes = [vp, vp, vp, i32, i64, vp, vp, vp, C.c_size_t, vp]
         lib.jc_angular_cl_jvp_f64.restype = C.c_int
+        lib.jc_gaussian_loglike_f64.argtypes = [vp, i64, vp, vp, i64, i32, i32, i32, vp, vp, vp]
+        lib.jc_gaussian_loglike_f64.restype = C.c_int
         lib.jc_angular_cl_host_f64.argtypes = [vp, vp, i64, vp]
         lib.jc_angular_cl_host_f64.restype = C.c_int
         lib.jc_noise_f64.argtypes = [vp, dp]
@@ -381,6 +383,24 @@ def get_plan(probes, ell, transfer_fn=None, nonlinear_fn=None, device=None):
         plan = Plan(pb, ell, device=None if dev < 0 else dev)
         _plan_cache[key] = plan
     return plan
+
+
+def gaussian_loglike_device(data_dev, mu_dev, cov_dev, include_logdet=True):
+    """CUDA float64 tensors: data [N] or [B,N], mu [B,N], cov [B,P,P,L] (sparse block layout) -> loglike [B]."""
+    import torch
+
+    B, P, _, L = cov_dev.shape
+    assert mu_dev.shape == (B, P * L) and cov_dev.is_contiguous() and mu_dev.is_contiguous()
+    data_dev = data_dev.contiguous()
+    stride = 0 if data_dev.dim() == 1 else P * L
+    assert data_dev.shape[-1] == P * L
+    out = torch.empty(B, dtype=torch.float64, device=cov_dev.device)
+    scratch = torch.empty((B, L, 2), dtype=torch.float64, device=cov_dev.device)
+    st = load_library().jc_gaussian_loglike_f64(data_dev.data_ptr(), stride, mu_dev.data_ptr(), cov_dev.data_ptr(), B, P, L,
+                                                1 if include_logdet else 0, out.data_ptr(), scratch.data_ptr(),
+                                                torch.cuda.current_stream(cov_dev.device).cuda_stream)
+    check(st, "jc_gaussian_loglike_f64")
+    return out
 
 
 def debug_math(fn, x):

@@ -1,0 +1,42 @@
+"""Drop-in for jax_cosmo/likelihood.py on the sparse block covariance layout (BASELINE config 3).
+
+`gaussian_log_likelihood(data, mu, C, include_logdet=True, inverse_method="inverse")` has the reference's
+signature and sign convention (likelihood.py:9-61: -0.5 * (r^T C^-1 r - log det C), r = mu - data).  The
+sparse layout [n_cls, n_cls, n_ell] (what `gaussian_cl_covariance_and_mean(..., sparse=True)` returns)
+runs in the CUDA kernel csrc/jc_loglike.cu: one CTA per ell slice, packed Cholesky in shared memory.
+A dense [N, N] covariance is outside the accelerated path and raises (no CPU fallback).
+"""
+import numpy as np
+
+from jax_cosmo_b200 import _native
+
+__all__ = ["gaussian_log_likelihood", "gaussian_log_likelihood_batch"]
+
+
+def gaussian_log_likelihood(data, mu, C, include_logdet=True, inverse_method="inverse"):
+    """Gaussian log-likelihood of `data` [N] given mean `mu` [N] and sparse covariance C [P, P, L]
+    (N = P*L, cls-major).  `inverse_method` is ignored for sparse covariances, as in the reference."""
+    import torch
+
+    C = np.asarray(C, dtype=np.float64)
+    if C.ndim != 3 or C.shape[0] != C.shape[1]:
+        raise NotImplementedError(
+            "only the sparse block layout [n_cls, n_cls, n_ell] is on the B200 path (use sparse=True in "
+            "gaussian_cl_covariance_and_mean); dense covariances are not accelerated and there is no CPU fallback")
+    P, _, L = C.shape
+    mu = np.asarray(mu, dtype=np.float64).reshape(-1)
+    data = np.asarray(data, dtype=np.float64).reshape(-1)
+    if mu.shape != (P * L,) or data.shape != (P * L,):
+        raise ValueError("data and mu must have %d elements" % (P * L))
+    if not torch.cuda.is_available():
+        raise _native.JcError("jax_cosmo_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    out = _native.gaussian_loglike_device(torch.as_tensor(data, device="cuda"),
+                                          torch.as_tensor(mu[None], device="cuda"),
+                                          torch.as_tensor(np.ascontiguousarray(C)[None], device="cuda"), include_logdet)
+    return float(out[0].item())
+
+
+def gaussian_log_likelihood_batch(data, mu, C, include_logdet=True):
+    """Device form for batches: CUDA tensors data [N] or [B, N], mu [B, N], C [B, P, P, L] -> [B]
+    (stream-ordered; pairs with `Plan.angular_cl_device` + `Plan.gaussian_cov_device`)."""
+    return _native.gaussian_loglike_device(data, mu, C, include_logdet)

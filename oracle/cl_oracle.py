@@ -552,3 +552,36 @@ def gaussian_cl_covariance_and_mean(cosmo_row, ell, problem, f_sky=0.25, sparse=
     nl = noise_cl(ell, problem)
     cov = gaussian_cl_covariance(ell, len(problem["tracers"]), cl, nl, f_sky, sparse)
     return cl.flatten(), cov
+
+
+# ----------------------------------------------------------------------------------------------
+# likelihood.py / sparse.py (config 3 consumer)
+# ----------------------------------------------------------------------------------------------
+def sparse_to_dense(sp):
+    """sparse.py:52-68: [ny, nx, n] block-diagonal-of-diagonals -> dense [ny*n, nx*n]."""
+    ny, nx, n = sp.shape
+    out = np.zeros((ny, n, nx, n))
+    idx = np.arange(n)
+    out[:, idx, :, idx] = np.moveaxis(sp, 2, 0)
+    return out.reshape(ny * n, nx * n)
+
+
+def gaussian_log_likelihood(data, mu, C, include_logdet=True):
+    """likelihood.py:9-61 for a sparse covariance [P, P, L] (sparse.inv = per-ell inverse,
+    sparse.py:295-315; slogdet = sum over ell, sparse.py:335-366), evaluated densely.  Keeps the
+    reference's sign convention -0.5 * (chi2 - logdet) (likelihood.py:61)."""
+    r = np.asarray(mu, dtype=np.float64) - np.asarray(data, dtype=np.float64)
+    C = np.asarray(C, dtype=np.float64)
+    P, _, L = C.shape
+    if P * L <= 2000:  # literal dense evaluation
+        dense = sparse_to_dense(C)
+        chi2 = r @ np.linalg.solve(dense, r)
+        logdet = np.linalg.slogdet(dense)[1]
+    else:  # the dense matrix would be [P L, P L]: use its block structure (what sparse.inv / slogdet do)
+        Cl = np.moveaxis(C, 2, 0)  # [L, P, P]
+        rl = r.reshape(P, L).T  # [L, P]
+        chi2 = float(np.sum(rl * np.linalg.solve(Cl, rl[:, :, None])[:, :, 0]))
+        logdet = float(np.sum(np.linalg.slogdet(Cl)[1]))
+    if not include_logdet:
+        return -0.5 * chi2
+    return -0.5 * (chi2 - logdet)

@@ -84,12 +84,44 @@ def run_stages(name, cdict):
     return out
 
 
+def run_likelihood():
+    """The reference's own likelihood test scenario (tests/test_likelihood.py:12-35) and a 2+2 3x2pt case:
+    gaussian_log_likelihood on the sparse covariance, with and without the log-determinant."""
+    from jax_cosmo.likelihood import gaussian_log_likelihood
+    nz1, nz2 = sc.smail(1.0, 2.0, 1.0), sc.smail(1.0, 2.0, 0.5)
+    cases = {
+        "reftest": sc.scenario("like_reftest", sc.PLANCK15, np.logspace(1, 3, 5),
+                               [sc.nc([nz1, nz2], sc.bias("constant", 1.0))]),
+        "3x2pt": sc.scenario("like_3x2pt", sc.WCDM, np.logspace(1, 3, 7),
+                             [sc.wl([nz1, nz2]), sc.nc([nz1, nz2], sc.bias("constant", 1.2))]),
+    }
+    out = {}
+    for tag, scn in cases.items():
+        cosmo = sc.build_cosmo(scn, jc)
+        probes = sc.build_probes(scn, jc)
+        ell = np.array(scn["ell"])
+        mu, cov = gaussian_cl_covariance_and_mean(cosmo, ell, probes, sparse=True)
+        mu, cov = np.asarray(mu), np.asarray(cov)
+        data = 1.1 * mu
+        out[tag + "_spec"] = np.array(json.dumps(scn))
+        out[tag + "_mu"], out[tag + "_cov"], out[tag + "_data"] = mu, cov, data
+        out[tag + "_loglike_logdet"] = np.asarray(gaussian_log_likelihood(data, mu, cov, include_logdet=True))
+        out[tag + "_loglike_nologdet"] = np.asarray(gaussian_log_likelihood(data, mu, cov, include_logdet=False))
+        print("likelihood %-8s %s %s" % (tag, out[tag + "_loglike_logdet"], out[tag + "_loglike_nologdet"]), flush=True)
+    return out
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
     ap.add_argument("--stages", action="store_true")
+    ap.add_argument("--likelihood", action="store_true")
     args = ap.parse_args()
     os.makedirs(OUT, exist_ok=True)
+    if args.likelihood or (args.only is None and not args.stages):
+        np.savez(os.path.join(OUT, "likelihood.npz"), **run_likelihood())
+        if args.likelihood:
+            sys.exit(0)
     if args.stages or args.only is None:
         row0 = dict(zip(sc.COSMO_KEYS, sc.config5_cosmologies(1)[0]))
         for name, c in [("planck15", sc.PLANCK15), ("testcosmo", sc.TESTCOSMO),

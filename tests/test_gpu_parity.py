@@ -290,6 +290,38 @@ def test_jvp_batch(jc, torch_cuda):
     assert float(((fwd - cl).abs() / fwd.abs()).max()) < 1e-12
 
 
+def test_likelihood_golden_and_config3(jc, torch_cuda):
+    """Config 3: gaussian_cl_covariance_and_mean + Gaussian log-likelihood in the sparse block layout.
+    (a) the reference's likelihood values (golden, incl. tests/test_likelihood.py's scenario), rtol 1e-9
+    (the reference test itself asserts 1e-6); (b) 10+10 bins, 100 ell on a batch, device end to end,
+    against the dense NumPy evaluation of the oracle."""
+    from conftest import GOLDEN
+    torch = torch_cuda
+    g = np.load(os.path.join(GOLDEN, "likelihood.npz"))
+    for tag in ("reftest", "3x2pt"):
+        for key, inc in (("loglike_logdet", True), ("loglike_nologdet", False)):
+            v = jc.likelihood.gaussian_log_likelihood(g[tag + "_data"], g[tag + "_mu"], g[tag + "_cov"], include_logdet=inc)
+            assert abs(v / float(g[tag + "_" + key]) - 1) < RTOL, (tag, key, v)
+    with pytest.raises(NotImplementedError):
+        jc.likelihood.gaussian_log_likelihood(np.zeros(4), np.zeros(4), np.eye(4))
+    # full config 3 on the device: mean + covariance + likelihood for 3 cosmologies, shared data vector
+    scn = sc.scenario("c3", sc.PLANCK15, sc.ELL_CFG2, [sc.sources(10, 1.0), sc.lenses(10, 1.0)])
+    plan, probes = _plan(jc, scn)
+    rows = np.concatenate([sc.cosmo_row(sc.PLANCK15)[None], sc.config5_cosmologies(2)])
+    cl = plan.angular_cl_device(torch.as_tensor(rows, device="cuda"))
+    cov = plan.gaussian_cov_device(cl, f_sky=0.25)
+    mu = cl.reshape(3, -1)
+    data = 1.02 * mu[0]
+    for inc in (True, False):
+        ll = jc.likelihood.gaussian_log_likelihood_batch(data, mu, cov, include_logdet=inc).cpu().numpy()
+        for b in range(3):
+            ref = o.gaussian_log_likelihood(data.cpu().numpy(), mu[b].cpu().numpy(), cov[b].cpu().numpy(), inc)
+            assert abs(ll[b] / ref - 1) < 1e-8, (b, inc, ll[b], ref)
+    # the mean itself reproduces chi2 = 0
+    ll0 = jc.likelihood.gaussian_log_likelihood_batch(mu[0], mu[:1].contiguous(), cov[:1].contiguous(), include_logdet=False)
+    assert float(ll0[0]) == 0.0
+
+
 def _nccl_worker(rank, world, port, out_dir):
     import torch
     import torch.distributed as dist

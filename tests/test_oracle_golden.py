@@ -69,6 +69,23 @@ def test_stages(name):
         assert np.all(mine[~nzm] == 0)
 
 
+def test_likelihood_golden():
+    """oracle.gaussian_log_likelihood against the reference's likelihood.py + sparse.py run on the shim
+    (tests/golden/likelihood.npz; incl. the reference's own test scenario tests/test_likelihood.py:12-35)."""
+    g = np.load(os.path.join(GOLDEN, "likelihood.npz"))
+    for tag in ("reftest", "3x2pt"):
+        data, mu, cov = g[tag + "_data"], g[tag + "_mu"], g[tag + "_cov"]
+        for key, inc in (("loglike_logdet", True), ("loglike_nologdet", False)):
+            v = o.gaussian_log_likelihood(data, mu, cov, inc)
+            assert abs(v / float(g[tag + "_" + key]) - 1) < 1e-12
+        # per-ell factorisation used by the CUDA kernel == dense evaluation
+        r = mu - data
+        P, _, L = cov.shape
+        chi2 = sum(r.reshape(P, L)[:, l] @ np.linalg.solve(cov[:, :, l], r.reshape(P, L)[:, l]) for l in range(L))
+        assert abs(-0.5 * chi2 / float(g[tag + "_loglike_nologdet"]) - 1) < 1e-12
+        assert np.array_equal(o.sparse_to_dense(cov), __import__("jax_cosmo_b200").sparse.to_dense(cov))
+
+
 def test_survey_appendix_b_values():
     """SURVEY.md Appendix B spot values (reference source on the shim, recorded by the survey)."""
     scn, g = load_golden(os.path.join(GOLDEN, "cl_appB_halofit.npz"))
