@@ -100,13 +100,16 @@ __device__ __forceinline__ void mma_stage_nt(int ntw, const double* Rs, const do
 // are split over gridDim.z CTAs.  out_cosmo_stride: doubles between consecutive cosmologies of `out`.
 template <int KC, int WARPS, int MINB, bool JVP>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
-jc_contract_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64_t out_cosmo_stride) {
+jc_contract_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64_t out_cosmo_stride, int msplit) {
   constexpr int NKC = (JC_NA + KC - 1) / KC;
   constexpr int NIMG = JVP ? 2 : 1;
   constexpr int MAX_SLOTS = (NIMG * KC * (18 + NCOLS / 2) + WARPS * 32 - 1) / (WARPS * 32);  // TS <= 36
   extern __shared__ __align__(16) double smem[];
   const int c = blockIdx.y;
-  const int l0 = blockIdx.x * NCOLS;
+  // blockIdx.x = pair-share z (fastest, so the shares of one cosmology are launched back to back and
+  // co-reside on an SM) + msplit * ell-group
+  const int zsplit = blockIdx.x % msplit, zgroup = blockIdx.x / msplit;
+  const int l0 = zgroup * NCOLS;
   const int ncols = min(NCOLS, pl.Lpad - l0);  // multiple of 4 (Lpad is)
   const int ntw = (min(pl.L - l0, NCOLS) + 7) >> 3;
   const int TS = pl.TS;
@@ -115,8 +118,8 @@ jc_contract_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64_t o
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int g = lane >> 2, tig = lane & 3;
   const int mtiles_all = (pl.P + 7) >> 3;
-  const int m_per_cta = (mtiles_all + gridDim.z - 1) / gridDim.z;
-  const int m_lo = blockIdx.z * m_per_cta;
+  const int m_per_cta = (mtiles_all + msplit - 1) / msplit;
+  const int m_lo = zsplit * m_per_cta;
   const int mtiles = min(mtiles_all, m_lo + m_per_cta);  // this CTA owns pair tiles [m_lo, mtiles)
   const double* Rg = ws.rker + (size_t)c * JC_NA_PAD * TS;
   const double* Vg = ws.vtab + (size_t)c * JC_NA * pl.Lpad + l0;
@@ -162,8 +165,11 @@ jc_contract_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64_t o
     // deal the round's pair tiles to the warps: base or base+1 each, the extras to the lowest warps
     const int m_round = min(2 * nwarps, mtiles - m_base);
     const int base = m_round / nwarps, extra = m_round - base * nwarps;
-    const int cnt = base + (warp < extra ? 1 : 0);
-    const int m_first = m_base + warp * base + min(warp, extra);
+    // odd shares hand their extras to the highest warps instead, so that the SMSP (= warp % 4) loads of two
+    // co-resident shares add up evenly (27 tiles at P = 210: 4,4,3,3 + 3,3,3,4 = 7,7,6,7)
+    const bool rev = zsplit & 1;
+    const int cnt = base + ((rev ? nwarps - 1 - warp : warp) < extra ? 1 : 0);
+    const int m_first = m_base + warp * base + (rev ? max(0, warp - (nwarps - extra)) : min(warp, extra));
     int ti[2], tj[2];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
@@ -232,7 +238,7 @@ void launch_cfg(const JcDevPlan& pl, const Ws& ws, double* out, int64_t stride, 
     cudaFuncSetAttribute(jc_contract_kernel<KC, WARPS, MINB, JVP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     attr_done = true;
   }
-  jc_contract_kernel<KC, WARPS, MINB, JVP><<<dim3(ngroups, chunk, msplit), WARPS * 32, smem, s>>>(pl, ws, out, stride);
+  jc_contract_kernel<KC, WARPS, MINB, JVP><<<dim3(ngroups * msplit, chunk), WARPS * 32, smem, s>>>(pl, ws, out, stride, msplit);
 }
 
 int g_contract_cfg = -1;

@@ -16,6 +16,8 @@ namespace {
 
 constexpr int LENS_CGROUPS = 4;  // cosmology groups per CTA
 constexpr int LENS_NODES = 128;  // nodes per CTA
+constexpr int LENS_MR = 4;       // z' rows per pipeline stage
+constexpr int LENS_STAGES = 3;
 
 // NCOS: cosmologies per thread (4 for double, 2 for Dual: same accumulator register budget)
 template <class T, int NS, int NCOS>
@@ -39,30 +41,91 @@ jc_lens_kernel(JcDevPlan pl, Ws ws, int n_cosmo, int s0) {
   __syncthreads();
   const T(*chit)[JC_NCHI] = s_chit + cg * NCOS;
   const size_t NL = (size_t)JC_NLENS * JC_NLENS_COLS;
-  // sources s0..s0+NS-1 are consecutive [257][512] slabs (the launcher guarantees s0+NS <= n_src)
-  const double* nw0 = pl.lens_nw + (size_t)s0 * NL + n;
   T acc[NCOS][NS];
 #pragma unroll
   for (int c = 0; c < NCOS; ++c)
 #pragma unroll
     for (int s = 0; s < NS; ++s) acc[c][s] = T(0.0);
 
-#pragma unroll 2
-  for (int m = 0; m < JC_NLENS; ++m) {
-    const size_t o = (size_t)m * JC_NLENS_COLS;
-    const double t = __ldg(pl.lens_t + o + n);
-    const int ix = __ldg(pl.lens_ix + o + n);
-    const int i0 = ix & 255, i1 = ix >> 8;
-    double wv[NS];
+  // The [257 x 128] slices of lens_t / lens_ix / lens_nw (sources s0..s0+NS-1, consecutive slabs) of this
+  // CTA's node block stream through a LENS_STAGES-deep cp.async pipeline of LENS_MR z'-rows per stage;
+  // all 16 warps read them from shared memory (the kernel was L2-latency bound with direct loads:
+  // FP64 pipe 26 % at 16 warps/SM, profiles/r01_ncu_summary.md).
+  extern __shared__ __align__(16) unsigned char lens_smem[];
+  constexpr int ROW_T = LENS_NODES * 8, ROW_IX = LENS_NODES * 2;          // bytes per z'-row
+  constexpr int STAGE_BYTES = LENS_MR * (ROW_T * (1 + NS) + ROW_IX);
+  constexpr int OFF_NW = LENS_MR * ROW_T, OFF_IX = LENS_MR * ROW_T * (1 + NS);
+  constexpr int PIECES = STAGE_BYTES / 16;
+  constexpr int SLOTS = (PIECES + LENS_NODES * LENS_CGROUPS - 1) / (LENS_NODES * LENS_CGROUPS);
+  constexpr int NSTAGE = (JC_NLENS + LENS_MR - 1) / LENS_MR;
+  const int node0 = blockIdx.x * LENS_NODES;
+  const unsigned char* slot_src[SLOTS];
+  int slot_dst[SLOTS], slot_row[SLOTS], slot_step[SLOTS];
 #pragma unroll
-    for (int s = 0; s < NS; ++s) wv[s] = __ldg(nw0 + o + s * NL);
+  for (int j = 0; j < SLOTS; ++j) {
+    const int q = threadIdx.x + j * (LENS_NODES * LENS_CGROUPS);
+    const int b = q * 16;  // byte offset inside the stage image
+    if (q >= PIECES) {
+      slot_src[j] = nullptr; slot_dst[j] = 0; slot_row[j] = 0; slot_step[j] = 0;
+    } else if (b < OFF_NW) {  // t rows
+      const int r = b / ROW_T, o = b - r * ROW_T;
+      slot_src[j] = (const unsigned char*)(pl.lens_t + (size_t)r * JC_NLENS_COLS + node0) + o;
+      slot_row[j] = r; slot_step[j] = LENS_MR * JC_NLENS_COLS * 8; slot_dst[j] = b;
+    } else if (b < OFF_IX) {  // nw rows: [row][source][node]
+      const int bb = b - OFF_NW;
+      const int r = bb / (ROW_T * NS), s = (bb - r * ROW_T * NS) / ROW_T, o = bb - (r * NS + s) * ROW_T;
+      slot_src[j] = (const unsigned char*)(pl.lens_nw + (size_t)(s0 + s) * NL + (size_t)r * JC_NLENS_COLS + node0) + o;
+      slot_row[j] = r; slot_step[j] = LENS_MR * JC_NLENS_COLS * 8; slot_dst[j] = b;
+    } else {  // ix rows (uint16)
+      const int bb = b - OFF_IX;
+      const int r = bb / ROW_IX, o = bb - r * ROW_IX;
+      slot_src[j] = (const unsigned char*)(pl.lens_ix + (size_t)r * JC_NLENS_COLS + node0) + o;
+      slot_row[j] = r; slot_step[j] = LENS_MR * JC_NLENS_COLS * 2; slot_dst[j] = b;
+    }
+  }
+  auto load_stage = [&](int st) {
+    unsigned char* base = lens_smem + (size_t)(st % LENS_STAGES) * STAGE_BYTES;
 #pragma unroll
-    for (int c = 0; c < NCOS; ++c) {
-      const T f0 = chit[c][i0], f1 = chit[c][i1];
-      const T chip = jx_max(f0 + (f1 - f0) * t, 0.0);                      // background.py:242
-      const T g = jx_max(chip - chin[c], 0.0) * jx_rcp(jx_max(chip, 1.0));  // probes.py:49
+    for (int j = 0; j < SLOTS; ++j)
+      if (slot_src[j] && st * LENS_MR + slot_row[j] < JC_NLENS) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(base + slot_dst[j]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(slot_src[j] + (size_t)st * slot_step[j]));
+      }
+  };
 #pragma unroll
-      for (int s = 0; s < NS; ++s) acc[c][s] = acc[c][s] + wv[s] * g;
+  for (int st = 0; st < LENS_STAGES - 1; ++st) {
+    load_stage(st);
+    asm volatile("cp.async.commit_group;\n" ::);
+  }
+  const int nl = (warp & 3) * 32 + lane;  // node within the CTA's block
+  for (int st = 0; st < NSTAGE; ++st) {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(LENS_STAGES - 2));
+    __syncthreads();  // stage st landed; stage st-1 (refilled below) is no longer read
+    if (st + LENS_STAGES - 1 < NSTAGE) load_stage(st + LENS_STAGES - 1);
+    asm volatile("cp.async.commit_group;\n" ::);
+    const unsigned char* base = lens_smem + (size_t)(st % LENS_STAGES) * STAGE_BYTES;
+    const double* st_t = (const double*)base + nl;
+    const double* st_nw = (const double*)(base + OFF_NW) + nl;
+    const unsigned short* st_ix = (const unsigned short*)(base + OFF_IX) + nl;
+    const int rows = min(LENS_MR, JC_NLENS - st * LENS_MR);
+#pragma unroll
+    for (int r = 0; r < LENS_MR; ++r) {
+      if (r < rows) {
+        const double t = st_t[r * LENS_NODES];
+        const int ix = st_ix[r * LENS_NODES];
+        const int i0 = ix & 255, i1 = ix >> 8;
+        double wv[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) wv[s] = st_nw[(r * NS + s) * LENS_NODES];
+#pragma unroll
+        for (int c = 0; c < NCOS; ++c) {
+          const T f0 = chit[c][i0], f1 = chit[c][i1];
+          const T chip = jx_max(f0 + (f1 - f0) * t, 0.0);                      // background.py:242
+          const T g = jx_max(chip - chin[c], 0.0) * jx_rcp(jx_max(chip, 1.0));  // probes.py:49
+#pragma unroll
+          for (int s = 0; s < NS; ++s) acc[c][s] = acc[c][s] + wv[s] * g;
+        }
+      }
     }
   }
   const double dz = pl.lens_zmax - pl.limb_z[n];  // simps: dx * N (probes.py:51)
@@ -106,7 +169,13 @@ template <class T, int NS, int NCOS>
 void launch_lens(const JcDevPlan& pl, const Ws& ws, int chunk, int s0, cudaStream_t st) {
   constexpr int CTA_COSMO = NCOS * LENS_CGROUPS;
   dim3 grid(JC_NLENS_COLS / LENS_NODES, (chunk + CTA_COSMO - 1) / CTA_COSMO);
-  jc_lens_kernel<T, NS, NCOS><<<grid, LENS_NODES * LENS_CGROUPS, 0, st>>>(pl, ws, chunk, s0);
+  constexpr int smem = LENS_STAGES * LENS_MR * (LENS_NODES * 8 * (1 + NS) + LENS_NODES * 2);
+  static bool attr_done = false;  // idempotent attribute; racing writers set the same value
+  if (!attr_done) {
+    cudaFuncSetAttribute(jc_lens_kernel<T, NS, NCOS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_done = true;
+  }
+  jc_lens_kernel<T, NS, NCOS><<<grid, LENS_NODES * LENS_CGROUPS, smem, st>>>(pl, ws, chunk, s0);
 }
 
 template <class T, int NCOS>
