@@ -54,7 +54,13 @@ typedef enum jc_status {
 } jc_status;
 
 /* n(z) families: jax_cosmo/redshift.py */
-enum { JC_NZ_SMAIL = 1 /* redshift.py:61-77: z^a exp(-(z/z0)^b), params = {a, b, z0} */ };
+enum {
+  JC_NZ_SMAIL = 1, /* redshift.py:61-77   z^a exp(-(z/z0)^b), params = {a, b, z0}                        */
+  JC_NZ_FU = 2,    /* redshift.py:80-105  (z^a + z^(ab)) / (z^b + c), params = {a, b, c}                  */
+  JC_NZ_DELTA = 3, /* redshift.py:108-123 source plane at params[0]; weak lensing without IA only
+                      (probes.py:53-64; the reference raises for density / NLA kernels, probes.py:82,107) */
+  JC_NZ_KDE = 4    /* redshift.py:126-156 Gaussian KDE of a catalogue: kde_z / kde_w / kde_n / kde_bw     */
+};
 /* bias families: jax_cosmo/bias.py */
 enum {
   JC_BIAS_NONE = 0,
@@ -82,6 +88,10 @@ typedef struct jc_nz {
   double shifts[JC_MAX_SHIFTS];
   double gals_per_arcmin2;
   double zmax;
+  const double* kde_z; /* JC_NZ_KDE: HOST arrays [kde_n] (catalogue redshifts, weights); read during   */
+  const double* kde_w; /*            jc_plan_create only                                                */
+  int64_t kde_n;
+  double kde_bw;       /* bandwidth (config["bw"])                                                      */
 } jc_nz;
 
 typedef struct jc_bias {

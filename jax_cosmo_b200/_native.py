@@ -17,7 +17,7 @@ JC_ABI_VERSION = 1
 JC_MAX_TRACERS = 32
 JC_MAX_SHIFTS = 4
 JC_OK, JC_ERR_INVALID, JC_ERR_UNSUPPORTED, JC_ERR_WORKSPACE, JC_ERR_CUDA, JC_ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5
-JC_NZ_SMAIL = 1
+JC_NZ = {"smail": 1, "fu": 2, "delta": 3, "kde": 4}
 JC_BIAS = {"constant": 1, "inverse_growth": 2, "des_y1_ia": 3}
 JC_TRACER_WL, JC_TRACER_NC = 1, 2
 JC_PK_LINEAR, JC_PK_HALOFIT = 0, 1
@@ -40,7 +40,8 @@ EXPORTS = ["jc_plan_create", "jc_plan_destroy", "jc_plan_n_tracers", "jc_plan_n_
 class jc_nz(C.Structure):
     _fields_ = [("family", C.c_int32), ("n_shifts", C.c_int32), ("params", C.c_double * 4),
                 ("shifts", C.c_double * JC_MAX_SHIFTS), ("gals_per_arcmin2", C.c_double),
-                ("zmax", C.c_double)]
+                ("zmax", C.c_double), ("kde_z", C.POINTER(C.c_double)), ("kde_w", C.POINTER(C.c_double)),
+                ("kde_n", C.c_int64), ("kde_bw", C.c_double)]
 
 
 class jc_bias(C.Structure):
@@ -182,6 +183,8 @@ def build_problem(probes, transfer_fn=None, nonlinear_fn=None):
         raise NotImplementedError("nonlinear_fn: only power.halofit (takahashi2012) and power.linear are on the B200 path")
 
     pb = jc_problem()
+    pb._keepalive = []       # arrays referenced by pointer fields
+    pb._content_key = b""    # their contents (the plan cache must not key on addresses)
     pb.abi_version = JC_ABI_VERSION
     pb.transfer = JC_TF_EH_OSC
     pb.nonlinear = nl
@@ -202,11 +205,23 @@ def build_problem(probes, transfer_fn=None, nonlinear_fn=None):
             tr = pb.tracers[t]
             tr.kind = kind
             fam, p, shifts = pz._describe()
-            if fam != "smail":
+            if fam not in JC_NZ:
                 raise NotImplementedError("n(z) family %s" % fam)
             if len(shifts) > JC_MAX_SHIFTS:
                 raise NotImplementedError("more than %d nested systematic_shift" % JC_MAX_SHIFTS)
-            tr.nz.family = JC_NZ_SMAIL
+            if fam == "delta" and (kind != JC_TRACER_WL or probe.config.get("ia_enabled") or shifts):
+                # the reference raises in density_kernel / nla_kernel (probes.py:82-85,107-110)
+                raise NotImplementedError("delta_nz is only implemented for weak lensing without IA")
+            tr.nz.family = JC_NZ[fam]
+            if fam == "kde":
+                zcat, w, bw = p
+                pb._keepalive.extend([zcat, w])  # host arrays are read by jc_plan_create
+                pb._content_key += zcat.tobytes() + w.tobytes()
+                tr.nz.kde_z = zcat.ctypes.data_as(C.POINTER(C.c_double))
+                tr.nz.kde_w = w.ctypes.data_as(C.POINTER(C.c_double))
+                tr.nz.kde_n = len(zcat)
+                tr.nz.kde_bw = bw
+                p = ()
             for k, v in enumerate(p):
                 tr.nz.params[k] = v
             tr.nz.n_shifts = len(shifts)
@@ -375,7 +390,11 @@ def get_plan(probes, ell, transfer_fn=None, nonlinear_fn=None, device=None):
     pb = build_problem(probes, transfer_fn, nonlinear_fn)
     ell = np.ascontiguousarray(np.atleast_1d(np.asarray(ell, dtype=np.float64)))
     dev = (torch.cuda.current_device() if torch.cuda.is_available() else -1) if device is None else int(device)
-    key = (bytes(pb), ell.tobytes(), dev)
+    masked = jc_problem.from_buffer_copy(bytes(pb))  # key on contents, never on host addresses
+    for t in range(JC_MAX_TRACERS):
+        masked.tracers[t].nz.kde_z = None
+        masked.tracers[t].nz.kde_w = None
+    key = (bytes(masked), pb._content_key, ell.tobytes(), dev)
     plan = _plan_cache.get(key)
     if plan is None:
         if len(_plan_cache) >= 8:

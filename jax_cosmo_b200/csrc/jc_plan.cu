@@ -108,13 +108,34 @@ struct NzDev {
   double p[4];
   double shifts[JC_MAX_SHIFTS];
   double zmax;
+  const double* kde_z;  // device copies of the catalogue (JC_NZ_KDE)
+  const double* kde_w;
+  long long kde_n;
+  double kde_bw;
 };
 struct NzDevAll { NzDev nz[JC_MAX_TRACERS]; };
 
 __device__ __forceinline__ double pz_fn(const NzDev& nz, double z) {
-  // systematic_shift chain (redshift.py:169-171), then smail (redshift.py:75-77)
+  // systematic_shift chain (redshift.py:169-171), then the family's un-normalised n(z)
   for (int s = 0; s < nz.n_shifts; ++s) z = fmax(z - nz.shifts[s], 0.0);
-  return pow(z, nz.p[0]) * exp(-pow(z / nz.p[2], nz.p[1]));
+  switch (nz.family) {
+    case JC_NZ_FU:  // redshift.py:103-105
+      return (pow(z, nz.p[0]) + pow(z, nz.p[0] * nz.p[1])) / (pow(z, nz.p[1]) + nz.p[2]);
+    case JC_NZ_KDE: {  // redshift.py:142-156
+      const double bw = nz.kde_bw, norm = 1.0 / sqrt(2.0 * 3.141592653589793) / bw;
+      double s = 0.0, q = 0.0;
+      for (long long i = 0; i < nz.kde_n; ++i) {
+        const double d = nz.kde_z[i] - z;
+        s += nz.kde_w[i] * (norm * exp(-(d * d) / (bw * bw * 2.0)));
+        q += nz.kde_w[i];
+      }
+      return s / q;
+    }
+    case JC_NZ_DELTA:  // never evaluated as a distribution (lensing uses the source plane directly)
+      return 0.0;
+    default:  // JC_NZ_SMAIL, redshift.py:75-77
+      return pow(z, nz.p[0]) * exp(-pow(z / nz.p[2], nz.p[1]));
+  }
 }
 
 // norm[t] = simps(pz_fn, 0, zmax, 256)  (redshift.py:29-30); one block of 256+ threads per tracer
@@ -134,7 +155,7 @@ __global__ void jc_nz_norm_kernel(NzDevAll all, double* __restrict__ norm) {
   if (i == 0) {
     double s = 0.0;
     for (int j = 0; j <= 256; ++j) s += red[j];
-    norm[blockIdx.x] = nz.zmax / 256.0 / 3.0 * s;
+    norm[blockIdx.x] = nz.family == JC_NZ_DELTA ? 1.0 : nz.zmax / 256.0 / 3.0 * s;  // redshift.py:118
   }
 }
 
@@ -174,7 +195,14 @@ int validate(const jc_problem* pb, int n_ell) {
     const jc_tracer& tr = pb->tracers[t];
     if (tr.kind != JC_TRACER_WEAK_LENSING && tr.kind != JC_TRACER_NUMBER_COUNTS)
       return JC_ERR_INVALID;
-    if (tr.nz.family != JC_NZ_SMAIL) return JC_ERR_UNSUPPORTED;
+    if (tr.nz.family < JC_NZ_SMAIL || tr.nz.family > JC_NZ_KDE) return JC_ERR_UNSUPPORTED;
+    if (tr.nz.family == JC_NZ_KDE && (!tr.nz.kde_z || !tr.nz.kde_w || tr.nz.kde_n < 1 || !(tr.nz.kde_bw > 0.0)))
+      return JC_ERR_INVALID;
+    // delta planes: weak lensing without IA only, not under a shift (the reference raises NotImplementedError
+    // in density_kernel / nla_kernel, probes.py:82-85,107-110)
+    if (tr.nz.family == JC_NZ_DELTA &&
+        (tr.kind != JC_TRACER_WEAK_LENSING || tr.ia_enabled || tr.nz.n_shifts != 0 || !(tr.nz.params[0] >= 0.0)))
+      return JC_ERR_UNSUPPORTED;
     if (tr.nz.n_shifts < 0 || tr.nz.n_shifts > JC_MAX_SHIFTS) return JC_ERR_UNSUPPORTED;
     if (!(tr.nz.zmax > 0.0) || !(tr.probe_zmax > 0.0)) return JC_ERR_INVALID;
     if (!(tr.nz.gals_per_arcmin2 > 0.0)) return JC_ERR_INVALID;
@@ -220,8 +248,8 @@ extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int3
   const int P = T * (T + 1) / 2;
   double zmax = 0.0, lens_zmax = 0.0;
   int n_src = 0;
-  std::vector<int> tr_kind(T), tr_inv(T, 0), tr_ia(T, 0), tr_src(T, -1), src_tracer;
-  std::vector<double> tr_m1(T, 1.0);
+  std::vector<int> tr_kind(T), tr_inv(T, 0), tr_ia(T, 0), tr_src(T, -1), src_tracer, tr_delta_ix(T, -1);
+  std::vector<double> tr_m1(T, 1.0), tr_delta_t(T, 0.0);
   for (int t = 0; t < T; ++t) {
     const jc_tracer& tr = pb->tracers[t];
     if (tr.probe_zmax > zmax) zmax = tr.probe_zmax;  // angular_cl.py:63
@@ -230,8 +258,10 @@ extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int3
     tr_inv[t] = needs_bias && tr.bias.family == JC_BIAS_INVERSE_GROWTH;
     if (tr.kind == JC_TRACER_WEAK_LENSING) {
       tr_ia[t] = tr.ia_enabled ? 1 : 0;
-      tr_src[t] = n_src++;
-      src_tracer.push_back(t);
+      if (tr.nz.family != JC_NZ_DELTA) {  // extended distributions go through the lensing-efficiency integral
+        tr_src[t] = n_src++;
+        src_tracer.push_back(t);
+      }
       tr_m1[t] = 1.0 + tr.m_bias;
       lens_zmax = tr.probe_zmax;
     }
@@ -249,6 +279,14 @@ extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int3
   // ---- chi table grid -----------------------------------------------------------------------
   std::vector<double> e256 = linspace(-3.0, 0.0, JC_NCHI), atab(JC_NCHI), xtab(JC_NCHI);
   for (int i = 0; i < JC_NCHI; ++i) { atab[i] = std::pow(10.0, e256[i]); xtab[i] = std::log(atab[i]); }
+  for (int t = 0; t < T; ++t) {  // delta_nz source planes: chi-table bracket of a_s = 1/(1+z_s) (probes.py:57-59)
+    const jc_tracer& tr = pb->tracers[t];
+    if (tr.kind == JC_TRACER_WEAK_LENSING && tr.nz.family == JC_NZ_DELTA) {
+      int i0, i1;
+      bracket(1.0 / (1.0 + tr.nz.params[0]), atab, &i0, &i1, &tr_delta_t[t]);
+      tr_delta_ix[t] = i0 | (i1 << 8);
+    }
+  }
   std::vector<double> chi_pt_a(511), chi_pt_lna(511), chi_h6(255);
   for (int i = 0; i < JC_NCHI; ++i) { chi_pt_a[2 * i] = atab[i]; chi_pt_lna[2 * i] = xtab[i]; }
   for (int i = 0; i < JC_NCHI - 1; ++i) {
@@ -374,6 +412,15 @@ extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int3
   size_t o_nz_node = B.reserve((size_t)JC_NA_PAD * d.TS * sizeof(double));
   size_t o_bias_node = B.add(bias_node);
   size_t o_kind = B.add(tr_kind), o_inv = B.add(tr_inv), o_ia = B.add(tr_ia), o_src = B.add(tr_src);
+  size_t o_dix = B.add(tr_delta_ix), o_dt = B.add(tr_delta_t);
+  std::vector<size_t> o_kde_z(T, 0), o_kde_w(T, 0);
+  for (int t = 0; t < T; ++t) {
+    const jc_nz& nz = pb->tracers[t].nz;
+    if (nz.family == JC_NZ_KDE) {
+      o_kde_z[t] = B.add(nz.kde_z, (size_t)nz.kde_n * sizeof(double));
+      o_kde_w[t] = B.add(nz.kde_w, (size_t)nz.kde_n * sizeof(double));
+    }
+  }
   size_t o_m1 = B.add(tr_m1), o_srct = B.add(src_tracer);
   size_t o_ell = B.add(ell), o_ellp5 = B.add(ellp5), o_lnellp5 = B.add(lnellp5);
   size_t o_ellfac = B.add(ellfac), o_covnorm = B.add(covnorm);
@@ -403,6 +450,7 @@ extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int3
   d.lens_t = DP(double, o_lens_t); d.lens_ix = DP(uint16_t, o_lens_ix); d.lens_nw = DP(double, o_lens_nw);
   d.nz_node = DP(double, o_nz_node); d.bias_node = DP(double, o_bias_node);
   d.tr_kind = DP(int, o_kind); d.tr_inv_growth = DP(int, o_inv); d.tr_ia = DP(int, o_ia); d.tr_src = DP(int, o_src);
+  d.tr_delta_ix = DP(int, o_dix); d.tr_delta_t = DP(double, o_dt);
   d.tr_m1 = DP(double, o_m1); d.src_tracer = DP(int, o_srct);
   d.ell = DP(double, o_ell); d.ellp5 = DP(double, o_ellp5); d.lnellp5 = DP(double, o_lnellp5);
   d.ellfac = DP(double, o_ellfac); d.covnorm = DP(double, o_covnorm);
@@ -419,6 +467,12 @@ extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int3
     all.nz[t].family = nz.family; all.nz[t].n_shifts = nz.n_shifts; all.nz[t].zmax = nz.zmax;
     for (int i = 0; i < 4; ++i) all.nz[t].p[i] = nz.params[i];
     for (int i = 0; i < JC_MAX_SHIFTS; ++i) all.nz[t].shifts[i] = nz.shifts[i];
+    if (nz.family == JC_NZ_KDE) {
+      all.nz[t].kde_z = (const double*)(base + o_kde_z[t]);
+      all.nz[t].kde_w = (const double*)(base + o_kde_w[t]);
+      all.nz[t].kde_n = nz.kde_n;
+      all.nz[t].kde_bw = nz.kde_bw;
+    }
   }
   double* norm = (double*)(base + o_norm);
   jc_nz_norm_kernel<<<T, 288>>>(all, norm);

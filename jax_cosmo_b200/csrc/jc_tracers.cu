@@ -155,7 +155,16 @@ __global__ void __launch_bounds__(256) jc_tracer_finish_kernel(JcDevPlan pl, Ws 
   T r;
   if (pl.tr_kind[t] == JC_TRACER_WEAK_LENSING) {
     const T chi = JxMem<T>::ld(node_ptr(ws, c, JC_NODE_CHI) + n, doff);
-    const T q = (n < JC_NLENS_COLS) ? JxMem<T>::ld(out, doff) : T(0.0);  // node 512 is a=1: chi=0, kernel = 0
+    T q;
+    const int dix = pl.tr_delta_ix[t];
+    if (dix >= 0) {  // delta_nz source plane (probes.py:53-64): clip(chi_s - chi, 0) / clip(chi_s, 1)
+      const double* ct = ws.chitab + (size_t)c * JC_NCHI;
+      const T f0 = JxMem<T>::ld(ct + (dix & 255), doff), f1 = JxMem<T>::ld(ct + (dix >> 8), doff);
+      const T chis = jx_max(f0 + (f1 - f0) * pl.tr_delta_t[t], 0.0);
+      q = jx_max(chis - chi, 0.0) / jx_max(chis, 1.0);
+    } else {
+      q = (n < JC_NLENS_COLS) ? JxMem<T>::ld(out, doff) : T(0.0);  // node 512 is a=1: chi=0, kernel = 0
+    }
     r = q * (1.0 + pl.limb_z[n]) * chi * (3.0 * JC_H0 * JC_H0 / 2.0 / JC_C_LIGHT) * Om;
     if (pl.tr_ia[t]) r = r + nz * b * H * (-(JC_C1_RHOCRIT)*Om / D);  // probes.py:119-123
     r = r * pl.tr_m1[t];

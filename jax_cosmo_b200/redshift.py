@@ -3,7 +3,8 @@
 These objects only describe n(z); evaluation happens in the CUDA plan kernels
 (csrc/jc_plan.cu: jc_nz_norm_kernel / jc_nz_node_kernel / jc_nz_lens_kernel).  Families that the
 B200 path does not cover (fu_nz, delta_nz, kde_nz) are constructible but raise
-NotImplementedError when handed to angular_cl -- there is no CPU fallback."""
+NotImplementedError when handed to angular_cl -- there is no CPU fallback.  All four families of the
+reference (smail_nz, fu_nz, delta_nz, kde_nz) and systematic_shift are on the path."""
 from jax_cosmo_b200.jax_utils import container
 
 steradian_to_arcmin2 = 11818102.86004228  # redshift.py:10
@@ -54,14 +55,32 @@ class systematic_shift(redshift_distribution):
 
 
 class fu_nz(redshift_distribution):
-    pass
+    """n(z) = (z^a + z^(ab)) / (z^b + c) (Fu et al. 2008; redshift.py:80-105)."""
+
+    def _describe(self):
+        a, b, c = self.params
+        return "fu", (float(a), float(b), float(c)), []
 
 
 class delta_nz(redshift_distribution):
+    """Single source plane at z0 (redshift.py:108-123); weak lensing without IA only, as in the reference."""
+
     def __init__(self, *args, **kwargs):
         super(delta_nz, self).__init__(*args, **kwargs)
         self._norm = 1.0
 
+    def _describe(self):
+        return "delta", (float(self.params[0]),), []
+
 
 class kde_nz(redshift_distribution):
-    pass
+    """Gaussian KDE of a catalogue: kde_nz(zcat, weights, bw=...) (redshift.py:126-156)."""
+
+    def _describe(self):
+        import numpy as np
+        zcat, weight = self.params[:2]
+        zcat = np.ascontiguousarray(np.atleast_1d(np.asarray(zcat, dtype=np.float64)))
+        w = np.ascontiguousarray(np.atleast_1d(np.asarray(weight, dtype=np.float64)))
+        if w.shape != zcat.shape:
+            w = np.ascontiguousarray(np.broadcast_to(w, zcat.shape))
+        return "kde", (zcat, w, float(self.config["bw"])), []

@@ -376,10 +376,18 @@ def pz_fn(nz, z):
     z = np.asarray(z, dtype=np.float64)
     for s in nz["shifts"]:
         z = np.clip(z - s, 0, None)
-    if nz["family"] != "smail":
-        raise NotImplementedError(nz["family"])
-    a, b, z0 = nz["params"]
-    return z ** a * np.exp(-((z / z0) ** b))
+    fam = nz["family"]
+    if fam == "smail":
+        a, b, z0 = nz["params"]
+        return z ** a * np.exp(-((z / z0) ** b))
+    if fam == "fu":  # redshift.py:103-105
+        a, b, c = nz["params"]
+        return (z ** a + z ** (a * b)) / (z ** b + c)
+    if fam == "kde":  # redshift.py:142-156: Gaussian kernel, weights normalised by their sum
+        zcat, w, bw = np.asarray(nz["zcat"]), np.asarray(nz["weights"]), nz["bw"]
+        k = (1.0 / np.sqrt(2 * np.pi) / bw) * np.exp(-((zcat.reshape((-1,) + (1,) * z.ndim) - z) ** 2) / (bw ** 2 * 2.0))
+        return np.tensordot(w, k, axes=(0, 0)) / np.sum(w)
+    raise NotImplementedError(fam)
 
 
 def nz_norm(nz):  # redshift.py:29-30
@@ -435,11 +443,18 @@ def radial_kernels(bg, tracers, z):
     wl_idx = [i for i, t in enumerate(tracers) if t["kind"] == "wl"]
     # lensing efficiency is computed per probe in the reference; all WL tracers sharing the same
     # probe_zmax share the z' grid
-    for pz in sorted(set(tracers[i]["probe_zmax"] for i in wl_idx)):
-        idx = [i for i in wl_idx if tracers[i]["probe_zmax"] == pz]
+    ext_idx = [i for i in wl_idx if tracers[i]["nz"]["family"] != "delta"]
+    for pz in sorted(set(tracers[i]["probe_zmax"] for i in ext_idx)):
+        idx = [i for i in ext_idx if tracers[i]["probe_zmax"] == pz]
         q = lensing_efficiency(bg, [tracers[i]["nz"] for i in idx], z, pz)
         for j, i in enumerate(idx):
             R[i] = q[j] * (3.0 * H0 ** 2 * c.Omega_m / 2.0 / C_LIGHT)  # probes.py:71
+    chi = bg.chi(a)
+    for i in wl_idx:  # delta_nz source planes (probes.py:53-64): no integral
+        if tracers[i]["nz"]["family"] == "delta":
+            chis = bg.chi(1.0 / (1.0 + np.array([tracers[i]["nz"]["params"][0]])))
+            R[i] = np.clip(chis - chi, 0, None) / np.clip(chis, 1.0, None) * (1.0 + z) * chi * (
+                3.0 * H0 ** 2 * c.Omega_m / 2.0 / C_LIGHT)
     for i, t in enumerate(tracers):
         if t["kind"] == "wl":
             is_wl[i] = True

@@ -46,6 +46,23 @@ def smail(a, b, z0, n=1.0, zmax=10.0, shift=None):
                 gals_per_arcmin2=float(n), zmax=float(zmax), shift=shift)
 
 
+def fu(a, b, c, n=1.0, zmax=10.0, shift=None):
+    """fu_nz (redshift.py:80-105)."""
+    return dict(family="fu", params=[float(a), float(b), float(c)], gals_per_arcmin2=float(n),
+                zmax=float(zmax), shift=shift)
+
+
+def delta(z0, n=1.0, zmax=10.0):
+    """delta_nz source plane (redshift.py:108-123)."""
+    return dict(family="delta", params=[float(z0)], gals_per_arcmin2=float(n), zmax=float(zmax), shift=None)
+
+
+def kde(zcat, weights, bw, n=1.0, zmax=10.0, shift=None):
+    """kde_nz (redshift.py:126-156): Gaussian KDE of a catalogue."""
+    return dict(family="kde", params=[], zcat=[float(v) for v in zcat], weights=[float(v) for v in weights],
+                bw=float(bw), gals_per_arcmin2=float(n), zmax=float(zmax), shift=shift)
+
+
 def bias(family, *params):
     return dict(family=family, params=[float(p) for p in params])
 
@@ -117,6 +134,20 @@ def golden_scenarios():
     for r, row in enumerate(rows):
         S.append(scenario("cfg5_10p10_row%d" % r, dict(zip(COSMO_KEYS, row)), ELL_CFG2[[5, 95]],
                           [sources(10, 1.0), lenses(10, 1.0)]))
+    # the remaining n(z) families.  delta_nz source planes as in the reference's
+    # tests/test_angular_cl.py:54-105 (alone, and mixed with Smail bins), fu_nz with the Martinet+2021
+    # parameters, kde_nz of a small seeded catalogue (also under a photo-z shift), as sources and lenses.
+    nzs2 = smail(1.4, 2.0, 1.0)
+    S.append(scenario("reftest_lensing_delta", TESTCOSMO, ell_t, [wl([delta(1.0)])]))
+    S.append(scenario("reftest_lensing_delta_mix", TESTCOSMO, ell_t[[1, 3]], [wl([delta(1.0), nz1, nzs2])]))
+    rng = np.random.default_rng(11)
+    zcat = np.round(rng.gamma(4.0, 0.2, 48), 6)
+    wcat = np.round(rng.uniform(0.2, 1.0, 48), 6)
+    S.append(scenario("families_fu_kde", WCDM, [20.0, 200.0, 2000.0],
+                      [wl([fu(0.4710, 5.1843, 0.7259, 30.0), kde(zcat, wcat, 0.1, 4.0), kde(zcat, wcat, 0.15, shift=0.02),
+                           delta(0.8)], m=[0.0, 0.01, 0.0, -0.01]),
+                       nc([fu(0.4710, 5.1843, 0.7259, 10.0), kde(zcat, wcat, 0.1, 3.0)],
+                          [bias("constant", 1.1), bias("inverse_growth", 1.3)])]))
     return S
 
 
@@ -124,8 +155,18 @@ def golden_scenarios():
 # spec -> objects of a jax_cosmo-compatible namespace (reference OR product)
 # ----------------------------------------------------------------------------------------
 def build_nz(spec, ns):
-    nz = ns.redshift.smail_nz(*spec["params"], gals_per_arcmin2=spec["gals_per_arcmin2"],
-                              zmax=spec["zmax"])
+    kw = dict(gals_per_arcmin2=spec["gals_per_arcmin2"], zmax=spec["zmax"])
+    fam = spec["family"]
+    if fam == "smail":
+        nz = ns.redshift.smail_nz(*spec["params"], **kw)
+    elif fam == "fu":
+        nz = ns.redshift.fu_nz(*spec["params"], **kw)
+    elif fam == "delta":
+        nz = ns.redshift.delta_nz(*spec["params"], **kw)
+    elif fam == "kde":
+        nz = ns.redshift.kde_nz(np.array(spec["zcat"]), np.array(spec["weights"]), bw=spec["bw"], **kw)
+    else:
+        raise ValueError(fam)
     if spec.get("shift") is not None:
         nz = ns.redshift.systematic_shift(nz, spec["shift"])
     return nz
@@ -177,6 +218,7 @@ def flatten_spec(scn):
         pz = max((10.0 if b.get("shift") is not None else b["zmax"]) for b in p["bins"])
         for i, b in enumerate(p["bins"]):
             nzd = dict(family=b["family"], params=list(b["params"]), zmax=b["zmax"],
+                       zcat=b.get("zcat"), weights=b.get("weights"), bw=b.get("bw"),
                        shifts=[] if b.get("shift") is None else [b["shift"]],
                        # systematic_shift does not inherit gals_per_arcmin2 (redshift.py:16,159)
                        gals_per_arcmin2=(b["gals_per_arcmin2"] if b.get("shift") is None else 1.0))

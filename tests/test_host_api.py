@@ -27,7 +27,7 @@ def test_struct_sizes_match_header():
     import ctypes as C
 
     from jax_cosmo_b200 import _native
-    assert C.sizeof(_native.jc_nz) == 8 + 8 * (4 + 4 + 2)
+    assert C.sizeof(_native.jc_nz) == 8 + 8 * (4 + 4 + 2) + 4 * 8
     assert C.sizeof(_native.jc_bias) == 8 + 24
     assert C.sizeof(_native.jc_tracer) == 8 + C.sizeof(_native.jc_nz) + C.sizeof(_native.jc_bias) + 24
     assert C.sizeof(_native.jc_problem) == 16 + 32 * C.sizeof(_native.jc_tracer)
@@ -83,8 +83,19 @@ def test_unsupported_options_raise(jc):
         _native.build_problem([wl], transfer_fn=lambda *a: None)
     with pytest.raises(NotImplementedError):
         _native.build_problem([wl], nonlinear_fn=lambda *a: None)
+    # delta_nz: weak lensing without IA only (the reference raises in density_kernel / nla_kernel)
+    assert _native.build_problem([jc.probes.WeakLensing([jc.redshift.delta_nz(1.0)])]).tracers[0].nz.family == 3
     with pytest.raises(NotImplementedError):
-        _native.build_problem([jc.probes.WeakLensing([jc.redshift.delta_nz(1.0)])])
+        _native.build_problem([jc.probes.NumberCounts([jc.redshift.delta_nz(1.0)], jc.bias.constant_linear_bias(1.0))])
+    with pytest.raises(NotImplementedError):
+        _native.build_problem([jc.probes.WeakLensing([jc.redshift.delta_nz(1.0)], ia_bias=jc.bias.constant_linear_bias(1.0))])
+    # kde_nz: arrays travel by pointer, the plan-cache key is built from their contents
+    z1, w1 = np.array([0.5, 0.7, 1.1]), np.array([1.0, 0.5, 0.25])
+    pa = _native.build_problem([jc.probes.WeakLensing([jc.redshift.kde_nz(z1, w1, bw=0.1)])])
+    pb_ = _native.build_problem([jc.probes.WeakLensing([jc.redshift.kde_nz(z1.copy(), w1.copy(), bw=0.1)])])
+    pc = _native.build_problem([jc.probes.WeakLensing([jc.redshift.kde_nz(z1 + 0.1, w1, bw=0.1)])])
+    assert pa.tracers[0].nz.family == 4 and pa.tracers[0].nz.kde_n == 3 and pa.tracers[0].nz.kde_bw == 0.1
+    assert pa._content_key == pb_._content_key != pc._content_key
     with pytest.raises(NotImplementedError):
         jc.Cosmology(0.3, 0.05, 0.7, 0.96, 0.8, 0.0, -1.0, 0.0, gamma=0.55).to_row()
     with pytest.raises(NotImplementedError):
