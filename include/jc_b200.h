@@ -74,9 +74,13 @@ enum {
 };
 enum {
   JC_PK_LINEAR = 0,               /* power.py:81-83   nonlinear_fn=power.linear  */
-  JC_PK_HALOFIT_TAKAHASHI2012 = 1 /* power.py:144-262 nonlinear_fn=power.halofit */
+  JC_PK_HALOFIT_TAKAHASHI2012 = 1, /* power.py:144-262 nonlinear_fn=power.halofit */
+  JC_PK_HALOFIT_SMITH2003 = 2      /* power.py:182-198,239-242  partial(power.halofit, prescription="smith2003") */
 };
-enum { JC_TF_EISENSTEIN_HU_OSC = 1 /* transfer.py:10-156, type="eisenhu_osc" */ };
+enum {
+  JC_TF_EISENSTEIN_HU_OSC = 1,     /* transfer.py:10-156, type="eisenhu_osc" (default) */
+  JC_TF_EISENSTEIN_HU_NOWIGGLE = 2 /* transfer.py:99-105, partial(Eisenstein_Hu, type="eisenhu") */
+};
 
 /* One redshift bin.  `shifts` is the chain of systematic_shift wrappers (redshift.py:159-171),
  * outermost first: pz_fn(z) = parent.pz_fn(clip(z - shift, 0)).  `zmax` is the n(z)'s own
@@ -163,6 +167,7 @@ enum {
   JC_NODE_NSILK,      /* (k_silk max(chi,1))^-1.4      : (k/k_silk)^1.4 = (l+1/2)^1.4 * this */
   JC_NODE_NAMP,       /* max(chi,1)^-(3+n_s) D^2 pknorm/(2 pi^2) : Delta^2_L = (l+1/2)^(3+n_s) T^2 * this */
   JC_NODE_GK,         /* GEOM * 2 pi^2 max(chi,1)^3    : V = Delta^2 (l+1/2)^-3 * this */
+  JC_NODE_MU,         /* mu_n (0 for takahashi2012, power.py:223)       */
   JC_NODE_FIELDS
 };
 /* fields of the per-cosmology scalar block (index into ws.scal) */
@@ -182,6 +187,8 @@ enum {
   JC_SCAL_PKNORM,      /* sigma8^2 / sigmasqr(8)  power.py:47   */
   JC_SCAL_SIGMASQR8,   /* raw sigmasqr(cosmo, 8)  power.py:56-78 */
   JC_SCAL_OMEGA_M,
+  JC_SCAL_ALPHA_GAMMA, /* no-wiggle fit  transfer.py:87-91    */
+  JC_SCAL_OMH_T27,     /* Omega_m h / (tcmb/2.7)^2: q = k / (this * gamma shape), transfer.py:92-100 */
   JC_SCAL_FIELDS = 32
 };
 

@@ -20,13 +20,13 @@ JC_OK, JC_ERR_INVALID, JC_ERR_UNSUPPORTED, JC_ERR_WORKSPACE, JC_ERR_CUDA, JC_ERR
 JC_NZ = {"smail": 1, "fu": 2, "delta": 3, "kde": 4}
 JC_BIAS = {"constant": 1, "inverse_growth": 2, "des_y1_ia": 3}
 JC_TRACER_WL, JC_TRACER_NC = 1, 2
-JC_PK_LINEAR, JC_PK_HALOFIT = 0, 1
-JC_TF_EH_OSC = 1
+JC_PK_LINEAR, JC_PK_HALOFIT, JC_PK_HALOFIT_SMITH = 0, 1, 2
+JC_TF_EH_OSC, JC_TF_EH_NOWIGGLE = 1, 2
 
 NODE_FIELDS = ["CHI", "INVCHIC", "LNCHIC", "GEOM", "GROWTH", "HUBBLE", "AMP", "RNL", "LNKNL", "NEFF",
-               "CURV", "AN", "BN", "LNCF", "P3", "ALPHA", "BETA", "NU", "E1", "E2", "NQ108", "NSILK", "NAMP", "GK"]
+               "CURV", "AN", "BN", "LNCF", "P3", "ALPHA", "BETA", "NU", "E1", "E2", "NQ108", "NSILK", "NAMP", "GK", "MU"]
 SCAL_FIELDS = ["LN13KEQ", "INV13KEQ", "BETA_C", "C14_ALPHA_C", "SH_D", "LNKSILK", "ALPHA_B", "BETA_B",
-               "BETA_NODE", "FB", "FC", "NS", "PKNORM", "SIGMASQR8", "OMEGA_M"]
+               "BETA_NODE", "FB", "FC", "NS", "PKNORM", "SIGMASQR8", "OMEGA_M", "ALPHA_GAMMA", "OMH_T27"]
 
 # every symbol include/jc_b200.h declares
 EXPORTS = ["jc_plan_create", "jc_plan_destroy", "jc_plan_n_tracers", "jc_plan_n_cls", "jc_plan_n_ell",
@@ -169,24 +169,47 @@ def build_problem(probes, transfer_fn=None, nonlinear_fn=None):
     from jax_cosmo_b200 import transfer as _transfer
     from jax_cosmo_b200.probes import NumberCounts, WeakLensing
 
+    import functools
+
+    def unwrap(fn, allowed_kw):
+        """The reference selects variants with functools.partial(fn, kw=...) (transfer.py:10, power.py:144)."""
+        kw = {}
+        while isinstance(fn, functools.partial):
+            if fn.args:
+                raise NotImplementedError("positional arguments bound into transfer_fn / nonlinear_fn")
+            kw = dict(fn.keywords, **kw)
+            fn = fn.func
+        extra = set(kw) - set(allowed_kw)
+        if extra:
+            raise NotImplementedError("unsupported keyword(s) %s" % sorted(extra))
+        return fn, kw
+
     if transfer_fn is None:
         transfer_fn = _transfer.Eisenstein_Hu
     if nonlinear_fn is None:
         nonlinear_fn = _power.halofit
-    if transfer_fn is not _transfer.Eisenstein_Hu:
+    tf, tkw = unwrap(transfer_fn, ("type",))
+    if tf is not _transfer.Eisenstein_Hu:
         raise NotImplementedError("transfer_fn: only jax_cosmo_b200.transfer.Eisenstein_Hu is on the B200 path")
-    if nonlinear_fn is _power.halofit:
-        nl = JC_PK_HALOFIT
-    elif nonlinear_fn is _power.linear:
+    ttype = tkw.get("type", "eisenhu_osc")
+    if ttype not in ("eisenhu_osc", "eisenhu"):
+        raise NotImplementedError("Eisenstein_Hu type %r (transfer.py:155)" % (ttype,))
+    nlf, nkw = unwrap(nonlinear_fn, ("prescription",))
+    if nlf is _power.halofit:
+        presc = nkw.get("prescription", "takahashi2012")
+        if presc not in ("takahashi2012", "smith2003"):
+            raise NotImplementedError("halofit prescription %r (power.py:226,244)" % (presc,))
+        nl = JC_PK_HALOFIT if presc == "takahashi2012" else JC_PK_HALOFIT_SMITH
+    elif nlf is _power.linear and not nkw:
         nl = JC_PK_LINEAR
     else:
-        raise NotImplementedError("nonlinear_fn: only power.halofit (takahashi2012) and power.linear are on the B200 path")
+        raise NotImplementedError("nonlinear_fn: only power.halofit (takahashi2012 / smith2003) and power.linear are on the B200 path")
 
     pb = jc_problem()
     pb._keepalive = []       # arrays referenced by pointer fields
     pb._content_key = b""    # their contents (the plan cache must not key on addresses)
     pb.abi_version = JC_ABI_VERSION
-    pb.transfer = JC_TF_EH_OSC
+    pb.transfer = JC_TF_EH_OSC if ttype == "eisenhu_osc" else JC_TF_EH_NOWIGGLE
     pb.nonlinear = nl
     t = 0
     for probe in probes:

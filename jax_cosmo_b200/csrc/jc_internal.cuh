@@ -36,7 +36,9 @@
 
 // Device-side view of the plan: cosmology-independent tables (all device pointers).
 struct JcDevPlan {
-  int T, P, L, Lpad, nonlinear;
+  int T, P, L, Lpad;
+  int nonlinear;             // JC_PK_*: 0 linear, 1 halofit takahashi2012, 2 halofit smith2003
+  int transfer;              // JC_TF_*: 1 Eisenstein-Hu with wiggles, 2 no-wiggle fit
   int TS;                    // tracer stride of the node-major R table (>= T, TS mod 16 in {4,12})
   int n_src;                 // number of weak-lensing tracers
   double zmax;               // Limber zmax (max over probes), angular_cl.py:63

@@ -187,9 +187,8 @@ int validate(const jc_problem* pb, int n_ell) {
   if (pb->abi_version != JC_ABI_VERSION) return JC_ERR_INVALID;
   if (pb->n_tracers < 1 || pb->n_tracers > JC_MAX_TRACERS) return JC_ERR_INVALID;
   if (n_ell < 1) return JC_ERR_INVALID;
-  if (pb->transfer != JC_TF_EISENSTEIN_HU_OSC) return JC_ERR_UNSUPPORTED;
-  if (pb->nonlinear != JC_PK_LINEAR && pb->nonlinear != JC_PK_HALOFIT_TAKAHASHI2012)
-    return JC_ERR_UNSUPPORTED;
+  if (pb->transfer != JC_TF_EISENSTEIN_HU_OSC && pb->transfer != JC_TF_EISENSTEIN_HU_NOWIGGLE) return JC_ERR_UNSUPPORTED;
+  if (pb->nonlinear < JC_PK_LINEAR || pb->nonlinear > JC_PK_HALOFIT_SMITH2003) return JC_ERR_UNSUPPORTED;
   double lens_zmax = -1.0;
   for (int t = 0; t < pb->n_tracers; ++t) {
     const jc_tracer& tr = pb->tracers[t];
@@ -271,7 +270,7 @@ extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int3
   Blob B;
   JcDevPlan d;
   memset(&d, 0, sizeof(d));
-  d.T = T; d.P = P; d.L = L; d.Lpad = (L + 3) & ~3; d.nonlinear = pb->nonlinear;
+  d.T = T; d.P = P; d.L = L; d.Lpad = (L + 3) & ~3; d.nonlinear = pb->nonlinear; d.transfer = pb->transfer;
   d.TS = T;  // bank-conflict-free A-fragment gathers in the contraction kernel need TS = 4 or 12 (mod 16)
   while (d.TS % 16 != 4 && d.TS % 16 != 12) ++d.TS;
   d.n_src = n_src; d.zmax = zmax; d.lens_zmax = lens_zmax;

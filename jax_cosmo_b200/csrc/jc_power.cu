@@ -23,13 +23,14 @@
 namespace {
 
 struct PowerK {
-  double e1, c699, c142, c386, c18, inv54, inv52, eighth, quarter;
+  double e1, c699, c142, c386, c18, inv54, inv52, eighth, quarter, c043, two_e1, c625, c731;
 };
 static __constant__ PowerK PK = {2.718281828459045 /* np.exp(1.0) */, 69.9, 14.2, 386.0, 1.8,
-                                 1.0 / 5.4, 1.0 / 5.2, 0.125, 0.25};
+                                 1.0 / 5.4, 1.0 / 5.2, 0.125, 0.25, 0.43, 2.0 * 2.718281828459045, 62.5, 731.0};
 
-// NPT: Limber nodes per thread; MINB: CTAs per SM the register allocation must allow.
-template <class T, int NPT, int MINB>
+// NPT: Limber nodes per thread; MINB: CTAs per SM the register allocation must allow; NOWIG: the
+// no-wiggle Eisenstein-Hu fit (transfer.py:99-105) instead of the default "eisenhu_osc".
+template <class T, int NPT, int MINB, bool NOWIG>
 __global__ void __launch_bounds__(256, MINB) jc_power_kernel(JcDevPlan pl, Ws ws, unsigned inv_L) {
   constexpr int NGRP = (JC_NA + NPT - 1) / NPT;
   __shared__ __align__(16) double s_tab[JCM_TAB_DOUBLES];
@@ -44,6 +45,7 @@ __global__ void __launch_bounds__(256, MINB) jc_power_kernel(JcDevPlan pl, Ws ws
   const T shd = SC(JC_SCAL_SH_D), alpha_b = SC(JC_SCAL_ALPHA_B), fb = SC(JC_SCAL_FB), fc = SC(JC_SCAL_FC);
   const T bnode = SC(JC_SCAL_BETA_NODE), bb = SC(JC_SCAL_BETA_B);
   const T bnode3 = bnode * bnode * bnode, bb3 = bb * bb * bb;
+  const T alpha_g = SC(JC_SCAL_ALPHA_GAMMA), omh_t27 = SC(JC_SCAL_OMH_T27);  // no-wiggle fit only
   const double* nd = ws.node + (size_t)c * JC_NODE_FIELDS * JC_NA_PAD;
 #define NODE(f) JxMem<T>::ld(nd + (f)*JC_NA_PAD + n, doff)
 
@@ -62,6 +64,16 @@ __global__ void __launch_bounds__(256, MINB) jc_power_kernel(JcDevPlan pl, Ws ws
     for (int n = n0; n < n1; ++n) {
       const T lnk = lnl - NODE(JC_NODE_LNCHIC);
       const T k = lp5 * NODE(JC_NODE_INVCHIC);  // angular_cl.py:73
+      T Tk;
+      if constexpr (NOWIG) {  // no-wiggle fit (transfer.py:92-105)
+        const T ks43 = PK.c043 * (k * shd);
+        const T k2 = ks43 * ks43;
+        const T q = k * jx_rcp(omh_t27 * (alpha_g + (JCK.one - alpha_g) * jx_rcp(k2 * k2 + JCK.one)));
+        const T L = jx_log_t(PK.c18 * q + PK.two_e1, s_tab);
+        const T Wn = PK.c625 * q + JCK.one;                  // C = 14.2 + 731/Wn
+        const T LW = L * Wn;
+        Tk = LW * jx_rcp(LW + (PK.c142 * Wn + PK.c731) * (q * q));
+      } else {
       // ---- Eisenstein & Hu (transfer.py:113-153) ------------------------------------------------
       const T q = k * inv13keq;
       const T q2 = q * q;
@@ -91,7 +103,8 @@ __global__ void __launch_bounds__(256, MINB) jc_power_kernel(JcDevPlan pl, Ws ws
       const T N3X = N3 * X52;
       const T numB = (L2W * BB + alpha_b * ks3 * silk * N3X) * jx_sin(arg);
       const T denB = N3X * BB * arg;
-      const T Tk = ((fb * numB) * denC + fc * numC * denB) * jx_rcp(denB * denC);
+      Tk = ((fb * numB) * denC + fc * numC * denB) * jx_rcp(denB * denC);
+      }
       // ---- Delta^2_L = k^3 P_lin / (2 pi^2)  (power.py:49-52, :250) -----------------------------------
       const T d2l = lpns * NODE(JC_NODE_NAMP) * (Tk * Tk);
       T d2;
@@ -106,7 +119,9 @@ __global__ void __launch_bounds__(256, MINB) jc_power_kernel(JcDevPlan pl, Ws ws
         const T ye2 = jx_exp_t(NODE(JC_NODE_E2) * lny, s_tab);
         const T cfy = jx_exp_t(NODE(JC_NODE_P3) * (NODE(JC_NODE_LNCF) + lny), s_tab);
         const T Nh = NODE(JC_NODE_AN) * ye1 * y2;
-        const T Dh = (NODE(JC_NODE_BN) * ye2 + JCK.one + cfy) * (y2 + NODE(JC_NODE_NU));
+        T ynu = y2 + NODE(JC_NODE_NU);  // 1/(1 + mu/y + nu/y^2) = y^2 / (y^2 + mu y + nu)
+        if (pl.nonlinear == JC_PK_HALOFIT_SMITH2003) ynu = ynu + NODE(JC_NODE_MU) * y;  // mu = 0 in takahashi2012
+        const T Dh = (NODE(JC_NODE_BN) * ye2 + JCK.one + cfy) * ynu;
         d2 = (Nq * Dh + Nh * Dq) * jx_rcp(Dq * Dh);  // Delta^2_Q + Delta^2_H
       } else {
         d2 = d2l;
@@ -125,7 +140,10 @@ void launch_power_cfg(const JcDevPlan& pl, const Ws& ws, int chunk, int split, c
   const unsigned inv_L = (pl.L >= 2 && pl.L <= 2048) ? (unsigned)((0x100000000ull + pl.L - 1) / pl.L) : 0u;
   const int full = (NGRP * pl.L + 255) / 256;
   const int gx = split < full ? split : full;
-  jc_power_kernel<T, NPT, MINB><<<dim3(gx, chunk), 256, 0, s>>>(pl, ws, inv_L);
+  if (pl.transfer == JC_TF_EISENSTEIN_HU_NOWIGGLE)
+    jc_power_kernel<T, NPT, MINB, true><<<dim3(gx, chunk), 256, 0, s>>>(pl, ws, inv_L);
+  else
+    jc_power_kernel<T, NPT, MINB, false><<<dim3(gx, chunk), 256, 0, s>>>(pl, ws, inv_L);
 }
 
 }  // namespace
@@ -135,7 +153,6 @@ void jc_launch_power(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t 
   if (cfg < 0) { const char* e = getenv("JC_POWER_CFG"); cfg = e ? atoi(e) : 0; }  // tuning knob
   switch (cfg) {
     case 1: launch_power_cfg<double, 4, 1>(pl, ws, chunk, 8, s); break;  // unconstrained registers
-    case 2: launch_power_cfg<double, 1, 6>(pl, ws, chunk, 8, s); break;  // one node per thread, 40 registers
     // fastest (profiles/r01_tuning.md): 4 nodes per thread, 64 registers, 8 CTAs per cosmology
     default: launch_power_cfg<double, 4, 4>(pl, ws, chunk, 8, s); break;
   }

@@ -27,8 +27,17 @@ template <class T> __device__ __forceinline__ T esqr(const Bg<T>& c, double a, d
 }
 
 // T(k) of transfer.py:113-153 ("eisenhu_osc") at a fixed-grid k (sigma8 and halofit nodes)
-template <class T> __device__ __forceinline__ T eh_transfer(const T* __restrict__ s, double k, double lnk) {
+template <class T> __device__ __forceinline__ T eh_transfer(const T* __restrict__ s, double k, double lnk, int kind) {
   const double E1 = 2.718281828459045;  // np.exp(1.0)
+  if (kind == JC_TF_EISENSTEIN_HU_NOWIGGLE) {  // transfer.py:92-105
+    const T ks43 = 0.43 * k * s[JC_SCAL_SH_D];
+    const T k2 = ks43 * ks43;
+    const T ag = s[JC_SCAL_ALPHA_GAMMA];
+    const T q = k / (s[JC_SCAL_OMH_T27] * (ag + (1.0 - ag) / (1.0 + k2 * k2)));
+    const T L = jx_log(2.0 * E1 + 1.8 * q);
+    const T C = 14.2 + 731.0 / (1.0 + 62.5 * q);
+    return L / (L + C * q * q);
+  }
   const T q = k * s[JC_SCAL_INV13KEQ];
   const T q2 = q * q;
   const T q108 = jx_exp(1.08 * (lnk - s[JC_SCAL_LN13KEQ]));
@@ -55,7 +64,7 @@ template <class T> __device__ __forceinline__ T eh_transfer(const T* __restrict_
 template <class T> struct SetupSmem {
   T f[512];  // chi integrand at nodes+midpoints; later the normalised growth table; later (as doubles) k nodes
   T cum[256], chitab[256], gr_r[256], gr_q[256], M[127 * 4], gtab[128], sc[JC_SCAL_FIELDS];
-  T d2w[JC_NHFK], S[JC_NHFR], D2[JC_NA], omm[JC_NA], odew[JC_NA], rnl[JC_NA], red[8];
+  T d2w[JC_NHFK], S[JC_NHFR], D2[JC_NA], omm[JC_NA], ode[JC_NA], odew[JC_NA], rnl[JC_NA], red[8];
 };
 
 // =================================================================================================
@@ -133,6 +142,9 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
     S.sc[JC_SCAL_FC] = fc;
     S.sc[JC_SCAL_NS] = ns;
     S.sc[JC_SCAL_OMEGA_M] = bg.Om;
+    // no-wiggle fit (transfer.py:87-100): alpha_gamma and Omega_m h / (tcmb/2.7)^2
+    S.sc[JC_SCAL_ALPHA_GAMMA] = 1.0 - 0.328 * jx_log(431.0 * w_m) * w_b / w_m + 0.38 * jx_log(22.3 * w_m) * (fb * fb);
+    S.sc[JC_SCAL_OMH_T27] = bg.Om * h / T27;
   }
 
   // ---- chi table -------------------------------------------------------------------------------
@@ -236,6 +248,7 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
     put(node(JC_NODE_HUBBLE, n), JC_H0 * se);                      // background.py:143
     S.D2[n] = D * D;
     S.omm[n] = bg.Om * (ia * ia * ia) / e2;
+    S.ode[n] = de / e2;
     S.odew[n] = de / e2 * (1.0 + (w0 + (1.0 - a) * wa));
   }
   __syncthreads();  // also publishes S.sc
@@ -245,7 +258,7 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
     T v = T(0.0);
     if (tid < JC_NROMB) {
       const double k = pl.romb_k[tid], lnk = pl.romb_lnk[tid];
-      const T Tk = eh_transfer<T>(S.sc, k, lnk);
+      const T Tk = eh_transfer<T>(S.sc, k, lnk, pl.transfer);
       v = pl.romb_f[tid] * (Tk * Tk) * jx_exp(ns * lnk);
     }
     for (int o = 16; o > 0; o >>= 1) v = v + jx_shfl_xor(v, o);
@@ -281,7 +294,7 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
   const T g1sq = S.D2[JC_NA - 1];
   for (int i = tid; i < JC_NHFK; i += 256) {
     const double k = pl.hf_k[i], lnk = pl.hf_lnk[i];
-    const T Tk = eh_transfer<T>(S.sc, k, lnk);
+    const T Tk = eh_transfer<T>(S.sc, k, lnk, pl.transfer);
     const T pk = jx_exp(ns * lnk) * (Tk * Tk) * g1sq * pknorm;  // power.py:49-52
     S.d2w[i] = pl.hf_wk[i] * (pk * (k * k * k) / JC_TWO_PI_SQ);
   }
@@ -372,6 +385,24 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
     const T ne = JxMem<T>::ld(node(JC_NODE_NEFF, n), doff), C = JxMem<T>::ld(node(JC_NODE_CURV, n), doff);
     const T n2 = ne * ne, n3 = n2 * ne, n4 = n2 * n2;
     const T odew = S.odew[n], lom = jx_log(S.omm[n]);
+    if (pl.nonlinear == JC_PK_HALOFIT_SMITH2003) {  // power.py:182-198, 239-242
+      const T frac = S.ode[n] / (1.0 - S.omm[n]);
+      const T f1 = frac * jx_exp(-0.0307 * lom) + (1.0 - frac) * jx_exp(-0.0732 * lom);
+      const T f2 = frac * jx_exp(-0.0585 * lom) + (1.0 - frac) * jx_exp(-0.1423 * lom);
+      const T f3 = frac * jx_exp(0.0743 * lom) + (1.0 - frac) * jx_exp(0.0725 * lom);
+      put(node(JC_NODE_AN, n), jx_exp(LN10 * (1.4861 + 1.8369 * ne + 1.6762 * n2 + 0.7940 * n3 + 0.1670 * n4 - 0.6206 * C)));
+      put(node(JC_NODE_BN, n), jx_exp(LN10 * (0.9463 + 0.9466 * ne + 0.3084 * n2 - 0.9400 * C)));
+      put(node(JC_NODE_LNCF, n), LN10 * (-0.2807 + 0.6669 * ne + 0.3214 * n2 - 0.0793 * C) + jx_log(f3));
+      put(node(JC_NODE_P3, n), 3.0 - (0.8649 + 0.2989 * ne + 0.1631 * C));
+      put(node(JC_NODE_ALPHA, n), 1.3884 + 0.3700 * ne - 0.1452 * n2);
+      put(node(JC_NODE_BETA, n), 0.8291 + 0.9854 * ne + 0.3401 * n2);
+      put(node(JC_NODE_MU, n), jx_exp(LN10 * (-3.5442 + 0.1908 * ne)));
+      put(node(JC_NODE_NU, n), jx_exp(LN10 * (0.9585 + 1.2857 * ne)));
+      put(node(JC_NODE_E1, n), 3.0 * f1);
+      put(node(JC_NODE_E2, n), f2);
+      continue;
+    }
+    put(node(JC_NODE_MU, n), T(0.0));  // power.py:223
     const T a_n = jx_exp(LN10 * (1.5222 + 2.8553 * ne + 2.3706 * n2 + 0.9903 * n3 + 0.2250 * n4 - 0.6038 * C + 0.1749 * odew));
     const T b_n = jx_exp(LN10 * (-0.5642 + 0.5864 * ne + 0.5716 * n2 - 1.5474 * C + 0.2279 * odew));
     const T lnc_n = LN10 * (0.3698 + 2.0404 * ne + 0.8161 * n2 + 0.5869 * C);

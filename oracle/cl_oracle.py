@@ -241,6 +241,14 @@ def eisenstein_hu(c, k):
     a2 = np.power(12.0 * w_m, 0.424) * (1.0 + np.power(45.0 * w_m, -0.582))
     alpha_c = np.power(a1, -fb) * np.power(a2, -(fb ** 3))
     b1 = 0.944 / (1.0 + np.power(458.0 * w_m, -0.708))
+    if getattr(c, "transfer_type", "eisenhu_osc") == "eisenhu":  # no-wiggle fit, transfer.py:87-105
+        alpha_gamma = (1.0 - 0.328 * np.log(431.0 * w_m) * w_b / w_m
+                       + 0.38 * np.log(22.3 * w_m) * (c.Omega_b / c.Omega_m) ** 2)
+        gamma_eff = c.Omega_m * c.h * (alpha_gamma + (1.0 - alpha_gamma) / (1.0 + (0.43 * k * sh_d) ** 4))
+        q = k * np.power(TCMB / 2.7, 2) / gamma_eff
+        L = np.log(2.0 * np.exp(1.0) + 1.8 * q)
+        C = 14.2 + 731.0 / (1.0 + 62.5 * q)
+        return L / (L + C * q * q)
     b2 = np.power(0.395 * w_m, -0.0266)
     beta_c = 1.0 / (1.0 + b1 * (np.power(fc, b2) - 1.0))
 
@@ -338,6 +346,21 @@ class Power:
         om_de = Omega_de_a(c, a)
         w = w_de(c, a)
         co = dict(k_nl=k_nl, n_eff=n, C_hf=C, root_ind=ind, S_tab=self._hf_tables()[4])
+        if getattr(c, "prescription", "takahashi2012") == "smith2003":  # power.py:182-198, 239-242
+            co["a_n"] = 10 ** (1.4861 + 1.8369 * n + 1.6762 * n ** 2 + 0.7940 * n ** 3 + 0.1670 * n ** 4 - 0.6206 * C)
+            co["b_n"] = 10 ** (0.9463 + 0.9466 * n + 0.3084 * n ** 2 - 0.9400 * C)
+            co["c_n"] = 10 ** (-0.2807 + 0.6669 * n + 0.3214 * n ** 2 - 0.0793 * C)
+            co["gamma_n"] = 0.8649 + 0.2989 * n + 0.1631 * C
+            co["alpha_n"] = 1.3884 + 0.3700 * n - 0.1452 * n ** 2
+            co["beta_n"] = 0.8291 + 0.9854 * n + 0.3401 * n ** 2
+            co["mu_n"] = 10 ** (-3.5442 + 0.1908 * n)
+            co["nu_n"] = 10 ** (0.9585 + 1.2857 * n)
+            frac = om_de / (1.0 - om_m)
+            co["f1"] = frac * om_m ** (-0.0307) + (1 - frac) * om_m ** (-0.0732)
+            co["f2"] = frac * om_m ** (-0.0585) + (1 - frac) * om_m ** (-0.1423)
+            co["f3"] = frac * om_m ** (0.0743) + (1 - frac) * om_m ** 0.0725
+            return co
+        co["mu_n"] = np.zeros_like(n)
         co["a_n"] = 10 ** (1.5222 + 2.8553 * n + 2.3706 * n ** 2 + 0.9903 * n ** 3
                            + 0.2250 * n ** 4 - 0.6038 * C + 0.1749 * om_de * (1 + w))
         co["b_n"] = 10 ** (-0.5642 + 0.5864 * n + 0.5716 * n ** 2 - 1.5474 * C
@@ -363,7 +386,7 @@ class Power:
             -(y / 4.0 + y ** 2 / 8.0))
         d2hp = co["a_n"] * y ** (3 * co["f1"]) / (
             1.0 + co["b_n"] * y ** co["f2"] + (co["c_n"] * co["f3"] * y) ** (3.0 - co["gamma_n"]))
-        d2h = d2hp / (1.0 + 0.0 / y + co["nu_n"] / y ** 2)
+        d2h = d2hp / (1.0 + co["mu_n"] / y + co["nu_n"] / y ** 2)
         return 2.0 * np.pi ** 2 / k ** 3 * (d2q + d2h)
 
 
@@ -483,6 +506,8 @@ def pair_index(i, j, T):
 def angular_cl(cosmo_row, ell, problem, stages=None):
     """angular_cl.py:49-98 -> [P, L].  `problem` = oracle.scenarios.flatten_spec(...)."""
     c = Cosmo(cosmo_row)
+    c.transfer_type = problem.get("transfer", "eisenhu_osc")      # transfer.py:10 `type`
+    c.prescription = problem.get("prescription", "takahashi2012")  # power.py:144 `prescription`
     bg = Background(c)
     pw = Power(bg)
     ell = np.atleast_1d(np.asarray(ell, dtype=np.float64))
@@ -506,7 +531,7 @@ def angular_cl(cosmo_row, ell, problem, stages=None):
             -(y / 4.0 + y ** 2 / 8.0))
         d2hp = co["a_n"] * y ** (3 * co["f1"]) / (
             1.0 + co["b_n"] * y ** co["f2"] + (co["c_n"] * co["f3"] * y) ** (3.0 - co["gamma_n"]))
-        d2h = d2hp / (1.0 + 0.0 / y + co["nu_n"] / y ** 2)
+        d2h = d2hp / (1.0 + co["mu_n"] / y + co["nu_n"] / y ** 2)
         pk = 2.0 * np.pi ** 2 / kk ** 3 * (d2q + d2h)
     else:
         pk = kk ** c.n_s * eisenstein_hu(c, kk) ** 2 * (bg.growth(a) ** 2)[None, :] * pw.pknorm

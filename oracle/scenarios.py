@@ -97,9 +97,12 @@ ELL_CFG1 = np.logspace(1, 3, 50)
 ELL_CFG2 = np.logspace(1, np.log10(3000), 100)
 
 
-def scenario(name, cosmo, ell, probes, nonlinear="halofit", f_sky=0.25):
+def scenario(name, cosmo, ell, probes, nonlinear="halofit", f_sky=0.25, transfer="eisenhu_osc",
+             prescription="takahashi2012"):
+    """nonlinear: "halofit" | "linear"; prescription (halofit only): "takahashi2012" | "smith2003"
+    (power.py:144); transfer: "eisenhu_osc" | "eisenhu" (transfer.py:10)."""
     return dict(name=name, cosmo=dict(cosmo), ell=[float(x) for x in np.atleast_1d(ell)],
-                probes=probes, nonlinear=nonlinear, f_sky=f_sky)
+                probes=probes, nonlinear=nonlinear, f_sky=f_sky, transfer=transfer, prescription=prescription)
 
 
 def golden_scenarios():
@@ -148,6 +151,14 @@ def golden_scenarios():
                            delta(0.8)], m=[0.0, 0.01, 0.0, -0.01]),
                        nc([fu(0.4710, 5.1843, 0.7259, 10.0), kde(zcat, wcat, 0.1, 3.0)],
                           [bias("constant", 1.1), bias("inverse_growth", 1.3)])]))
+    # non-default physics switches: smith2003 halofit (power.py:182-198,239-242) and the
+    # no-wiggle Eisenstein-Hu fit (transfer.py:99-105); an open (Omega_k != 0) wCDM model so that the smith2003
+    # f1,f2,f3 interpolation (frac != 1) is exercised
+    open_wcdm = dict(WCDM, Omega_k=0.04)
+    sw = [wl([nz1, nz2], ia=bias("des_y1_ia", 0.5, 0.0, 0.62)), nc([nz2], bias("constant", 1.2))]
+    S.append(scenario("switch_smith2003", open_wcdm, [20.0, 200.0, 2000.0], sw, prescription="smith2003"))
+    S.append(scenario("switch_nowiggle", WCDM, [20.0, 200.0, 2000.0], sw, transfer="eisenhu"))
+    S.append(scenario("switch_nowiggle_smith_linear", open_wcdm, [50.0, 500.0], sw, "linear", transfer="eisenhu"))
     return S
 
 
@@ -203,8 +214,16 @@ def build_cosmo(scn, ns):
 
 
 def build_fns(scn, ns):
+    """(transfer_fn, nonlinear_fn) as a user of the reference passes them: non-default variants are
+    functools.partial objects over the module functions."""
+    from functools import partial
     nl = {"halofit": ns.power.halofit, "linear": ns.power.linear}[scn["nonlinear"]]
-    return ns.transfer.Eisenstein_Hu, nl
+    if scn["nonlinear"] == "halofit" and scn.get("prescription", "takahashi2012") != "takahashi2012":
+        nl = partial(ns.power.halofit, prescription=scn["prescription"])
+    tf = ns.transfer.Eisenstein_Hu
+    if scn.get("transfer", "eisenhu_osc") != "eisenhu_osc":
+        tf = partial(ns.transfer.Eisenstein_Hu, type=scn["transfer"])
+    return tf, nl
 
 
 # ----------------------------------------------------------------------------------------
@@ -235,4 +254,5 @@ def flatten_spec(scn):
                 bb = p["bias"][i] if isinstance(p["bias"], list) else p["bias"]
                 tracers.append(dict(kind="nc", nz=nzd, bias=bb, probe_zmax=pz))
     zmax = max(t["probe_zmax"] for t in tracers)
-    return dict(tracers=tracers, zmax=zmax, nonlinear=(scn["nonlinear"] == "halofit"))
+    return dict(tracers=tracers, zmax=zmax, nonlinear=(scn["nonlinear"] == "halofit"),
+                transfer=scn.get("transfer", "eisenhu_osc"), prescription=scn.get("prescription", "takahashi2012"))

@@ -83,6 +83,15 @@ def test_unsupported_options_raise(jc):
         _native.build_problem([wl], transfer_fn=lambda *a: None)
     with pytest.raises(NotImplementedError):
         _native.build_problem([wl], nonlinear_fn=lambda *a: None)
+    # variants are selected like in the reference: functools.partial over the module functions
+    from functools import partial
+    pbs = _native.build_problem([wl], partial(jc.transfer.Eisenstein_Hu, type="eisenhu"),
+                                partial(jc.power.halofit, prescription="smith2003"))
+    assert pbs.transfer == _native.JC_TF_EH_NOWIGGLE and pbs.nonlinear == _native.JC_PK_HALOFIT_SMITH
+    with pytest.raises(NotImplementedError):
+        _native.build_problem([wl], nonlinear_fn=partial(jc.power.halofit, prescription="mead2020"))
+    with pytest.raises(NotImplementedError):
+        _native.build_problem([wl], transfer_fn=partial(jc.transfer.Eisenstein_Hu, type="bbks"))
     # delta_nz: weak lensing without IA only (the reference raises in density_kernel / nla_kernel)
     assert _native.build_problem([jc.probes.WeakLensing([jc.redshift.delta_nz(1.0)])]).tracers[0].nz.family == 3
     with pytest.raises(NotImplementedError):
