@@ -254,6 +254,13 @@ int jc_gaussian_loglike_f64(const double* data_dev, int64_t data_stride, const d
                             const double* cov_dev, int64_t n_cosmo, int32_t P, int32_t L,
                             int32_t include_logdet, double* loglike_dev, double* scratch_dev, void* stream);
 
+/* Fisher matrix F[b] = J^T C^-1 J on the sparse block covariance (the reference's recipe
+ * sparse.dot(dmu.T, sparse.inv(cov), dmu), docs/notebooks/jax-cosmo-intro.ipynb cell 51; pairs with
+ * jc_angular_cl_jvp_f64): jac_dev [B, K, P*L] (one row per parameter, cls-major), cov_dev [B, P, P, L],
+ * fisher_dev [B, K, K], scratch_dev [B, L, K*K + 1] doubles; K <= 16. */
+int jc_fisher_f64(const double* jac_dev, const double* cov_dev, int64_t n_cosmo, int32_t n_params,
+                  int32_t P, int32_t L, double* fisher_dev, double* scratch_dev, void* stream);
+
 /* Per-stage device timing (CUDA events recorded on the launch stream between the stages of
  * jc_angular_cl_f64).  Stages: 0 setup, 1 lensing efficiency, 2 tracer finish, 3 power, 4 pair
  * contraction.  While enabled the plan is not re-entrant.  jc_profile_read synchronises the

@@ -31,7 +31,7 @@ SCAL_FIELDS = ["LN13KEQ", "INV13KEQ", "BETA_C", "C14_ALPHA_C", "SH_D", "LNKSILK"
 # every symbol include/jc_b200.h declares
 EXPORTS = ["jc_plan_create", "jc_plan_destroy", "jc_plan_n_tracers", "jc_plan_n_cls", "jc_plan_n_ell",
            "jc_workspace_bytes", "jc_workspace_layout", "jc_angular_cl_f64", "jc_angular_cl_host_f64",
-           "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64", "jc_gaussian_loglike_f64",
+           "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64", "jc_gaussian_loglike_f64", "jc_fisher_f64",
            "jc_noise_f64", "jc_gaussian_cov_f64", "jc_profile_enable", "jc_profile_read",
            "jc_fp64_peak_tflops", "jc_debug_math_f64", "jc_status_string",
            "jc_last_cuda_error", "jc_abi_version"]
@@ -98,6 +98,8 @@ def load_library():
         lib.jc_angular_cl_jvp_f64.restype = C.c_int
         lib.jc_gaussian_loglike_f64.argtypes = [vp, i64, vp, vp, i64, i32, i32, i32, vp, vp, vp]
         lib.jc_gaussian_loglike_f64.restype = C.c_int
+        lib.jc_fisher_f64.argtypes = [vp, vp, i64, i32, i32, i32, vp, vp, vp]
+        lib.jc_fisher_f64.restype = C.c_int
         lib.jc_angular_cl_host_f64.argtypes = [vp, vp, i64, vp]
         lib.jc_angular_cl_host_f64.restype = C.c_int
         lib.jc_noise_f64.argtypes = [vp, dp]
@@ -442,6 +444,21 @@ def gaussian_loglike_device(data_dev, mu_dev, cov_dev, include_logdet=True):
                                                 1 if include_logdet else 0, out.data_ptr(), scratch.data_ptr(),
                                                 torch.cuda.current_stream(cov_dev.device).cuda_stream)
     check(st, "jc_gaussian_loglike_f64")
+    return out
+
+
+def fisher_device(jac_dev, cov_dev):
+    """CUDA float64 tensors: jac [B,K,P,L] (or [B,K,P*L]), cov [B,P,P,L] -> Fisher matrices [B,K,K]."""
+    import torch
+
+    B, P, _, L = cov_dev.shape
+    K = jac_dev.shape[1]
+    jac_dev = jac_dev.reshape(B, K, P * L).contiguous()
+    out = torch.empty((B, K, K), dtype=torch.float64, device=cov_dev.device)
+    scratch = torch.empty((B, L, K * K + 1), dtype=torch.float64, device=cov_dev.device)
+    st = load_library().jc_fisher_f64(jac_dev.data_ptr(), cov_dev.contiguous().data_ptr(), B, K, P, L, out.data_ptr(),
+                                      scratch.data_ptr(), torch.cuda.current_stream(cov_dev.device).cuda_stream)
+    check(st, "jc_fisher_f64")
     return out
 
 

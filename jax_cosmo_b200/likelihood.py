@@ -10,7 +10,7 @@ import numpy as np
 
 from jax_cosmo_b200 import _native
 
-__all__ = ["gaussian_log_likelihood", "gaussian_log_likelihood_batch"]
+__all__ = ["gaussian_log_likelihood", "gaussian_log_likelihood_batch", "fisher_matrix"]
 
 
 def gaussian_log_likelihood(data, mu, C, include_logdet=True, inverse_method="inverse"):
@@ -34,6 +34,26 @@ def gaussian_log_likelihood(data, mu, C, include_logdet=True, inverse_method="in
                                           torch.as_tensor(mu[None], device="cuda"),
                                           torch.as_tensor(np.ascontiguousarray(C)[None], device="cuda"), include_logdet)
     return float(out[0].item())
+
+
+def fisher_matrix(jac, C):
+    """Fisher matrix F = J^T C^-1 J for a sparse covariance C [P, P, L] and a Jacobian `jac`
+    [n_params, P, L] (what `angular_cl_jacobian` returns) -- the reference notebook's
+    `sparse.dot(dmu.T, sparse.inv(cov), dmu)` (docs/notebooks/jax-cosmo-intro.ipynb cell 51).
+    CUDA tensors with a leading batch dimension ([B, K, P, L], [B, P, P, L]) are also accepted and
+    stay on the device."""
+    import torch
+
+    if isinstance(jac, torch.Tensor) and jac.is_cuda:
+        return _native.fisher_device(jac, C)
+    C = np.ascontiguousarray(np.asarray(C, dtype=np.float64))
+    jac = np.ascontiguousarray(np.asarray(jac, dtype=np.float64))
+    if C.ndim != 3 or C.shape[0] != C.shape[1] or jac.ndim != 3 or jac.shape[1:] != (C.shape[0], C.shape[2]):
+        raise ValueError("expected jac [n_params, P, L] and a sparse covariance [P, P, L]")
+    if not torch.cuda.is_available():
+        raise _native.JcError("jax_cosmo_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    out = _native.fisher_device(torch.as_tensor(jac[None], device="cuda"), torch.as_tensor(C[None], device="cuda"))
+    return out[0].cpu().numpy()
 
 
 def gaussian_log_likelihood_batch(data, mu, C, include_logdet=True):

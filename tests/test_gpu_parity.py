@@ -322,6 +322,22 @@ def test_likelihood_golden_and_config3(jc, torch_cuda):
     assert float(ll0[0]) == 0.0
 
 
+def test_fisher_matrix(jc, torch_cuda):
+    """Config 4 consumer: F = J^T C^-1 J from the JVP Jacobian and the sparse Gaussian covariance
+    (the notebook's sparse.dot(dmu.T, sparse.inv(cov), dmu)) against a dense NumPy evaluation."""
+    scn = sc.scenario("c4", sc.PLANCK15, sc.ELL_CFG2[::10], [sc.sources(5, 2.0), sc.lenses(5, 2.0)])
+    probes = sc.build_probes(scn, jc)
+    cosmo = jc.Planck15()
+    cl, jac = jc.cl.angular_cl_jacobian(cosmo, scn["ell"], probes)
+    mu, cov = jc.cl.gaussian_cl_covariance_and_mean(cosmo, scn["ell"], probes, sparse=True)
+    F = jc.likelihood.fisher_matrix(jac, cov)
+    assert F.shape == (7, 7) and np.allclose(F, F.T, rtol=1e-12, atol=0)
+    assert np.all(np.linalg.eigvalsh(F) > 0)
+    J = jac.reshape(7, -1).T  # [N, n_params], the jax.jacfwd layout
+    ref = J.T @ np.linalg.solve(o.sparse_to_dense(cov), J)
+    assert relerr(F, ref) < 1e-9, relerr(F, ref)
+
+
 def _nccl_worker(rank, world, port, out_dir):
     import torch
     import torch.distributed as dist
