@@ -229,21 +229,25 @@ __global__ void __launch_bounds__(256) jc_dfma_probe_kernel(double* out, int ite
   if (s == 12345.678) out[0] = s;  // keep the chain alive
 }
 
-__global__ void __launch_bounds__(256) jc_dmma_probe_kernel(double* out, int iters, double seed) {
-  double c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0};
+// NACC independent accumulator tiles per warp, 16 DMMA per iteration (NACC = 4) or NACC per iteration
+template <int NACC>
+__global__ void __launch_bounds__(512) jc_dmma_probe_kernel(double* out, int iters, double seed) {
+  double c0[NACC], c1[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) c0[i] = c1[i] = 0.0;
   double a = seed + threadIdx.x * 1e-9, b = 1.0 + threadIdx.x * 1e-12;
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 16 / NACC + (16 % NACC ? 1 : 0); ++u) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < NACC; ++i)
         asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                      : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
     }
   }
   double s = 0.0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) s += c0[i] + c1[i];
+  for (int i = 0; i < NACC; ++i) s += c0[i] + c1[i];
   if (s == 12345.678) out[0] = s;
 }
 
@@ -277,7 +281,11 @@ __global__ void __launch_bounds__(256) jc_mixed_probe_kernel(double* out, int it
 }
 
 extern "C" int jc_fp64_peak_tflops(int32_t mode, double seconds, double* tflops_out) {
-  if (!tflops_out || mode < 0 || mode > 2) return JC_ERR_INVALID;
+  // mode & 15: 0 DFMA, 1 DMMA, 2 both interleaved.  DMMA only: (mode >> 4) & 15 = warps per SM sub-partition
+  // (0 = full occupancy), mode >> 8 = 1 selects 16 independent accumulator tiles per warp instead of 4.
+  const int wps = (mode >> 4) & 15, wide = mode >> 8;
+  mode &= 15;
+  if (!tflops_out || mode < 0 || mode > 2 || wps > 4 || wide > 1 || ((wps || wide) && mode != 1)) return JC_ERR_INVALID;
   int dev = 0, sms = 0;
   JC_CUDA_TRY(cudaGetDevice(&dev));
   JC_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -286,7 +294,7 @@ extern "C" int jc_fp64_peak_tflops(int32_t mode, double seconds, double* tflops_
   cudaEvent_t e0, e1;
   JC_CUDA_TRY(cudaEventCreate(&e0));
   JC_CUDA_TRY(cudaEventCreate(&e1));
-  const int blocks = sms * 8, threads = 256, iters = 4096;
+  const int blocks = wps ? sms : sms * 8, threads = wps ? 128 * wps : 256, iters = 4096;
   // flops per launch
   const double f_dfma = (double)blocks * threads * iters * 64.0 * 2.0;
   const double f_dmma = (double)blocks * (threads / 32) * iters * 16.0 * (8 * 8 * 4 * 2.0);
@@ -294,7 +302,8 @@ extern "C" int jc_fp64_peak_tflops(int32_t mode, double seconds, double* tflops_
   double flops = mode == 0 ? f_dfma : (mode == 1 ? f_dmma : f_dmma + (double)blocks * threads * iters * 128.0 * 2.0);
   auto launch = [&]() {
     if (mode == 0) jc_dfma_probe_kernel<<<blocks, threads>>>(d_out, iters, 1.0);
-    else if (mode == 1) jc_dmma_probe_kernel<<<blocks, threads>>>(d_out, iters, 1.0);
+    else if (mode == 1 && wide) jc_dmma_probe_kernel<16><<<blocks, threads>>>(d_out, iters, 1.0);
+    else if (mode == 1) jc_dmma_probe_kernel<4><<<blocks, threads>>>(d_out, iters, 1.0);
     else jc_mixed_probe_kernel<<<blocks, threads>>>(d_out, iters, 1.0);
   };
   launch();  // warm-up

@@ -96,6 +96,36 @@ __device__ __forceinline__ void mma_stage_nt(int ntw, const double* Rs, const do
   }
 }
 
+// Epilogue of a warp's <= 2 pair tiles: the weak-lensing ell factors (probes.py:73) and the store of C[p, l0:].
+__device__ __forceinline__ void store_tiles(const JcDevPlan& pl, const double (&acc)[2][NTW][2], int cnt, int m_first,
+                                            const int (&ti)[2], const int (&tj)[2], int l0, int g, int tig, bool vec2,
+                                            double* __restrict__ out_cosmo) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const int p = (m_first + mt) * 8 + g;
+    if (mt >= cnt || p >= pl.P) continue;
+    const bool wi = pl.tr_kind[ti[mt]] == JC_TRACER_WEAK_LENSING;
+    const bool wj = pl.tr_kind[tj[mt]] == JC_TRACER_WEAK_LENSING;
+    double* out = out_cosmo + (size_t)p * pl.L;
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt) {
+      const int l = l0 + nt * 8 + 2 * tig;
+      double v[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const double ef = (l + h < pl.L) ? pl.ellfac[l + h] : 1.0;
+        v[h] = acc[mt][nt][h] * ((wi ? ef : 1.0) * (wj ? ef : 1.0));  // probes.py:73
+      }
+      if (vec2 && l + 1 < pl.L) {
+        *reinterpret_cast<double2*>(out + l) = make_double2(v[0], v[1]);
+      } else {
+        if (l < pl.L) out[l] = v[0];
+        if (l + 1 < pl.L) out[l + 1] = v[1];
+      }
+    }
+  }
+}
+
 // KC: Limber nodes per pipeline stage (KC/4 k-steps); WARPS per CTA; MINB CTAs per SM; the pair tiles
 // are split over gridDim.z CTAs.  out_cosmo_stride: doubles between consecutive cosmologies of `out`.
 template <int KC, int WARPS, int MINB, bool JVP>
@@ -202,31 +232,186 @@ jc_contract_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64_t o
     cp_async_wait<0>();
 
     const bool vec2 = (pl.L & 1) == 0 && (out_cosmo_stride & 1) == 0;
+    store_tiles(pl, acc, cnt, m_first, ti, tj, l0, g, tig, vec2, out_base + (size_t)c * out_cosmo_stride);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Persistent TMA variant (>= 17 pair tiles, i.e. T >= 16).  ncu on the kernel above (profiles/r01_ncu_summary.md):
+// DMMA pipe 73 % busy although one warp per SM sub-partition saturates it from registers
+// (scripts/dmma_occupancy.py) -- the idle quarter is warps parked at the per-stage __syncthreads (24 % of
+// stall samples) behind the warps that own 2 pair tiles instead of 1, and 14 + 13 tiles never balance over
+// the 4 sub-partitions of two independently scheduled CTAs.  Here one CTA of 16 warps (4 per sub-partition,
+// 128 registers) per SM walks over cosmologies:
+//   * the [R | V] stages arrive by TMA bulk copies (cp.async.bulk, mbarrier complete_tx) in an 8-stage ring that
+//     runs on across cosmology boundaries;
+//   * there is no CTA-wide barrier and no producer warp (a 17th warp would cost every warp 32 registers): a
+//     warp waits on the stage's `full` mbarrier, runs its DMMA burst and arrives on the stage's `empty`
+//     mbarrier; the warp holding the fewest tiles of the item waits for `empty` and issues the copies of the
+//     stage 8 ahead into that buffer (letting the LAST warp out do it put the issue on the critical path:
+//     7.0 ms against 6.4 ms with a separate producer warp at 96 registers);
+//   * a warp owns <= 2 pair tiles x <= 7 ell tiles; 27 tiles are dealt 7,7,7,6 over the sub-partitions and the
+//     light one rotates from item to item; a warp with one tile runs ahead instead of idling at a barrier.
+// R is read KC rows at a time up to row 516 > 513: the finish kernel zeroes the pad rows of R, so the stale
+// (finite) V rows of the last stage meet A = 0.
+// ---------------------------------------------------------------------------------------------------
+constexpr int TMA_CW = 16;      // warps per CTA
+constexpr int TMA_STAGES = 8;   // power of two
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) {
+  const unsigned a = smem_u32(b);
+  unsigned ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+// 1-D TMA bulk copy global -> shared; completion is counted in bytes on `bar`.  16-byte aligned both sides.
+__device__ __forceinline__ void tma_load(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(smem_u32(dst)), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int KC, bool JVP>
+__global__ void __launch_bounds__(TMA_CW * 32, 1)
+jc_contract_tma_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64_t out_cosmo_stride, int chunk) {
+  constexpr int NKC = (JC_NA + KC - 1) / KC;
+  constexpr int NIMG = JVP ? 2 : 1;
+  static_assert(NKC * KC <= JC_NA_PAD, "R stages read whole KC-row blocks: they must stay inside the padded rows");
+  static_assert(KC < 31, "one lane per V row + lane 31 for R");
+  static_assert((TMA_STAGES & (TMA_STAGES - 1)) == 0, "ring index by mask");
+  extern __shared__ __align__(16) double smem[];
+  const int TS = pl.TS;
+  const int half = KC * (TS + LSV);  // one [R | V] image
+  const int stage_doubles = NIMG * half;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)TMA_STAGES * stage_doubles);
+  uint64_t* empty = full + TMA_STAGES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ngroups = (pl.L + NCOLS - 1) / NCOLS;
+  const int mtiles_all = (pl.P + 7) >> 3;
+  const int nrounds = (mtiles_all + 2 * TMA_CW - 1) / (2 * TMA_CW);
+  const int my_cosmo = (chunk - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total_stages = my_cosmo * ngroups * nrounds * NKC;  // stage q = ((ci * ngroups + grp) * nrounds + r) * NKC + kc
+
+  // warp-collective: arm full[q % STAGES] and issue the TMA copies of stage q into that buffer
+  auto issue_stage = [&](int q) {
+    const int sb = q & (TMA_STAGES - 1);
+    const int item = q / NKC, kc = q - item * NKC;
+    const int t = item / nrounds;
+    const int ci = t / ngroups, grp = t - ci * ngroups;
+    const int c = blockIdx.x + ci * gridDim.x;
+    const int l0 = grp * NCOLS;
+    const int ncols = min(NCOLS, pl.Lpad - l0);  // multiple of 4 doubles: 32-byte pieces
+    const int rows = min(KC, JC_NA - kc * KC);
+    double* st = smem + (size_t)sb * stage_doubles;
+    if (lane == 0) mbar_expect_tx(full + sb, (unsigned)(NIMG * (KC * TS + rows * ncols) * sizeof(double)));
+    __syncwarp();
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-      const int p = (m_first + mt) * 8 + g;
-      if (mt >= cnt || p >= pl.P) continue;
-      const bool wi = pl.tr_kind[ti[mt]] == JC_TRACER_WEAK_LENSING;
-      const bool wj = pl.tr_kind[tj[mt]] == JC_TRACER_WEAK_LENSING;
-      double* out = out_base + (size_t)c * out_cosmo_stride + (size_t)p * pl.L;
+    for (int img = 0; img < NIMG; ++img) {
+      const ptrdiff_t goff = img ? ws.doff : 0;
+      if (lane < rows)
+        tma_load(st + img * half + KC * TS + lane * LSV,
+                 ws.vtab + goff + ((size_t)c * JC_NA + kc * KC + lane) * pl.Lpad + l0, (unsigned)(ncols * sizeof(double)),
+                 full + sb);
+      else if (lane == 31)
+        tma_load(st + img * half, ws.rker + goff + ((size_t)c * JC_NA_PAD + kc * KC) * TS,
+                 (unsigned)(KC * TS * sizeof(double)), full + sb);
+    }
+  };
+
+  // stale rows of a partially filled last stage must be finite the first time round the ring
+  for (int i = threadIdx.x; i < TMA_STAGES * stage_doubles; i += blockDim.x) smem[i] = 0.0;
+  if (threadIdx.x == 0) {
+    for (int sb = 0; sb < TMA_STAGES; ++sb) {
+      mbar_init(full + sb, 1);
+      mbar_init(empty + sb, TMA_CW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic zero fill before async-proxy writes
+  __syncthreads();
+  if (warp == 0)
+    for (int q = 0; q < min(TMA_STAGES, total_stages); ++q) issue_stage(q);
+
+  const int g = lane >> 2, tig = lane & 3;
+  const bool vec2 = (pl.L & 1) == 0 && (out_cosmo_stride & 1) == 0;
+  int q = 0;
+  int rot = blockIdx.x;
+  for (int c = blockIdx.x; c < chunk; c += gridDim.x) {
+    for (int grp = 0; grp < ngroups; ++grp) {
+      const int l0 = grp * NCOLS;
+      const int ntw = (min(pl.L - l0, NCOLS) + 7) >> 3;
+      for (int m_base = 0; m_base < mtiles_all; m_base += 2 * TMA_CW, ++rot) {
+        // deal the round's pair tiles: `base` or base+1 per warp, the extras to the lowest virtual warps; the
+        // virtual index rotates so that the sub-partition (= warp % 4) holding the fewest tiles moves on
+        const int m_round = min(2 * TMA_CW, mtiles_all - m_base);
+        const int base = m_round / TMA_CW, extra = m_round - base * TMA_CW;
+        const int v = (warp + rot) & (TMA_CW - 1);
+        const int cnt = base + (v < extra ? 1 : 0);
+        const int m_first = m_base + v * base + min(v, extra);
+        int ti[2], tj[2];
 #pragma unroll
-      for (int nt = 0; nt < NTW; ++nt) {
-        const int l = l0 + nt * 8 + 2 * tig;
-        double v[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const double ef = (l + h < pl.L) ? pl.ellfac[l + h] : 1.0;
-          v[h] = acc[mt][nt][h] * ((wi ? ef : 1.0) * (wj ? ef : 1.0));  // probes.py:73
+        for (int mt = 0; mt < 2; ++mt) {
+          const int p = min((m_first + mt) * 8 + g, pl.P - 1);  // clamped rows are never stored
+          ti[mt] = pl.pair_i[p];
+          tj[mt] = pl.pair_j[p];
         }
-        if (vec2 && l + 1 < pl.L) {
-          *reinterpret_cast<double2*>(out + l) = make_double2(v[0], v[1]);
-        } else {
-          if (l < pl.L) out[l] = v[0];
-          if (l + 1 < pl.L) out[l + 1] = v[1];
+        double acc[2][NTW][2];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < NTW; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+
+        for (int kc = 0; kc < NKC; ++kc, ++q) {
+          const int sb = q & (TMA_STAGES - 1);
+          mbar_wait(full + sb, (q / TMA_STAGES) & 1);
+          const double* Rs = smem + (size_t)sb * stage_doubles;
+          const double* Vs = Rs + KC * TS;
+          if (cnt == 2) mma_stage_nt<KC, 2, JVP>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+          else if (cnt == 1) mma_stage_nt<KC, 1, JVP>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty + sb);
+          // the lightest-loaded warp of the item (v = 15 holds `base` tiles) doubles as the producer: once all 16
+          // warps have left the stage it refills the buffer with the stage 8 ahead -- off the critical path
+          if (v == TMA_CW - 1 && q + TMA_STAGES < total_stages) {
+            mbar_wait(empty + sb, (q / TMA_STAGES) & 1);
+            issue_stage(q + TMA_STAGES);
+          }
         }
+        store_tiles(pl, acc, cnt, m_first, ti, tj, l0, g, tig, vec2, out_base + (size_t)c * out_cosmo_stride);
       }
     }
   }
+}
+
+template <int KC, bool JVP>
+void launch_tma(const JcDevPlan& pl, const Ws& ws, double* out, int64_t stride, int chunk, cudaStream_t s) {
+  const size_t smem = (size_t)(JVP ? 2 : 1) * TMA_STAGES * KC * (pl.TS + LSV) * sizeof(double) + 2 * TMA_STAGES * sizeof(uint64_t);
+  static int sms = 0;  // idempotent; racing writers set the same values
+  if (!sms) {
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(jc_contract_tma_kernel<KC, JVP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    sms = n > 0 ? n : 148;
+  }
+  jc_contract_tma_kernel<KC, JVP><<<chunk < sms ? chunk : sms, TMA_CW * 32, smem, s>>>(pl, ws, out, stride, chunk);
+}
+
+// TMA bulk copies need 16-byte aligned rows on both sides
+bool tma_ok(const JcDevPlan& pl, const Ws& ws) {
+  return (pl.P + 7) / 8 > TMA_CW && ((reinterpret_cast<uintptr_t>(ws.rker) | reinterpret_cast<uintptr_t>(ws.vtab)) & 15) == 0 &&
+         (ws.doff & 1) == 0 && (pl.TS & 1) == 0 && (pl.Lpad & 3) == 0;
 }
 
 template <int KC, int WARPS, int MINB, bool JVP>
@@ -259,13 +444,18 @@ void jc_launch_contract(const JcDevPlan& pl, const Ws& ws, double* cl, int chunk
   switch (g_contract_cfg) {
     case 1: launch_cfg<12, 16, 1, false>(pl, ws, cl, stride, chunk, 1, s); break;
     case 2: launch_cfg<24, 16, 1, false>(pl, ws, cl, stride, chunk, 1, s); break;
-    // fastest (profiles/r01_tuning.md): 8 warps, 2 CTAs per SM, pair tiles split over 2 CTAs
-    default: launch_cfg<12, 8, 2, false>(pl, ws, cl, stride, chunk, mtiles > 16 ? 2 : 1, s); break;
+    // 8 warps, 2 CTAs per SM, pair tiles split over 2 CTAs, cp.async staging (the default up to 16 pair tiles)
+    case 3: launch_cfg<12, 8, 2, false>(pl, ws, cl, stride, chunk, mtiles > 16 ? 2 : 1, s); break;
+    default:
+      if (tma_ok(pl, ws)) launch_tma<12, false>(pl, ws, cl, stride, chunk, s);
+      else launch_cfg<12, 8, 2, false>(pl, ws, cl, stride, chunk, mtiles > 16 ? 2 : 1, s);
+      break;
   }
 }
 
 void jc_launch_contract_jvp(const JcDevPlan& pl, const Ws& ws, double* dcl, int64_t dcl_cosmo_stride, int chunk,
                             cudaStream_t s) {
   const int mtiles = (pl.P + 7) / 8;
-  launch_cfg<12, 8, 2, true>(pl, ws, dcl, dcl_cosmo_stride, chunk, mtiles > 16 ? 2 : 1, s);
+  if (g_contract_cfg != 3 && tma_ok(pl, ws)) launch_tma<12, true>(pl, ws, dcl, dcl_cosmo_stride, chunk, s);
+  else launch_cfg<12, 8, 2, true>(pl, ws, dcl, dcl_cosmo_stride, chunk, mtiles > 16 ? 2 : 1, s);
 }

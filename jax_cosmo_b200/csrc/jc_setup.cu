@@ -65,6 +65,7 @@ template <class T> struct SetupSmem {
   T f[512];  // chi integrand at nodes+midpoints; later the normalised growth table; later (as doubles) k nodes
   T cum[256], chitab[256], gr_r[256], gr_q[256], M[127 * 4], gtab[128], sc[JC_SCAL_FIELDS];
   T d2w[JC_NHFK], S[JC_NHFR], D2[JC_NA], omm[JC_NA], ode[JC_NA], odew[JC_NA], rnl[JC_NA], red[8];
+  double tab[JCM_TAB_DOUBLES];  // table-driven exp (jc_math.cuh) for the two halofit sums (~200k exp per cosmology)
 };
 
 // =================================================================================================
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
   const int c = blockIdx.x;
   const int tid = threadIdx.x;
   const ptrdiff_t doff = ws.doff;
+  for (int i = tid; i < JCM_TAB_DOUBLES; i += 256) S.tab[i] = pl.math_tab[i];  // published by the barriers below
   auto put = [&](double* p, T x) { JxMem<T>::st(p, doff, x); };
   auto node = [&](int field, int n) { return node_ptr(ws, c, field) + n; };
 
@@ -311,10 +313,10 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
     int i = 0;
     for (; i + 1 < imax; i += 2) {
       const double ya = s_hfk[i] * r, yb = s_hfk[i + 1] * r;
-      acc0 = acc0 + S.d2w[i] * jcm_exp(-(ya * ya));
-      acc1 = acc1 + S.d2w[i + 1] * jcm_exp(-(yb * yb));
+      acc0 = acc0 + S.d2w[i] * jcm_exp_t(-(ya * ya), S.tab);
+      acc1 = acc1 + S.d2w[i + 1] * jcm_exp_t(-(yb * yb), S.tab);
     }
-    if (i < imax) { const double ya = s_hfk[i] * r; acc0 = acc0 + S.d2w[i] * jcm_exp(-(ya * ya)); }
+    if (i < imax) { const double ya = s_hfk[i] * r; acc0 = acc0 + S.d2w[i] * jcm_exp_t(-(ya * ya), S.tab); }
     const T acc = acc0 + acc1;
     S.S[tid] = acc;
     put(ws.stab + (size_t)c * JC_NHFR + tid, acc);
@@ -363,7 +365,7 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
       for (int i = lane; i < imax; i += 32) {
         const T y = s_hfk[i] * rnl;
         const T y2 = y * y;
-        const T res = S.d2w[i] * jx_exp(-y2);
+        const T res = S.d2w[i] * jx_exp_t(-y2, S.tab);
         r0 = r0 + 2.0 * res * y2;
         r1 = r1 + 4.0 * res * (y2 - y2 * y2);
       }
