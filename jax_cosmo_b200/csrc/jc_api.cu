@@ -251,6 +251,48 @@ __global__ void __launch_bounds__(512) jc_dmma_probe_kernel(double* out, int ite
   if (s == 12345.678) out[0] = s;
 }
 
+// The contraction's register tile: 2 A fragments x 8 B fragments -> 16 accumulator tiles, 16 DMMA per iteration.
+// SRC 0: fragments stay in registers; SRC 1: every iteration reloads them from shared memory (4 + 8 LDS.64)
+// and forms the A fragments as products (2 DMUL), like jc_contract's k-step.
+template <int SRC>
+__global__ void __launch_bounds__(512) jc_dmma_tile_probe_kernel(double* out, int iters, double seed) {
+  __shared__ double sh[512 * 3];
+  for (int i = threadIdx.x; i < 512 * 3; i += blockDim.x) sh[i] = seed + i * 1e-9;
+  __syncthreads();
+  double c0[2][8], c1[2][8];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int n = 0; n < 8; ++n) c0[m][n] = c1[m][n] = 0.0;
+  double a[2], b[8];
+  a[0] = seed + threadIdx.x * 1e-9; a[1] = a[0] + 1.0;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) b[n] = 1.0 + n + threadIdx.x * 1e-12;
+  const int lane = threadIdx.x & 31;
+  for (int it = 0; it < iters; ++it) {
+    if (SRC == 1) {
+      const double* r = sh + ((it & 15) * 20 + (lane & 3) * 20 * 16) % 512;
+      const double* v = sh + 512 + ((it & 15) * 60 + (lane & 3) * 60 + (lane >> 2)) % 448;
+#pragma unroll
+      for (int m = 0; m < 2; ++m) a[m] = r[(lane >> 2) + m * 8] * r[(lane >> 3) + 4 + m];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) b[n] = v[n * 8];
+    }
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                     : "+d"(c0[m][n]), "+d"(c1[m][n]) : "d"(a[m]), "d"(b[n]));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int n = 0; n < 8; ++n) s += c0[m][n] + c1[m][n];
+  if (s == 12345.678) out[0] = s;
+}
+
 // mode 2: every warp interleaves 16 DFMA with 4 DMMA per iteration (128 FMA-lanes each side):
 // if the two share one datapath the rate stays at the single-pipe peak, otherwise it adds up.
 __global__ void __launch_bounds__(256) jc_mixed_probe_kernel(double* out, int iters, double seed) {
@@ -285,7 +327,7 @@ extern "C" int jc_fp64_peak_tflops(int32_t mode, double seconds, double* tflops_
   // (0 = full occupancy), mode >> 8 = 1 selects 16 independent accumulator tiles per warp instead of 4.
   const int wps = (mode >> 4) & 15, wide = mode >> 8;
   mode &= 15;
-  if (!tflops_out || mode < 0 || mode > 2 || wps > 4 || wide > 1 || ((wps || wide) && mode != 1)) return JC_ERR_INVALID;
+  if (!tflops_out || mode < 0 || mode > 2 || wps > 4 || wide > 3 || ((wps || wide) && mode != 1)) return JC_ERR_INVALID;
   int dev = 0, sms = 0;
   JC_CUDA_TRY(cudaGetDevice(&dev));
   JC_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -302,6 +344,8 @@ extern "C" int jc_fp64_peak_tflops(int32_t mode, double seconds, double* tflops_
   double flops = mode == 0 ? f_dfma : (mode == 1 ? f_dmma : f_dmma + (double)blocks * threads * iters * 128.0 * 2.0);
   auto launch = [&]() {
     if (mode == 0) jc_dfma_probe_kernel<<<blocks, threads>>>(d_out, iters, 1.0);
+    else if (mode == 1 && wide == 3) jc_dmma_tile_probe_kernel<1><<<blocks, threads>>>(d_out, iters, 1.0);
+    else if (mode == 1 && wide == 2) jc_dmma_tile_probe_kernel<0><<<blocks, threads>>>(d_out, iters, 1.0);
     else if (mode == 1 && wide) jc_dmma_probe_kernel<16><<<blocks, threads>>>(d_out, iters, 1.0);
     else if (mode == 1) jc_dmma_probe_kernel<4><<<blocks, threads>>>(d_out, iters, 1.0);
     else jc_mixed_probe_kernel<<<blocks, threads>>>(d_out, iters, 1.0);

@@ -44,9 +44,16 @@ __device__ __forceinline__ double jcm_rcp(double x) {
   return r;
 }
 
+// x < -708 -> -708 as an integer compare on the high word (negative doubles order like unsigned integers):
+// ISETP + 2 SEL instead of fmax's DSETP.MAX / FSEL / SEL / NaN fix-up / register moves.
+__device__ __forceinline__ double jcm_clamp_exp_arg(double x) {
+  const bool low = (unsigned)__double2hiint(x) > 0xC0862000u;  // hi word of -708.0
+  return low ? JCK.exp_lo : x;
+}
+
 // exp(x) for x <= 709.  x < -708 is clamped (returns ~3e-308 instead of a denormal / 0).
 __device__ __forceinline__ double jcm_exp(double x) {
-  x = fmax(x, JCK.exp_lo);
+  x = jcm_clamp_exp_arg(x);
   const double kd = fma(x, JCK.log2e, JCK.magic);
   const int k = __double2loint(kd);
   const double kf = kd - JCK.magic;
@@ -99,7 +106,7 @@ static __constant__ JcMathT JCT = {
 
 // exp(x), x <= 709 (x < -708 clamped): 2^n * T[j] * p(r), |r| <= ln2/64, degree-6 Taylor (3.5e-18).
 __device__ __forceinline__ double jcm_exp_t(double x, const double* __restrict__ tab) {
-  x = fmax(x, JCK.exp_lo);
+  x = jcm_clamp_exp_arg(x);
   const double kd = fma(x, JCT.k32, JCT.magic);
   const int k = __double2loint(kd);
   const double kf = kd - JCT.magic;

@@ -120,8 +120,8 @@ jc_lens_kernel(JcDevPlan pl, Ws ws, int n_cosmo, int s0) {
 #pragma unroll
         for (int c = 0; c < NCOS; ++c) {
           const T f0 = chit[c][i0], f1 = chit[c][i1];
-          const T chip = jx_max(f0 + (f1 - f0) * t, 0.0);                      // background.py:242
-          const T g = jx_max(chip - chin[c], 0.0) * jx_rcp(jx_max(chip, 1.0));  // probes.py:49
+          const T chip = jx_clip0(f0 + (f1 - f0) * t);                          // background.py:242
+          const T g = jx_clip0(chip - chin[c]) * jx_rcp(jx_floor1(chip));       // probes.py:49
 #pragma unroll
           for (int s = 0; s < NS; ++s) acc[c][s] = acc[c][s] + wv[s] * g;
         }
@@ -161,8 +161,8 @@ __global__ void __launch_bounds__(512) jc_tracer_finish_kernel(JcDevPlan pl, Ws 
     if (dix >= 0) {  // delta_nz source plane (probes.py:53-64): clip(chi_s - chi, 0) / clip(chi_s, 1)
       const double* ct = ws.chitab + (size_t)c * JC_NCHI;
       const T f0 = JxMem<T>::ld(ct + (dix & 255), doff), f1 = JxMem<T>::ld(ct + (dix >> 8), doff);
-      const T chis = jx_max(f0 + (f1 - f0) * pl.tr_delta_t[t], 0.0);
-      q = jx_max(chis - chi, 0.0) / jx_max(chis, 1.0);
+      const T chis = jx_clip0(f0 + (f1 - f0) * pl.tr_delta_t[t]);
+      q = jx_clip0(chis - chi) / jx_floor1(chis);
     } else {
       q = (n < JC_NLENS_COLS) ? JxMem<T>::ld(out, doff) : T(0.0);  // node 512 is a=1: chi=0, kernel = 0
     }
