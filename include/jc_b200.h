@@ -22,7 +22,9 @@
  *
  * Layouts (row-major, last index fastest)
  *   cosmo  [B, 8]      Omega_c, Omega_b, h, n_s, sigma8, Omega_k, w0, wa
- *                      (= Cosmology.tree_flatten order, jax_cosmo/core.py:99-108)
+ *                      (= Cosmology.tree_flatten order, jax_cosmo/core.py:99-108); [B, 9] with the
+ *                      growth index gamma appended when jc_problem.growth == JC_GROWTH_GAMMA
+ *                      (core.py:104-105); tangent rows have the same width
  *   ell    [L]
  *   cl     [B, P, L]   P = T(T+1)/2 tracer pairs (i<=j), row-major upper triangle
  *                      (jax_cosmo/angular_cl.py:15-25); one [P, L] slab == the reference's output
@@ -38,10 +40,11 @@
 extern "C" {
 #endif
 
-#define JC_ABI_VERSION 1
+#define JC_ABI_VERSION 2
 #define JC_MAX_TRACERS 32
 #define JC_MAX_SHIFTS 4
-#define JC_N_COSMO_PARAMS 8
+#define JC_N_COSMO_PARAMS 8     /* row width with JC_GROWTH_ODE; +1 (gamma) with JC_GROWTH_GAMMA */
+#define JC_MAX_COSMO_PARAMS 9
 #define JC_N_LIMBER_NODES 513 /* simps(..., 512) in a, jax_cosmo/angular_cl.py:96 */
 
 typedef enum jc_status {
@@ -82,6 +85,11 @@ enum {
   JC_TF_EISENSTEIN_HU_NOWIGGLE = 2 /* transfer.py:99-105, partial(Eisenstein_Hu, type="eisenhu") */
 };
 
+enum {
+  JC_GROWTH_ODE = 0,  /* background.py:443-488  linear growth ODE (cosmologies with gamma=None)         */
+  JC_GROWTH_GAMMA = 1 /* background.py:515-582  f = Omega_m(a)^gamma, D = exp(int f dln a), D(1) = 1   */
+};
+
 /* One redshift bin.  `shifts` is the chain of systematic_shift wrappers (redshift.py:159-171),
  * outermost first: pz_fn(z) = parent.pz_fn(clip(z - shift, 0)).  `zmax` is the n(z)'s own
  * normalisation range (redshift.py:16,29-30). */
@@ -120,6 +128,8 @@ typedef struct jc_problem {
   int32_t n_tracers;
   int32_t transfer;  /* JC_TF_*  */
   int32_t nonlinear; /* JC_PK_*  */
+  int32_t growth;    /* JC_GROWTH_*: selects the growth-factor table and the cosmology row width */
+  int32_t reserved;
   jc_tracer tracers[JC_MAX_TRACERS];
 } jc_problem;
 
@@ -204,6 +214,7 @@ void jc_plan_destroy(jc_plan* plan);
 int32_t jc_plan_n_tracers(const jc_plan* plan);
 int32_t jc_plan_n_cls(const jc_plan* plan); /* P = T(T+1)/2 */
 int32_t jc_plan_n_ell(const jc_plan* plan);
+int32_t jc_plan_n_cosmo_params(const jc_plan* plan); /* width of a cosmology / tangent row: 8 or 9 */
 
 /* Workspace: recommended size for n_cosmo cosmologies (processed in chunks of at most
  * JC_MAX_CHUNK) and the table offsets for a given size.  Any ws_bytes >= jc_workspace_bytes(plan,

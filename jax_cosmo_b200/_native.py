@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libjc_b200.so")
 
-JC_ABI_VERSION = 1
+JC_ABI_VERSION = 2
 JC_MAX_TRACERS = 32
 JC_MAX_SHIFTS = 4
 JC_OK, JC_ERR_INVALID, JC_ERR_UNSUPPORTED, JC_ERR_WORKSPACE, JC_ERR_CUDA, JC_ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5
@@ -29,7 +29,7 @@ SCAL_FIELDS = ["LN13KEQ", "INV13KEQ", "BETA_C", "C14_ALPHA_C", "SH_D", "LNKSILK"
                "BETA_NODE", "FB", "FC", "NS", "PKNORM", "SIGMASQR8", "OMEGA_M", "ALPHA_GAMMA", "OMH_T27"]
 
 # every symbol include/jc_b200.h declares
-EXPORTS = ["jc_plan_create", "jc_plan_destroy", "jc_plan_n_tracers", "jc_plan_n_cls", "jc_plan_n_ell",
+EXPORTS = ["jc_plan_create", "jc_plan_destroy", "jc_plan_n_tracers", "jc_plan_n_cls", "jc_plan_n_ell", "jc_plan_n_cosmo_params",
            "jc_workspace_bytes", "jc_workspace_layout", "jc_angular_cl_f64", "jc_angular_cl_host_f64",
            "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64", "jc_gaussian_loglike_f64", "jc_fisher_f64",
            "jc_noise_f64", "jc_gaussian_cov_f64", "jc_profile_enable", "jc_profile_read",
@@ -55,7 +55,8 @@ class jc_tracer(C.Structure):
 
 class jc_problem(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("n_tracers", C.c_int32), ("transfer", C.c_int32),
-                ("nonlinear", C.c_int32), ("tracers", jc_tracer * JC_MAX_TRACERS)]
+                ("nonlinear", C.c_int32), ("growth", C.c_int32), ("reserved", C.c_int32),
+                ("tracers", jc_tracer * JC_MAX_TRACERS)]
 
 
 class jc_ws_layout(C.Structure):
@@ -83,7 +84,7 @@ def load_library():
         lib.jc_plan_create.restype = C.c_int
         lib.jc_plan_destroy.argtypes = [vp]
         lib.jc_plan_destroy.restype = None
-        for f in ("jc_plan_n_tracers", "jc_plan_n_cls", "jc_plan_n_ell"):
+        for f in ("jc_plan_n_tracers", "jc_plan_n_cls", "jc_plan_n_ell", "jc_plan_n_cosmo_params"):
             getattr(lib, f).argtypes = [vp]
             getattr(lib, f).restype = i32
         lib.jc_workspace_bytes.argtypes = [vp, i64, C.POINTER(C.c_size_t)]
@@ -164,7 +165,7 @@ def _fill_bias(dst, b):
         dst.params[k] = float(v)
 
 
-def build_problem(probes, transfer_fn=None, nonlinear_fn=None):
+def build_problem(probes, transfer_fn=None, nonlinear_fn=None, growth=0):
     """Flatten a list of WeakLensing / NumberCounts probes (reference objects of this package)
     into the C descriptor.  Tracer order = probe order, then bin order (angular_cl.py:15-25)."""
     from jax_cosmo_b200 import power as _power
@@ -213,6 +214,7 @@ def build_problem(probes, transfer_fn=None, nonlinear_fn=None):
     pb.abi_version = JC_ABI_VERSION
     pb.transfer = JC_TF_EH_OSC if ttype == "eisenhu_osc" else JC_TF_EH_NOWIGGLE
     pb.nonlinear = nl
+    pb.growth = int(growth)  # JC_GROWTH_ODE = 0 / JC_GROWTH_GAMMA = 1 (cosmology rows [B, 9])
     t = 0
     for probe in probes:
         if isinstance(probe, WeakLensing):
@@ -292,6 +294,7 @@ class Plan:
         self.T = lib.jc_plan_n_tracers(handle)
         self.P = lib.jc_plan_n_cls(handle)
         self.L = lib.jc_plan_n_ell(handle)
+        self.ncp = lib.jc_plan_n_cosmo_params(handle)  # 8, or 9 with the growth index gamma
         self._ws = None
         self._noise_dev = None
 
@@ -322,12 +325,18 @@ class Plan:
             self._ws = torch.empty(need // 8, dtype=torch.float64, device="cuda:%d" % self.device)
         return self._ws
 
+    def _check_rows(self, rows, what="cosmology rows"):
+        if rows.ndim != 2 or rows.shape[1] != self.ncp:
+            raise ValueError("%s must have shape [n, %d] for this plan (Omega_c, Omega_b, h, n_s, sigma8, Omega_k, "
+                             "w0, wa%s), got %s" % (what, self.ncp, ", gamma" if self.ncp == 9 else "", tuple(rows.shape)))
+
     # -- calls -----------------------------------------------------------------------------------
     def angular_cl_device(self, cosmo_dev, out=None, workspace=None):
         """cosmo_dev: CUDA float64 tensor [B,8] -> CUDA tensor [B,P,L]; async on torch's current stream."""
         import torch
 
         assert cosmo_dev.is_cuda and cosmo_dev.dtype == torch.float64 and cosmo_dev.is_contiguous()
+        self._check_rows(cosmo_dev)
         B = cosmo_dev.shape[0]
         if out is None:
             out = torch.empty((B, self.P, self.L), dtype=torch.float64, device=cosmo_dev.device)
@@ -344,6 +353,8 @@ class Plan:
 
         assert cosmo_dev.is_cuda and cosmo_dev.dtype == torch.float64 and cosmo_dev.is_contiguous()
         assert tangents_dev.is_cuda and tangents_dev.dtype == torch.float64 and tangents_dev.is_contiguous()
+        self._check_rows(cosmo_dev)
+        self._check_rows(tangents_dev, "tangents")
         B, K = cosmo_dev.shape[0], tangents_dev.shape[0]
         need = C.c_size_t()
         check(load_library().jc_workspace_bytes_jvp(self._h, B, C.byref(need)), "jc_workspace_bytes_jvp")
@@ -362,6 +373,7 @@ class Plan:
 
         is_t = isinstance(cosmo_rows, torch.Tensor)
         rows = cosmo_rows if is_t else np.ascontiguousarray(cosmo_rows, dtype=np.float64)
+        self._check_rows(rows)
         B = rows.shape[0]
         if out is None:
             out = (torch.empty((B, self.P, self.L), dtype=torch.float64, pin_memory=True) if is_t
@@ -408,11 +420,11 @@ class Plan:
 _plan_cache = {}
 
 
-def get_plan(probes, ell, transfer_fn=None, nonlinear_fn=None, device=None):
+def get_plan(probes, ell, transfer_fn=None, nonlinear_fn=None, device=None, growth=0):
     """Plans are cached per (problem bytes, ell bytes, device)."""
     import torch
 
-    pb = build_problem(probes, transfer_fn, nonlinear_fn)
+    pb = build_problem(probes, transfer_fn, nonlinear_fn, growth)
     ell = np.ascontiguousarray(np.atleast_1d(np.asarray(ell, dtype=np.float64)))
     dev = (torch.cuda.current_device() if torch.cuda.is_available() else -1) if device is None else int(device)
     masked = jc_problem.from_buffer_copy(bytes(pb))  # key on contents, never on host addresses

@@ -50,23 +50,30 @@ def _rows(cosmo):
     rows = np.ascontiguousarray(np.asarray(cosmo, dtype=np.float64))
     if rows.ndim == 1:
         rows = rows[None, :]
-    if rows.ndim != 2 or rows.shape[1] != 8:
-        raise ValueError("cosmology rows must have shape [B, 8] (Omega_c, Omega_b, h, n_s, sigma8, Omega_k, w0, wa)")
+    if rows.ndim != 2 or rows.shape[1] not in (8, 9):
+        raise ValueError("cosmology rows must have shape [B, 8] (Omega_c, Omega_b, h, n_s, sigma8, Omega_k, w0, wa) "
+                         "or [B, 9] with the growth index gamma appended (core.py:104-105)")
     return rows
+
+
+def _growth(rows):
+    """JC_GROWTH_GAMMA for 9-column rows (a Cosmology built with gamma=...), else the growth ODE."""
+    return 1 if rows.shape[-1] == 9 else 0
 
 
 def angular_cl(cosmo, ell, probes, transfer_fn=tklib.Eisenstein_Hu, nonlinear_fn=power.halofit):
     """Angular C_ell of all tracer pairs in the Limber approximation -> [n_cls, n_ell]
     (the reference's actual output layout, angular_cl.py:66,98)."""
-    plan = _native.get_plan(probes, ell, transfer_fn, nonlinear_fn)
-    return plan.angular_cl_host(_rows(cosmo))[0]
+    rows = _rows(cosmo)
+    plan = _native.get_plan(probes, ell, transfer_fn, nonlinear_fn, growth=_growth(rows))
+    return plan.angular_cl_host(rows)[0]
 
 
 def angular_cl_batch(cosmo_rows, ell, probes, transfer_fn=tklib.Eisenstein_Hu, nonlinear_fn=power.halofit,
                      out=None):
     """Batch of cosmologies [B,8] -> [B, n_cls, n_ell].  CUDA tensors in -> CUDA tensor out
     (stream-ordered, no host sync); host arrays in -> host array out."""
-    plan = _native.get_plan(probes, ell, transfer_fn, nonlinear_fn)
+    plan = _native.get_plan(probes, ell, transfer_fn, nonlinear_fn, growth=_growth(cosmo_rows))
     try:
         import torch
         if isinstance(cosmo_rows, torch.Tensor) and cosmo_rows.is_cuda:
@@ -78,7 +85,7 @@ def angular_cl_batch(cosmo_rows, ell, probes, transfer_fn=tklib.Eisenstein_Hu, n
     return plan.angular_cl_host(_rows(cosmo_rows), out=out)
 
 
-_PARAM_INDEX = {"Omega_c": 0, "Omega_b": 1, "h": 2, "n_s": 3, "sigma8": 4, "Omega_k": 5, "w0": 6, "wa": 7}
+_PARAM_INDEX = {"Omega_c": 0, "Omega_b": 1, "h": 2, "n_s": 3, "sigma8": 4, "Omega_k": 5, "w0": 6, "wa": 7, "gamma": 8}
 WCDM_PARAMS = ("Omega_c", "Omega_b", "h", "n_s", "sigma8", "w0", "wa")  # BASELINE config 4
 
 
@@ -89,12 +96,13 @@ def angular_cl_jvp(cosmo, ell, probes, tangents, transfer_fn=tklib.Eisenstein_Hu
     NumPy arrays (B = 1 for a Cosmology object)."""
     import torch
 
-    plan = _native.get_plan(probes, ell, transfer_fn, nonlinear_fn)
+    rows = _rows(cosmo)
+    plan = _native.get_plan(probes, ell, transfer_fn, nonlinear_fn, growth=_growth(rows))
     dev = "cuda:%d" % plan.device
-    rows = torch.as_tensor(_rows(cosmo), device=dev)
     tang = np.ascontiguousarray(np.atleast_2d(np.asarray(tangents, dtype=np.float64)))
-    if tang.shape[1] != 8:
-        raise ValueError("tangents must have shape [K, 8]")
+    if tang.shape[1] != rows.shape[1]:
+        raise ValueError("tangents must have shape [K, %d]" % rows.shape[1])
+    rows = torch.as_tensor(rows, device=dev)
     cl, dcl = plan.angular_cl_jvp_device(rows, torch.as_tensor(tang, device=dev))
     return cl.cpu().numpy(), dcl.cpu().numpy()
 
@@ -104,9 +112,10 @@ def angular_cl_jacobian(cosmo, ell, probes, params=WCDM_PARAMS, transfer_fn=tkli
     """(cl [n_cls, n_ell], jac [n_params, n_cls, n_ell]): d cl / d theta for the named parameters,
     default the 7 wCDM parameters of BASELINE config 4.  `jac.reshape(n_params, -1).T` is the
     [n_cls*n_ell, n_params] layout of `jax.jacfwd(mean_fn)` (jax-cosmo-intro.ipynb:1039)."""
-    tang = np.zeros((len(params), 8))
+    width = _rows(cosmo).shape[1]
+    tang = np.zeros((len(params), width))
     for k, name in enumerate(params):
-        if name not in _PARAM_INDEX:
+        if name not in _PARAM_INDEX or _PARAM_INDEX[name] >= width:
             raise ValueError("unknown parameter %r" % (name,))
         tang[k, _PARAM_INDEX[name]] = 1.0
     cl, dcl = angular_cl_jvp(cosmo, ell, probes, tang, transfer_fn, nonlinear_fn)
@@ -159,9 +168,10 @@ def gaussian_cl_covariance_and_mean(cosmo, ell, probes, transfer_fn=tklib.Eisens
     import torch
 
     ell = np.atleast_1d(np.asarray(ell, dtype=np.float64))
-    plan = _native.get_plan(probes, ell, transfer_fn, nonlinear_fn)
+    rows = _rows(cosmo)
+    plan = _native.get_plan(probes, ell, transfer_fn, nonlinear_fn, growth=_growth(rows))
     dev = "cuda:%d" % plan.device
-    cl_dev = plan.angular_cl_device(torch.as_tensor(_rows(cosmo), device=dev))
+    cl_dev = plan.angular_cl_device(torch.as_tensor(rows, device=dev))
     cov = plan.gaussian_cov_device(cl_dev, f_sky=f_sky)[0]
     P, L = plan.P, plan.L
     mean = cl_dev[0].reshape(-1).cpu().numpy()

@@ -45,11 +45,12 @@ class Cosmology:
         return cls(gamma=gamma, **kw)
 
     def to_row(self):
-        """[8] float64 row for the C ABI.  gamma-growth (core.py:56-60) is outside the hot path."""
+        """[8] float64 row for the C ABI; [9] with the growth index appended for a gamma-growth
+        cosmology (core.py:56-60,104-105), which selects JC_GROWTH_GAMMA in the plan."""
+        row = [float(getattr(self, "_" + k)) for k in _FIELDS]
         if self._flags["gamma_growth"]:
-            raise NotImplementedError(
-                "gamma-parametrised growth is not on the B200 angular_cl path (no fallback)")
-        return np.array([float(getattr(self, "_" + k)) for k in _FIELDS], dtype=np.float64)
+            row.append(float(self._gamma))
+        return np.array(row, dtype=np.float64)
 
     @property
     def Omega(self):

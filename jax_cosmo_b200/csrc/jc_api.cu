@@ -63,7 +63,7 @@ extern "C" int jc_angular_cl_host_f64(jc_plan* plan, const double* cosmo_host, i
   if (st != JC_OK) return st;
   if ((st = ensure(&plan->arena_ws, &plan->arena_ws_bytes, ws_need)) != JC_OK) return st;
   if ((st = ensure((void**)&plan->arena_cosmo, &plan->arena_cosmo_bytes,
-                   (size_t)n_cosmo * JC_N_COSMO_PARAMS * sizeof(double))) != JC_OK) return st;
+                   (size_t)n_cosmo * plan->d.ncp * sizeof(double))) != JC_OK) return st;
   size_t cl_need = (size_t)chunk * pl_elems * sizeof(double);
   if (plan->arena_cl_bytes < cl_need) {
     for (int i = 0; i < 2; ++i) {
@@ -74,14 +74,14 @@ extern "C" int jc_angular_cl_host_f64(jc_plan* plan, const double* cosmo_host, i
     for (int i = 0; i < 2; ++i) JC_CUDA_TRY(cudaMalloc((void**)&plan->arena_cl[i], cl_need));
     plan->arena_cl_bytes = cl_need;
   }
-  JC_CUDA_TRY(cudaMemcpyAsync(plan->arena_cosmo, cosmo_host, (size_t)n_cosmo * JC_N_COSMO_PARAMS * sizeof(double),
+  JC_CUDA_TRY(cudaMemcpyAsync(plan->arena_cosmo, cosmo_host, (size_t)n_cosmo * plan->d.ncp * sizeof(double),
                               cudaMemcpyHostToDevice, plan->s_compute));
   int k = 0;
   for (int64_t c0 = 0; c0 < n_cosmo; c0 += chunk, ++k) {
     const int b = k & 1;
     const int64_t nc = (n_cosmo - c0) < chunk ? (n_cosmo - c0) : chunk;
     if (k >= 2) JC_CUDA_TRY(cudaStreamWaitEvent(plan->s_compute, plan->ev_copied[b], 0));
-    st = jc_angular_cl_f64(plan, plan->arena_cosmo + c0 * JC_N_COSMO_PARAMS, nc, plan->arena_cl[b],
+    st = jc_angular_cl_f64(plan, plan->arena_cosmo + c0 * plan->d.ncp, nc, plan->arena_cl[b],
                            plan->arena_ws, plan->arena_ws_bytes, plan->s_compute);
     if (st != JC_OK) return st;
     JC_CUDA_TRY(cudaEventRecord(plan->ev_done[b], plan->s_compute));

@@ -65,7 +65,7 @@ extern "C" int jc_angular_cl_jvp_f64(const jc_plan* plan, const double* cosmo_de
   for (int64_t c0 = 0; c0 < n_cosmo; c0 += lo.chunk) {
     const int chunk = (int)((n_cosmo - c0) < lo.chunk ? (n_cosmo - c0) : lo.chunk);
     for (int k = 0; k < n_tangents; ++k) {
-      jc_launch_setup_jvp(pl, cosmo_dev + c0 * JC_N_COSMO_PARAMS, tangents_dev + (size_t)k * JC_N_COSMO_PARAMS, ws, chunk, s);
+      jc_launch_setup_jvp(pl, cosmo_dev + c0 * pl.ncp, tangents_dev + (size_t)k * pl.ncp, ws, chunk, s);
       jc_launch_tracers_jvp(pl, ws, chunk, s);
       jc_launch_finish_jvp(pl, ws, chunk, s);
       jc_launch_power_jvp(pl, ws, chunk, s);
@@ -114,7 +114,7 @@ extern "C" int jc_angular_cl_f64(const jc_plan* plan, const double* cosmo_dev, i
     if (prof && prof->used < JC_PROF_SLOTS) { ev = prof->ev[prof->used]; nl = prof->launches[prof->used]; ++prof->used; }
 #define JC_MARK(i) do { if (ev) cudaEventRecord(ev[i], s); } while (0)
     JC_MARK(0);
-    jc_launch_setup(pl, cosmo_dev + c0 * JC_N_COSMO_PARAMS, ws, chunk, s);
+    jc_launch_setup(pl, cosmo_dev + c0 * pl.ncp, ws, chunk, s);
     JC_MARK(1);
     const int n_lens = jc_launch_tracers(pl, ws, chunk, s);
     JC_MARK(2);

@@ -189,6 +189,7 @@ int validate(const jc_problem* pb, int n_ell) {
   if (n_ell < 1) return JC_ERR_INVALID;
   if (pb->transfer != JC_TF_EISENSTEIN_HU_OSC && pb->transfer != JC_TF_EISENSTEIN_HU_NOWIGGLE) return JC_ERR_UNSUPPORTED;
   if (pb->nonlinear < JC_PK_LINEAR || pb->nonlinear > JC_PK_HALOFIT_SMITH2003) return JC_ERR_UNSUPPORTED;
+  if (pb->growth != JC_GROWTH_ODE && pb->growth != JC_GROWTH_GAMMA) return JC_ERR_UNSUPPORTED;
   double lens_zmax = -1.0;
   for (int t = 0; t < pb->n_tracers; ++t) {
     const jc_tracer& tr = pb->tracers[t];
@@ -271,6 +272,7 @@ extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int3
   JcDevPlan d;
   memset(&d, 0, sizeof(d));
   d.T = T; d.P = P; d.L = L; d.Lpad = (L + 3) & ~3; d.nonlinear = pb->nonlinear; d.transfer = pb->transfer;
+  d.growth = pb->growth; d.ncp = JC_N_COSMO_PARAMS + (pb->growth == JC_GROWTH_GAMMA ? 1 : 0);
   d.TS = T;  // bank-conflict-free A-fragment gathers in the contraction kernel need TS = 4 or 12 (mod 16)
   while (d.TS % 16 != 4 && d.TS % 16 != 12) ++d.TS;
   d.n_src = n_src; d.zmax = zmax; d.lens_zmax = lens_zmax;
@@ -300,11 +302,21 @@ extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int3
   for (int i = 0; i < JC_NGROW; ++i) ag[i] = std::pow(10.0, e128[i]);
   std::vector<double> gr_pt_a(255), gr_pt_lna(255), gr_h(127);
   for (int i = 0; i < JC_NGROW; ++i) gr_pt_a[2 * i] = ag[i];
-  for (int i = 0; i < JC_NGROW - 1; ++i) {
-    gr_h[i] = ag[i + 1] - ag[i];
-    gr_pt_a[2 * i + 1] = ag[i] + gr_h[i] / 2;
+  if (pb->growth == JC_GROWTH_GAMMA) {
+    // odeint over t = log(atab) (background.py:536-542): steps and midpoints in ln a, xa = exp(loga)
+    for (int i = 0; i < JC_NGROW; ++i) { gr_pt_lna[2 * i] = std::log(ag[i]); gr_pt_a[2 * i] = std::exp(gr_pt_lna[2 * i]); }
+    for (int i = 0; i < JC_NGROW - 1; ++i) {
+      gr_h[i] = gr_pt_lna[2 * i + 2] - gr_pt_lna[2 * i];
+      gr_pt_lna[2 * i + 1] = gr_pt_lna[2 * i] + gr_h[i] / 2;
+      gr_pt_a[2 * i + 1] = std::exp(gr_pt_lna[2 * i + 1]);
+    }
+  } else {
+    for (int i = 0; i < JC_NGROW - 1; ++i) {
+      gr_h[i] = ag[i + 1] - ag[i];
+      gr_pt_a[2 * i + 1] = ag[i] + gr_h[i] / 2;
+    }
+    for (int i = 0; i < 255; ++i) gr_pt_lna[i] = std::log(gr_pt_a[i]);
   }
-  for (int i = 0; i < 255; ++i) gr_pt_lna[i] = std::log(gr_pt_a[i]);
   // ---- Limber nodes ---------------------------------------------------------------------------
   double amin = 1.0 / (1.0 + zmax);  // z2a(zmax), utils.py:2-4
   std::vector<double> la = linspace(amin, 1.0, JC_NA), llna(JC_NA), lz(JC_NA);
@@ -511,6 +523,7 @@ extern "C" void jc_plan_destroy(jc_plan* plan) {
 extern "C" int32_t jc_plan_n_tracers(const jc_plan* plan) { return plan ? plan->d.T : 0; }
 extern "C" int32_t jc_plan_n_cls(const jc_plan* plan) { return plan ? plan->d.P : 0; }
 extern "C" int32_t jc_plan_n_ell(const jc_plan* plan) { return plan ? plan->d.L : 0; }
+extern "C" int32_t jc_plan_n_cosmo_params(const jc_plan* plan) { return plan ? plan->d.ncp : 0; }
 
 extern "C" int jc_noise_f64(const jc_plan* plan, double* noise_host) {
   if (!plan || !noise_host) return JC_ERR_INVALID;

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
   auto put = [&](double* p, T x) { JxMem<T>::st(p, doff, x); };
   auto node = [&](int field, int n) { return node_ptr(ws, c, field) + n; };
 
-  const double* cp = cosmo + (size_t)c * JC_N_COSMO_PARAMS;
+  const double* cp = cosmo + (size_t)c * pl.ncp;
   T par[JC_N_COSMO_PARAMS];
 #pragma unroll
   for (int i = 0; i < JC_N_COSMO_PARAMS; ++i) {
@@ -97,6 +97,11 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
     if constexpr (sizeof(T) != sizeof(double)) par[i].d = tangent[i];
   }
   const T Oc = par[0], Ob = par[1], h = par[2], ns = par[3], s8 = par[4], Ok = par[5], w0 = par[6], wa = par[7];
+  T gam = T(0.0);  // growth index (core.py:104-105), JC_GROWTH_GAMMA rows only
+  if (pl.growth == JC_GROWTH_GAMMA) {
+    gam = T(cp[JC_N_COSMO_PARAMS]);
+    if constexpr (sizeof(T) != sizeof(double)) gam.d = tangent[JC_N_COSMO_PARAMS];
+  }
   Bg<T> bg;
   bg.Om = Ob + Oc;                 // core.py:144-146
   bg.Ok = Ok;
@@ -186,9 +191,26 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
     const T ode = de / e2;                      // background.py:196
     const T w = w0 + (1.0 - a) * wa;            // background.py:52
     S.gr_q[tid] = (2.0 - 0.5 * (om + (1.0 + 3.0 * w) * ode)) / a;  // background.py:467-475
-    S.gr_r[tid] = 1.5 * om / a / a;
+    S.gr_r[tid] = pl.growth == JC_GROWTH_GAMMA ? jx_pow(om, gam) : 1.5 * om / a / a;  // background.py:582
   }
   __syncthreads();
+  if (pl.growth == JC_GROWTH_GAMMA) {
+    // ln D by RK4 on a y-independent rhs f(ln a) = Omega_m(a)^gamma (background.py:538-542): per step
+    // h/6 (k1 + 2 k2 + 2 k3 + k4) with k2 = k3 at the ln-a midpoint; y0 = ln a_0
+    if (tid < 127) {
+      const T k1 = S.gr_r[2 * tid], k2 = S.gr_r[2 * tid + 1], k4 = S.gr_r[2 * tid + 2];
+      S.M[tid] = (1.0 / 6.0 * pl.gr_h[tid]) * (k1 + 2.0 * k2 + 2.0 * k2 + k4);  // scipy/ode.py:19
+    }
+    __syncthreads();
+    if (tid == 0) {
+      T y = T(pl.gr_pt_lna[0]);
+      S.gtab[0] = jx_exp(y);
+      for (int n = 0; n < 127; ++n) {
+        y = y + S.M[n];
+        S.gtab[n + 1] = jx_exp(y);
+      }
+    }
+  } else {
   if (tid < 127) {
     const double hh = pl.gr_h[tid];
     const M2<T> A0 = {T(0.0), T(1.0), S.gr_r[2 * tid], -S.gr_q[2 * tid]};
@@ -215,6 +237,7 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
       S.gtab[n + 1] = y0;
     }
   }
+  }  // growth ODE
   __syncthreads();
   if (tid < 128) {
     const T g = S.gtab[tid] / S.gtab[127];  // background.py:480

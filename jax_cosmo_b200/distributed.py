@@ -20,7 +20,7 @@ def angular_cl_sharded(cosmo_rows, ell, probes, transfer_fn=None, nonlinear_fn=N
                        gather=False, compute=None):
     """Compute C_ell for the rows owned by this rank.
 
-    cosmo_rows : [B, 8] array, identical on every rank (cheap: 64 B per cosmology).
+    cosmo_rows : [B, 8] array ([B, 9] with the growth index gamma), identical on every rank (cheap: 64 B per cosmology).
     gather     : all-gather the blocks so that every rank returns the full [B, P, L] tensor.
     compute    : callable(rows_shard) -> [n, P, L] tensor; defaults to the CUDA path
                  (`angular_cl_batch` on this rank's device).  Injected by the CPU (gloo) tests.
@@ -33,8 +33,8 @@ def angular_cl_sharded(cosmo_rows, ell, probes, transfer_fn=None, nonlinear_fn=N
     from jax_cosmo_b200.angular_cl import angular_cl_batch
 
     rows = np.ascontiguousarray(np.asarray(cosmo_rows, dtype=np.float64))
-    if rows.ndim != 2 or rows.shape[1] != 8:
-        raise ValueError("cosmo_rows must have shape [B, 8]")
+    if rows.ndim != 2 or rows.shape[1] not in (8, 9):
+        raise ValueError("cosmo_rows must have shape [B, 8] (or [B, 9] with gamma)")
     distributed = dist.is_available() and dist.is_initialized()
     world = dist.get_world_size(group) if distributed else 1
     rank = dist.get_rank(group) if distributed else 0

@@ -114,11 +114,13 @@ def interp_fast(x, xp, fp):
 # background.py
 # ----------------------------------------------------------------------------------------------
 class Cosmo:
-    """[8] row in tree_flatten order (core.py:99-108) + derived Omega_m, Omega_de (core.py:144-162)."""
+    """[8] row in tree_flatten order (core.py:99-108) + derived Omega_m, Omega_de (core.py:144-162);
+    a 9th entry is the growth index gamma of a gamma-growth cosmology (core.py:56-60,104-105)."""
 
     def __init__(self, row):
         (self.Omega_c, self.Omega_b, self.h, self.n_s, self.sigma8, self.Omega_k, self.w0,
-         self.wa) = [float(v) for v in row]
+         self.wa) = [float(v) for v in row[:8]]
+        self.gamma = float(row[8]) if len(row) > 8 else None
         self.Omega_m = self.Omega_b + self.Omega_c
         self.Omega_de = (1.0 - self.Omega_k) - self.Omega_m
 
@@ -164,8 +166,29 @@ def chi_table(c):
     return atab, cum[-1] - cum
 
 
+def growth_table_gamma(c):
+    """background.py:515-548,582: ln D by RK4 over t = log(atab) of f = Omega_m(a)^gamma (y-independent
+    rhs, so each step is h/6 (k1 + 2 k2 + 2 k3 + k4) with k2 = k3), y0 = log(atab[0]); D = exp(y) / exp(y)[-1]."""
+    atab = np.logspace(-3, 0.0, N_GROWTH)
+    t = np.log(atab)
+    h = t[1:] - t[:-1]
+
+    def f(loga):
+        return Omega_m_a(c, np.exp(loga)) ** c.gamma
+
+    k1, k2, k4 = f(t[:-1]), f(t[:-1] + h / 2), f(t[1:])
+    inc = 1.0 / 6.0 * h * (k1 + 2 * k2 + 2 * k2 + k4)
+    y = [t[0]]
+    for n in range(N_GROWTH - 1):
+        y.append(y[-1] + inc[n])
+    g = np.exp(np.array(y))
+    return atab, g / g[-1]
+
+
 def growth_table(c):
     """background.py:461-481: RK4 in a over logspace(-3,0,128) of y=(D,D'), y0=(a0,1)."""
+    if getattr(c, "gamma", None) is not None:
+        return growth_table_gamma(c)
     atab = np.logspace(-3, 0.0, N_GROWTH)
 
     def A(x):

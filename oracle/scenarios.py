@@ -26,8 +26,12 @@ COSMO_KEYS = ("Omega_c", "Omega_b", "h", "n_s", "sigma8", "Omega_k", "w0", "wa")
 
 
 def cosmo_row(c):
-    """dict -> [8] array in the reference's tree_flatten order (core.py:99-108)."""
-    return np.array([c[k] for k in COSMO_KEYS], dtype=np.float64)
+    """dict -> [8] array in the reference's tree_flatten order (core.py:99-108); [9] with the growth
+    index appended for a gamma-growth cosmology (core.py:104-105)."""
+    row = [c[k] for k in COSMO_KEYS]
+    if c.get("gamma") is not None:
+        row.append(c["gamma"])
+    return np.array(row, dtype=np.float64)
 
 
 def config5_cosmologies(B, seed=20240607):
@@ -159,6 +163,11 @@ def golden_scenarios():
     S.append(scenario("switch_smith2003", open_wcdm, [20.0, 200.0, 2000.0], sw, prescription="smith2003"))
     S.append(scenario("switch_nowiggle", WCDM, [20.0, 200.0, 2000.0], sw, transfer="eisenhu"))
     S.append(scenario("switch_nowiggle_smith_linear", open_wcdm, [50.0, 500.0], sw, "linear", transfer="eisenhu"))
+    # gamma-parametrised growth, Cosmology(..., gamma=...) (core.py:56-60, background.py:515-582): D(a) enters
+    # P_lin, halofit, the NLA kernel and inverse_growth_linear_bias
+    swg = [wl([nz1, nz2], ia=bias("des_y1_ia", 0.5, 0.0, 0.62)), nc([nz2, nz1], [bias("constant", 1.2), bias("inverse_growth", 1.1)])]
+    S.append(scenario("switch_gamma_growth", dict(WCDM, gamma=0.55), [20.0, 200.0, 2000.0], swg))
+    S.append(scenario("switch_gamma_growth_open_linear", dict(open_wcdm, gamma=0.68), [50.0, 500.0], swg, "linear"))
     return S
 
 

@@ -274,6 +274,30 @@ def test_jvp_config4(jc, torch_cuda, variant):
         assert relerr(jac[4], 2.0 * cl / row[4]) < 1e-12
 
 
+def test_jvp_gamma_growth(jc, torch_cuda):
+    """Cosmology(..., gamma=...): 9-column rows; d/d(Omega_c, sigma8, w0, gamma) against the FD oracle."""
+    from oracle import derivatives as od
+    scn = [s for s in sc.golden_scenarios() if s["name"] == "switch_gamma_growth"][0]
+    probes = sc.build_probes(scn, jc)
+    tf, nl = sc.build_fns(scn, jc)
+    cosmo = sc.build_cosmo(scn, jc)
+    row = sc.cosmo_row(scn["cosmo"])
+    assert row.shape == (9,)
+    params = ("Omega_c", "sigma8", "w0", "gamma")
+    ell = sc.ELL_CFG2[::12]
+    cl, jac = jc.cl.angular_cl_jacobian(cosmo, ell, probes, params=params, transfer_fn=tf, nonlinear_fn=nl)
+    cl_ref, jac_ref, _ = od.fd_jacobian(row, ell, sc.flatten_spec(scn), params=params)
+    assert relerr(cl, cl_ref) < RTOL
+    scale = np.abs(jac_ref).max(axis=2, keepdims=True)
+    worst = (np.abs(jac - jac_ref) / scale).reshape(len(params), -1).max(axis=1)
+    print("gamma growth: max |dC - FD| / max|dC| per parameter:", " ".join("%s=%.1e" % kv for kv in zip(params, worst)))
+    assert worst.max() < 1e-6, worst
+    assert np.abs(jac[3]).max() > 0  # the growth index moves every spectrum
+    # 8-column rows on a gamma plan (and the reverse) are rejected before anything is launched
+    with pytest.raises(ValueError):
+        jc.cl.angular_cl_jvp(cosmo, ell, probes, np.zeros((1, 8)), transfer_fn=tf, nonlinear_fn=nl)
+
+
 def test_jvp_batch(jc, torch_cuda):
     """JVP on a batch: every row equals its single-cosmology call; Fisher-style layout check."""
     torch = torch_cuda

@@ -30,7 +30,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_native.jc_nz) == 8 + 8 * (4 + 4 + 2) + 4 * 8
     assert C.sizeof(_native.jc_bias) == 8 + 24
     assert C.sizeof(_native.jc_tracer) == 8 + C.sizeof(_native.jc_nz) + C.sizeof(_native.jc_bias) + 24
-    assert C.sizeof(_native.jc_problem) == 16 + 32 * C.sizeof(_native.jc_tracer)
+    assert C.sizeof(_native.jc_problem) == 24 + 32 * C.sizeof(_native.jc_tracer)  # 6 int32 header (ABI 2)
     assert C.sizeof(_native.jc_ws_layout) == 13 * 8
 
 
@@ -105,8 +105,10 @@ def test_unsupported_options_raise(jc):
     pc = _native.build_problem([jc.probes.WeakLensing([jc.redshift.kde_nz(z1 + 0.1, w1, bw=0.1)])])
     assert pa.tracers[0].nz.family == 4 and pa.tracers[0].nz.kde_n == 3 and pa.tracers[0].nz.kde_bw == 0.1
     assert pa._content_key == pb_._content_key != pc._content_key
-    with pytest.raises(NotImplementedError):
-        jc.Cosmology(0.3, 0.05, 0.7, 0.96, 0.8, 0.0, -1.0, 0.0, gamma=0.55).to_row()
+    # gamma-growth cosmologies carry a 9th column and select JC_GROWTH_GAMMA (core.py:56-60,104-105)
+    row9 = jc.Cosmology(0.3, 0.05, 0.7, 0.96, 0.8, 0.0, -1.0, 0.0, gamma=0.55).to_row()
+    assert row9.shape == (9,) and row9[8] == 0.55
+    assert _native.build_problem([wl], growth=1).growth == 1 and _native.build_problem([wl]).growth == 0
     with pytest.raises(NotImplementedError):
         jc.power.halofit(None, None, None, None)
     with pytest.raises(ValueError):
