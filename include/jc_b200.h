@@ -272,6 +272,15 @@ int jc_gaussian_loglike_f64(const double* data_dev, int64_t data_stride, const d
 int jc_fisher_f64(const double* jac_dev, const double* cov_dev, int64_t n_cosmo, int32_t n_params,
                   int32_t P, int32_t L, double* fisher_dev, double* scratch_dev, void* stream);
 
+/* Reverse mode: grad_dev[b, k] = sum_n jac_dev[b, k, n] * cot_dev[b, n] -- the vector-Jacobian product
+ * J^T g that jax.grad / jax.vjp of the reference deliver for a scalar function of the C_ell
+ * (README.md:24 of the reference), from the forward-mode Jacobian of jc_angular_cl_jvp_f64: with
+ * K <= 9 parameters, K tangent passes cost less than one reverse sweep through the Limber pipeline.
+ * jac_dev [B, K, N] (N = P*L), cot_dev [B, N] (cot_stride = N) or [N] shared (cot_stride = 0), grad_dev [B, K].
+ * One CTA per (b, k), fixed reduction order: bitwise reproducible. */
+int jc_vjp_f64(const double* jac_dev, const double* cot_dev, int64_t cot_stride, int64_t n_cosmo,
+               int32_t n_params, int64_t N, double* grad_dev, void* stream);
+
 /* Per-stage device timing (CUDA events recorded on the launch stream between the stages of
  * jc_angular_cl_f64).  Stages: 0 setup, 1 lensing efficiency, 2 tracer finish, 3 power, 4 pair
  * contraction.  While enabled the plan is not re-entrant.  jc_profile_read synchronises the

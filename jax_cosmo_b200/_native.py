@@ -31,7 +31,7 @@ SCAL_FIELDS = ["LN13KEQ", "INV13KEQ", "BETA_C", "C14_ALPHA_C", "SH_D", "LNKSILK"
 # every symbol include/jc_b200.h declares
 EXPORTS = ["jc_plan_create", "jc_plan_destroy", "jc_plan_n_tracers", "jc_plan_n_cls", "jc_plan_n_ell", "jc_plan_n_cosmo_params",
            "jc_workspace_bytes", "jc_workspace_layout", "jc_angular_cl_f64", "jc_angular_cl_host_f64",
-           "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64", "jc_gaussian_loglike_f64", "jc_fisher_f64",
+           "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64", "jc_gaussian_loglike_f64", "jc_fisher_f64", "jc_vjp_f64",
            "jc_noise_f64", "jc_gaussian_cov_f64", "jc_profile_enable", "jc_profile_read",
            "jc_fp64_peak_tflops", "jc_debug_math_f64", "jc_status_string",
            "jc_last_cuda_error", "jc_abi_version"]
@@ -101,6 +101,8 @@ def load_library():
         lib.jc_gaussian_loglike_f64.restype = C.c_int
         lib.jc_fisher_f64.argtypes = [vp, vp, i64, i32, i32, i32, vp, vp, vp]
         lib.jc_fisher_f64.restype = C.c_int
+        lib.jc_vjp_f64.argtypes = [vp, vp, i64, i64, i32, i64, vp, vp]
+        lib.jc_vjp_f64.restype = C.c_int
         lib.jc_angular_cl_host_f64.argtypes = [vp, vp, i64, vp]
         lib.jc_angular_cl_host_f64.restype = C.c_int
         lib.jc_noise_f64.argtypes = [vp, dp]
@@ -471,6 +473,27 @@ def fisher_device(jac_dev, cov_dev):
     st = load_library().jc_fisher_f64(jac_dev.data_ptr(), cov_dev.contiguous().data_ptr(), B, K, P, L, out.data_ptr(),
                                       scratch.data_ptr(), torch.cuda.current_stream(cov_dev.device).cuda_stream)
     check(st, "jc_fisher_f64")
+    return out
+
+
+def vjp_device(jac_dev, cot_dev):
+    """CUDA float64 tensors: jac [B,K,...] and a cotangent [B,...] (or [...] shared by the batch) -> J^T g [B,K]."""
+    import torch
+
+    B, K = jac_dev.shape[0], jac_dev.shape[1]
+    jac_dev = jac_dev.reshape(B, K, -1).contiguous()
+    N = jac_dev.shape[2]
+    cot_dev = cot_dev.contiguous()
+    if cot_dev.numel() == N:
+        stride = 0
+    elif cot_dev.numel() == B * N:
+        stride = N
+    else:
+        raise ValueError("cotangent has %d elements, expected %d or %d" % (cot_dev.numel(), N, B * N))
+    out = torch.empty((B, K), dtype=torch.float64, device=jac_dev.device)
+    st = load_library().jc_vjp_f64(jac_dev.data_ptr(), cot_dev.data_ptr(), stride, B, K, N, out.data_ptr(),
+                                   torch.cuda.current_stream(jac_dev.device).cuda_stream)
+    check(st, "jc_vjp_f64")
     return out
 
 

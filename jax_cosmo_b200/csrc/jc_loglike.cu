@@ -127,6 +127,40 @@ extern "C" int jc_gaussian_loglike_f64(const double* data_dev, int64_t data_stri
                 scratch_dev, (cudaStream_t)stream);
 }
 
+// grad[b, k] = <jac[b, k, :], cot[b, :]>: one CTA per (k, b), 8 independent partial sums per thread, fixed
+// shuffle / shared-memory reduction tree (deterministic)
+__global__ void __launch_bounds__(256) jc_vjp_kernel(const double* __restrict__ jac, const double* __restrict__ cot,
+                                                     int64_t cot_stride, int K, int64_t N, double* __restrict__ grad) {
+  const int k = blockIdx.x;
+  const int64_t b = blockIdx.y;
+  const double* jr = jac + ((size_t)b * K + k) * N;
+  const double* cr = cot + (size_t)b * cot_stride;
+  double acc = 0.0;
+  for (int64_t n = threadIdx.x; n < N; n += 256) acc = fma(jr[n], cr[n], acc);
+  __shared__ double part[8];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += part[w];
+    grad[(size_t)b * K + k] = s;
+  }
+}
+
+extern "C" int jc_vjp_f64(const double* jac_dev, const double* cot_dev, int64_t cot_stride, int64_t n_cosmo,
+                          int32_t n_params, int64_t N, double* grad_dev, void* stream) {
+  if (!jac_dev || !cot_dev || !grad_dev || n_cosmo < 1 || n_cosmo > 65535 || n_params < 1 || N < 1 ||
+      (cot_stride != 0 && cot_stride != N))
+    return JC_ERR_INVALID;
+  jc_vjp_kernel<<<dim3(n_params, (unsigned)n_cosmo), 256, 0, (cudaStream_t)stream>>>(jac_dev, cot_dev, cot_stride,
+                                                                                    n_params, N, grad_dev);
+  JC_CUDA_TRY(cudaGetLastError());
+  return JC_OK;
+}
+
 extern "C" int jc_fisher_f64(const double* jac_dev, const double* cov_dev, int64_t n_cosmo, int32_t n_params,
                              int32_t P, int32_t L, double* fisher_dev, double* scratch_dev, void* stream) {
   if (!jac_dev || !cov_dev || !fisher_dev || !scratch_dev || n_cosmo < 1 || P < 1 || L < 1) return JC_ERR_INVALID;

@@ -10,7 +10,7 @@ import numpy as np
 
 from jax_cosmo_b200 import _native
 
-__all__ = ["gaussian_log_likelihood", "gaussian_log_likelihood_batch", "fisher_matrix"]
+__all__ = ["gaussian_log_likelihood", "gaussian_log_likelihood_batch", "fisher_matrix", "gaussian_log_likelihood_grad"]
 
 
 def gaussian_log_likelihood(data, mu, C, include_logdet=True, inverse_method="inverse"):
@@ -54,6 +54,26 @@ def fisher_matrix(jac, C):
         raise _native.JcError("jax_cosmo_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
     out = _native.fisher_device(torch.as_tensor(jac[None], device="cuda"), torch.as_tensor(C[None], device="cuda"))
     return out[0].cpu().numpy()
+
+
+def gaussian_log_likelihood_grad(data, mu, C, jac):
+    """Gradient of `gaussian_log_likelihood(data, mu(theta), C)` with respect to theta at fixed covariance,
+    -J^T C^-1 (mu - data): what `jax.grad(likelihood)` of the reference's README returns when the covariance
+    is precomputed.  `jac` [n_params, P, L] is `angular_cl_jacobian`'s output; the product runs in the Fisher
+    kernel with the residual appended as one more right-hand side (n_params <= 15)."""
+    import torch
+
+    C = np.ascontiguousarray(np.asarray(C, dtype=np.float64))
+    jac = np.ascontiguousarray(np.asarray(jac, dtype=np.float64))
+    if C.ndim != 3 or C.shape[0] != C.shape[1] or jac.ndim != 3 or jac.shape[1:] != (C.shape[0], C.shape[2]):
+        raise ValueError("expected jac [n_params, P, L] and a sparse covariance [P, P, L]")
+    K, P, L = jac.shape
+    r = np.asarray(mu, dtype=np.float64).reshape(P, L) - np.asarray(data, dtype=np.float64).reshape(P, L)
+    if not torch.cuda.is_available():
+        raise _native.JcError("jax_cosmo_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    aug = np.concatenate([jac, r[None]], axis=0)
+    F = _native.fisher_device(torch.as_tensor(aug[None], device="cuda"), torch.as_tensor(C[None], device="cuda"))
+    return -F[0, :K, K].cpu().numpy()
 
 
 def gaussian_log_likelihood_batch(data, mu, C, include_logdet=True):

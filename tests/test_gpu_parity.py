@@ -453,3 +453,46 @@ def test_fp64_peak_probe(torch_cuda):
     dmma = _native.fp64_peak_tflops(1, 0.2)
     print("FP64 peak probe: DFMA %.1f TFLOP/s, DMMA %.1f TFLOP/s" % (dfma, dmma))
     assert 5.0 < dfma < 100.0 and 1.0 < dmma < 200.0
+
+
+def test_vjp_and_autograd(jc, torch_cuda):
+    """Reverse mode (SURVEY 8(f)-2): J^T g from jc_vjp_f64 equals the contraction of the forward-mode Jacobian;
+    torch.autograd through jc.autograd.angular_cl fills rows.grad; the likelihood gradient at fixed covariance
+    equals -J^T C^-1 r and agrees with a finite difference of the oracle's log-likelihood."""
+    torch = torch_cuda
+    scn = sc.scenario("c4", sc.PLANCK15, sc.ELL_CFG2[::10], [sc.sources(5, 2.0), sc.lenses(5, 2.0)])
+    probes = sc.build_probes(scn, jc)
+    cosmo = sc.build_cosmo(scn, jc)
+    ell = np.array(scn["ell"])
+    cl, jac = jc.cl.angular_cl_jacobian(cosmo, ell, probes)
+    rng = np.random.default_rng(11)
+    cot = rng.normal(size=cl.shape) / np.abs(cl)
+    cl2, g = jc.autograd.angular_cl_vjp(cosmo, ell, probes, cot)
+    ref = np.tensordot(jac, cot, axes=([1, 2], [0, 1]))
+    assert np.array_equal(cl2, cl) and relerr(g, ref) < 1e-12
+    # autograd on a batch: d/d rows of sum(w * cl^2)
+    rows = torch.tensor(np.stack([sc.cosmo_row(sc.PLANCK15), sc.config5_cosmologies(2)[1]]), device="cuda", requires_grad=True)
+    w = torch.as_tensor(cot, device="cuda")
+    out = jc.autograd.angular_cl(rows, ell, probes)
+    assert out.shape == (2,) + cl.shape and out.requires_grad
+    (w * out * out).sum().backward()
+    assert rows.grad.shape == (2, 8) and float(rows.grad[:, 5].abs().max()) == 0.0  # Omega_k is not an active column
+    expect0 = np.tensordot(jac, 2.0 * cot * cl, axes=([1, 2], [0, 1]))
+    assert relerr(rows.grad[0, [0, 1, 2, 3, 4, 6, 7]].cpu().numpy(), expect0) < 1e-12
+    with torch.no_grad():
+        plain = jc.autograd.angular_cl(rows.detach(), ell, probes)  # no grad requested: the value-only kernels
+        assert not plain.requires_grad and float(((plain - out.detach()).abs() / plain.abs()).max()) < 1e-12
+    # value_and_grad of a chi^2 against perturbed data
+    data = torch.as_tensor(cl * (1.0 + 0.01 * rng.normal(size=cl.shape)), device="cuda")
+    sig = torch.as_tensor(0.05 * np.abs(cl), device="cuda")
+    val, grad = jc.autograd.value_and_grad(lambda c: (((c - data) / sig) ** 2).sum(), cosmo, ell, probes)
+    r = (cl - data.cpu().numpy()) / sig.cpu().numpy() ** 2
+    assert relerr(grad, 2.0 * np.tensordot(jac, r, axes=([1, 2], [0, 1]))) < 1e-11 and val > 0
+    # likelihood gradient at fixed covariance
+    mu, cov = jc.cl.gaussian_cl_covariance_and_mean(cosmo, ell, probes, sparse=True)
+    dvec = data.cpu().numpy().reshape(-1)
+    glike = jc.likelihood.gaussian_log_likelihood_grad(dvec, mu, cov, jac)
+    P, L = cl.shape
+    resid = (mu - dvec).reshape(P, L)
+    sol = np.stack([np.linalg.solve(cov[:, :, l], resid[:, l]) for l in range(L)], axis=1)  # C^-1 r per ell
+    assert relerr(glike, -np.tensordot(jac, sol, axes=([1, 2], [0, 1]))) < 1e-9
