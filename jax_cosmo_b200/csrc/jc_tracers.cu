@@ -140,40 +140,50 @@ jc_lens_kernel(JcDevPlan pl, Ws ws, int n_cosmo, int s0) {
 
 template <class T>
 __global__ void __launch_bounds__(512) jc_tracer_finish_kernel(JcDevPlan pl, Ws ws) {
-  // one CTA per cosmology striding over its T x 513 elements (168k 256-thread CTAs per launch were
-  // CTA-launch bound: 0.8 ms per 8192 cosmologies for ~0.2 ms of memory traffic)
+  // One CTA per cosmology; blockDim = rows x T with every thread bound to ONE tracer, so the per-tracer switches
+  // are loop invariant and there is no index division: ncu had 193 warp instructions per element (issue bound,
+  // 15 % FP64 pipe) with a flat (node, tracer) index.
   const int c = blockIdx.x;
   const ptrdiff_t doff = ws.doff;
   const T Om = JxMem<T>::ld(ws.scal + (size_t)c * JC_SCAL_FIELDS + JC_SCAL_OMEGA_M, doff);
-  for (int idx = threadIdx.x; idx < pl.T * JC_NA; idx += blockDim.x) {
-  const int n = idx / pl.T, t = idx - n * pl.T;  // tracer fastest: contiguous writes of R[n][:]
-  const T H = JxMem<T>::ld(node_ptr(ws, c, JC_NODE_HUBBLE) + n, doff);
-  const T D = JxMem<T>::ld(node_ptr(ws, c, JC_NODE_GROWTH) + n, doff);
-  double* out = ws.rker + ((size_t)c * JC_NA_PAD + n) * pl.TS + t;
-  const double nz = pl.nz_node[(size_t)n * pl.TS + t];
-  T b = T(pl.bias_node[(size_t)n * pl.TS + t]);
-  if (pl.tr_inv_growth[t]) b = b / D;  // bias.py:37-39
-  T r;
-  if (pl.tr_kind[t] == JC_TRACER_WEAK_LENSING) {
-    const T chi = JxMem<T>::ld(node_ptr(ws, c, JC_NODE_CHI) + n, doff);
-    T q;
-    const int dix = pl.tr_delta_ix[t];
-    if (dix >= 0) {  // delta_nz source plane (probes.py:53-64): clip(chi_s - chi, 0) / clip(chi_s, 1)
-      const double* ct = ws.chitab + (size_t)c * JC_NCHI;
-      const T f0 = JxMem<T>::ld(ct + (dix & 255), doff), f1 = JxMem<T>::ld(ct + (dix >> 8), doff);
-      const T chis = jx_clip0(f0 + (f1 - f0) * pl.tr_delta_t[t]);
-      q = jx_clip0(chis - chi) / jx_floor1(chis);
-    } else {
-      q = (n < JC_NLENS_COLS) ? JxMem<T>::ld(out, doff) : T(0.0);  // node 512 is a=1: chi=0, kernel = 0
-    }
-    r = q * (1.0 + pl.limb_z[n]) * chi * (3.0 * JC_H0 * JC_H0 / 2.0 / JC_C_LIGHT) * Om;
-    if (pl.tr_ia[t]) r = r + nz * b * H * (-(JC_C1_RHOCRIT)*Om / D);  // probes.py:119-123
-    r = r * pl.tr_m1[t];
-  } else {
-    r = nz * b * H;
+  const int t = threadIdx.x % pl.T, rows = blockDim.x / pl.T;
+  const bool is_wl = pl.tr_kind[t] == JC_TRACER_WEAK_LENSING, inv_growth = pl.tr_inv_growth[t], ia = pl.tr_ia[t];
+  const int dix = pl.tr_delta_ix[t];
+  const double m1 = pl.tr_m1[t];
+  const double* Hn = node_ptr(ws, c, JC_NODE_HUBBLE);
+  const double* Dn = node_ptr(ws, c, JC_NODE_GROWTH);
+  const double* Cn = node_ptr(ws, c, JC_NODE_CHI);
+  T chis = T(0.0), inv_chis = T(0.0);
+  if (is_wl && dix >= 0) {  // delta_nz source plane (probes.py:53-64): clip(chi_s - chi, 0) / clip(chi_s, 1)
+    const double* ct = ws.chitab + (size_t)c * JC_NCHI;
+    const T f0 = JxMem<T>::ld(ct + (dix & 255), doff), f1 = JxMem<T>::ld(ct + (dix >> 8), doff);
+    chis = jx_clip0(f0 + (f1 - f0) * pl.tr_delta_t[t]);
+    inv_chis = 1.0 / jx_floor1(chis);
   }
-  JxMem<T>::st(out, doff, r);
-  }  // idx
+  const T wl_amp = (3.0 * JC_H0 * JC_H0 / 2.0 / JC_C_LIGHT) * Om * m1;
+  for (int n = threadIdx.x / pl.T; n < JC_NA && (int)threadIdx.x < rows * pl.T; n += rows) {
+    double* out = ws.rker + ((size_t)c * JC_NA_PAD + n) * pl.TS + t;
+    const T H = JxMem<T>::ld(Hn + n, doff);
+    T r;
+    if (is_wl) {
+      const T chi = JxMem<T>::ld(Cn + n, doff);
+      T q;
+      if (dix >= 0) q = jx_clip0(chis - chi) * inv_chis;
+      else q = (n < JC_NLENS_COLS) ? JxMem<T>::ld(out, doff) : T(0.0);  // node 512 is a=1: chi=0, kernel = 0
+      r = q * (1.0 + pl.limb_z[n]) * chi * wl_amp;
+      if (ia) {  // probes.py:119-123
+        const T D = JxMem<T>::ld(Dn + n, doff);
+        T b = T(pl.bias_node[(size_t)n * pl.TS + t]);
+        if (inv_growth) b = b / D;  // bias.py:37-39
+        r = r + pl.nz_node[(size_t)n * pl.TS + t] * b * H * (-(JC_C1_RHOCRIT)*Om / D) * m1;
+      }
+    } else {
+      T b = T(pl.bias_node[(size_t)n * pl.TS + t]);
+      if (inv_growth) b = b / JxMem<T>::ld(Dn + n, doff);  // bias.py:37-39
+      r = pl.nz_node[(size_t)n * pl.TS + t] * b * H;
+    }
+    JxMem<T>::st(out, doff, r);
+  }
   // pad rows 513..519: the TMA contraction reads R in whole 12-row blocks (up to row 515) and relies on zeros
   for (int idx = threadIdx.x; idx < (JC_NA_PAD - JC_NA) * pl.TS; idx += blockDim.x)
     JxMem<T>::st(ws.rker + ((size_t)c * JC_NA_PAD + JC_NA) * pl.TS + idx, doff, T(0.0));
@@ -218,8 +228,8 @@ int jc_launch_tracers_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStre
   return launch_all_lens<Dual, 2>(pl, ws, chunk, s);
 }
 void jc_launch_finish(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s) {
-  jc_tracer_finish_kernel<double><<<chunk, 512, 0, s>>>(pl, ws);
+  jc_tracer_finish_kernel<double><<<chunk, (512 / pl.T) * pl.T, 0, s>>>(pl, ws);
 }
 void jc_launch_finish_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s) {
-  jc_tracer_finish_kernel<Dual><<<chunk, 512, 0, s>>>(pl, ws);
+  jc_tracer_finish_kernel<Dual><<<chunk, (512 / pl.T) * pl.T, 0, s>>>(pl, ws);
 }
