@@ -8,7 +8,8 @@ Workload (config.workload): 3x2pt with 10 source + 10 lens Smail bins (T=20 trac
 
   value      whole-job C_ell evaluations (cosmology x ell x pair) per second, inputs resident in HBM
   e2e        same metric through the drop-in host API (pinned host buffers, H2D + D2H inside)
-  roofline   dominant kernel (jc_power_kernel) against the measured FP64 FMA peak, plus whole step
+  roofline   dominant kernel of the step (jc_power_kernel or jc_contract_tma_kernel, whichever took longer)
+             against the measured FP64 FMA peak, plus the whole step
   cpu_baseline  the NumPy oracle (a port of the reference, see oracle/) on all host cores, bounded sample
 
 `--impl reference` times the reference's CPU path: the reference is pure Python on JAX and JAX is
@@ -277,7 +278,7 @@ def main():
     lo = plan.workspace_layout(ws_bytes)
     chunk = min(int(lo.chunk), B)
     kernels = {"setup": "jc_setup_kernel", "lens": "jc_lens_kernel", "finish": "jc_tracer_finish_kernel",
-               "power": "jc_power_kernel", "contract": "jc_contract_kernel"}
+               "power": "jc_power_kernel", "contract": "jc_contract_tma_kernel"}
     dom = max(("power", "contract", "setup", "lens"), key=lambda k: stage_ms[k])  # dominant kernel of the step
     n_launch = max(stage_n[dom], 1)
     launch_ms = stage_ms[dom] / n_launch              # average launch duration (CUDA events on the launch stream)
@@ -285,9 +286,10 @@ def main():
     achieved = 2.0 * slots[dom] * cosmo_per_launch / (launch_ms * 1e-3) / 1e12
     # FP64 work the compiled kernels actually execute (ncu, profiles/r01_ncu_summary.md): FP64-pipe warp
     # instructions per (ell, node) point x 64 flop for K3; DMMA m8n8k4 count x 512 flop for K4
-    sass_flops = {"power": 264.0 * 2 * N_ELL * A, "contract": 45279.0 * 512}
-    # DRAM bytes per launch of `chunk` cosmologies, scaled from the ncu --set full capture at 592 cosmologies
-    ncu_dram_per_cosmo = {"power": (42.63e6 + 186.98e6) / 592, "contract": (291.70e6 + 79.22e6) / 592}
+    sass_flops = {"power": 196.0 * 2 * N_ELL * A, "contract": 45279.0 * 512}
+    # DRAM bytes per launch of `chunk` cosmologies, scaled from the ncu --set full captures at 592 cosmologies
+    # (power: prof_r01_v6, contraction: prof_r01_v8tma; profiles/r01_ncu_summary.md)
+    ncu_dram_per_cosmo = {"power": (42.55e6 + 195.78e6) / 592, "contract": (299.39e6 + 76.44e6) / 592}
     step_tflops = 2.0 * slots["total"] * B * args.steps / (ms * 1e-3) / 1e12
     roofline = {"bound": "fp64", "kernel": kernels[dom], "achieved": achieved, "peak": peak_sustained,
                 "unit": "TFLOP/s", "frac": achieved / peak_sustained,
