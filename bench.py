@@ -302,6 +302,10 @@ def main():
                 "peak_source": peak_src, "peak_burst": peak_burst, "peak_dmma": peak_dmma,
                 "flops_convention": "SURVEY 8(d) v0 (2 x issue slots): power 500 slots/point, contraction 1 slot/(ell,node,pair)",
                 "achieved_sass": (sass_flops[dom] * cosmo_per_launch / (launch_ms * 1e-3) / 1e12) if dom in sass_flops else None,
+                "frac_sass": (sass_flops[dom] * cosmo_per_launch / (launch_ms * 1e-3) / 1e12 / peak_sustained) if dom in sass_flops else None,
+                "frac_note": "frac follows the SURVEY 8(d) v0 convention and can exceed 1 for jc_power_kernel: v0 books 500 issue "
+                             "slots per P(k) point, the compiled kernel needs 196 FP64 instructions (separable power laws, merged "
+                             "divisions, table-driven exp/log); frac_sass = executed FP64 flops / peak is the pipe utilisation",
                 "launch_ms": launch_ms, "cosmologies_per_launch": cosmo_per_launch,
                 "step": {"achieved": step_tflops, "frac": step_tflops / peak_sustained,
                          "slots_per_cosmology": slots["total"]},
