@@ -496,3 +496,42 @@ def test_vjp_and_autograd(jc, torch_cuda):
     resid = (mu - dvec).reshape(P, L)
     sol = np.stack([np.linalg.solve(cov[:, :, l], resid[:, l]) for l in range(L)], axis=1)  # C^-1 r per ell
     assert relerr(glike, -np.tensordot(jac, sol, axes=([1, 2], [0, 1]))) < 1e-9
+
+
+@pytest.mark.parametrize("shape", ["t17_l61", "t32_l9", "t16_l113"])
+def test_tma_contraction_shapes(jc, torch_cuda, shape):
+    """The persistent TMA contraction (>= 17 pair tiles) on ragged shapes against the oracle: odd ell counts (scalar
+    stores, partial last ell tile), one to three ell groups, two to three tile rounds (T = 32: 66 pair tiles),
+    IA + inverse-growth tracers, value and forward-mode tangent planes."""
+    from oracle import derivatives as od
+    n_src, n_lens, L = {"t17_l61": (9, 8, 61), "t32_l9": (16, 16, 9), "t16_l113": (6, 10, 113)}[shape]
+    src = [sc.smail(1.0, 2.0, 0.3 + 0.07 * i, 1.5, shift=(0.01 if i % 3 == 0 else None)) for i in range(n_src)]
+    lns = [sc.smail(2.0, 4.0, 0.25 + 0.06 * i, 2.0) for i in range(n_lens)]
+    probes_spec = [sc.wl(src, ia=sc.bias("des_y1_ia", 0.5, 0.0, 0.62), m=[0.01 * (-1) ** i for i in range(n_src)]),
+                   sc.nc(lns, [sc.bias("inverse_growth" if i % 2 else "constant", 1.0 + 0.05 * i) for i in range(n_lens)])]
+    ell = np.logspace(1, np.log10(2500), L)
+    scn = sc.scenario(shape, sc.WCDM, ell, probes_spec)
+    probes = sc.build_probes(scn, jc)
+    cosmo = sc.build_cosmo(scn, jc)
+    row = sc.cosmo_row(scn["cosmo"])
+    prob = sc.flatten_spec(scn)
+    cl = jc.cl.angular_cl(cosmo, ell, probes)
+    T = n_src + n_lens
+    assert cl.shape == (T * (T + 1) // 2, L)
+    ref = o.angular_cl(row, ell, prob)
+    assert relerr(cl, ref) < RTOL, relerr(cl, ref)
+    # a batch larger than the SM count (persistent CTAs walk over several cosmologies) equals the single rows bitwise
+    torch = torch_cuda
+    rows = np.concatenate([row[None], sc.config5_cosmologies(200)])
+    batch = jc.cl.angular_cl_batch(torch.as_tensor(rows, device="cuda"), ell, probes).cpu().numpy()
+    assert np.array_equal(batch[0], cl)
+    for k in (1, 149, 200):
+        assert np.array_equal(batch[k], jc.cl.angular_cl(rows[k], ell, probes))
+    # tangent planes through the same kernel: d/d(Omega_c, sigma8) against the FD oracle on a thinned ell set
+    sub = slice(None, None, max(1, L // 6))
+    params = ("Omega_c", "sigma8")
+    cl_j, jac = jc.cl.angular_cl_jacobian(cosmo, ell, probes, params=params)
+    assert relerr(cl_j, cl) < 1e-12
+    _, jac_ref, _ = od.fd_jacobian(row, ell[sub], prob, params=params)
+    scale = np.abs(jac_ref).max(axis=2, keepdims=True)
+    assert (np.abs(jac[:, :, sub] - jac_ref) / scale).max() < 1e-6
