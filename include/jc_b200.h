@@ -281,6 +281,22 @@ int jc_fisher_f64(const double* jac_dev, const double* cov_dev, int64_t n_cosmo,
 int jc_vjp_f64(const double* jac_dev, const double* cot_dev, int64_t cot_stride, int64_t n_cosmo,
                int32_t n_params, int64_t N, double* grad_dev, void* stream);
 
+/* jax_cosmo.sparse on the device (sparse.py): a block matrix of [ny, nx] diagonal blocks of size n is S[ny, nx, n].
+ * jc_sparse_bmm_f64: C[i,k,l] = sum_j A[i,j,l] * B[j,k,l] for i < I, j < J, k < K, l < L, every operand addressed
+ * by element strides (in doubles; a stride of 0 broadcasts) -- one entry point behind sparse.dot's seven
+ * combinations (sparse.py:72-292): sparse @ vec, sparse @ dense, vec @ sparse, dense @ sparse, sparse @ sparse and
+ * dense @ sparse @ dense (two calls, the second with L = 1).  Fixed summation order over j. */
+int jc_sparse_bmm_f64(const double* A_dev, int64_t sAi, int64_t sAj, int64_t sAl, const double* B_dev, int64_t sBj,
+                      int64_t sBk, int64_t sBl, double* C_dev, int64_t sCi, int64_t sCk, int64_t sCl, int32_t I,
+                      int32_t J, int32_t K, int32_t L, void* stream);
+/* sparse.inv / sparse.slogdet / sparse.det (sparse.py:296-389) for a square sparse matrix S[P, P, L]: per diagonal
+ * position l the inverse of S[:, :, l] and sign / log|det| by Gauss-Jordan elimination with partial pivoting (what
+ * np.linalg.inv / slogdet do per slice in the reference).  inv_dev [P, P, L], sign_dev [L], logdet_dev [L] (any of
+ * the three may be NULL); scratch_dev [L, P, 2P] doubles.  The reference's slogdet of the whole matrix is
+ * (prod_l sign[l], sum_l logdet[l]). */
+int jc_sparse_inv_f64(const double* sparse_dev, int32_t P, int32_t L, double* inv_dev, double* sign_dev,
+                      double* logdet_dev, double* scratch_dev, void* stream);
+
 /* Per-stage device timing (CUDA events recorded on the launch stream between the stages of
  * jc_angular_cl_f64).  Stages: 0 setup, 1 lensing efficiency, 2 tracer finish, 3 power, 4 pair
  * contraction.  While enabled the plan is not re-entrant.  jc_profile_read synchronises the

@@ -31,7 +31,7 @@ SCAL_FIELDS = ["LN13KEQ", "INV13KEQ", "BETA_C", "C14_ALPHA_C", "SH_D", "LNKSILK"
 # every symbol include/jc_b200.h declares
 EXPORTS = ["jc_plan_create", "jc_plan_destroy", "jc_plan_n_tracers", "jc_plan_n_cls", "jc_plan_n_ell", "jc_plan_n_cosmo_params",
            "jc_workspace_bytes", "jc_workspace_layout", "jc_angular_cl_f64", "jc_angular_cl_host_f64",
-           "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64", "jc_gaussian_loglike_f64", "jc_fisher_f64", "jc_vjp_f64",
+           "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64", "jc_gaussian_loglike_f64", "jc_fisher_f64", "jc_vjp_f64", "jc_sparse_bmm_f64", "jc_sparse_inv_f64",
            "jc_noise_f64", "jc_gaussian_cov_f64", "jc_profile_enable", "jc_profile_read",
            "jc_fp64_peak_tflops", "jc_debug_math_f64", "jc_status_string",
            "jc_last_cuda_error", "jc_abi_version"]
@@ -103,6 +103,10 @@ def load_library():
         lib.jc_fisher_f64.restype = C.c_int
         lib.jc_vjp_f64.argtypes = [vp, vp, i64, i64, i32, i64, vp, vp]
         lib.jc_vjp_f64.restype = C.c_int
+        lib.jc_sparse_bmm_f64.argtypes = [vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64, i32, i32, i32, i32, vp]
+        lib.jc_sparse_bmm_f64.restype = C.c_int
+        lib.jc_sparse_inv_f64.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
+        lib.jc_sparse_inv_f64.restype = C.c_int
         lib.jc_angular_cl_host_f64.argtypes = [vp, vp, i64, vp]
         lib.jc_angular_cl_host_f64.restype = C.c_int
         lib.jc_noise_f64.argtypes = [vp, dp]

@@ -2,6 +2,7 @@
 // probe, status strings.
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "jc_internal.cuh"
@@ -33,7 +34,9 @@ extern "C" const char* jc_status_string(int status) {
 // a second stream (double-buffered), so PCIe traffic overlaps the FP64 kernels when the host
 // buffers are pinned.
 // ---------------------------------------------------------------------------------------------
-#define JC_HOST_CHUNK 1024
+// 2 cosmologies per SM and chunk: the D2H stream is the bottleneck (PCIe, ~54 GB/s), so the exposed part is the
+// first chunk's compute; measured e2e at config 5: 1024 -> 6.15e9, 592 -> 6.26e9, 444 -> 6.34e9, 296 -> 6.40e9 C_ell/s
+#define JC_HOST_CHUNK 296
 
 static int ensure(void** p, size_t* have, size_t need) {
   if (*have >= need) return JC_OK;
@@ -56,7 +59,13 @@ extern "C" int jc_angular_cl_host_f64(jc_plan* plan, const double* cosmo_host, i
       JC_CUDA_TRY(cudaEventCreateWithFlags(&plan->ev_copied[i], cudaEventDisableTiming));
     }
   }
-  const int64_t chunk = n_cosmo < JC_HOST_CHUNK ? n_cosmo : JC_HOST_CHUNK;
+  static int64_t host_chunk = 0;  // idempotent; JC_HOST_CHUNK env = tuning knob (profiles/r01_tuning.md)
+  if (!host_chunk) {
+    const char* e = getenv("JC_HOST_CHUNK");
+    const int64_t v = e ? atoll(e) : 0;
+    host_chunk = v > 0 ? v : JC_HOST_CHUNK;
+  }
+  const int64_t chunk = n_cosmo < host_chunk ? n_cosmo : host_chunk;
   const size_t pl_elems = (size_t)plan->d.P * plan->d.L;
   size_t ws_need = 0;
   int st = jc_workspace_bytes(plan, chunk, &ws_need);
