@@ -22,6 +22,7 @@
 #include <cstdlib>
 
 #include "jc_internal.cuh"
+#include "jc_tma.cuh"
 
 namespace {
 
@@ -258,30 +259,6 @@ jc_contract_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64_t o
 constexpr int TMA_CW = 16;      // warps per CTA
 constexpr int TMA_STAGES = 8;   // power of two
 
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* b, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) {
-  const unsigned a = smem_u32(b);
-  unsigned ok;
-  do {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-// 1-D TMA bulk copy global -> shared; completion is counted in bytes on `bar`.  16-byte aligned both sides.
-__device__ __forceinline__ void tma_load(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-               ::"r"(smem_u32(dst)), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 template <int KC, bool JVP>
 __global__ void __launch_bounds__(TMA_CW * 32, 1)
 jc_contract_tma_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64_t out_cosmo_stride, int chunk) {
@@ -336,9 +313,9 @@ jc_contract_tma_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64
       mbar_init(full + sb, 1);
       mbar_init(empty + sb, TMA_CW);
     }
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    mbar_fence_init();
   }
-  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic zero fill before async-proxy writes
+  fence_proxy_async();  // generic zero fill before async-proxy writes
   __syncthreads();
   if (warp == 0)
     for (int q = 0; q < min(TMA_STAGES, total_stages); ++q) issue_stage(q);
