@@ -51,6 +51,9 @@ __device__ __forceinline__ double jx_log(double x) { return jcm_log(x); }
 __device__ __forceinline__ Dual jx_log(Dual x) { return Dual(jcm_log(x.v), x.d * jcm_rcp(x.v)); }
 __device__ __forceinline__ double jx_exp_t(double x, const double* tab) { return jcm_exp_t(x, tab); }
 __device__ __forceinline__ Dual jx_exp_t(Dual x, const double* tab) { const double e = jcm_exp_t(x.v, tab); return Dual(e, e * x.d); }
+// exp of a bounded argument (|x| < 700): no underflow clamp
+__device__ __forceinline__ double jx_exp_tb(double x, const double* tab) { return jcm_exp_t<false>(x, tab); }
+__device__ __forceinline__ Dual jx_exp_tb(Dual x, const double* tab) { const double e = jcm_exp_t<false>(x.v, tab); return Dual(e, e * x.d); }
 __device__ __forceinline__ double jx_log_t(double x, const double* tab) { return jcm_log_t(x, tab); }
 __device__ __forceinline__ Dual jx_log_t(Dual x, const double* tab) { return Dual(jcm_log_t(x.v, tab), x.d * jcm_rcp(x.v)); }
 __device__ __forceinline__ double jx_sqrt(double x) { return sqrt(x); }

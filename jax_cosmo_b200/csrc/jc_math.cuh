@@ -105,8 +105,9 @@ static __constant__ JcMathT JCT = {
     {-0.5, 1.0 / 3, -0.25, 0.2, -1.0 / 6, 1.0 / 7}};
 
 // exp(x), x <= 709 (x < -708 clamped): 2^n * T[j] * p(r), |r| <= ln2/64, degree-6 Taylor (3.5e-18).
+template <bool CLAMP = true>
 __device__ __forceinline__ double jcm_exp_t(double x, const double* __restrict__ tab) {
-  x = jcm_clamp_exp_arg(x);
+  if (CLAMP) x = jcm_clamp_exp_arg(x);  // CLAMP = false: caller guarantees |x| < 700 (3 issue slots less)
   const double kd = fma(x, JCT.k32, JCT.magic);
   const int k = __double2loint(kd);
   const double kf = kd - JCT.magic;

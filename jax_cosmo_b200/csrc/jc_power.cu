@@ -115,9 +115,10 @@ __global__ void __launch_bounds__(256, MINB) jc_power_kernel(JcDevPlan pl, Ws ws
         // Delta^2_Q = D2L (1+D2L)^beta / (1 + alpha D2L) exp(-(y/4 + y^2/8))
         const T Nq = d2l * jx_exp_t(NODE(JC_NODE_BETA) * jx_log_t(JCK.one + d2l, s_tab) - (y2 * PK.eighth + PK.quarter * y), s_tab);
         const T Dq = NODE(JC_NODE_ALPHA) * d2l + JCK.one;
-        const T ye1 = jx_exp_t(NODE(JC_NODE_E1) * lny, s_tab);
-        const T ye2 = jx_exp_t(NODE(JC_NODE_E2) * lny, s_tab);
-        const T cfy = jx_exp_t(NODE(JC_NODE_P3) * (NODE(JC_NODE_LNCF) + lny), s_tab);
+        // y^(3 f1), y^(f2), c f3 y^(3-gamma): |ln y| < 30 and exponents of order one -- bounded arguments, no clamp
+        const T ye1 = jx_exp_tb(NODE(JC_NODE_E1) * lny, s_tab);
+        const T ye2 = jx_exp_tb(NODE(JC_NODE_E2) * lny, s_tab);
+        const T cfy = jx_exp_tb(NODE(JC_NODE_P3) * (NODE(JC_NODE_LNCF) + lny), s_tab);
         const T Nh = NODE(JC_NODE_AN) * ye1 * y2;
         T ynu = y2 + NODE(JC_NODE_NU);  // 1/(1 + mu/y + nu/y^2) = y^2 / (y^2 + mu y + nu)
         if (pl.nonlinear == JC_PK_HALOFIT_SMITH2003) ynu = ynu + NODE(JC_NODE_MU) * y;  // mu = 0 in takahashi2012
@@ -153,6 +154,10 @@ void jc_launch_power(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t 
   if (cfg < 0) { const char* e = getenv("JC_POWER_CFG"); cfg = e ? atoi(e) : 0; }  // tuning knob
   switch (cfg) {
     case 1: launch_power_cfg<double, 4, 1>(pl, ws, chunk, 8, s); break;  // unconstrained registers
+    case 2: launch_power_cfg<double, 4, 3>(pl, ws, chunk, 8, s); break;  // 80 registers, 3 CTAs / SM
+    case 3: launch_power_cfg<double, 4, 2>(pl, ws, chunk, 8, s); break;  // 128 registers, 2 CTAs / SM
+    case 4: launch_power_cfg<double, 2, 3>(pl, ws, chunk, 8, s); break;
+    case 5: launch_power_cfg<double, 8, 3>(pl, ws, chunk, 8, s); break;
     // fastest (profiles/r01_tuning.md): 4 nodes per thread, 64 registers, 8 CTAs per cosmology
     default: launch_power_cfg<double, 4, 4>(pl, ws, chunk, 8, s); break;
   }
