@@ -95,7 +95,7 @@ struct JcDevPlan {
   const double* ell14;       // [L] (l+1/2)^1.4
   const double* ellm3;       // [L] (l+1/2)^-3
   const double* covnorm;     // [L] (2l+1) gradient(l)   (angular_cl.py:139, without f_sky)
-  const double* math_tab;    // [288] exp2 / log tables of jc_math.cuh (JCM_TAB_*)
+  const double* math_tab;    // [JCM_TAB_DOUBLES] exp2 / log tables of jc_math.cuh (JCM_TAB_*)
   // pairs
   const uint8_t* pair_i;     // [P]
   const uint8_t* pair_j;     // [P]

@@ -88,23 +88,27 @@ __device__ __forceinline__ double jcm_log(double x) {
 }
 
 // ---- table-driven variants (tables: plan.math_tab, staged in shared memory by the caller) -------------
-// layout of the table: [0,32) 2^(j/32);  [32, 32+256) pairs {c_j, -ln c_j}, j = top 7 mantissa bits,
+// layout of the table: [0,256) 2^(j/256);  [256, 256+256) pairs {c_j, -ln c_j}, j = top 7 mantissa bits,
 // c_j = 1/(1 + (j+1/2)/128) (c_0 = 1 so that log stays relatively accurate next to 1).
+#define JCM_EXP_BITS 8
+#define JCM_EXP_N (1 << JCM_EXP_BITS)
 #define JCM_TAB_EXP 0
-#define JCM_TAB_LOG 32
-#define JCM_TAB_DOUBLES (32 + 256)
+#define JCM_TAB_LOG JCM_EXP_N
+#define JCM_TAB_DOUBLES (JCM_EXP_N + 256)
 
 struct JcMathT {
-  double k32, magic, l32_hi, l32_lo;  // 32/ln2, 1.5*2^52, ln2/32 split
+  double k32, magic, l32_hi, l32_lo;  // N/ln2, 1.5*2^52, ln2/N split (N = JCM_EXP_N table entries per octave)
   double e[5];                        // 1/2, 1/6, 1/24, 1/120, 1/720
   double l[6];                        // -1/2, 1/3, -1/4, 1/5, -1/6, 1/7
 };
 static __constant__ JcMathT JCT = {
-    46.166241308446828384, 6755399441055744.0, 6.93147180369123816490e-01 / 32, 1.90821492927058770002e-10 / 32,
+    1.4426950408889634074 * JCM_EXP_N, 6755399441055744.0, 6.93147180369123816490e-01 / JCM_EXP_N,
+    1.90821492927058770002e-10 / JCM_EXP_N,
     {0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720},
     {-0.5, 1.0 / 3, -0.25, 0.2, -1.0 / 6, 1.0 / 7}};
 
-// exp(x), x <= 709 (x < -708 clamped): 2^n * T[j] * p(r), |r| <= ln2/64, degree-6 Taylor (3.5e-18).
+// exp(x), x <= 709 (x < -708 clamped): 2^n * T[j] * p(r), 256 table entries per octave, |r| <= ln2/512,
+// degree-4 Taylor (truncation r^5/120 < 3.8e-17; a 32-entry table needs degree 6: two more dependent DFMAs).
 template <bool CLAMP = true>
 __device__ __forceinline__ double jcm_exp_t(double x, const double* __restrict__ tab) {
   if (CLAMP) x = jcm_clamp_exp_arg(x);  // CLAMP = false: caller guarantees |x| < 700 (3 issue slots less)
@@ -113,14 +117,12 @@ __device__ __forceinline__ double jcm_exp_t(double x, const double* __restrict__
   const double kf = kd - JCT.magic;
   double r = fma(kf, -JCT.l32_hi, x);
   r = fma(kf, -JCT.l32_lo, r);
-  double p = fma(JCT.e[4], r, JCT.e[3]);
-  p = fma(p, r, JCT.e[2]);
-  p = fma(p, r, JCT.e[1]);
+  double p = fma(JCT.e[2], r, JCT.e[1]);
   p = fma(p, r, JCT.e[0]);
   p = fma(p, r, JCK.one);
   p = fma(p, r, JCK.one);
-  p *= tab[JCM_TAB_EXP + (k & 31)];
-  return __hiloint2double(__double2hiint(p) + ((k >> 5) << 20), __double2loint(p));
+  p *= tab[JCM_TAB_EXP + (k & (JCM_EXP_N - 1))];
+  return __hiloint2double(__double2hiint(p) + ((k >> JCM_EXP_BITS) << 20), __double2loint(p));
 }
 
 // log(x) for finite normal x >= 1 (absolute error ~1e-16 max(1, |log x|); relative next to x = 1).

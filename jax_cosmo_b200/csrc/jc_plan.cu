@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "jc_internal.cuh"
+#include "jc_math.cuh"
 
 namespace {
 
@@ -223,11 +224,11 @@ int validate(const jc_problem* pb, int n_ell) {
 }  // namespace
 
 void jc_math_table(double* out) {
-  for (int j = 0; j < 32; ++j) out[j] = std::exp2(j / 32.0);
+  for (int j = 0; j < JCM_EXP_N; ++j) out[JCM_TAB_EXP + j] = std::exp2(j / (double)JCM_EXP_N);
   for (int j = 0; j < 128; ++j) {
     const double cj = j == 0 ? 1.0 : 1.0 / (1.0 + (j + 0.5) / 128.0);
-    out[32 + 2 * j] = cj;
-    out[32 + 2 * j + 1] = j == 0 ? 0.0 : -std::log(cj);
+    out[JCM_TAB_LOG + 2 * j] = cj;
+    out[JCM_TAB_LOG + 2 * j + 1] = j == 0 ? 0.0 : -std::log(cj);
   }
 }
 
@@ -437,8 +438,8 @@ extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int3
   size_t o_ellfac = B.add(ellfac), o_covnorm = B.add(covnorm);
   size_t o_ell108 = B.add(ell108), o_ell14 = B.add(ell14), o_ellm3 = B.add(ellm3);
   size_t o_pi = B.add(pi), o_pj = B.add(pj);
-  // tables of the kernels' table-driven exp / log (jc_math.cuh): 2^(j/32); {c_j, -ln c_j}
-  std::vector<double> math_tab(32 + 256);
+  // tables of the kernels' table-driven exp / log (jc_math.cuh): 2^(j/256); {c_j, -ln c_j}
+  std::vector<double> math_tab(JCM_TAB_DOUBLES);
   jc_math_table(math_tab.data());
   size_t o_math = B.add(math_tab);
   size_t o_norm = B.reserve(JC_MAX_TRACERS * sizeof(double));
