@@ -9,18 +9,19 @@
 // K2b  finish: WL = (q (1+z) chi 3 H0^2 Om/(2c) + NLA) (1+m)   probes.py:51,71-74,102-129,201-207
 //              NC = n_i(z) b_i(z) H(a)                           probes.py:77-99
 // Both are templates on the scalar type (double / Dual, see jc_dual.cuh).
+#include <cstdlib>
+
 #include "jc_internal.cuh"
 #include "jc_dual.cuh"
 
 namespace {
 
-constexpr int LENS_CGROUPS = 4;  // cosmology groups per CTA
 constexpr int LENS_NODES = 128;  // nodes per CTA
 constexpr int LENS_MR = 4;       // z' rows per pipeline stage
 constexpr int LENS_STAGES = 3;
 
-// NCOS: cosmologies per thread (4 for double, 2 for Dual: same accumulator register budget)
-template <class T, int NS, int NCOS>
+// NCOS: cosmologies per thread; LENS_CGROUPS: cosmology groups (of 4 warps) per CTA
+template <class T, int NS, int NCOS, int LENS_CGROUPS>
 __global__ void __launch_bounds__(LENS_NODES * LENS_CGROUPS)
 jc_lens_kernel(JcDevPlan pl, Ws ws, int n_cosmo, int s0) {
   constexpr int CTA_COSMO = NCOS * LENS_CGROUPS;
@@ -189,32 +190,32 @@ __global__ void __launch_bounds__(512) jc_tracer_finish_kernel(JcDevPlan pl, Ws 
     JxMem<T>::st(ws.rker + ((size_t)c * JC_NA_PAD + JC_NA) * pl.TS + idx, doff, T(0.0));
 }
 
-template <class T, int NS, int NCOS>
+template <class T, int NS, int NCOS, int LENS_CGROUPS>
 void launch_lens(const JcDevPlan& pl, const Ws& ws, int chunk, int s0, cudaStream_t st) {
   constexpr int CTA_COSMO = NCOS * LENS_CGROUPS;
   dim3 grid(JC_NLENS_COLS / LENS_NODES, (chunk + CTA_COSMO - 1) / CTA_COSMO);
   constexpr int smem = LENS_STAGES * LENS_MR * (LENS_NODES * 8 * (1 + NS) + LENS_NODES * 2);
   static bool attr_done = false;  // idempotent attribute; racing writers set the same value
   if (!attr_done) {
-    cudaFuncSetAttribute(jc_lens_kernel<T, NS, NCOS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(jc_lens_kernel<T, NS, NCOS, LENS_CGROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr_done = true;
   }
-  jc_lens_kernel<T, NS, NCOS><<<grid, LENS_NODES * LENS_CGROUPS, smem, st>>>(pl, ws, chunk, s0);
+  jc_lens_kernel<T, NS, NCOS, LENS_CGROUPS><<<grid, LENS_NODES * LENS_CGROUPS, smem, st>>>(pl, ws, chunk, s0);
 }
 
-template <class T, int NCOS>
+template <class T, int NCOS, int CG>
 int launch_all_lens(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s) {
   int n_launch = 0;
   for (int s0 = 0; s0 < pl.n_src; ++n_launch) {
     const int rem = pl.n_src - s0;
-    if (rem >= 10) { launch_lens<T, 10, NCOS>(pl, ws, chunk, s0, s); s0 += 10; }
-    else if (rem >= 8) { launch_lens<T, 8, NCOS>(pl, ws, chunk, s0, s); s0 += 8; }
-    else if (rem >= 6) { launch_lens<T, 6, NCOS>(pl, ws, chunk, s0, s); s0 += 6; }
-    else if (rem >= 5) { launch_lens<T, 5, NCOS>(pl, ws, chunk, s0, s); s0 += 5; }
-    else if (rem == 4) { launch_lens<T, 4, NCOS>(pl, ws, chunk, s0, s); s0 += 4; }
-    else if (rem == 3) { launch_lens<T, 3, NCOS>(pl, ws, chunk, s0, s); s0 += 3; }
-    else if (rem == 2) { launch_lens<T, 2, NCOS>(pl, ws, chunk, s0, s); s0 += 2; }
-    else { launch_lens<T, 1, NCOS>(pl, ws, chunk, s0, s); s0 += 1; }
+    if (rem >= 10) { launch_lens<T, 10, NCOS, CG>(pl, ws, chunk, s0, s); s0 += 10; }
+    else if (rem >= 8) { launch_lens<T, 8, NCOS, CG>(pl, ws, chunk, s0, s); s0 += 8; }
+    else if (rem >= 6) { launch_lens<T, 6, NCOS, CG>(pl, ws, chunk, s0, s); s0 += 6; }
+    else if (rem >= 5) { launch_lens<T, 5, NCOS, CG>(pl, ws, chunk, s0, s); s0 += 5; }
+    else if (rem == 4) { launch_lens<T, 4, NCOS, CG>(pl, ws, chunk, s0, s); s0 += 4; }
+    else if (rem == 3) { launch_lens<T, 3, NCOS, CG>(pl, ws, chunk, s0, s); s0 += 3; }
+    else if (rem == 2) { launch_lens<T, 2, NCOS, CG>(pl, ws, chunk, s0, s); s0 += 2; }
+    else { launch_lens<T, 1, NCOS, CG>(pl, ws, chunk, s0, s); s0 += 1; }
   }
   return n_launch;
 }
@@ -222,10 +223,16 @@ int launch_all_lens(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s
 }  // namespace
 
 int jc_launch_tracers(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s) {
-  return launch_all_lens<double, 4>(pl, ws, chunk, s);
+  static int cfg = -1;
+  if (cfg < 0) { const char* e = getenv("JC_LENS_CFG"); cfg = e ? atoi(e) : 0; }  // tuning knob
+  switch (cfg) {
+    case 1: return launch_all_lens<double, 2, 8>(pl, ws, chunk, s);  // 2 cosmologies per thread, 1024-thread CTAs
+    case 2: return launch_all_lens<double, 2, 4>(pl, ws, chunk, s);
+    default: return launch_all_lens<double, 4, 4>(pl, ws, chunk, s);
+  }
 }
 int jc_launch_tracers_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s) {
-  return launch_all_lens<Dual, 2>(pl, ws, chunk, s);
+  return launch_all_lens<Dual, 2, 4>(pl, ws, chunk, s);
 }
 void jc_launch_finish(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s) {
   jc_tracer_finish_kernel<double><<<chunk, (512 / pl.T) * pl.T, 0, s>>>(pl, ws);
