@@ -6,8 +6,9 @@
 //      the 256-entry chi table differs.  CTA = 128 nodes x 16 cosmologies: warp = (32 nodes, 4
 //      cosmologies); the 4 warps that share a node block read the same table lines (L1 hits), so L2
 //      traffic per cosmology is 1/16 of the table set.  g is computed once for all sources.
-// K2b  finish: WL = (q (1+z) chi 3 H0^2 Om/(2c) + NLA) (1+m)   probes.py:51,71-74,102-129,201-207
-//              NC = n_i(z) b_i(z) H(a)                           probes.py:77-99
+//      Epilogue: WL = (q (1+z) chi 3 H0^2 Om/(2c) + NLA) (1+m)    probes.py:51,71-74,102-129,201-207
+// K2b  finish: NC = n_i(z) b_i(z) H(a)                            probes.py:77-99
+//              + delta_nz source planes and node 512 of the extended sources
 // Both are templates on the scalar type (double / Dual, see jc_dual.cuh).
 #include <cstdlib>
 
@@ -129,13 +130,23 @@ jc_lens_kernel(JcDevPlan pl, Ws ws, int n_cosmo, int s0) {
       }
     }
   }
-  const double dz = pl.lens_zmax - pl.limb_z[n];  // simps: dx * N (probes.py:51)
+  // Epilogue = the lensing term of the tracer kernel, written straight into R[n][t] (the finish kernel then only
+  // touches number counts, delta planes, node 512 and -- in place -- the NLA term of IA-enabled sources):
+  //   q (1+z) chi 3 H0^2 Om / (2c) (1+m)                                                   probes.py:51,71-74,201-207
+  const double zfac = (pl.lens_zmax - pl.limb_z[n]) /* simps: dx * N (probes.py:51) */ * (1.0 + pl.limb_z[n]) *
+                      (3.0 * JC_H0 * JC_H0 / 2.0 / JC_C_LIGHT);
 #pragma unroll
   for (int c = 0; c < NCOS; ++c) {
-    if (c0 + c >= n_cosmo) break;
-    double* row = ws.rker + ((size_t)(c0 + c) * JC_NA_PAD + n) * pl.TS;
+    const int cc = c0 + c;
+    if (cc >= n_cosmo) break;
+    double* row = ws.rker + ((size_t)cc * JC_NA_PAD + n) * pl.TS;
+    const T Om = JxMem<T>::ld(ws.scal + (size_t)cc * JC_SCAL_FIELDS + JC_SCAL_OMEGA_M, doff);
+    const T amp = (zfac * chin[c]) * Om;
 #pragma unroll
-    for (int s = 0; s < NS; ++s) JxMem<T>::st(row + pl.src_tracer[s0 + s], doff, acc[c][s] * dz);
+    for (int s = 0; s < NS; ++s) {
+      const int t = pl.src_tracer[s0 + s];
+      JxMem<T>::st(row + t, doff, acc[c][s] * amp * pl.tr_m1[t]);  // the NLA term is added by the finish kernel
+    }
   }
 }
 
@@ -162,16 +173,21 @@ __global__ void __launch_bounds__(512) jc_tracer_finish_kernel(JcDevPlan pl, Ws 
     inv_chis = 1.0 / jx_floor1(chis);
   }
   const T wl_amp = (3.0 * JC_H0 * JC_H0 / 2.0 / JC_C_LIGHT) * Om * m1;
-  for (int n = threadIdx.x / pl.T; n < JC_NA && (int)threadIdx.x < rows * pl.T; n += rows) {
+  // extended weak-lensing sources are finished by the lens kernel's epilogue for nodes 0..511; here only node 512
+  // (a = 1: chi = 0, so the lensing term vanishes and the NLA term remains)
+  const bool staged = is_wl && dix < 0;
+  for (int n = (staged && !ia) ? JC_NLENS_COLS + threadIdx.x / pl.T : threadIdx.x / pl.T;
+       n < JC_NA && (int)threadIdx.x < rows * pl.T; n += rows) {
     double* out = ws.rker + ((size_t)c * JC_NA_PAD + n) * pl.TS + t;
     const T H = JxMem<T>::ld(Hn + n, doff);
     T r;
     if (is_wl) {
-      const T chi = JxMem<T>::ld(Cn + n, doff);
-      T q;
-      if (dix >= 0) q = jx_clip0(chis - chi) * inv_chis;
-      else q = (n < JC_NLENS_COLS) ? JxMem<T>::ld(out, doff) : T(0.0);  // node 512 is a=1: chi=0, kernel = 0
-      r = q * (1.0 + pl.limb_z[n]) * chi * wl_amp;
+      if (staged) {  // lensing term already in place for nodes 0..511 (lens kernel epilogue); node 512: chi = 0
+        r = n < JC_NLENS_COLS ? JxMem<T>::ld(out, doff) : T(0.0);
+      } else {
+        const T chi = JxMem<T>::ld(Cn + n, doff);
+        r = jx_clip0(chis - chi) * inv_chis * (1.0 + pl.limb_z[n]) * chi * wl_amp;
+      }
       if (ia) {  // probes.py:119-123
         const T D = JxMem<T>::ld(Dn + n, doff);
         T b = T(pl.bias_node[(size_t)n * pl.TS + t]);
