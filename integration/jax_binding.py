@@ -1,0 +1,72 @@
+"""jax.ffi binding of the B200 path (north_star: XLA-FFI custom call) -- the file a jax_cosmo maintainer adds.
+
+NOT importable in this repository's image: JAX is not installed and cannot be installed (no network), so this module
+is documentation-grade code that has never run; the tested binding of the same C ABI is jax_cosmo_b200/_native.py
+(ctypes) with PyTorch owning device memory.  With JAX available:
+
+    import jax; jax.config.update("jax_enable_x64", True)
+    from integration.jax_binding import angular_cl          # drop-in for jax_cosmo.angular_cl.angular_cl
+    cl = jax.jit(lambda c: angular_cl(c, ell, probes))(cosmo)
+    jac = jax.jacfwd(lambda c: angular_cl(c, ell, probes))(cosmo)      # forward mode: jc_angular_cl_jvp_f64
+    g = jax.grad(lambda c: loss(angular_cl(c, ell, probes)))(cosmo)    # reverse mode: Jacobian passes + jc_vjp_f64
+"""
+import ctypes
+import os
+
+import numpy as np
+
+import jax
+import jax.numpy as jnp
+
+from jax_cosmo_b200 import _native
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = ctypes.CDLL(os.path.join(_HERE, "..", "jax_cosmo_b200", "libjc_xla_ffi.so"))
+for _name, _sym in (("jc_angular_cl", "JcAngularCl"), ("jc_angular_cl_jvp", "JcAngularClJvp"), ("jc_vjp", "JcVjp"),
+                    ("jc_gaussian_cov", "JcGaussianCov")):
+    jax.ffi.register_ffi_target(_name, jax.ffi.pycapsule(getattr(_lib, _sym)), platform="CUDA")
+
+
+def _plan_for(cosmo_leaves, ell, probes, transfer_fn, nonlinear_fn):
+    growth = 1 if len(cosmo_leaves) == 9 else 0
+    return _native.get_plan(probes, np.asarray(ell), transfer_fn, nonlinear_fn, growth=growth)
+
+
+def _call(rows, plan):
+    B = rows.shape[0]
+    ws = plan.workspace_bytes(B)
+    cl, _ = jax.ffi.ffi_call(
+        "jc_angular_cl",
+        (jax.ShapeDtypeStruct((B, plan.P, plan.L), jnp.float64), jax.ShapeDtypeStruct((ws,), jnp.uint8)),
+        vmap_method="expand_dims")(rows, plan=np.int64(plan._h.value))
+    return cl
+
+
+def _call_jvp(rows, tangents, plan):
+    B, K = rows.shape[0], tangents.shape[0]
+    need = ctypes.c_size_t()
+    _native.check(_native.load_library().jc_workspace_bytes_jvp(plan._h, B, ctypes.byref(need)), "jc_workspace_bytes_jvp")
+    cl, dcl, _ = jax.ffi.ffi_call(
+        "jc_angular_cl_jvp",
+        (jax.ShapeDtypeStruct((B, plan.P, plan.L), jnp.float64), jax.ShapeDtypeStruct((B, K, plan.P, plan.L), jnp.float64),
+         jax.ShapeDtypeStruct((need.value,), jnp.uint8)))(rows, tangents, plan=np.int64(plan._h.value))
+    return cl, dcl
+
+
+def angular_cl(cosmo, ell, probes, transfer_fn=None, nonlinear_fn=None):
+    """Same signature and output layout [n_cls, n_ell] as jax_cosmo.angular_cl.angular_cl (angular_cl.py:49-98);
+    differentiable in the cosmology leaves in both modes."""
+    leaves, treedef = jax.tree_util.tree_flatten(cosmo)
+    plan = _plan_for(leaves, ell, probes, transfer_fn, nonlinear_fn)
+
+    @jax.custom_jvp
+    def f(row):
+        return _call(row[None, :], plan)[0]
+
+    @f.defjvp
+    def f_jvp(primals, tangents):
+        (row,), (drow,) = primals, tangents
+        cl, dcl = _call_jvp(row[None, :], drow[None, :], plan)
+        return cl[0], dcl[0, 0]
+
+    return f(jnp.stack([jnp.asarray(x, dtype=jnp.float64) for x in leaves]))

@@ -1,0 +1,79 @@
+// jc_xla_ffi.cc -- XLA FFI custom-call handlers over the C ABI of include/jc_b200.h (north_star: "Python host code
+// calls hand-written sm_100a CUDA kernels through a thin XLA-FFI custom call").
+//
+// NOT built in this repository: the image has neither jax/jaxlib nor the xla/ffi/api headers, so this file cannot
+// be compiled or tested here.  It is the ~100-line shim a maintainer adds next to
+// libjc_b200.so; it only unpacks buffers and forwards to the extern "C" entry points -- no arithmetic lives here.
+//
+//   g++ -O2 -fPIC -shared -std=c++17 -I$(python -c "import jax; print(jax.ffi.include_dir())") -Iinclude \
+//       integration/jc_xla_ffi.cc -Ljax_cosmo_b200 -ljc_b200 -lcudart -o jax_cosmo_b200/libjc_xla_ffi.so
+//
+// Python side: integration/jax_binding.py.
+#include <cuda_runtime_api.h>
+
+#include <cstdint>
+
+#include "jc_b200.h"
+#include "xla/ffi/api/ffi.h"
+
+namespace ffi = xla::ffi;
+
+static ffi::Error status(int st, const char* what) {
+  if (st == JC_OK) return ffi::Error::Success();
+  return ffi::Error(st == JC_ERR_UNSUPPORTED ? ffi::ErrorCode::kUnimplemented : ffi::ErrorCode::kInvalidArgument,
+                    std::string(what) + ": " + jc_status_string(st) + " " + jc_last_cuda_error());
+}
+
+// cl[B, P, L] = angular_cl(cosmo[B, 8|9]); `plan` is the jc_plan* created once per (probes, ell) on the host
+// (jc_plan_create) and passed as an int64 attribute; the workspace is an extra XLA-owned result buffer.
+static ffi::Error AngularClImpl(cudaStream_t stream, ffi::Buffer<ffi::F64> cosmo, int64_t plan,
+                                ffi::ResultBuffer<ffi::F64> cl, ffi::ResultBuffer<ffi::U8> ws) {
+  auto* p = reinterpret_cast<jc_plan*>(plan);
+  const int64_t B = cosmo.dimensions()[0];
+  return status(jc_angular_cl_f64(p, cosmo.typed_data(), B, cl->typed_data(), ws->typed_data(), ws->element_count(), stream),
+                "jc_angular_cl_f64");
+}
+
+// forward mode: (cl[B, P, L], dcl[B, K, P, L]) for tangents[K, 8|9]  -- the rule behind jax.custom_jvp / jax.jacfwd
+static ffi::Error AngularClJvpImpl(cudaStream_t stream, ffi::Buffer<ffi::F64> cosmo, ffi::Buffer<ffi::F64> tangents,
+                                   int64_t plan, ffi::ResultBuffer<ffi::F64> cl, ffi::ResultBuffer<ffi::F64> dcl,
+                                   ffi::ResultBuffer<ffi::U8> ws) {
+  auto* p = reinterpret_cast<jc_plan*>(plan);
+  const int64_t B = cosmo.dimensions()[0];
+  const int32_t K = static_cast<int32_t>(tangents.dimensions()[0]);
+  return status(jc_angular_cl_jvp_f64(p, cosmo.typed_data(), tangents.typed_data(), K, B, cl->typed_data(),
+                                      dcl->typed_data(), ws->typed_data(), ws->element_count(), stream),
+                "jc_angular_cl_jvp_f64");
+}
+
+// reverse mode: grad[B, K] = sum_n jac[B, K, n] cot[B, n]  -- the backward rule of jax.custom_vjp
+static ffi::Error VjpImpl(cudaStream_t stream, ffi::Buffer<ffi::F64> jac, ffi::Buffer<ffi::F64> cot,
+                          ffi::ResultBuffer<ffi::F64> grad) {
+  const auto d = jac.dimensions();  // [B, K, P, L]
+  const int64_t B = d[0], N = d[2] * d[3];
+  return status(jc_vjp_f64(jac.typed_data(), cot.typed_data(), N, B, static_cast<int32_t>(d[1]), N, grad->typed_data(), stream),
+                "jc_vjp_f64");
+}
+
+// cov[B, P, P, L] = gaussian_cl_covariance(cl[B, P, L], noise[T]) in the jax_cosmo.sparse block layout
+static ffi::Error GaussianCovImpl(cudaStream_t stream, ffi::Buffer<ffi::F64> cl, ffi::Buffer<ffi::F64> noise, int64_t plan,
+                                  double f_sky, ffi::ResultBuffer<ffi::F64> cov) {
+  auto* p = reinterpret_cast<jc_plan*>(plan);
+  return status(jc_gaussian_cov_f64(p, cl.typed_data(), noise.typed_data(), cl.dimensions()[0], f_sky, cov->typed_data(), stream),
+                "jc_gaussian_cov_f64");
+}
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(JcAngularCl, AngularClImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::Buffer<ffi::F64>>()
+                                  .Attr<int64_t>("plan").Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::U8>>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(JcAngularClJvp, AngularClJvpImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>().Attr<int64_t>("plan").Ret<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::U8>>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(JcVjp, VjpImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::F64>>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(JcGaussianCov, GaussianCovImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>().Attr<int64_t>("plan").Attr<double>("f_sky")
+                                  .Ret<ffi::Buffer<ffi::F64>>());
