@@ -8,7 +8,10 @@ is documentation-grade code that has never run; the tested binding of the same C
     from integration.jax_binding import angular_cl          # drop-in for jax_cosmo.angular_cl.angular_cl
     cl = jax.jit(lambda c: angular_cl(c, ell, probes))(cosmo)
     jac = jax.jacfwd(lambda c: angular_cl(c, ell, probes))(cosmo)      # forward mode: jc_angular_cl_jvp_f64
-    g = jax.grad(lambda c: loss(angular_cl(c, ell, probes)))(cosmo)    # reverse mode: Jacobian passes + jc_vjp_f64
+    g = jax.grad(lambda c: loss(angular_cl_rev(c, ell, probes)))(cosmo)  # reverse mode: Jacobian passes + jc_vjp_f64
+
+An opaque custom call carries either a custom_jvp or a custom_vjp rule, not both (JAX cannot transpose the FFI JVP), hence
+the two entry points; both share the plan and the kernels.
 """
 import ctypes
 import os
@@ -69,4 +72,27 @@ def angular_cl(cosmo, ell, probes, transfer_fn=None, nonlinear_fn=None):
         cl, dcl = _call_jvp(row[None, :], drow[None, :], plan)
         return cl[0], dcl[0, 0]
 
+    return f(jnp.stack([jnp.asarray(x, dtype=jnp.float64) for x in leaves]))
+
+
+def angular_cl_rev(cosmo, ell, probes, transfer_fn=None, nonlinear_fn=None):
+    """angular_cl with a reverse-mode rule (jax.grad / jax.vjp): the forward pass saves the Jacobian with respect to
+    all leaves (one tangent pass per leaf), the backward pass is jc_vjp_f64."""
+    leaves, treedef = jax.tree_util.tree_flatten(cosmo)
+    plan = _plan_for(leaves, ell, probes, transfer_fn, nonlinear_fn)
+    n = len(leaves)
+
+    @jax.custom_vjp
+    def f(row):
+        return _call(row[None, :], plan)[0]
+
+    def fwd(row):
+        cl, dcl = _call_jvp(row[None, :], jnp.eye(n, dtype=jnp.float64), plan)
+        return cl[0], dcl
+
+    def bwd(dcl, cot):
+        grad = jax.ffi.ffi_call("jc_vjp", jax.ShapeDtypeStruct((1, n), jnp.float64))(dcl, cot[None])
+        return (grad[0],)
+
+    f.defvjp(fwd, bwd)
     return f(jnp.stack([jnp.asarray(x, dtype=jnp.float64) for x in leaves]))
