@@ -8,6 +8,7 @@ __version__ = "0.1.0"
 import jax_cosmo_b200.angular_cl as angular_cl  # module, as in the reference
 import jax_cosmo_b200.angular_cl as cl
 import jax_cosmo_b200.autograd as autograd
+import jax_cosmo_b200.background as background
 import jax_cosmo_b200.bias as bias
 import jax_cosmo_b200.likelihood as likelihood
 import jax_cosmo_b200.power as power

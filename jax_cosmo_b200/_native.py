@@ -31,7 +31,7 @@ SCAL_FIELDS = ["LN13KEQ", "INV13KEQ", "BETA_C", "C14_ALPHA_C", "SH_D", "LNKSILK"
 # every symbol include/jc_b200.h declares
 EXPORTS = ["jc_plan_create", "jc_plan_destroy", "jc_plan_n_tracers", "jc_plan_n_cls", "jc_plan_n_ell", "jc_plan_n_cosmo_params",
            "jc_workspace_bytes", "jc_workspace_layout", "jc_angular_cl_f64", "jc_angular_cl_host_f64",
-           "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64", "jc_gaussian_loglike_f64", "jc_fisher_f64", "jc_vjp_f64", "jc_sparse_bmm_f64", "jc_sparse_inv_f64",
+           "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64", "jc_gaussian_loglike_f64", "jc_fisher_f64", "jc_vjp_f64", "jc_sparse_bmm_f64", "jc_sparse_inv_f64", "jc_grid_plan_create", "jc_grid_eval_f64",
            "jc_noise_f64", "jc_gaussian_cov_f64", "jc_profile_enable", "jc_profile_read",
            "jc_fp64_peak_tflops", "jc_debug_math_f64", "jc_status_string",
            "jc_last_cuda_error", "jc_abi_version"]
@@ -107,6 +107,10 @@ def load_library():
         lib.jc_sparse_bmm_f64.restype = C.c_int
         lib.jc_sparse_inv_f64.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
         lib.jc_sparse_inv_f64.restype = C.c_int
+        lib.jc_grid_plan_create.argtypes = [i32, i32, i32, dp, i32, dp, i32, i32, C.POINTER(C.c_void_p)]
+        lib.jc_grid_plan_create.restype = C.c_int
+        lib.jc_grid_eval_f64.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
+        lib.jc_grid_eval_f64.restype = C.c_int
         lib.jc_angular_cl_host_f64.argtypes = [vp, vp, i64, vp]
         lib.jc_angular_cl_host_f64.restype = C.c_int
         lib.jc_noise_f64.argtypes = [vp, dp]
@@ -421,6 +425,73 @@ class Plan:
                                                 cov.data_ptr(), stream)
         check(st, "jc_gaussian_cov_f64")
         return cov
+
+
+class GridPlan(Plan):
+    """jc_grid_plan_create: the path's setup and power kernels on a caller-chosen (scale factor, wavenumber) grid
+    (stand-alone background.* / power.* functions).  n_a <= 512."""
+
+    def __init__(self, k, a, transfer=JC_TF_EH_OSC, nonlinear=JC_PK_HALOFIT, growth=0, device=None):
+        import torch
+
+        lib = load_library()
+        if not torch.cuda.is_available():
+            raise JcError("jax_cosmo_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.k = np.ascontiguousarray(np.atleast_1d(np.asarray(k, dtype=np.float64)))
+        self.a = np.ascontiguousarray(np.atleast_1d(np.asarray(a, dtype=np.float64)))
+        handle = C.c_void_p()
+        dp = C.POINTER(C.c_double)
+        with torch.cuda.device(self.device):
+            st = lib.jc_grid_plan_create(int(transfer), int(nonlinear), int(growth), self.k.ctypes.data_as(dp), len(self.k),
+                                         self.a.ctypes.data_as(dp), len(self.a), self.device, C.byref(handle))
+        check(st, "jc_grid_plan_create")
+        self._h = handle
+        self.T = lib.jc_plan_n_tracers(handle)
+        self.P = lib.jc_plan_n_cls(handle)
+        self.L = lib.jc_plan_n_ell(handle)
+        self.ncp = lib.jc_plan_n_cosmo_params(handle)
+        self._ws = None
+        self._noise_dev = None
+
+    def evaluate(self, cosmo_dev, want=("pk", "chi", "chi_transverse", "growth", "hubble")):
+        """cosmo_dev CUDA [B, ncp] -> dict of CUDA tensors: pk [B, n_a, n_k], the others [B, n_a]."""
+        import torch
+
+        assert cosmo_dev.is_cuda and cosmo_dev.dtype == torch.float64 and cosmo_dev.is_contiguous()
+        self._check_rows(cosmo_dev)
+        B, na, nk = cosmo_dev.shape[0], len(self.a), len(self.k)
+        out = {}
+        for name in ("pk", "chi", "chi_transverse", "growth", "hubble"):
+            if name in want:
+                shape = (B, na, nk) if name == "pk" else (B, na)
+                out[name] = torch.empty(shape, dtype=torch.float64, device=cosmo_dev.device)
+        ptr = lambda n: out[n].data_ptr() if n in out else None
+        ws = self.workspace(B)
+        st = load_library().jc_grid_eval_f64(self._h, cosmo_dev.data_ptr(), B, ptr("pk"), ptr("chi"), ptr("chi_transverse"),
+                                             ptr("growth"), ptr("hubble"), ws.data_ptr(), ws.numel() * 8,
+                                             torch.cuda.current_stream(cosmo_dev.device).cuda_stream)
+        check(st, "jc_grid_eval_f64")
+        return out
+
+
+_grid_cache = {}
+
+
+def get_grid_plan(k, a, transfer=JC_TF_EH_OSC, nonlinear=JC_PK_HALOFIT, growth=0):
+    import torch
+
+    k = np.ascontiguousarray(np.atleast_1d(np.asarray(k, dtype=np.float64)))
+    a = np.ascontiguousarray(np.atleast_1d(np.asarray(a, dtype=np.float64)))
+    dev = torch.cuda.current_device() if torch.cuda.is_available() else -1
+    key = (k.tobytes(), a.tobytes(), int(transfer), int(nonlinear), int(growth), dev)
+    plan = _grid_cache.get(key)
+    if plan is None:
+        if len(_grid_cache) >= 8:
+            _grid_cache.pop(next(iter(_grid_cache)))
+        plan = GridPlan(k, a, transfer, nonlinear, growth)
+        _grid_cache[key] = plan
+    return plan
 
 
 _plan_cache = {}

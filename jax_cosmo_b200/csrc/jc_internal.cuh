@@ -48,6 +48,7 @@ struct JcDevPlan {
   const double* chi_pt_lna;  // [511]
   const double* chi_h6;      // [255]  h_i / 6
   int growth, ncp;           // JC_GROWTH_*; doubles per cosmology / tangent row (8 or 9)
+  int grid_mode, grid_na;    // grid plan (jc_grid_plan_create): nodes = caller's scale factors, "ell + 1/2" = caller's k
   // growth table quadrature: points p = 2i (node), 2i+1 (a_i + h_i/2; JC_GROWTH_GAMMA: ln a_i + h_i/2 with h in ln a)
   const double* gr_pt_a;     // [255]
   const double* gr_pt_lna;   // [255]

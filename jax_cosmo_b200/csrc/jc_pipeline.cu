@@ -52,7 +52,7 @@ extern "C" int jc_workspace_bytes_jvp(const jc_plan* plan, int64_t n_cosmo, size
 extern "C" int jc_angular_cl_jvp_f64(const jc_plan* plan, const double* cosmo_dev, const double* tangents_dev,
                                      int32_t n_tangents, int64_t n_cosmo, double* cl_dev, double* dcl_dev,
                                      void* ws_dev, size_t ws_bytes, void* stream) {
-  if (!plan || !cosmo_dev || !tangents_dev || !dcl_dev || !ws_dev || n_cosmo < 1 || n_tangents < 1)
+  if (!plan || plan->d.grid_mode || !cosmo_dev || !tangents_dev || !dcl_dev || !ws_dev || n_cosmo < 1 || n_tangents < 1)
     return JC_ERR_INVALID;
   jc_ws_layout lo;
   int st = jc_workspace_layout(plan, ws_bytes / 2, &lo);
@@ -96,7 +96,7 @@ extern "C" int jc_workspace_layout(const jc_plan* plan, size_t ws_bytes, jc_ws_l
 
 extern "C" int jc_angular_cl_f64(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo,
                                  double* cl_dev, void* ws_dev, size_t ws_bytes, void* stream) {
-  if (!plan || !cosmo_dev || !cl_dev || !ws_dev || n_cosmo < 1) return JC_ERR_INVALID;
+  if (!plan || plan->d.grid_mode || !cosmo_dev || !cl_dev || !ws_dev || n_cosmo < 1) return JC_ERR_INVALID;
   jc_ws_layout lo;
   int st = jc_workspace_layout(plan, ws_bytes, &lo);
   if (st != JC_OK) return st;
@@ -126,6 +126,64 @@ extern "C" int jc_angular_cl_f64(const jc_plan* plan, const double* cosmo_dev, i
     JC_MARK(5);
 #undef JC_MARK
     if (nl) { nl[0] = 1; nl[1] = n_lens; nl[2] = 1; nl[3] = 1; nl[4] = 1; }
+  }
+  JC_CUDA_TRY(cudaGetLastError());
+  return JC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Grid plans: the reference's stand-alone background.* / power.* functions on the caller's (a, k) grid.
+// K1 (+ K3 when a power spectrum is requested) run unchanged; this kernel gathers the first n_a nodes.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) jc_grid_gather_kernel(JcDevPlan pl, Ws ws, const double* __restrict__ cosmo, int chunk,
+                                                             double* __restrict__ pk, double* __restrict__ chi,
+                                                             double* __restrict__ chi_t, double* __restrict__ growth,
+                                                             double* __restrict__ hubble) {
+  const int c = blockIdx.y, na = pl.grid_na;
+  const int tid = blockIdx.x * 256 + threadIdx.x;
+  if (pk && tid < na * pl.L) {
+    const int n = tid / pl.L, l = tid - n * pl.L;
+    pk[((size_t)c * na + n) * pl.L + l] = ws.vtab[((size_t)c * JC_NA + n) * pl.Lpad + l];
+  }
+  if (tid < na) {
+    const double x = node_ptr(ws, c, JC_NODE_CHI)[tid];
+    if (chi) chi[(size_t)c * na + tid] = x;
+    if (chi_t) {  // transverse comoving distance, background.py:297-344 (cosmo.k = -sign(Omega_k), core.py:79-84)
+      const double Ok = cosmo[(size_t)c * pl.ncp + 5];
+      const double sk = sqrt(fabs(Ok));
+      double v = x;
+      if (Ok > 0.0) v = JC_RH / sk * sinh(sk * x / JC_RH);
+      else if (Ok < 0.0) v = JC_RH / sk * sin(sk * x / JC_RH);
+      chi_t[(size_t)c * na + tid] = v;
+    }
+    if (growth) growth[(size_t)c * na + tid] = node_ptr(ws, c, JC_NODE_GROWTH)[tid];
+    if (hubble) hubble[(size_t)c * na + tid] = node_ptr(ws, c, JC_NODE_HUBBLE)[tid];
+  }
+}
+}  // namespace
+
+extern "C" int jc_grid_eval_f64(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo, double* pk_dev,
+                                double* chi_dev, double* chi_transverse_dev, double* growth_dev, double* hubble_dev,
+                                void* ws_dev, size_t ws_bytes, void* stream) {
+  if (!plan || !plan->d.grid_mode || !cosmo_dev || !ws_dev || n_cosmo < 1) return JC_ERR_INVALID;
+  jc_ws_layout lo;
+  int st = jc_workspace_layout(plan, ws_bytes, &lo);
+  if (st != JC_OK) return st;
+  const JcDevPlan& pl = plan->d;
+  cudaStream_t s = (cudaStream_t)stream;
+  Ws ws;
+  resolve(lo, (double*)ws_dev, 0, &ws);
+  const int na = pl.grid_na;
+  const int per = na * pl.L > na ? na * pl.L : na;
+  for (int64_t c0 = 0; c0 < n_cosmo; c0 += lo.chunk) {
+    const int chunk = (int)((n_cosmo - c0) < lo.chunk ? (n_cosmo - c0) : lo.chunk);
+    jc_launch_setup(pl, cosmo_dev + c0 * pl.ncp, ws, chunk, s);
+    if (pk_dev) jc_launch_power(pl, ws, chunk, s);
+    jc_grid_gather_kernel<<<dim3((per + 255) / 256, chunk), 256, 0, s>>>(
+        pl, ws, cosmo_dev + c0 * pl.ncp, chunk, pk_dev ? pk_dev + (size_t)c0 * na * pl.L : nullptr,
+        chi_dev ? chi_dev + (size_t)c0 * na : nullptr, chi_transverse_dev ? chi_transverse_dev + (size_t)c0 * na : nullptr,
+        growth_dev ? growth_dev + (size_t)c0 * na : nullptr, hubble_dev ? hubble_dev + (size_t)c0 * na : nullptr);
   }
   JC_CUDA_TRY(cudaGetLastError());
   return JC_OK;

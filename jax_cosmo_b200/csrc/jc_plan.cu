@@ -232,8 +232,10 @@ void jc_math_table(double* out) {
   }
 }
 
-extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int32_t n_ell,
-                              int32_t device, jc_plan** plan_out) {
+// grid_a != nullptr: grid plan -- the 513 "Limber nodes" are the caller's n_grid_a <= 512 scale factors (padded with
+// a = 1, which node 512 must be: halofit normalises sigma^2(R) with D(1)) and ell_host holds wavenumbers k.
+static int create_plan(const jc_problem* pb, const double* ell_host, int32_t n_ell, int32_t device,
+                       const double* grid_a, int32_t n_grid_a, jc_plan** plan_out) {
   if (!plan_out || !ell_host) return JC_ERR_INVALID;
   *plan_out = nullptr;
   int st = validate(pb, n_ell);
@@ -274,6 +276,7 @@ extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int3
   memset(&d, 0, sizeof(d));
   d.T = T; d.P = P; d.L = L; d.Lpad = (L + 3) & ~3; d.nonlinear = pb->nonlinear; d.transfer = pb->transfer;
   d.growth = pb->growth; d.ncp = JC_N_COSMO_PARAMS + (pb->growth == JC_GROWTH_GAMMA ? 1 : 0);
+  d.grid_mode = grid_a ? 1 : 0; d.grid_na = grid_a ? n_grid_a : 0;
   d.TS = T;  // bank-conflict-free A-fragment gathers in the contraction kernel need TS = 4 or 12 (mod 16)
   while (d.TS % 16 != 4 && d.TS % 16 != 12) ++d.TS;
   d.n_src = n_src; d.zmax = zmax; d.lens_zmax = lens_zmax;
@@ -321,6 +324,8 @@ extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int3
   // ---- Limber nodes ---------------------------------------------------------------------------
   double amin = 1.0 / (1.0 + zmax);  // z2a(zmax), utils.py:2-4
   std::vector<double> la = linspace(amin, 1.0, JC_NA), llna(JC_NA), lz(JC_NA);
+  if (grid_a)
+    for (int n = 0; n < JC_NA; ++n) la[n] = n < n_grid_a ? grid_a[n] : 1.0;
   std::vector<double> lw = simpson_weights(512, (1.0 - amin) / 512);
   std::vector<double> lct(JC_NA), lgt(JC_NA);
   std::vector<uint16_t> lcix(JC_NA), lgix(JC_NA);
@@ -375,12 +380,13 @@ extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int3
   std::vector<double> ell(ell_host, ell_host + L), ellp5(L), lnellp5(L), ellfac(L), covnorm(L), ell108(L), ell14(L), ellm3(L);
   for (int l = 0; l < L; ++l) {
     double e = ell[l];
-    ellp5[l] = e + 0.5;
-    lnellp5[l] = std::log(e + 0.5);
-    ell108[l] = std::pow(e + 0.5, 1.08);
-    ell14[l] = std::pow(e + 0.5, 1.4);
-    ellm3[l] = 1.0 / ((e + 0.5) * (e + 0.5) * (e + 0.5));
-    ellfac[l] = std::sqrt((e - 1) * e * (e + 1) * (e + 2)) / ((e + 0.5) * (e + 0.5));  // probes.py:73
+    const double ep5 = grid_a ? e : e + 0.5;  // grid plan: the table entry is the wavenumber itself
+    ellp5[l] = ep5;
+    lnellp5[l] = std::log(ep5);
+    ell108[l] = std::pow(ep5, 1.08);
+    ell14[l] = std::pow(ep5, 1.4);
+    ellm3[l] = 1.0 / (ep5 * ep5 * ep5);
+    ellfac[l] = grid_a ? 1.0 : std::sqrt((e - 1) * e * (e + 1) * (e + 2)) / ((e + 0.5) * (e + 0.5));  // probes.py:73
     double g;  // np.gradient(ell), unit spacing (angular_cl.py:139)
     if (L == 1) g = 0.0;
     else if (l == 0) g = ell[1] - ell[0];
@@ -498,6 +504,31 @@ extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int3
 #undef DP
   *plan_out = plan;
   return JC_OK;
+}
+
+extern "C" int jc_plan_create(const jc_problem* pb, const double* ell_host, int32_t n_ell,
+                              int32_t device, jc_plan** plan_out) {
+  return create_plan(pb, ell_host, n_ell, device, nullptr, 0, plan_out);
+}
+
+// Grid plan for the stand-alone background / matter-power functions (background.py, power.py of the reference): K1 and
+// K3 run unchanged on the caller's scale factors and wavenumbers; tracer kernels and the contraction are not used.
+extern "C" int jc_grid_plan_create(int32_t transfer, int32_t nonlinear, int32_t growth, const double* k_host, int32_t n_k,
+                                   const double* a_host, int32_t n_a, int32_t device, jc_plan** plan_out) {
+  if (!k_host || !a_host || n_k < 1 || n_a < 1 || n_a > JC_NA - 1) return JC_ERR_INVALID;
+  for (int i = 0; i < n_k; ++i) if (!(k_host[i] > 0.0)) return JC_ERR_INVALID;
+  for (int i = 0; i < n_a; ++i) if (!(a_host[i] > 0.0)) return JC_ERR_INVALID;
+  jc_problem pb;
+  memset(&pb, 0, sizeof(pb));
+  pb.abi_version = JC_ABI_VERSION;
+  pb.n_tracers = 1;  // placeholder tracer: its tables are built but never read in grid mode
+  pb.transfer = transfer; pb.nonlinear = nonlinear; pb.growth = growth;
+  jc_tracer& tr = pb.tracers[0];
+  tr.kind = JC_TRACER_NUMBER_COUNTS;
+  tr.nz.family = JC_NZ_SMAIL; tr.nz.params[0] = 2.0; tr.nz.params[1] = 2.0; tr.nz.params[2] = 1.0;
+  tr.nz.gals_per_arcmin2 = 1.0; tr.nz.zmax = 10.0; tr.probe_zmax = 10.0;
+  tr.bias.family = JC_BIAS_CONSTANT; tr.bias.params[0] = 1.0;
+  return create_plan(&pb, k_host, n_k, device, a_host, n_a, plan_out);
 }
 
 extern "C" void jc_plan_destroy(jc_plan* plan) {

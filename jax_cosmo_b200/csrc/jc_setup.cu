@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
     T de;
     const T e2 = esqr(bg, a, lna, &de);
     const T se = jx_sqrt(e2);
-    const T chic = jx_max(chi, 1.0);                               // angular_cl.py:73
+    const T chic = pl.grid_mode ? T(1.0) : jx_max(chi, 1.0);       // angular_cl.py:73; grid plan: k is given, not (l+1/2)/chi
     const T dchida = JC_RH / (a * a * se);                         // background.py:294
     const double ia = 1.0 / a;
     const T lnchic = jx_log(chic);
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
     put(node(JC_NODE_INVCHIC, n), 1.0 / chic);
     put(node(JC_NODE_LNCHIC, n), lnchic);
     put(node(JC_NODE_GEOM, n), geom);
-    put(node(JC_NODE_GK, n), geom * JC_TWO_PI_SQ * (chic * chic * chic));
+    put(node(JC_NODE_GK, n), pl.grid_mode ? T(JC_TWO_PI_SQ) : geom * JC_TWO_PI_SQ * (chic * chic * chic));  // grid plan: V = P(k, a)
     S.rnl[n] = lnchic;  // scratch until the halofit root phase
     put(node(JC_NODE_GROWTH, n), D);
     put(node(JC_NODE_HUBBLE, n), JC_H0 * se);                      // background.py:143

@@ -111,13 +111,57 @@ def run_likelihood():
     return out
 
 
+def run_grid_functions():
+    """Stand-alone background / power functions of the reference (background.py, power.py) on (a, k) grids: flat, open,
+    closed and gamma-growth cosmologies; linear, halofit takahashi2012 and smith2003, both Eisenstein-Hu fits."""
+    from functools import partial
+
+    import jax_cosmo.background as bk
+    import jax_cosmo.power as pw
+    import jax_cosmo.transfer as tk
+
+    a = np.array([0.02, 0.09090909090909091, 0.15, 0.25, 0.4, 0.5, 0.62, 0.75, 0.9, 0.97, 1.0])
+    k = np.logspace(-3.5, 1.5, 24)
+    cosmos = {"planck15": sc.PLANCK15, "open_wcdm": dict(sc.WCDM, Omega_k=0.04), "closed_wcdm": dict(sc.WCDM, Omega_k=-0.03),
+              "gamma": dict(sc.WCDM, gamma=0.55)}
+    out = dict(a=a, k=k, names=np.array(json.dumps(list(cosmos))))
+    for name, cdict in cosmos.items():
+        t = time.time()
+        cosmo = jc.Cosmology(**cdict)
+        out[name + "_row"] = sc.cosmo_row(cdict)
+        out[name + "_chi"] = np.asarray(bk.radial_comoving_distance(cosmo, a))
+        out[name + "_chi_transverse"] = np.asarray(bk.transverse_comoving_distance(cosmo, a))
+        out[name + "_dA"] = np.asarray(bk.angular_diameter_distance(cosmo, a))
+        out[name + "_growth"] = np.asarray(bk.growth_factor(cosmo, a))
+        out[name + "_H"] = np.asarray(bk.H(cosmo, a))
+        out[name + "_Esqr"] = np.asarray(bk.Esqr(cosmo, a))
+        kk, aa = k[:, None], a  # the reference's own pattern (angular_cl.py:75-80): k [..., n_a] against a [n_a]
+        cosmo = jc.Cosmology(**cdict)
+        out[name + "_plin"] = np.asarray(pw.linear_matter_power(cosmo, kk, aa))
+        cosmo = jc.Cosmology(**cdict)
+        out[name + "_plin_nowiggle"] = np.asarray(pw.linear_matter_power(cosmo, kk, aa, transfer_fn=partial(tk.Eisenstein_Hu, type="eisenhu")))
+        cosmo = jc.Cosmology(**cdict)
+        out[name + "_pnl"] = np.asarray(pw.nonlinear_matter_power(cosmo, kk, aa))
+        cosmo = jc.Cosmology(**cdict)
+        out[name + "_pnl_smith"] = np.asarray(pw.nonlinear_matter_power(cosmo, kk, aa, nonlinear_fn=partial(pw.halofit, prescription="smith2003")))
+        cosmo = jc.Cosmology(**cdict)
+        out[name + "_pnl_a1"] = np.asarray(pw.nonlinear_matter_power(cosmo, k))  # the notebook's call: a = 1
+        print("grid %-12s %.1fs" % (name, time.time() - t), flush=True)
+    return out
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
     ap.add_argument("--stages", action="store_true")
     ap.add_argument("--likelihood", action="store_true")
+    ap.add_argument("--grid", action="store_true")
     args = ap.parse_args()
     os.makedirs(OUT, exist_ok=True)
+    if args.grid or (args.only is None and not args.stages and not args.likelihood):
+        np.savez(os.path.join(OUT, "grid_functions.npz"), **run_grid_functions())
+        if args.grid:
+            sys.exit(0)
     if args.likelihood or (args.only is None and not args.stages):
         np.savez(os.path.join(OUT, "likelihood.npz"), **run_likelihood())
         if args.likelihood:

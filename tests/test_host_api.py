@@ -109,8 +109,8 @@ def test_unsupported_options_raise(jc):
     row9 = jc.Cosmology(0.3, 0.05, 0.7, 0.96, 0.8, 0.0, -1.0, 0.0, gamma=0.55).to_row()
     assert row9.shape == (9,) and row9[8] == 0.55
     assert _native.build_problem([wl], growth=1).growth == 1 and _native.build_problem([wl]).growth == 0
-    with pytest.raises(NotImplementedError):
-        jc.power.halofit(None, None, None, None)
+    with pytest.raises(NotImplementedError):  # stand-alone halofit: unknown prescription (power.py:226,244)
+        jc.power.halofit(jc.Planck15(), 1.0, 1.0, jc.transfer.Eisenstein_Hu, prescription="mead2020")
     with pytest.raises(ValueError):
         _native.build_problem([jc.probes.WeakLensing([nz, nz], multiplicative_bias=[0.1])])
 
