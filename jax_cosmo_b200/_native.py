@@ -109,7 +109,7 @@ def load_library():
         lib.jc_sparse_inv_f64.restype = C.c_int
         lib.jc_grid_plan_create.argtypes = [i32, i32, i32, dp, i32, dp, i32, i32, C.POINTER(C.c_void_p)]
         lib.jc_grid_plan_create.restype = C.c_int
-        lib.jc_grid_eval_f64.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
+        lib.jc_grid_eval_f64.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
         lib.jc_grid_eval_f64.restype = C.c_int
         lib.jc_angular_cl_host_f64.argtypes = [vp, vp, i64, vp]
         lib.jc_angular_cl_host_f64.restype = C.c_int
@@ -462,14 +462,14 @@ class GridPlan(Plan):
         self._check_rows(cosmo_dev)
         B, na, nk = cosmo_dev.shape[0], len(self.a), len(self.k)
         out = {}
-        for name in ("pk", "chi", "chi_transverse", "growth", "hubble"):
+        for name in ("pk", "chi", "chi_transverse", "growth", "hubble", "transfer"):
             if name in want:
-                shape = (B, na, nk) if name == "pk" else (B, na)
+                shape = (B, na, nk) if name == "pk" else ((B, nk) if name == "transfer" else (B, na))
                 out[name] = torch.empty(shape, dtype=torch.float64, device=cosmo_dev.device)
         ptr = lambda n: out[n].data_ptr() if n in out else None
         ws = self.workspace(B)
         st = load_library().jc_grid_eval_f64(self._h, cosmo_dev.data_ptr(), B, ptr("pk"), ptr("chi"), ptr("chi_transverse"),
-                                             ptr("growth"), ptr("hubble"), ws.data_ptr(), ws.numel() * 8,
+                                             ptr("growth"), ptr("hubble"), ptr("transfer"), ws.data_ptr(), ws.numel() * 8,
                                              torch.cuda.current_stream(cosmo_dev.device).cuda_stream)
         check(st, "jc_grid_eval_f64")
         return out

@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(256) jc_grid_gather_kernel(JcDevPlan pl, Ws ws
 
 extern "C" int jc_grid_eval_f64(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo, double* pk_dev,
                                 double* chi_dev, double* chi_transverse_dev, double* growth_dev, double* hubble_dev,
-                                void* ws_dev, size_t ws_bytes, void* stream) {
+                                double* transfer_dev, void* ws_dev, size_t ws_bytes, void* stream) {
   if (!plan || !plan->d.grid_mode || !cosmo_dev || !ws_dev || n_cosmo < 1) return JC_ERR_INVALID;
   jc_ws_layout lo;
   int st = jc_workspace_layout(plan, ws_bytes, &lo);
@@ -180,6 +180,7 @@ extern "C" int jc_grid_eval_f64(const jc_plan* plan, const double* cosmo_dev, in
     const int chunk = (int)((n_cosmo - c0) < lo.chunk ? (n_cosmo - c0) : lo.chunk);
     jc_launch_setup(pl, cosmo_dev + c0 * pl.ncp, ws, chunk, s);
     if (pk_dev) jc_launch_power(pl, ws, chunk, s);
+    if (transfer_dev) jc_launch_transfer(pl, ws, chunk, transfer_dev + (size_t)c0 * pl.L, s);
     jc_grid_gather_kernel<<<dim3((per + 255) / 256, chunk), 256, 0, s>>>(
         pl, ws, cosmo_dev + c0 * pl.ncp, chunk, pk_dev ? pk_dev + (size_t)c0 * na * pl.L : nullptr,
         chi_dev ? chi_dev + (size_t)c0 * na : nullptr, chi_transverse_dev ? chi_transverse_dev + (size_t)c0 * na : nullptr,

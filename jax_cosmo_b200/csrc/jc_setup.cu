@@ -447,7 +447,19 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
   }
 }
 
+// T(k) of the Eisenstein-Hu fits at the plan's wavenumbers from the per-cosmology constants K1 left in ws.scal
+// (grid plans: transfer.Eisenstein_Hu as a stand-alone call)
+__global__ void __launch_bounds__(256) jc_transfer_kernel(JcDevPlan pl, Ws ws, double* __restrict__ tk) {
+  const int c = blockIdx.y, l = blockIdx.x * 256 + threadIdx.x;
+  if (l >= pl.L) return;
+  tk[(size_t)c * pl.L + l] = eh_transfer<double>(ws.scal + (size_t)c * JC_SCAL_FIELDS, pl.ellp5[l], pl.lnellp5[l], pl.transfer);
+}
+
 }  // namespace
+
+void jc_launch_transfer(const JcDevPlan& pl, const Ws& ws, int chunk, double* tk, cudaStream_t s) {
+  jc_transfer_kernel<<<dim3((pl.L + 255) / 256, chunk), 256, 0, s>>>(pl, ws, tk);
+}
 
 int jc_setup_init() {
   JC_CUDA_TRY(cudaFuncSetAttribute(jc_setup_kernel<Dual>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -146,6 +146,8 @@ def run_grid_functions():
         out[name + "_pnl_smith"] = np.asarray(pw.nonlinear_matter_power(cosmo, kk, aa, nonlinear_fn=partial(pw.halofit, prescription="smith2003")))
         cosmo = jc.Cosmology(**cdict)
         out[name + "_pnl_a1"] = np.asarray(pw.nonlinear_matter_power(cosmo, k))  # the notebook's call: a = 1
+        out[name + "_tk"] = np.asarray(tk.Eisenstein_Hu(cosmo, k))
+        out[name + "_tk_nowiggle"] = np.asarray(tk.Eisenstein_Hu(cosmo, k, type="eisenhu"))
         print("grid %-12s %.1fs" % (name, time.time() - t), flush=True)
     return out
 

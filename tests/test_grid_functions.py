@@ -36,6 +36,10 @@ def test_oracle_grid_functions_vs_reference_golden():
         ft = chi if c.Omega_k == 0 else (o.RH / sk * (np.sinh if c.Omega_k > 0 else np.sin)(sk * chi / o.RH))
         assert relerr(ft[:-1], g[name + "_chi_transverse"][:-1]) < 1e-12
         assert relerr((a * ft)[:-1], g[name + "_dA"][:-1]) < 1e-12
+        for key, ttype in (("_tk", "eisenhu_osc"), ("_tk_nowiggle", "eisenhu")):
+            c2 = o.Cosmo(row)
+            c2.transfer_type = ttype
+            assert relerr(o.eisenstein_hu(c2, k), g[name + key]) < 1e-12
         kk, aa = np.broadcast_arrays(k[:, None], a[None, :])
         for key, ttype, presc in (("_plin", "eisenhu_osc", None), ("_plin_nowiggle", "eisenhu", None),
                                   ("_pnl", "eisenhu_osc", "takahashi2012"), ("_pnl_smith", "eisenhu_osc", "smith2003")):
@@ -74,7 +78,9 @@ def test_gpu_background_and_power_vs_reference_golden(jc):
                "_plin_nowiggle": pw.linear_matter_power(cosmo, kk, a, transfer_fn=nowig),
                "_pnl": pw.nonlinear_matter_power(cosmo, kk, a),
                "_pnl_smith": pw.nonlinear_matter_power(cosmo, kk, a, nonlinear_fn=smith),
-               "_pnl_a1": pw.nonlinear_matter_power(cosmo, k)}
+               "_pnl_a1": pw.nonlinear_matter_power(cosmo, k),
+               "_tk": jc.transfer.Eisenstein_Hu(cosmo, k),
+               "_tk_nowiggle": jc.transfer.Eisenstein_Hu(cosmo, k, type="eisenhu")}
         for key, val in got.items():
             assert val.shape == g[name + key].shape, (key, val.shape)
             e = relerr(val, g[name + key])
