@@ -328,7 +328,8 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
   __syncthreads();
   {  // S(R_j), one R per thread (power.py:98-111 with g^2 factored out)
     // terms with (k r)^2 > HF_CUT are < e^-80 = 2e-35 of the leading ones: the k loop stops at
-    // ln k <= ln sqrt(HF_CUT) - ln r (the ln k grid is uniform), which also makes it unrollable
+    // ln k <= ln sqrt(HF_CUT) - ln r (the ln k grid is uniform), which also makes it unrollable and bounds the exp
+    // argument (>= -110: the unclamped table exp)
     const double r = pl.hf_r[tid];
     const double dlnk = pl.hf_lnk[1] - pl.hf_lnk[0];
     const int imax = min(JC_NHFK, (int)((HF_HALF_LN_CUT - pl.hf_logr[tid] - pl.hf_lnk[0]) / dlnk) + 2);
@@ -336,10 +337,10 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
     int i = 0;
     for (; i + 1 < imax; i += 2) {
       const double ya = s_hfk[i] * r, yb = s_hfk[i + 1] * r;
-      acc0 = acc0 + S.d2w[i] * jcm_exp_t(-(ya * ya), S.tab);
-      acc1 = acc1 + S.d2w[i + 1] * jcm_exp_t(-(yb * yb), S.tab);
+      acc0 = acc0 + S.d2w[i] * jcm_exp_t<false>(-(ya * ya), S.tab);
+      acc1 = acc1 + S.d2w[i + 1] * jcm_exp_t<false>(-(yb * yb), S.tab);
     }
-    if (i < imax) { const double ya = s_hfk[i] * r; acc0 = acc0 + S.d2w[i] * jcm_exp_t(-(ya * ya), S.tab); }
+    if (i < imax) { const double ya = s_hfk[i] * r; acc0 = acc0 + S.d2w[i] * jcm_exp_t<false>(-(ya * ya), S.tab); }
     const T acc = acc0 + acc1;
     S.S[tid] = acc;
     put(ws.stab + (size_t)c * JC_NHFR + tid, acc);
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
       for (int i = lane; i < imax; i += 32) {
         const T y = s_hfk[i] * rnl;
         const T y2 = y * y;
-        const T res = S.d2w[i] * jx_exp_t(-y2, S.tab);
+        const T res = S.d2w[i] * jx_exp_tb(-y2, S.tab);  // (k R)^2 <= ~110 by the truncation: no underflow clamp
         r0 = r0 + 2.0 * res * y2;
         r1 = r1 + 4.0 * res * (y2 - y2 * y2);
       }
