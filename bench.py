@@ -286,10 +286,10 @@ def main():
     achieved = 2.0 * slots[dom] * cosmo_per_launch / (launch_ms * 1e-3) / 1e12
     # FP64 work the compiled kernels actually execute (ncu, profiles/r01_ncu_summary.md): FP64-pipe warp
     # instructions per (ell, node) point x 64 flop for K3; DMMA m8n8k4 count x 512 flop for K4
-    sass_flops = {"power": 196.0 * 2 * N_ELL * A, "contract": 45279.0 * 512}
+    sass_flops = {"power": 186.0 * 2 * N_ELL * A, "contract": 45279.0 * 512}
     # DRAM bytes per launch of `chunk` cosmologies, scaled from the ncu --set full captures at 592 cosmologies
-    # (power: prof_r01_v6, contraction: prof_r01_v8tma; profiles/r01_ncu_summary.md)
-    ncu_dram_per_cosmo = {"power": (42.55e6 + 195.78e6) / 592, "contract": (299.39e6 + 76.44e6) / 592}
+    # (prof_r01_v9; profiles/r01_ncu_summary.md section 8)
+    ncu_dram_per_cosmo = {"power": (42.55e6 + 194.5e6) / 592, "contract": (297.4e6 + 77.71e6) / 592}
     step_tflops = 2.0 * slots["total"] * B * args.steps / (ms * 1e-3) / 1e12
     roofline = {"bound": "fp64", "kernel": kernels[dom], "achieved": achieved, "peak": peak_sustained,
                 "unit": "TFLOP/s", "frac": achieved / peak_sustained,
@@ -304,7 +304,7 @@ def main():
                 "achieved_sass": (sass_flops[dom] * cosmo_per_launch / (launch_ms * 1e-3) / 1e12) if dom in sass_flops else None,
                 "frac_sass": (sass_flops[dom] * cosmo_per_launch / (launch_ms * 1e-3) / 1e12 / peak_sustained) if dom in sass_flops else None,
                 "frac_note": "frac follows the SURVEY 8(d) v0 convention and can exceed 1 for jc_power_kernel: v0 books 500 issue "
-                             "slots per P(k) point, the compiled kernel needs 196 FP64 instructions (separable power laws, merged "
+                             "slots per P(k) point, the compiled kernel needs 186 FP64 instructions (separable power laws, merged "
                              "divisions, table-driven exp/log); frac_sass = executed FP64 flops / peak is the pipe utilisation",
                 "launch_ms": launch_ms, "cosmologies_per_launch": cosmo_per_launch,
                 "step": {"achieved": step_tflops, "frac": step_tflops / peak_sustained,
