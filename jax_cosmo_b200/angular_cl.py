@@ -104,7 +104,7 @@ def angular_cl_jvp(cosmo, ell, probes, tangents, transfer_fn=tklib.Eisenstein_Hu
         raise ValueError("tangents must have shape [K, %d]" % rows.shape[1])
     rows = torch.as_tensor(rows, device=dev)
     cl, dcl = plan.angular_cl_jvp_device(rows, torch.as_tensor(tang, device=dev))
-    return cl.cpu().numpy(), dcl.cpu().numpy()
+    return _native.to_host(cl), _native.to_host(dcl)
 
 
 def angular_cl_jacobian(cosmo, ell, probes, params=WCDM_PARAMS, transfer_fn=tklib.Eisenstein_Hu,
@@ -156,10 +156,10 @@ def gaussian_cl_covariance(ell, probes, cl_signal, cl_noise, f_sky=0.25, sparse=
     cl_dev = torch.as_tensor(cl_signal + resid, device=dev).contiguous()[None]
     cov = plan.gaussian_cov_device(cl_dev, f_sky=f_sky, noise=nvec)[0]
     if sparse:
-        return cov.cpu().numpy()
+        return _native.to_host(cov)
     dense = torch.zeros((P, L, P, L), dtype=torch.float64, device=dev)
     dense.diagonal(dim1=1, dim2=3).copy_(cov)  # angular_cl.py:159-162
-    return dense.reshape(P * L, P * L).cpu().numpy()
+    return _native.to_host(dense.reshape(P * L, P * L))
 
 
 def gaussian_cl_covariance_and_mean(cosmo, ell, probes, transfer_fn=tklib.Eisenstein_Hu,
@@ -176,7 +176,7 @@ def gaussian_cl_covariance_and_mean(cosmo, ell, probes, transfer_fn=tklib.Eisens
     P, L = plan.P, plan.L
     mean = cl_dev[0].reshape(-1).cpu().numpy()
     if sparse:
-        return mean, cov.cpu().numpy()
+        return mean, _native.to_host(cov)
     dense = torch.zeros((P, L, P, L), dtype=torch.float64, device=dev)
     dense.diagonal(dim1=1, dim2=3).copy_(cov)
-    return mean, dense.reshape(P * L, P * L).cpu().numpy()
+    return mean, _native.to_host(dense.reshape(P * L, P * L))
