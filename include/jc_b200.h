@@ -297,6 +297,11 @@ int jc_grid_eval_f64(const jc_plan* plan, const double* cosmo_dev, int64_t n_cos
                      double* chi_transverse_dev, double* growth_dev, double* hubble_dev, double* transfer_dev,
                      void* ws_dev, size_t ws_bytes, void* stream);
 
+/* redshift_distribution.__call__ (redshift.py:27-31): the normalised n(z) = pz_fn(z) / simps(pz_fn, 0, zmax, 256) of
+ * one bin (smail / fu / kde, under its systematic_shift chain), evaluated by the device functions the plan tables are
+ * built from.  HOST pointers, synchronous.  JC_ERR_UNSUPPORTED for delta_nz (not a distribution). */
+int jc_nz_eval_f64(const jc_nz* nz, const double* z_host, int64_t n, double* out_host);
+
 /* jax_cosmo.sparse on the device (sparse.py): a block matrix of [ny, nx] diagonal blocks of size n is S[ny, nx, n].
  * jc_sparse_bmm_f64: C[i,k,l] = sum_j A[i,j,l] * B[j,k,l] for i < I, j < J, k < K, l < L, every operand addressed
  * by element strides (in doubles; a stride of 0 broadcasts) -- one entry point behind sparse.dot's seven

@@ -31,7 +31,7 @@ SCAL_FIELDS = ["LN13KEQ", "INV13KEQ", "BETA_C", "C14_ALPHA_C", "SH_D", "LNKSILK"
 # every symbol include/jc_b200.h declares
 EXPORTS = ["jc_plan_create", "jc_plan_destroy", "jc_plan_n_tracers", "jc_plan_n_cls", "jc_plan_n_ell", "jc_plan_n_cosmo_params",
            "jc_workspace_bytes", "jc_workspace_layout", "jc_angular_cl_f64", "jc_angular_cl_host_f64",
-           "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64", "jc_gaussian_loglike_f64", "jc_fisher_f64", "jc_vjp_f64", "jc_sparse_bmm_f64", "jc_sparse_inv_f64", "jc_grid_plan_create", "jc_grid_eval_f64",
+           "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64", "jc_gaussian_loglike_f64", "jc_fisher_f64", "jc_vjp_f64", "jc_sparse_bmm_f64", "jc_sparse_inv_f64", "jc_grid_plan_create", "jc_grid_eval_f64", "jc_nz_eval_f64",
            "jc_noise_f64", "jc_gaussian_cov_f64", "jc_profile_enable", "jc_profile_read",
            "jc_fp64_peak_tflops", "jc_debug_math_f64", "jc_status_string",
            "jc_last_cuda_error", "jc_abi_version"]
@@ -111,6 +111,8 @@ def load_library():
         lib.jc_grid_plan_create.restype = C.c_int
         lib.jc_grid_eval_f64.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
         lib.jc_grid_eval_f64.restype = C.c_int
+        lib.jc_nz_eval_f64.argtypes = [C.POINTER(jc_nz), dp, i64, dp]
+        lib.jc_nz_eval_f64.restype = C.c_int
         lib.jc_angular_cl_host_f64.argtypes = [vp, vp, i64, vp]
         lib.jc_angular_cl_host_f64.restype = C.c_int
         lib.jc_noise_f64.argtypes = [vp, dp]
@@ -173,6 +175,41 @@ def _fill_bias(dst, b):
     dst.family = JC_BIAS[fam]
     for k, v in enumerate(b.params[:3]):
         dst.params[k] = float(v)
+
+
+def nz_eval(pz, z):
+    """redshift_distribution.__call__ on the device (jc_nz_eval_f64): normalised n(z) at host z values."""
+    fam, p, shifts = pz._describe()
+    if fam not in JC_NZ:
+        raise NotImplementedError("n(z) family %s" % fam)
+    if len(shifts) > JC_MAX_SHIFTS:
+        raise NotImplementedError("more than %d nested systematic_shift" % JC_MAX_SHIFTS)
+    d = jc_nz()
+    d.family = JC_NZ[fam]
+    keep = []
+    if fam == "kde":
+        zcat, w, bw = p
+        keep = [zcat, w]
+        d.kde_z = zcat.ctypes.data_as(C.POINTER(C.c_double))
+        d.kde_w = w.ctypes.data_as(C.POINTER(C.c_double))
+        d.kde_n = len(zcat)
+        d.kde_bw = bw
+        p = ()
+    for k, v in enumerate(p):
+        d.params[k] = v
+    d.n_shifts = len(shifts)
+    for k, v in enumerate(shifts):
+        d.shifts[k] = v
+    d.gals_per_arcmin2 = float(pz.gals_per_arcmin2)
+    d.zmax = float(pz.zmax)
+    zz = np.ascontiguousarray(np.atleast_1d(np.asarray(z, dtype=np.float64)))
+    out = np.empty(zz.size, dtype=np.float64)
+    dp = C.POINTER(C.c_double)
+    check(load_library().jc_nz_eval_f64(C.byref(d), zz.reshape(-1).ctypes.data_as(dp), zz.size, out.ctypes.data_as(dp)),
+          "jc_nz_eval_f64")
+    del keep
+    out = out.reshape(zz.shape)
+    return float(out[0]) if np.ndim(z) == 0 else out
 
 
 def build_problem(probes, transfer_fn=None, nonlinear_fn=None, growth=0):

@@ -531,6 +531,47 @@ extern "C" int jc_grid_plan_create(int32_t transfer, int32_t nonlinear, int32_t 
   return create_plan(&pb, k_host, n_k, device, a_host, n_a, plan_out);
 }
 
+// n(z) as a stand-alone call: redshift_distribution.__call__ (redshift.py:27-31) = pz_fn(z) / simps(pz_fn, 0, zmax, 256),
+// with the same device functions the plan tables are built from.  Host pointers, synchronous.
+namespace {
+__global__ void jc_nz_eval_kernel(NzDevAll all, const double* __restrict__ norm, const double* __restrict__ z,
+                                  double* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) out[i] = pz_fn(all.nz[0], z[i]) / norm[0];
+}
+}  // namespace
+
+extern "C" int jc_nz_eval_f64(const jc_nz* nz, const double* z_host, int64_t n, double* out_host) {
+  if (!nz || !z_host || !out_host || n < 1) return JC_ERR_INVALID;
+  if (nz->family < JC_NZ_SMAIL || nz->family > JC_NZ_KDE || nz->family == JC_NZ_DELTA) return JC_ERR_UNSUPPORTED;
+  if (nz->n_shifts < 0 || nz->n_shifts > JC_MAX_SHIFTS || !(nz->zmax > 0.0)) return JC_ERR_INVALID;
+  if (nz->family == JC_NZ_KDE && (!nz->kde_z || !nz->kde_w || nz->kde_n < 1 || !(nz->kde_bw > 0.0))) return JC_ERR_INVALID;
+  const size_t kde_bytes = nz->family == JC_NZ_KDE ? (size_t)nz->kde_n * sizeof(double) : 0;
+  double* buf = nullptr;  // [z n][out n][norm 1][kde_z][kde_w]
+  JC_CUDA_TRY(cudaMalloc(&buf, (2 * (size_t)n + 1) * sizeof(double) + 2 * kde_bytes));
+  double *dz = buf, *dout = buf + n, *dnorm = buf + 2 * n, *dkz = dnorm + 1, *dkw = dkz + (kde_bytes / sizeof(double));
+  NzDevAll all;
+  memset(&all, 0, sizeof(all));
+  NzDev& d = all.nz[0];
+  d.family = nz->family; d.n_shifts = nz->n_shifts; d.zmax = nz->zmax;
+  for (int i = 0; i < 4; ++i) d.p[i] = nz->params[i];
+  for (int i = 0; i < JC_MAX_SHIFTS; ++i) d.shifts[i] = nz->shifts[i];
+  cudaError_t e = cudaMemcpy(dz, z_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && kde_bytes) {
+    e = cudaMemcpy(dkz, nz->kde_z, kde_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dkw, nz->kde_w, kde_bytes, cudaMemcpyHostToDevice);
+    d.kde_z = dkz; d.kde_w = dkw; d.kde_n = nz->kde_n; d.kde_bw = nz->kde_bw;
+  }
+  if (e == cudaSuccess) {
+    jc_nz_norm_kernel<<<1, 288>>>(all, dnorm);
+    jc_nz_eval_kernel<<<(unsigned)((n + 255) / 256), 256>>>(all, dnorm, dz, dout, (long long)n);
+    e = cudaMemcpy(out_host, dout, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
+  }
+  cudaFree(buf);
+  if (e != cudaSuccess) { jc_set_cuda_error(e, "jc_nz_eval_f64"); return JC_ERR_CUDA; }
+  return JC_OK;
+}
+
 extern "C" void jc_plan_destroy(jc_plan* plan) {
   if (!plan) return;
   cudaSetDevice(plan->device);

@@ -1,10 +1,9 @@
 """Redshift distributions with the reference's constructors (jax_cosmo/redshift.py).
 
-These objects only describe n(z); evaluation happens in the CUDA plan kernels
-(csrc/jc_plan.cu: jc_nz_norm_kernel / jc_nz_node_kernel / jc_nz_lens_kernel).  Families that the
-B200 path does not cover (fu_nz, delta_nz, kde_nz) are constructible but raise
-NotImplementedError when handed to angular_cl -- there is no CPU fallback.  All four families of the
-reference (smail_nz, fu_nz, delta_nz, kde_nz) and systematic_shift are on the path."""
+These objects describe n(z); evaluation happens in the CUDA plan kernels (csrc/jc_plan.cu: jc_nz_norm_kernel /
+jc_nz_node_kernel / jc_nz_lens_kernel).  All four families of the reference (smail_nz, fu_nz, delta_nz, kde_nz) and
+systematic_shift are on the path.  Calling a distribution, `nz(z)`, returns the normalised n(z) like the reference
+(redshift.py:27-31), evaluated by the same device functions (jc_nz_eval_f64); there is no CPU fallback."""
 from jax_cosmo_b200.jax_utils import container
 
 steradian_to_arcmin2 = 11818102.86004228  # redshift.py:10
@@ -29,6 +28,11 @@ class redshift_distribution(container):
     @property
     def gals_per_steradian(self):
         return self._gals_per_arcmin2 * steradian_to_arcmin2
+
+    def __call__(self, z):
+        """Normalised n(z) = pz_fn(z) / simps(pz_fn, 0, zmax, 256) (redshift.py:27-31)."""
+        from jax_cosmo_b200 import _native
+        return _native.nz_eval(self, z)
 
     def _describe(self):
         """-> (family, params, shifts) for the jc_nz descriptor."""

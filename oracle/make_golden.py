@@ -125,6 +125,19 @@ def run_grid_functions():
     cosmos = {"planck15": sc.PLANCK15, "open_wcdm": dict(sc.WCDM, Omega_k=0.04), "closed_wcdm": dict(sc.WCDM, Omega_k=-0.03),
               "gamma": dict(sc.WCDM, gamma=0.55)}
     out = dict(a=a, k=k, names=np.array(json.dumps(list(cosmos))))
+    # redshift_distribution.__call__ (redshift.py:27-31) for every family and a shifted bin
+    rng = np.random.default_rng(1)
+    zcat, wcat = rng.gamma(3.0, 0.3, size=64), rng.uniform(0.5, 1.5, size=64)
+    specs = {"smail": sc.smail(1.0, 2.0, 0.7, 3.0), "smail_zmax4": sc.smail(2.0, 1.5, 0.5, 1.0, zmax=4.0),
+             "fu": sc.fu(0.4710, 5.1843, 0.7259, 30.0), "kde": sc.kde(zcat, wcat, 0.1, 4.0),
+             "smail_shift": sc.smail(1.0, 2.0, 0.7, 3.0, shift=0.03)}
+    zq = np.concatenate([np.linspace(0.0, 4.0, 33), [6.5, 9.99]])
+    out["nz_z"] = zq
+    out["nz_specs"] = np.array(json.dumps({k_: dict(v, zcat=None if v.get("zcat") is None else list(v["zcat"]),
+                                                      weights=None if v.get("weights") is None else list(v["weights"]))
+                                           for k_, v in specs.items()}))
+    for nm, spec in specs.items():
+        out["nz_" + nm] = np.asarray(sc.build_nz(spec, jc)(zq))
     for name, cdict in cosmos.items():
         t = time.time()
         cosmo = jc.Cosmology(**cdict)

@@ -51,6 +51,41 @@ def test_oracle_grid_functions_vs_reference_golden():
             assert relerr(got, g[name + key]) < 1e-11, (name, key, relerr(got, g[name + key]))
 
 
+def _nz_specs(g):
+    specs = json.loads(str(g["nz_specs"]))
+    for v in specs.values():
+        if v.get("zcat") is not None:
+            v["zcat"], v["weights"] = np.array(v["zcat"]), np.array(v["weights"])
+    return specs
+
+
+def test_oracle_nz_call_vs_reference_golden():
+    """redshift_distribution.__call__ (redshift.py:27-31): oracle n(z) against the reference objects."""
+    g, _ = _golden()
+    for name, spec in _nz_specs(g).items():
+        nzd = dict(family=spec["family"], params=list(spec["params"]), zmax=10.0 if spec.get("shift") is not None else spec["zmax"],
+                   zcat=spec.get("zcat"), weights=spec.get("weights"), bw=spec.get("bw"),
+                   shifts=[] if spec.get("shift") is None else [spec["shift"]])
+        assert relerr(o.nz_eval(nzd, g["nz_z"]), g["nz_" + name], floor=1e-300) < 1e-12, name
+
+
+@pytest.mark.gpu
+def test_gpu_nz_call_vs_reference_golden(jc):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import scenarios as sc
+    g, _ = _golden()
+    for name, spec in _nz_specs(g).items():
+        nz = sc.build_nz(spec, jc)
+        got = nz(g["nz_z"])
+        assert got.shape == g["nz_z"].shape
+        assert np.max(np.abs(got - g["nz_" + name])) < RTOL * np.max(np.abs(g["nz_" + name])), name
+        assert isinstance(nz(0.5), float)
+    with pytest.raises(NotImplementedError):
+        jc.redshift.delta_nz(1.0)(0.5)
+
+
 @pytest.mark.gpu
 def test_gpu_background_and_power_vs_reference_golden(jc):
     import torch
