@@ -66,6 +66,7 @@ template <class T> struct SetupSmem {
   T cum[256], chitab[256], gr_r[256], gr_q[256], M[127 * 4], gtab[128], sc[JC_SCAL_FIELDS];
   T d2w[JC_NHFK], S[JC_NHFR], D2[JC_NA], omm[JC_NA], ode[JC_NA], odew[JC_NA], rnl[JC_NA], red[8];
   double tab[JCM_TAB_DOUBLES];  // table-driven exp (jc_math.cuh) for the two halofit sums (~200k exp per cosmology)
+  int imax[JC_NA];              // per node: number of ln k nodes inside the (k r_nl)^2 <= HF_CUT truncation
 };
 
 // =================================================================================================
@@ -372,6 +373,10 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
     const T root = m * 1.0 + (pl.hf_logr[ind] - m * xi);
     const T rnl = jx_max(jx_exp(root), 1e-6);  // power.py:113-115
     S.rnl[n] = rnl;
+    // truncation bound of the n_eff / C sums below, here once per node by one thread: ncu had 212 warp instructions
+    // per node in the warp-per-node loop around them, most of them this bound's log() and division
+    const double lnr = fmax(jx_val(root), -13.815510557964274);  // ln r_nl, ln 1e-6
+    S.imax[n] = min(JC_NHFK, (int)((HF_HALF_LN_CUT - lnr - pl.hf_lnk[0]) * (256.0 / (pl.hf_lnk[JC_NHFK - 1] - pl.hf_lnk[0]))) + 2);
     put(node(JC_NODE_RNL, n), rnl);
     put(node(JC_NODE_LNKNL, n), -jx_log(rnl));
   }
@@ -379,11 +384,9 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
   // n_eff and C (power.py:121-141): one node per warp round, ln k nodes strided over lanes
   {
     const int warp = tid >> 5, lane = tid & 31;
-    const double dlnk = pl.hf_lnk[1] - pl.hf_lnk[0], lnk0 = pl.hf_lnk[0];
     for (int n = warp; n < JC_NA; n += 8) {
       const T rnl = S.rnl[n];
-      // same (k R)^2 <= HF_CUT truncation as for S(R)
-      const int imax = min(JC_NHFK, (int)((HF_HALF_LN_CUT - log(jx_val(rnl)) - lnk0) / dlnk) + 2);
+      const int imax = S.imax[n];  // same (k R)^2 <= HF_CUT truncation as for S(R)
       T r0 = T(0.0), r1 = T(0.0);
 #pragma unroll 2
       for (int i = lane; i < imax; i += 32) {
