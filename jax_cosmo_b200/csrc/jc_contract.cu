@@ -257,14 +257,17 @@ jc_contract_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64_t o
 // (finite) V rows of the last stage meet A = 0.
 // ---------------------------------------------------------------------------------------------------
 constexpr int TMA_CW = 16;      // warps per CTA
-constexpr int TMA_STAGES = 8;   // power of two
 
-template <int KC, bool JVP>
+// KC nodes per stage (12 or 24), TMA_STAGES ring depth (power of two)
+template <int KC, int TMA_STAGES, bool JVP>
 __global__ void __launch_bounds__(TMA_CW * 32, 1)
 jc_contract_tma_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64_t out_cosmo_stride, int chunk) {
   constexpr int NKC = (JC_NA + KC - 1) / KC;
   constexpr int NIMG = JVP ? 2 : 1;
-  static_assert(NKC * KC <= JC_NA_PAD, "R stages read whole KC-row blocks: they must stay inside the padded rows");
+  // the last stage holds <= 12 valid nodes: it is consumed as a 12-node stage (3 k-steps) and only the R rows inside
+  // the padded table are copied
+  constexpr int TAIL_NODES = JC_NA - (NKC - 1) * KC;
+  static_assert(KC % 12 == 0 && TAIL_NODES <= 12 && (NKC - 1) * KC + 12 <= JC_NA_PAD, "tail stage = one 12-node block");
   static_assert(KC < 31, "one lane per V row + lane 31 for R");
   static_assert((TMA_STAGES & (TMA_STAGES - 1)) == 0, "ring index by mask");
   extern __shared__ __align__(16) double smem[];
@@ -290,8 +293,9 @@ jc_contract_tma_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64
     const int l0 = grp * NCOLS;
     const int ncols = min(NCOLS, pl.Lpad - l0);  // multiple of 4 doubles: 32-byte pieces
     const int rows = min(KC, JC_NA - kc * KC);
+    const int rrows = min(KC, JC_NA_PAD - kc * KC);  // R rows of the stage that exist in the padded table
     double* st = smem + (size_t)sb * stage_doubles;
-    if (lane == 0) mbar_expect_tx(full + sb, (unsigned)(NIMG * (KC * TS + rows * ncols) * sizeof(double)));
+    if (lane == 0) mbar_expect_tx(full + sb, (unsigned)(NIMG * (rrows * TS + rows * ncols) * sizeof(double)));
     __syncwarp();
 #pragma unroll
     for (int img = 0; img < NIMG; ++img) {
@@ -302,7 +306,7 @@ jc_contract_tma_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64
                  full + sb);
       else if (lane == 31)
         tma_load(st + img * half, ws.rker + goff + ((size_t)c * JC_NA_PAD + kc * KC) * TS,
-                 (unsigned)(KC * TS * sizeof(double)), full + sb);
+                 (unsigned)(rrows * TS * sizeof(double)), full + sb);
     }
   };
 
@@ -354,8 +358,13 @@ jc_contract_tma_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64
           mbar_wait(full + sb, (q / TMA_STAGES) & 1);
           const double* Rs = smem + (size_t)sb * stage_doubles;
           const double* Vs = Rs + KC * TS;
-          if (cnt == 2) mma_stage_nt<KC, 2, JVP>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
-          else if (cnt == 1) mma_stage_nt<KC, 1, JVP>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+          if (KC > 12 && kc == NKC - 1) {  // tail stage: nodes beyond the first 12 are stale
+            if (cnt == 2) mma_stage_nt<12, 2, JVP>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+            else if (cnt == 1) mma_stage_nt<12, 1, JVP>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+          } else {
+            if (cnt == 2) mma_stage_nt<KC, 2, JVP>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+            else if (cnt == 1) mma_stage_nt<KC, 1, JVP>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+          }
           __syncwarp();
           if (lane == 0) mbar_arrive(empty + sb);
           // the lightest-loaded warp of the item (v = 15 holds `base` tiles) doubles as the producer: once all 16
@@ -371,7 +380,7 @@ jc_contract_tma_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64
   }
 }
 
-template <int KC, bool JVP>
+template <int KC, int TMA_STAGES, bool JVP>
 void launch_tma(const JcDevPlan& pl, const Ws& ws, double* out, int64_t stride, int chunk, cudaStream_t s) {
   const size_t smem = (size_t)(JVP ? 2 : 1) * TMA_STAGES * KC * (pl.TS + LSV) * sizeof(double) + 2 * TMA_STAGES * sizeof(uint64_t);
   static int sms = 0;  // idempotent; racing writers set the same values
@@ -379,10 +388,10 @@ void launch_tma(const JcDevPlan& pl, const Ws& ws, double* out, int64_t stride, 
     int dev = 0, n = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(jc_contract_tma_kernel<KC, JVP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(jc_contract_tma_kernel<KC, TMA_STAGES, JVP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     sms = n > 0 ? n : 148;
   }
-  jc_contract_tma_kernel<KC, JVP><<<chunk < sms ? chunk : sms, TMA_CW * 32, smem, s>>>(pl, ws, out, stride, chunk);
+  jc_contract_tma_kernel<KC, TMA_STAGES, JVP><<<chunk < sms ? chunk : sms, TMA_CW * 32, smem, s>>>(pl, ws, out, stride, chunk);
 }
 
 // TMA bulk copies need 16-byte aligned rows on both sides
@@ -424,8 +433,10 @@ void jc_launch_contract(const JcDevPlan& pl, const Ws& ws, double* cl, int chunk
     // 8 warps, 2 CTAs per SM, pair tiles split over 2 CTAs, cp.async staging (the default up to 16 pair tiles)
     case 3: launch_cfg<12, 8, 2, false>(pl, ws, cl, stride, chunk, mtiles > 16 ? 2 : 1, s); break;
     default:
-      if (tma_ok(pl, ws)) launch_tma<12, false>(pl, ws, cl, stride, chunk, s);
-      else launch_cfg<12, 8, 2, false>(pl, ws, cl, stride, chunk, mtiles > 16 ? 2 : 1, s);
+      if (!tma_ok(pl, ws)) launch_cfg<12, 8, 2, false>(pl, ws, cl, stride, chunk, mtiles > 16 ? 2 : 1, s);
+      else if (g_contract_cfg == 4) launch_tma<24, 4, false>(pl, ws, cl, stride, chunk, s);  // 24 nodes per stage: 6.30 ms, no gain
+      else if (g_contract_cfg == 5) launch_tma<24, 8, false>(pl, ws, cl, stride, chunk, s);  // 6.31 ms
+      else launch_tma<12, 8, false>(pl, ws, cl, stride, chunk, s);
       break;
   }
 }
@@ -433,6 +444,6 @@ void jc_launch_contract(const JcDevPlan& pl, const Ws& ws, double* cl, int chunk
 void jc_launch_contract_jvp(const JcDevPlan& pl, const Ws& ws, double* dcl, int64_t dcl_cosmo_stride, int chunk,
                             cudaStream_t s) {
   const int mtiles = (pl.P + 7) / 8;
-  if (g_contract_cfg != 3 && tma_ok(pl, ws)) launch_tma<12, true>(pl, ws, dcl, dcl_cosmo_stride, chunk, s);
+  if (g_contract_cfg != 3 && tma_ok(pl, ws)) launch_tma<12, 8, true>(pl, ws, dcl, dcl_cosmo_stride, chunk, s);
   else launch_cfg<12, 8, 2, true>(pl, ws, dcl, dcl_cosmo_stride, chunk, mtiles > 16 ? 2 : 1, s);
 }
