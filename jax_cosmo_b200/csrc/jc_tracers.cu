@@ -61,38 +61,49 @@ jc_lens_kernel(JcDevPlan pl, Ws ws, int n_cosmo, int s0) {
   constexpr int SLOTS = (PIECES + LENS_NODES * LENS_CGROUPS - 1) / (LENS_NODES * LENS_CGROUPS);
   constexpr int NSTAGE = (JC_NLENS + LENS_MR - 1) / LENS_MR;
   const int node0 = blockIdx.x * LENS_NODES;
+  // Copy slots: a running global pointer and a 32-bit shared-memory offset per slot, validity and row kind as bit
+  // masks.  load_stage is called with st = 0, 1, 2, ... so the pointers simply advance by one stage per call (ncu: the
+  // indexed form -- row test, 64-bit multiply-add and generic-to-shared conversion per slot -- was 160 of the 754
+  // instructions a warp executes per stage).
+  constexpr int ROWS_LAST = JC_NLENS - (NSTAGE - 1) * LENS_MR;
+  constexpr int STEP_T = LENS_MR * JC_NLENS_COLS * 8, STEP_IX = LENS_MR * JC_NLENS_COLS * 2;
   const unsigned char* slot_src[SLOTS];
-  int slot_dst[SLOTS], slot_row[SLOTS], slot_step[SLOTS];
+  unsigned slot_dst[SLOTS];
+  unsigned valid = 0, tail_ok = 0, is_ix = 0;
 #pragma unroll
   for (int j = 0; j < SLOTS; ++j) {
     const int q = threadIdx.x + j * (LENS_NODES * LENS_CGROUPS);
     const int b = q * 16;  // byte offset inside the stage image
+    int r = 0;
+    slot_dst[j] = (unsigned)b;
     if (q >= PIECES) {
-      slot_src[j] = nullptr; slot_dst[j] = 0; slot_row[j] = 0; slot_step[j] = 0;
+      slot_src[j] = nullptr;
     } else if (b < OFF_NW) {  // t rows
-      const int r = b / ROW_T, o = b - r * ROW_T;
-      slot_src[j] = (const unsigned char*)(pl.lens_t + (size_t)r * JC_NLENS_COLS + node0) + o;
-      slot_row[j] = r; slot_step[j] = LENS_MR * JC_NLENS_COLS * 8; slot_dst[j] = b;
+      r = b / ROW_T;
+      slot_src[j] = (const unsigned char*)(pl.lens_t + (size_t)r * JC_NLENS_COLS + node0) + (b - r * ROW_T);
     } else if (b < OFF_IX) {  // nw rows: [row][source][node]
       const int bb = b - OFF_NW;
-      const int r = bb / (ROW_T * NS), s = (bb - r * ROW_T * NS) / ROW_T, o = bb - (r * NS + s) * ROW_T;
+      r = bb / (ROW_T * NS);
+      const int s = (bb - r * ROW_T * NS) / ROW_T, o = bb - (r * NS + s) * ROW_T;
       slot_src[j] = (const unsigned char*)(pl.lens_nw + (size_t)(s0 + s) * NL + (size_t)r * JC_NLENS_COLS + node0) + o;
-      slot_row[j] = r; slot_step[j] = LENS_MR * JC_NLENS_COLS * 8; slot_dst[j] = b;
     } else {  // ix rows (uint16)
       const int bb = b - OFF_IX;
-      const int r = bb / ROW_IX, o = bb - r * ROW_IX;
-      slot_src[j] = (const unsigned char*)(pl.lens_ix + (size_t)r * JC_NLENS_COLS + node0) + o;
-      slot_row[j] = r; slot_step[j] = LENS_MR * JC_NLENS_COLS * 2; slot_dst[j] = b;
+      r = bb / ROW_IX;
+      slot_src[j] = (const unsigned char*)(pl.lens_ix + (size_t)r * JC_NLENS_COLS + node0) + (bb - r * ROW_IX);
+      is_ix |= 1u << j;
     }
+    if (q < PIECES) valid |= 1u << j;
+    if (q < PIECES && r < ROWS_LAST) tail_ok |= 1u << j;
   }
+  const unsigned smem0 = (unsigned)__cvta_generic_to_shared(lens_smem);
   auto load_stage = [&](int st) {
-    unsigned char* base = lens_smem + (size_t)(st % LENS_STAGES) * STAGE_BYTES;
+    const unsigned sbase = smem0 + (unsigned)(st % LENS_STAGES) * STAGE_BYTES;
+    const unsigned ok = st == NSTAGE - 1 ? tail_ok : valid;
 #pragma unroll
-    for (int j = 0; j < SLOTS; ++j)
-      if (slot_src[j] && st * LENS_MR + slot_row[j] < JC_NLENS) {
-        const unsigned sa = (unsigned)__cvta_generic_to_shared(base + slot_dst[j]);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(slot_src[j] + (size_t)st * slot_step[j]));
-      }
+    for (int j = 0; j < SLOTS; ++j) {
+      if ((ok >> j) & 1) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sbase + slot_dst[j]), "l"(slot_src[j]));
+      slot_src[j] += ((is_ix >> j) & 1) ? STEP_IX : STEP_T;
+    }
   };
 #pragma unroll
   for (int st = 0; st < LENS_STAGES - 1; ++st) {

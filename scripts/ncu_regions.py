@@ -12,8 +12,8 @@ hdr = rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
 ins = []
 for r in rows[2:]:
-    if len(r) < len(hdr):
-        continue
+    if len(r) < len(hdr) or not r[idx["Instructions Executed"]].strip().isdigit():
+        continue  # short rows / repeated header blocks (one per matching kernel)
     ins.append((r[idx["Source"]].strip(), int(r[idx["Instructions Executed"]] or 0), int(r[idx["# Samples"]] or 0)))
 tot = sum(e for _, e, _ in ins)
 fp = re.compile(r"(@\S+\s+)?(DFMA|DMUL|DADD|DSETP|DMMA)")
