@@ -381,30 +381,48 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
     put(node(JC_NODE_LNKNL, n), -jx_log(rnl));
   }
   __syncthreads();
-  // n_eff and C (power.py:121-141): one node per warp round, ln k nodes strided over lanes
+  // n_eff and C (power.py:121-141): 8 lanes per node (4 nodes per warp round), the ln k nodes strided over the 8 lanes.
+  // With a whole warp per node the 5-step shuffle reduction and the store cost 60 of the ~240 warp instructions spent
+  // per node (ncu region attribution, scripts/ncu_regions.py); neighbouring nodes have almost equal trip counts.
   {
     const int warp = tid >> 5, lane = tid & 31;
-    for (int n = warp; n < JC_NA; n += 8) {
+    auto node_sums = [&](int n, int first, int stride, T& r0, T& r1) {
       const T rnl = S.rnl[n];
       const int imax = S.imax[n];  // same (k R)^2 <= HF_CUT truncation as for S(R)
-      T r0 = T(0.0), r1 = T(0.0);
+      r0 = T(0.0); r1 = T(0.0);
 #pragma unroll 2
-      for (int i = lane; i < imax; i += 32) {
+      for (int i = first; i < imax; i += stride) {
         const T y = s_hfk[i] * rnl;
         const T y2 = y * y;
         const T res = S.d2w[i] * jx_exp_tb(-y2, S.tab);  // (k R)^2 <= ~110 by the truncation: no underflow clamp
         r0 = r0 + 2.0 * res * y2;
         r1 = r1 + 4.0 * res * (y2 - y2 * y2);
       }
+    };
+    auto finish_node = [&](int n, T r0, T r1) {
+      r0 = r0 * S.D2[n]; r1 = r1 * S.D2[n];
+      put(node(JC_NODE_NEFF, n), r0 - 3.0);
+      put(node(JC_NODE_CURV, n), r0 * r0 + r1);
+    };
+    const int sub = lane & 7, grp = lane >> 3;
+    for (int n0 = warp * 4; n0 < JC_NA - 1; n0 += 32) {  // nodes 0..511: 16 full rounds of 8 warps x 4 nodes
+      const int n = n0 + grp;
+      T r0, r1;
+      node_sums(n, sub, 8, r0, r1);
+      for (int o = 4; o > 0; o >>= 1) {
+        r0 = r0 + jx_shfl_xor(r0, o);
+        r1 = r1 + jx_shfl_xor(r1, o);
+      }
+      if (sub == 0) finish_node(n, r0, r1);
+    }
+    if (warp == 7) {  // node 512 (a = 1)
+      T r0, r1;
+      node_sums(JC_NA - 1, lane, 32, r0, r1);
       for (int o = 16; o > 0; o >>= 1) {
         r0 = r0 + jx_shfl_xor(r0, o);
         r1 = r1 + jx_shfl_xor(r1, o);
       }
-      if (lane == 0) {
-        r0 = r0 * S.D2[n]; r1 = r1 * S.D2[n];
-        put(node(JC_NODE_NEFF, n), r0 - 3.0);
-        put(node(JC_NODE_CURV, n), r0 * r0 + r1);
-      }
+      if (lane == 0) finish_node(JC_NA - 1, r0, r1);
     }
   }
   __syncthreads();
