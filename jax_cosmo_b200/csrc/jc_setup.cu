@@ -389,15 +389,17 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
     auto node_sums = [&](int n, int first, int stride, T& r0, T& r1) {
       const T rnl = S.rnl[n];
       const int imax = S.imax[n];  // same (k R)^2 <= HF_CUT truncation as for S(R)
-      r0 = T(0.0); r1 = T(0.0);
+      T s1 = T(0.0), s2 = T(0.0);  // sum w e^{-y^2} y^2 and sum w e^{-y^2} y^4
 #pragma unroll 2
       for (int i = first; i < imax; i += stride) {
         const T y = s_hfk[i] * rnl;
         const T y2 = y * y;
-        const T res = S.d2w[i] * jx_exp_tb(-y2, S.tab);  // (k R)^2 <= ~110 by the truncation: no underflow clamp
-        r0 = r0 + 2.0 * res * y2;
-        r1 = r1 + 4.0 * res * (y2 - y2 * y2);
+        const T t = S.d2w[i] * jx_exp_tb(-y2, S.tab) * y2;  // (k R)^2 <= ~110 by the truncation: no underflow clamp
+        s1 = s1 + t;
+        s2 = jx_fma(t, y2, s2);
       }
+      r0 = 2.0 * s1;         // power.py:127-131: sum 2 y^2 (...)
+      r1 = 4.0 * (s1 - s2);  // power.py:134-138: sum 4 (y^2 - y^4) (...)
     };
     auto finish_node = [&](int n, T r0, T r1) {
       r0 = r0 * S.D2[n]; r1 = r1 * S.D2[n];
