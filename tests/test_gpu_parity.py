@@ -498,18 +498,19 @@ def test_vjp_and_autograd(jc, torch_cuda):
     assert relerr(glike, -np.tensordot(jac, sol, axes=([1, 2], [0, 1]))) < 1e-9
 
 
-@pytest.mark.parametrize("shape", ["t17_l61", "t32_l9", "t16_l113"])
+@pytest.mark.parametrize("shape", ["t17_l61", "t32_l9", "t16_l113", "t20_l300", "t17_l1"])
 def test_tma_contraction_shapes(jc, torch_cuda, shape):
     """The persistent TMA contraction (>= 17 pair tiles) on ragged shapes against the oracle: odd ell counts (scalar
     stores, partial last ell tile), one to three ell groups, two to three tile rounds (T = 32: 66 pair tiles),
     IA + inverse-growth tracers, value and forward-mode tangent planes."""
     from oracle import derivatives as od
-    n_src, n_lens, L = {"t17_l61": (9, 8, 61), "t32_l9": (16, 16, 9), "t16_l113": (6, 10, 113)}[shape]
+    n_src, n_lens, L = {"t17_l61": (9, 8, 61), "t32_l9": (16, 16, 9), "t16_l113": (6, 10, 113), "t20_l300": (10, 10, 300),
+                        "t17_l1": (8, 9, 1)}[shape]
     src = [sc.smail(1.0, 2.0, 0.3 + 0.07 * i, 1.5, shift=(0.01 if i % 3 == 0 else None)) for i in range(n_src)]
     lns = [sc.smail(2.0, 4.0, 0.25 + 0.06 * i, 2.0) for i in range(n_lens)]
     probes_spec = [sc.wl(src, ia=sc.bias("des_y1_ia", 0.5, 0.0, 0.62), m=[0.01 * (-1) ** i for i in range(n_src)]),
                    sc.nc(lns, [sc.bias("inverse_growth" if i % 2 else "constant", 1.0 + 0.05 * i) for i in range(n_lens)])]
-    ell = np.logspace(1, np.log10(2500), L)
+    ell = np.logspace(1, np.log10(2500), L) if L > 1 else np.array([137.0])
     scn = sc.scenario(shape, sc.WCDM, ell, probes_spec)
     probes = sc.build_probes(scn, jc)
     cosmo = sc.build_cosmo(scn, jc)
