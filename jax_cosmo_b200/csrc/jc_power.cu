@@ -158,8 +158,19 @@ void jc_launch_power(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t 
     case 3: launch_power_cfg<double, 4, 2>(pl, ws, chunk, 8, s); break;  // 128 registers, 2 CTAs / SM
     case 4: launch_power_cfg<double, 2, 3>(pl, ws, chunk, 8, s); break;
     case 5: launch_power_cfg<double, 8, 3>(pl, ws, chunk, 8, s); break;
-    // fastest (profiles/r01_tuning.md): 4 nodes per thread, 64 registers, 8 CTAs per cosmology
-    default: launch_power_cfg<double, 4, 4>(pl, ws, chunk, 8, s); break;
+    case 6: launch_power_cfg<double, 8, 4>(pl, ws, chunk, 8, s); break;   // 8 nodes per thread at 64 registers
+    case 7: launch_power_cfg<double, 8, 4>(pl, ws, chunk, 4, s); break;
+    case 8: launch_power_cfg<double, 16, 4>(pl, ws, chunk, 4, s); break;
+    case 9: launch_power_cfg<double, 4, 4>(pl, ws, chunk, 16, s); break;
+    case 10: launch_power_cfg<double, 32, 4>(pl, ws, chunk, 2, s); break;
+    case 11: launch_power_cfg<double, 32, 4>(pl, ws, chunk, 4, s); break;
+    case 12: launch_power_cfg<double, 64, 4>(pl, ws, chunk, 2, s); break;
+    case 13: launch_power_cfg<double, 16, 4>(pl, ws, chunk, 2, s); break;
+    case 14: launch_power_cfg<double, 16, 4>(pl, ws, chunk, 8, s); break;
+    case 15: launch_power_cfg<double, 4, 4>(pl, ws, chunk, 8, s); break;  // the round's earlier default: 6.34 ms
+    // fastest (profiles/r01_tuning.md): 16 nodes per thread (the ell-side loads and index arithmetic amortise over 16
+    // points), 64 registers, 8 CTAs per cosmology: 6.13 ms
+    default: launch_power_cfg<double, 16, 4>(pl, ws, chunk, 8, s); break;
   }
 }
 
