@@ -314,7 +314,7 @@ def main():
                 "stage_v0_frac": {k: (2.0 * slots[k] * B * args.steps / (stage_ms[k] * 1e-3) / 1e12 / peak_sustained)
                                   for k in ("setup", "lens", "power", "contract")}}
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # the CPU arm is timed beside the N = 1 run only
         cores = os.cpu_count() or 1
         sample = max(cores, min(args.cpu_sample, 8 * cores))
         rate, dt = cpu_oracle_rate(sample, cores)
