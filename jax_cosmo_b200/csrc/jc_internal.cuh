@@ -187,70 +187,3 @@ int jc_contract_init();
       return JC_ERR_CUDA;                          \
     }                                              \
   } while (0)
-
-// ---- device math helpers ------------------------------------------------------------------
-__device__ __forceinline__ double jc_fde(double w0, double wa, double a, double lna) {
-  return -3.0 * (1.0 + w0 + wa) * lna + 3.0 * wa * (a - 1.0);  // background.py:90
-}
-
-struct JcBg {
-  double Om, Ok, Ode, w0, wa;
-};
-
-// E^2(a), background.py:122-126.  Returns also the dark-energy term.
-__device__ __forceinline__ double jc_esqr(const JcBg& c, double a, double lna, double* de_term) {
-  double ia = 1.0 / a;
-  double ia2 = ia * ia;
-  double de = c.Ode * exp(jc_fde(c.w0, c.wa, a, lna));
-  *de_term = de;
-  return c.Om * (ia2 * ia) + c.Ok * ia2 + de;
-}
-
-// Eisenstein-Hu per-cosmology constants (transfer.py:47-136), computed once per cosmology.
-struct JcEH {
-  double ln13keq, inv13keq, beta_c, c14_alpha_c, sh_d, lnksilk, alpha_b, beta_b, beta_node, fb, fc;
-};
-
-__device__ __forceinline__ void jc_eh_load(JcEH& e, const double* __restrict__ s) {
-  e.ln13keq = s[JC_SCAL_LN13KEQ];
-  e.inv13keq = s[JC_SCAL_INV13KEQ];
-  e.beta_c = s[JC_SCAL_BETA_C];
-  e.c14_alpha_c = s[JC_SCAL_C14_ALPHA_C];
-  e.sh_d = s[JC_SCAL_SH_D];
-  e.lnksilk = s[JC_SCAL_LNKSILK];
-  e.alpha_b = s[JC_SCAL_ALPHA_B];
-  e.beta_b = s[JC_SCAL_BETA_B];
-  e.beta_node = s[JC_SCAL_BETA_NODE];
-  e.fb = s[JC_SCAL_FB];
-  e.fc = s[JC_SCAL_FC];
-}
-
-// T(k) of transfer.py:113-153 ("eisenhu_osc") given k and ln k.
-__device__ __forceinline__ double jc_eh_transfer(const JcEH& e, double k, double lnk) {
-  const double E1 = 2.718281828459045;  // np.exp(1.0)
-  double q = k * e.inv13keq;
-  double q2 = q * q;
-  double q108 = exp(1.08 * (lnk - e.ln13keq));  // np.power(q, 1.08)
-  double c386 = 386.0 / (1.0 + 69.9 * q108);
-  double L1 = log(E1 + 1.8 * e.beta_c * q);
-  double L2 = log(E1 + 1.8 * q);
-  double C1 = 14.2 + c386;            // alpha = 1
-  double C2 = e.c14_alpha_c + c386;   // alpha = alpha_c
-  double T1 = L1 / (L1 + C1 * q2);    // T_tilde(k, 1, beta_c)
-  double T2 = L1 / (L1 + C2 * q2);    // T_tilde(k, alpha_c, beta_c)
-  double T3 = L2 / (L2 + C1 * q2);    // T_tilde(k, 1, 1)
-  double ks = k * e.sh_d;
-  double x54 = ks / 5.4;
-  double x54_2 = x54 * x54;
-  double f = 1.0 / (1.0 + x54_2 * x54_2);
-  double Tc = f * T1 + (1.0 - f) * T2;
-  double bn = e.beta_node / ks;
-  double st = e.sh_d / cbrt(1.0 + bn * bn * bn);
-  double x52 = ks / 5.2;
-  double bb = e.beta_b / ks;
-  double silk = exp(-exp(1.4 * (lnk - e.lnksilk)));  // exp(-(k/k_silk)^1.4)
-  double arg = k * st;
-  double sinc = sin(arg) / arg;  // np.sinc(k s~/pi); k > 0 on this path
-  double Tb = (T3 / (1.0 + x52 * x52) + e.alpha_b / (1.0 + bb * bb * bb) * silk) * sinc;
-  return e.fb * Tb + e.fc * Tc;
-}
