@@ -127,16 +127,20 @@ jc_lens_kernel(JcDevPlan pl, Ws ws, int n_cosmo, int s0) {
         const double t = st_t[r * LENS_NODES];
         const int ix = st_ix[r * LENS_NODES];
         const int i0 = ix & 255, i1 = ix >> 8;
-        double wv[NS];
-#pragma unroll
-        for (int s = 0; s < NS; ++s) wv[s] = st_nw[(r * NS + s) * LENS_NODES];
+        // the NCOS lensing weights first, then one n(z') load per source feeding NCOS accumulators: NCOS live values
+        // instead of NS (the kernel sits at the 128-register cap with NCOS x NS accumulators)
+        T g[NCOS];
 #pragma unroll
         for (int c = 0; c < NCOS; ++c) {
           const T f0 = chit[c][i0], f1 = chit[c][i1];
           const T chip = jx_clip0(f0 + (f1 - f0) * t);                          // background.py:242
-          const T g = jx_clip0(chip - chin[c]) * jx_rcp(jx_floor1(chip));       // probes.py:49
+          g[c] = jx_clip0(chip - chin[c]) * jx_rcp(jx_floor1(chip));            // probes.py:49
+        }
 #pragma unroll
-          for (int s = 0; s < NS; ++s) acc[c][s] = acc[c][s] + wv[s] * g;
+        for (int s = 0; s < NS; ++s) {
+          const double w = st_nw[(r * NS + s) * LENS_NODES];
+#pragma unroll
+          for (int c = 0; c < NCOS; ++c) acc[c][s] = acc[c][s] + w * g[c];
         }
       }
     }
