@@ -6,6 +6,10 @@
 
 #include <cstdint>
 
+#ifndef JC_MBAR_BACKOFF_NS
+#define JC_MBAR_BACKOFF_NS 0  // sleep between failed try_wait polls (experiment knob; 0 = spin)
+#endif
+
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count) : "memory");
@@ -20,6 +24,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) {
   do {
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
                  : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (!ok && JC_MBAR_BACKOFF_NS) __nanosleep(JC_MBAR_BACKOFF_NS);
   } while (!ok);
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
