@@ -289,13 +289,17 @@ int jc_vjp_f64(const double* jac_dev, const double* cot_dev, int64_t cot_stride,
  * halofit root.  jc_angular_cl_* reject grid plans and jc_grid_eval_f64 rejects ordinary plans (JC_ERR_INVALID).
  * Outputs (device, any may be NULL): pk [B, n_a, n_k] in (Mpc/h)^3 (linear if the plan's nonlinear == JC_PK_LINEAR),
  * chi / chi_transverse [B, n_a] in Mpc/h, growth [B, n_a] (D(1) = 1), hubble [B, n_a] in km/s/(Mpc/h),
- * transfer [B, n_k]: the Eisenstein-Hu T(k) of the plan's fit (transfer.py:10-156).
+ * transfer [B, n_k]: the Eisenstein-Hu T(k) of the plan's fit (transfer.py:10-156),
+ * kernels [B, T, n_a]: the probes' radial kernels WeakLensing.kernel / NumberCounts.kernel (probes.py:188-281) without
+ * the weak-lensing ell factor (probes.py:73), for plans made by jc_grid_plan_create_probes (NULL otherwise).
  * Workspace: jc_workspace_bytes(plan, B). */
 int jc_grid_plan_create(int32_t transfer, int32_t nonlinear, int32_t growth, const double* k_host, int32_t n_k,
                         const double* a_host, int32_t n_a, int32_t device, jc_plan** plan_out);
 int jc_grid_eval_f64(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo, double* pk_dev, double* chi_dev,
                      double* chi_transverse_dev, double* growth_dev, double* hubble_dev, double* transfer_dev,
-                     void* ws_dev, size_t ws_bytes, void* stream);
+                     double* kernels_dev, void* ws_dev, size_t ws_bytes, void* stream);
+int jc_grid_plan_create_probes(const jc_problem* problem, const double* a_host, int32_t n_a, int32_t device,
+                               jc_plan** plan_out);
 
 /* redshift_distribution.__call__ (redshift.py:27-31): the normalised n(z) = pz_fn(z) / simps(pz_fn, 0, zmax, 256) of
  * one bin (smail / fu / kde, under its systematic_shift chain), evaluated by the device functions the plan tables are

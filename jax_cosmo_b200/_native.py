@@ -31,7 +31,7 @@ SCAL_FIELDS = ["LN13KEQ", "INV13KEQ", "BETA_C", "C14_ALPHA_C", "SH_D", "LNKSILK"
 # every symbol include/jc_b200.h declares
 EXPORTS = ["jc_plan_create", "jc_plan_destroy", "jc_plan_n_tracers", "jc_plan_n_cls", "jc_plan_n_ell", "jc_plan_n_cosmo_params",
            "jc_workspace_bytes", "jc_workspace_layout", "jc_angular_cl_f64", "jc_angular_cl_host_f64",
-           "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64", "jc_gaussian_loglike_f64", "jc_fisher_f64", "jc_vjp_f64", "jc_sparse_bmm_f64", "jc_sparse_inv_f64", "jc_grid_plan_create", "jc_grid_eval_f64", "jc_nz_eval_f64",
+           "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64", "jc_gaussian_loglike_f64", "jc_fisher_f64", "jc_vjp_f64", "jc_sparse_bmm_f64", "jc_sparse_inv_f64", "jc_grid_plan_create", "jc_grid_plan_create_probes", "jc_grid_eval_f64", "jc_nz_eval_f64",
            "jc_noise_f64", "jc_gaussian_cov_f64", "jc_profile_enable", "jc_profile_read",
            "jc_fp64_peak_tflops", "jc_debug_math_f64", "jc_status_string",
            "jc_last_cuda_error", "jc_abi_version"]
@@ -109,7 +109,9 @@ def load_library():
         lib.jc_sparse_inv_f64.restype = C.c_int
         lib.jc_grid_plan_create.argtypes = [i32, i32, i32, dp, i32, dp, i32, i32, C.POINTER(C.c_void_p)]
         lib.jc_grid_plan_create.restype = C.c_int
-        lib.jc_grid_eval_f64.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
+        lib.jc_grid_eval_f64.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
+        lib.jc_grid_plan_create_probes.argtypes = [C.POINTER(jc_problem), dp, i32, i32, C.POINTER(C.c_void_p)]
+        lib.jc_grid_plan_create_probes.restype = C.c_int
         lib.jc_grid_eval_f64.restype = C.c_int
         lib.jc_nz_eval_f64.argtypes = [C.POINTER(jc_nz), dp, i64, dp]
         lib.jc_nz_eval_f64.restype = C.c_int
@@ -468,7 +470,9 @@ class GridPlan(Plan):
     """jc_grid_plan_create: the path's setup and power kernels on a caller-chosen (scale factor, wavenumber) grid
     (stand-alone background.* / power.* functions).  n_a <= 512."""
 
-    def __init__(self, k, a, transfer=JC_TF_EH_OSC, nonlinear=JC_PK_HALOFIT, growth=0, device=None):
+    def __init__(self, k, a, transfer=JC_TF_EH_OSC, nonlinear=JC_PK_HALOFIT, growth=0, device=None, problem=None):
+        """problem=None: background / power grid (jc_grid_plan_create); a jc_problem: the radial kernels of its tracers
+        at the scale factors `a` (jc_grid_plan_create_probes; `k` is ignored)."""
         import torch
 
         lib = load_library()
@@ -479,9 +483,14 @@ class GridPlan(Plan):
         self.a = np.ascontiguousarray(np.atleast_1d(np.asarray(a, dtype=np.float64)))
         handle = C.c_void_p()
         dp = C.POINTER(C.c_double)
+        self.problem = problem
         with torch.cuda.device(self.device):
-            st = lib.jc_grid_plan_create(int(transfer), int(nonlinear), int(growth), self.k.ctypes.data_as(dp), len(self.k),
-                                         self.a.ctypes.data_as(dp), len(self.a), self.device, C.byref(handle))
+            if problem is None:
+                st = lib.jc_grid_plan_create(int(transfer), int(nonlinear), int(growth), self.k.ctypes.data_as(dp), len(self.k),
+                                             self.a.ctypes.data_as(dp), len(self.a), self.device, C.byref(handle))
+            else:
+                st = lib.jc_grid_plan_create_probes(C.byref(problem), self.a.ctypes.data_as(dp), len(self.a), self.device,
+                                                    C.byref(handle))
         check(st, "jc_grid_plan_create")
         self._h = handle
         self.T = lib.jc_plan_n_tracers(handle)
@@ -499,14 +508,14 @@ class GridPlan(Plan):
         self._check_rows(cosmo_dev)
         B, na, nk = cosmo_dev.shape[0], len(self.a), len(self.k)
         out = {}
-        for name in ("pk", "chi", "chi_transverse", "growth", "hubble", "transfer"):
+        for name in ("pk", "chi", "chi_transverse", "growth", "hubble", "transfer", "kernels"):
             if name in want:
-                shape = (B, na, nk) if name == "pk" else ((B, nk) if name == "transfer" else (B, na))
+                shape = {"pk": (B, na, nk), "transfer": (B, nk), "kernels": (B, self.T, na)}.get(name, (B, na))
                 out[name] = torch.empty(shape, dtype=torch.float64, device=cosmo_dev.device)
         ptr = lambda n: out[n].data_ptr() if n in out else None
         ws = self.workspace(B)
         st = load_library().jc_grid_eval_f64(self._h, cosmo_dev.data_ptr(), B, ptr("pk"), ptr("chi"), ptr("chi_transverse"),
-                                             ptr("growth"), ptr("hubble"), ptr("transfer"), ws.data_ptr(), ws.numel() * 8,
+                                             ptr("growth"), ptr("hubble"), ptr("transfer"), ptr("kernels"), ws.data_ptr(), ws.numel() * 8,
                                              torch.cuda.current_stream(cosmo_dev.device).cuda_stream)
         check(st, "jc_grid_eval_f64")
         return out

@@ -139,12 +139,16 @@ namespace {
 __global__ void __launch_bounds__(256) jc_grid_gather_kernel(JcDevPlan pl, Ws ws, const double* __restrict__ cosmo, int chunk,
                                                              double* __restrict__ pk, double* __restrict__ chi,
                                                              double* __restrict__ chi_t, double* __restrict__ growth,
-                                                             double* __restrict__ hubble) {
+                                                             double* __restrict__ hubble, double* __restrict__ kernels) {
   const int c = blockIdx.y, na = pl.grid_na;
   const int tid = blockIdx.x * 256 + threadIdx.x;
   if (pk && tid < na * pl.L) {
     const int n = tid / pl.L, l = tid - n * pl.L;
     pk[((size_t)c * na + n) * pl.L + l] = ws.vtab[((size_t)c * JC_NA + n) * pl.Lpad + l];
+  }
+  if (kernels && tid < na * pl.T) {  // [T, n_a] like the reference's (nbins, nz)
+    const int t = tid / na, n = tid - t * na;
+    kernels[((size_t)c * pl.T + t) * na + n] = ws.rker[((size_t)c * JC_NA_PAD + n) * pl.TS + t];
   }
   if (tid < na) {
     const double x = node_ptr(ws, c, JC_NODE_CHI)[tid];
@@ -165,7 +169,7 @@ __global__ void __launch_bounds__(256) jc_grid_gather_kernel(JcDevPlan pl, Ws ws
 
 extern "C" int jc_grid_eval_f64(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo, double* pk_dev,
                                 double* chi_dev, double* chi_transverse_dev, double* growth_dev, double* hubble_dev,
-                                double* transfer_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+                                double* transfer_dev, double* kernels_dev, void* ws_dev, size_t ws_bytes, void* stream) {
   if (!plan || !plan->d.grid_mode || !cosmo_dev || !ws_dev || n_cosmo < 1) return JC_ERR_INVALID;
   jc_ws_layout lo;
   int st = jc_workspace_layout(plan, ws_bytes, &lo);
@@ -175,16 +179,22 @@ extern "C" int jc_grid_eval_f64(const jc_plan* plan, const double* cosmo_dev, in
   Ws ws;
   resolve(lo, (double*)ws_dev, 0, &ws);
   const int na = pl.grid_na;
-  const int per = na * pl.L > na ? na * pl.L : na;
+  int per = na * pl.L > na ? na * pl.L : na;
+  if (kernels_dev && na * pl.T > per) per = na * pl.T;
   for (int64_t c0 = 0; c0 < n_cosmo; c0 += lo.chunk) {
     const int chunk = (int)((n_cosmo - c0) < lo.chunk ? (n_cosmo - c0) : lo.chunk);
     jc_launch_setup(pl, cosmo_dev + c0 * pl.ncp, ws, chunk, s);
     if (pk_dev) jc_launch_power(pl, ws, chunk, s);
+    if (kernels_dev) {
+      jc_launch_tracers(pl, ws, chunk, s);
+      jc_launch_finish(pl, ws, chunk, s);
+    }
     if (transfer_dev) jc_launch_transfer(pl, ws, chunk, transfer_dev + (size_t)c0 * pl.L, s);
     jc_grid_gather_kernel<<<dim3((per + 255) / 256, chunk), 256, 0, s>>>(
         pl, ws, cosmo_dev + c0 * pl.ncp, chunk, pk_dev ? pk_dev + (size_t)c0 * na * pl.L : nullptr,
         chi_dev ? chi_dev + (size_t)c0 * na : nullptr, chi_transverse_dev ? chi_transverse_dev + (size_t)c0 * na : nullptr,
-        growth_dev ? growth_dev + (size_t)c0 * na : nullptr, hubble_dev ? hubble_dev + (size_t)c0 * na : nullptr);
+        growth_dev ? growth_dev + (size_t)c0 * na : nullptr, hubble_dev ? hubble_dev + (size_t)c0 * na : nullptr,
+        kernels_dev ? kernels_dev + (size_t)c0 * pl.T * na : nullptr);
   }
   JC_CUDA_TRY(cudaGetLastError());
   return JC_OK;

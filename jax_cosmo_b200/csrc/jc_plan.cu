@@ -572,6 +572,16 @@ extern "C" int jc_nz_eval_f64(const jc_nz* nz, const double* z_host, int64_t n, 
   return JC_OK;
 }
 
+// Grid plan over a real tracer set: the radial kernels of the probes (probes.py: WeakLensing.kernel / NumberCounts.kernel)
+// at the caller's scale factors.  No wavenumbers: the power kernel is not used with this plan.
+extern "C" int jc_grid_plan_create_probes(const jc_problem* pb, const double* a_host, int32_t n_a, int32_t device,
+                                          jc_plan** plan_out) {
+  if (!pb || !a_host || n_a < 1 || n_a > JC_NA - 1) return JC_ERR_INVALID;
+  for (int i = 0; i < n_a; ++i) if (!(a_host[i] > 0.0)) return JC_ERR_INVALID;
+  const double k_dummy = 1.0;
+  return create_plan(pb, &k_dummy, 1, device, a_host, n_a, plan_out);
+}
+
 extern "C" void jc_plan_destroy(jc_plan* plan) {
   if (!plan) return;
   cudaSetDevice(plan->device);

@@ -6,6 +6,26 @@ from jax_cosmo_b200.jax_utils import container
 __all__ = ["WeakLensing", "NumberCounts"]
 
 
+def _radial_kernels(probe, cosmo, z):
+    """[n_bins, n_z] radial kernels of one probe at redshifts z, by the path's own setup / lensing-efficiency / tracer
+    kernels on a grid plan over the probe's tracers (include/jc_b200.h: jc_grid_plan_create_probes); the weak-lensing
+    ell factor is left out.  No CPU fallback."""
+    import torch
+
+    from jax_cosmo_b200 import _native
+
+    row = cosmo.to_row() if hasattr(cosmo, "to_row") else np.asarray(cosmo, dtype=np.float64)
+    zz = np.atleast_1d(np.asarray(z, dtype=np.float64)).reshape(-1)
+    pb = _native.build_problem([probe], growth=1 if len(row) == 9 else 0)
+    out = np.empty((probe.n_tracers, len(zz)))
+    for i0 in range(0, len(zz), 512):  # a grid plan holds <= 512 scale factors
+        a = 1.0 / (1.0 + zz[i0:i0 + 512])  # z2a, utils.py:2-4
+        plan = _native.GridPlan([1.0], a, problem=pb)
+        res = plan.evaluate(torch.as_tensor(row[None], device="cuda:%d" % plan.device), want=("kernels",))
+        out[:, i0:i0 + 512] = res["kernels"][0].cpu().numpy()
+    return out
+
+
 class WeakLensing(container):
     """probes.py:132-223.  params = (redshift_bins, multiplicative_bias[, ia_bias]);
     config = {sigma_e, ia_enabled}."""
@@ -28,6 +48,14 @@ class WeakLensing(container):
     @property
     def zmax(self):
         return max([pz.zmax for pz in self.params[0]])
+
+    def kernel(self, cosmo, z, ell):
+        """Radial kernels of all bins, shape (n_bins, n_z) (probes.py:188-208): lensing efficiency x (1+z) chi x
+        3 H0^2 Omega_m / 2c, plus the NLA term when IA is enabled, times (1 + m), times the ell factor
+        sqrt((l-1) l (l+1) (l+2)) / (l+1/2)^2 (probes.py:73)."""
+        ell = np.asarray(ell, dtype=np.float64)
+        ell_factor = np.sqrt((ell - 1) * ell * (ell + 1) * (ell + 2)) / (ell + 0.5) ** 2
+        return ell_factor * _radial_kernels(self, cosmo, z)
 
     def noise(self):
         """sigma_e^2 / n_gal per bin (probes.py:210-223)."""
@@ -53,6 +81,11 @@ class NumberCounts(container):
     @property
     def n_tracers(self):
         return len(self.params[0])
+
+    def kernel(self, cosmo, z, ell):
+        """Radial kernels n_i(z) b_i(z) H(z) of all bins, shape (n_bins, n_z) (probes.py:77-99, 260-272); no ell
+        dependence."""
+        return _radial_kernels(self, cosmo, z)
 
     def noise(self):
         """1 / n_gal per bin (probes.py:274-281)."""

@@ -138,6 +138,20 @@ def run_grid_functions():
                                            for k_, v in specs.items()}))
     for nm, spec in specs.items():
         out["nz_" + nm] = np.asarray(sc.build_nz(spec, jc)(zq))
+    # probe.kernel(cosmo, z, ell) (probes.py:188-208, 260-272): lensing with IA / m-bias / a delta plane, counts with
+    # constant and inverse-growth biases, on an open wCDM cosmology
+    nz1, nz2 = sc.smail(1.0, 2.0, 1.0, 2.0), sc.smail(1.0, 2.0, 0.5, 3.0, shift=0.02)
+    kscn = sc.scenario("kernels", dict(sc.WCDM, Omega_k=0.04), [100.0],
+                       [sc.wl([nz1, nz2], ia=sc.bias("des_y1_ia", 0.5, 0.0, 0.62), m=[0.01, -0.02]),
+                        sc.wl([nz1, sc.delta(0.8)]),
+                        sc.nc([nz1, nz2], [sc.bias("constant", 1.2), sc.bias("inverse_growth", 1.1)])])
+    zk = np.concatenate([[0.0, 0.01], np.linspace(0.05, 3.0, 30)])
+    out["kern_z"] = zk
+    out["kern_spec"] = np.array(json.dumps(kscn))
+    kcosmo = sc.build_cosmo(kscn, jc)
+    for i, probe in enumerate(sc.build_probes(kscn, jc)):
+        out["kern_%d_ell100" % i] = np.asarray(probe.kernel(kcosmo, zk, 100.0))
+        out["kern_%d_ell2" % i] = np.asarray(probe.kernel(kcosmo, zk, 2.0))
     for name, cdict in cosmos.items():
         t = time.time()
         cosmo = jc.Cosmology(**cdict)

@@ -69,6 +69,52 @@ def test_oracle_nz_call_vs_reference_golden():
         assert relerr(o.nz_eval(nzd, g["nz_z"]), g["nz_" + name], floor=1e-300) < 1e-12, name
 
 
+def _ell_factor(ell):
+    return np.sqrt((ell - 1) * ell * (ell + 1) * (ell + 2)) / (ell + 0.5) ** 2
+
+
+def test_oracle_probe_kernels_vs_reference_golden():
+    """probe.kernel(cosmo, z, ell) (probes.py:188-208, 260-272) per probe: IA + m-bias + shifted bin, a delta plane,
+    number counts with constant / inverse-growth bias."""
+    from oracle import scenarios as sc
+    g, _ = _golden()
+    scn = json.loads(str(g["kern_spec"]))
+    z = g["kern_z"]
+    for i, probe in enumerate(scn["probes"]):
+        one = dict(scn, probes=[probe])
+        bg = o.Background(o.Cosmo(sc.cosmo_row(scn["cosmo"])))
+        R, is_wl = o.radial_kernels(bg, sc.flatten_spec(one)["tracers"], z)
+        for ell in (100.0, 2.0):
+            ref = g["kern_%d_ell%d" % (i, int(ell))]
+            got = R * (_ell_factor(ell) if is_wl[0] else 1.0)
+            assert np.max(np.abs(got - ref)) < 1e-12 * np.max(np.abs(ref)), (i, ell)
+
+
+@pytest.mark.gpu
+def test_gpu_probe_kernels_vs_reference_golden(jc):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import scenarios as sc
+    g, _ = _golden()
+    scn = json.loads(str(g["kern_spec"]))
+    z = g["kern_z"]
+    cosmo = sc.build_cosmo(scn, jc)
+    for i, probe in enumerate(sc.build_probes(scn, jc)):
+        for ell in (100.0, 2.0):
+            ref = g["kern_%d_ell%d" % (i, int(ell))]
+            got = probe.kernel(cosmo, z, ell)
+            assert got.shape == ref.shape
+            scale = np.abs(ref).max(axis=1, keepdims=True)
+            assert np.max(np.abs(got - ref) / scale) < RTOL, (i, ell, np.max(np.abs(got - ref) / scale))
+    # more redshifts than one grid plan holds
+    zz = np.linspace(0.0, 2.5, 600)
+    probe = sc.build_probes(scn, jc)[2]
+    k600 = probe.kernel(cosmo, zz, 10.0)
+    R, _ = o.radial_kernels(o.Background(o.Cosmo(sc.cosmo_row(scn["cosmo"]))), sc.flatten_spec(dict(scn, probes=[scn["probes"][2]]))["tracers"], zz)
+    assert k600.shape == (2, 600) and np.max(np.abs(k600 - R)) < RTOL * np.abs(R).max()
+
+
 @pytest.mark.gpu
 def test_gpu_nz_call_vs_reference_golden(jc):
     import torch
