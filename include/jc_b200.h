@@ -306,6 +306,12 @@ int jc_grid_plan_create_probes(const jc_problem* problem, const double* a_host, 
  * built from.  HOST pointers, synchronous.  JC_ERR_UNSUPPORTED for delta_nz (not a distribution). */
 int jc_nz_eval_f64(const jc_nz* nz, const double* z_host, int64_t n, double* out_host);
 
+/* Diagnostics: run a subset of the pipeline stages of one chunk (n_cosmo <= the workspace's chunk) on `stream`.
+ * stage_mask bits: 0 setup, 1 lensing efficiency, 2 tracer finish, 3 power, 4 contraction (persistent TMA kernel),
+ * 5 contraction (8-warp cp.async kernel, one CTA per SM).  Used by scripts/overlap_probe.py. */
+int jc_debug_stages_f64(const jc_plan* plan, int32_t stage_mask, const double* cosmo_dev, int64_t n_cosmo, double* cl_dev,
+                        void* ws_dev, size_t ws_bytes, void* stream);
+
 /* jax_cosmo.sparse on the device (sparse.py): a block matrix of [ny, nx] diagonal blocks of size n is S[ny, nx, n].
  * jc_sparse_bmm_f64: C[i,k,l] = sum_j A[i,j,l] * B[j,k,l] for i < I, j < J, k < K, l < L, every operand addressed
  * by element strides (in doubles; a stride of 0 broadcasts) -- one entry point behind sparse.dot's seven

@@ -31,7 +31,7 @@ SCAL_FIELDS = ["LN13KEQ", "INV13KEQ", "BETA_C", "C14_ALPHA_C", "SH_D", "LNKSILK"
 # every symbol include/jc_b200.h declares
 EXPORTS = ["jc_plan_create", "jc_plan_destroy", "jc_plan_n_tracers", "jc_plan_n_cls", "jc_plan_n_ell", "jc_plan_n_cosmo_params",
            "jc_workspace_bytes", "jc_workspace_layout", "jc_angular_cl_f64", "jc_angular_cl_host_f64",
-           "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64", "jc_gaussian_loglike_f64", "jc_fisher_f64", "jc_vjp_f64", "jc_sparse_bmm_f64", "jc_sparse_inv_f64", "jc_grid_plan_create", "jc_grid_plan_create_probes", "jc_grid_eval_f64", "jc_nz_eval_f64",
+           "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64", "jc_gaussian_loglike_f64", "jc_fisher_f64", "jc_vjp_f64", "jc_sparse_bmm_f64", "jc_sparse_inv_f64", "jc_debug_stages_f64", "jc_grid_plan_create", "jc_grid_plan_create_probes", "jc_grid_eval_f64", "jc_nz_eval_f64",
            "jc_noise_f64", "jc_gaussian_cov_f64", "jc_profile_enable", "jc_profile_read",
            "jc_fp64_peak_tflops", "jc_debug_math_f64", "jc_status_string",
            "jc_last_cuda_error", "jc_abi_version"]
@@ -113,6 +113,8 @@ def load_library():
         lib.jc_grid_plan_create_probes.argtypes = [C.POINTER(jc_problem), dp, i32, i32, C.POINTER(C.c_void_p)]
         lib.jc_grid_plan_create_probes.restype = C.c_int
         lib.jc_grid_eval_f64.restype = C.c_int
+        lib.jc_debug_stages_f64.argtypes = [vp, i32, vp, i64, vp, vp, C.c_size_t, vp]
+        lib.jc_debug_stages_f64.restype = C.c_int
         lib.jc_nz_eval_f64.argtypes = [C.POINTER(jc_nz), dp, i64, dp]
         lib.jc_nz_eval_f64.restype = C.c_int
         lib.jc_angular_cl_host_f64.argtypes = [vp, vp, i64, vp]

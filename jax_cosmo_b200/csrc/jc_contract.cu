@@ -441,6 +441,21 @@ void jc_launch_contract(const JcDevPlan& pl, const Ws& ws, double* cl, int chunk
   }
 }
 
+// Experiment support (scripts/overlap_probe.py): the 8-warp cp.async kernel with a shared-memory request that admits one CTA
+// per SM next to other kernels' CTAs (co-residency of the contraction with the power kernel).
+void jc_launch_contract_1cta(const JcDevPlan& pl, const Ws& ws, double* cl, int chunk, cudaStream_t s) {
+  const int mtiles = (pl.P + 7) / 8;
+  const int msplit = mtiles > 16 ? 2 : 1;
+  const int ngroups = (pl.L + NCOLS - 1) / NCOLS;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(jc_contract_kernel<12, 8, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr_done = true;
+  }
+  // <.., 2, ..>: the 128-register build; the 120 KB request keeps it at one CTA per SM
+  jc_contract_kernel<12, 8, 2, false><<<dim3(ngroups * msplit, chunk), 256, 120 * 1024, s>>>(pl, ws, cl, (int64_t)pl.P * pl.L, msplit);
+}
+
 void jc_launch_contract_jvp(const JcDevPlan& pl, const Ws& ws, double* dcl, int64_t dcl_cosmo_stride, int chunk,
                             cudaStream_t s) {
   const int mtiles = (pl.P + 7) / 8;

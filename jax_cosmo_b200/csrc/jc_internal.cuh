@@ -163,6 +163,7 @@ __device__ __forceinline__ double jc_rcp(double x) {
 
 // per-stage launchers (one translation unit per kernel)
 void jc_launch_setup(const JcDevPlan& pl, const double* cosmo, const Ws& ws, int chunk, cudaStream_t s);
+void jc_launch_contract_1cta(const JcDevPlan& pl, const Ws& ws, double* cl, int chunk, cudaStream_t s);
 void jc_launch_transfer(const JcDevPlan& pl, const Ws& ws, int chunk, double* tk, cudaStream_t s);
 // JVP (Dual) variants: same kernels instantiated on value+tangent; `tangent` = direction [8] in parameter space
 void jc_launch_setup_jvp(const JcDevPlan& pl, const double* cosmo, const double* tangent, const Ws& ws, int chunk,

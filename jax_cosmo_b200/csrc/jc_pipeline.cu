@@ -199,3 +199,28 @@ extern "C" int jc_grid_eval_f64(const jc_plan* plan, const double* cosmo_dev, in
   JC_CUDA_TRY(cudaGetLastError());
   return JC_OK;
 }
+
+// Experiment support: run a subset of the pipeline stages of ONE chunk on `stream` (bit 0 setup, 1 lens, 2 finish, 3 power,
+// 4 contraction (persistent TMA kernel), 5 contraction (8-warp cp.async kernel, one CTA per SM)).  scripts/overlap_probe.py
+// uses it to time the power kernel of one chunk against the contraction of another on two streams.
+extern "C" int jc_debug_stages_f64(const jc_plan* plan, int32_t stage_mask, const double* cosmo_dev, int64_t n_cosmo,
+                                   double* cl_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+  if (!plan || plan->d.grid_mode || !cosmo_dev || !cl_dev || !ws_dev || n_cosmo < 1) return JC_ERR_INVALID;
+  jc_ws_layout lo;
+  int st = jc_workspace_layout(plan, ws_bytes, &lo);
+  if (st != JC_OK) return st;
+  if (n_cosmo > lo.chunk) return JC_ERR_WORKSPACE;
+  const JcDevPlan& pl = plan->d;
+  cudaStream_t s = (cudaStream_t)stream;
+  Ws ws;
+  resolve(lo, (double*)ws_dev, 0, &ws);
+  const int chunk = (int)n_cosmo;
+  if (stage_mask & 1) jc_launch_setup(pl, cosmo_dev, ws, chunk, s);
+  if (stage_mask & 2) jc_launch_tracers(pl, ws, chunk, s);
+  if (stage_mask & 4) jc_launch_finish(pl, ws, chunk, s);
+  if (stage_mask & 8) jc_launch_power(pl, ws, chunk, s);
+  if (stage_mask & 16) jc_launch_contract(pl, ws, cl_dev, chunk, s);
+  if (stage_mask & 32) jc_launch_contract_1cta(pl, ws, cl_dev, chunk, s);
+  JC_CUDA_TRY(cudaGetLastError());
+  return JC_OK;
+}
