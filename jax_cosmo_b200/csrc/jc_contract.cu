@@ -9,6 +9,9 @@
 // but needs 1/16 of the issue slots and pads P, L only to multiples of 8 (216 x 104) instead of the
 // 4x4-block x 32-lane tiling of a scalar kernel (240 x 128).
 //
+// Two kernels share the stage body (mma_stage): jc_contract_tma_kernel (>= 17 pair tiles, the bench configuration:
+// persistent CTAs, TMA bulk copies + mbarriers, no CTA-wide barrier -- described at its definition below) and
+// jc_contract_kernel (fewer pair tiles, and the baseline the TMA kernel was measured against):
 // CTA = (cosmology, group of <= 7 ell-tiles, share of the pair tiles).  The pair tiles (8 pairs each)
 // are dealt to the warps 2-or-1 each (balanced over the four SMSPs); a warp holds <= 2 x 7 accumulator
 // tiles (28 FP64 accumulators per lane).  R and V stream through a 4-stage cp.async pipeline of KC

@@ -1,6 +1,6 @@
 // jc_power.cu -- K3: V[n,l] = geom_n * P(k = (l+1/2)/max(chi_n,1), a_n) for every (node, ell).
 //
-// A thread owns one ell and NPT consecutive Limber nodes (l fastest across lanes, so a warp shares its
+// A thread owns one ell and NPT (= 16) consecutive Limber nodes (l fastest across lanes, so a warp shares its
 // node constants and V rows are written coalesced); the ell-side table entries, the per-cosmology EH
 // constants and the polynomial coefficients are loaded once per thread and reused over the NPT nodes.
 // Eisenstein-Hu "eisenhu_osc" transfer (transfer.py:113-153), linear power (power.py:49-52) and
@@ -11,7 +11,7 @@
 //     and a per-node (setup kernel) table entry;
 //   * (1+D2L)^beta * exp(-(y/4+y^2/8)) is one exp -- 5 exp, 3 log, 1 rcbrt, 1 sin remain per point;
 //   * the ~14 divisions of T(k) and of Delta^2_Q + Delta^2_H are merged into two reciprocals;
-//   * exp/log are table driven (jc_math.cuh: 2^n T[j] p6(r); {c_j, -ln c_j} + log1p degree 7), the tables
+//   * exp/log are table driven (jc_math.cuh: 2^n T[j] p4(r), 256 entries per octave; {c_j, -ln c_j} + log1p degree 7), the tables
 //     are staged in shared memory once per CTA and the CTA strides over its cosmology's index space;
 //     sin/rcbrt/rcp and all polynomial coefficients are constant-bank DFMA operands.
 // Template on the scalar type: double (hot path) or Dual (JVP pass, jc_dual.cuh).
