@@ -228,16 +228,25 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
     S.M[4 * tid + 3] = 1.0 + s * (K1.d + 2.0 * K2.d + 2.0 * K3.d + K4.d);
   }
   __syncthreads();
-  if (tid == 0) {  // ordered product applied to y0 = (a_0, 1), background.py:477-478
-    T y0 = T(pl.gr_pt_a[0]), y1 = T(1.0);
-    S.gtab[0] = y0;
-    for (int n = 0; n < 127; ++n) {
-      const T n0 = S.M[4 * n] * y0 + S.M[4 * n + 1] * y1;
-      const T n1 = S.M[4 * n + 2] * y0 + S.M[4 * n + 3] * y1;
-      y0 = n0; y1 = n1;
-      S.gtab[n + 1] = y0;
+  // y_{n+1} = M_n ... M_0 y_0 with y_0 = (a_0, 1), background.py:477-478: inclusive prefix product of the one-step
+  // matrices by a 7-step block scan (the 127 dependent matrix-vector steps of one thread held a barrier for 4 % of
+  // the kernel's warp time); the product is re-associated, the table differs from the sequential scan by a few ulp
+  for (int off = 1; off < 127; off <<= 1) {
+    M2<T> P = {T(0.0), T(0.0), T(0.0), T(0.0)};
+    if (tid < 127) {
+      P = {S.M[4 * tid], S.M[4 * tid + 1], S.M[4 * tid + 2], S.M[4 * tid + 3]};
+      if (tid >= off) {
+        const int o = tid - off;
+        const M2<T> Q = {S.M[4 * o], S.M[4 * o + 1], S.M[4 * o + 2], S.M[4 * o + 3]};
+        P = mul(P, Q);  // newer steps on the left
+      }
     }
+    __syncthreads();
+    if (tid < 127) { S.M[4 * tid] = P.a; S.M[4 * tid + 1] = P.b; S.M[4 * tid + 2] = P.c; S.M[4 * tid + 3] = P.d; }
+    __syncthreads();
   }
+  if (tid < 127) S.gtab[tid + 1] = S.M[4 * tid] * pl.gr_pt_a[0] + S.M[4 * tid + 1];
+  if (tid == 0) S.gtab[0] = T(pl.gr_pt_a[0]);
   }  // growth ODE
   __syncthreads();
   if (tid < 128) {
