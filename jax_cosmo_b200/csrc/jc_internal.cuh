@@ -84,6 +84,8 @@ struct JcDevPlan {
   const int* tr_ia;          // [T]
   const int* tr_src;         // [T] index into lens_nw or -1
   const int* src_tracer;     // [n_src] tracer index of each lensing source
+  const int* fin_idx;        // [n_fin] tracers the finish kernel evaluates at every node (NC, delta planes, IA sources)
+  int n_fin;
   const int* tr_delta_ix;    // [T] delta_nz source plane: chi-table bracket i0 | i1<<8 of a_s, else -1
   const double* tr_delta_t;  // [T] its interpolation weight
   const double* tr_m1;       // [T] 1 + m

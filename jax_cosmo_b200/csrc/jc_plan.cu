@@ -430,6 +430,12 @@ static int create_plan(const jc_problem* pb, const double* ell_host, int32_t n_e
   size_t o_nz_node = B.reserve((size_t)JC_NA_PAD * d.TS * sizeof(double));
   size_t o_bias_node = B.add(bias_node);
   size_t o_kind = B.add(tr_kind), o_inv = B.add(tr_inv), o_ia = B.add(tr_ia), o_src = B.add(tr_src);
+  std::vector<int> fin_idx;
+  for (int t = 0; t < T; ++t)
+    if (tr_kind[t] != JC_TRACER_WEAK_LENSING || tr_delta_ix[t] >= 0 || tr_ia[t]) fin_idx.push_back(t);
+  d.n_fin = (int)fin_idx.size();
+  if (fin_idx.empty()) fin_idx.push_back(0);
+  size_t o_fin = B.add(fin_idx);
   size_t o_dix = B.add(tr_delta_ix), o_dt = B.add(tr_delta_t);
   std::vector<size_t> o_kde_z(T, 0), o_kde_w(T, 0);
   for (int t = 0; t < T; ++t) {
@@ -468,7 +474,7 @@ static int create_plan(const jc_problem* pb, const double* ell_host, int32_t n_e
   d.lens_t = DP(double, o_lens_t); d.lens_ix = DP(uint16_t, o_lens_ix); d.lens_nw = DP(double, o_lens_nw);
   d.nz_node = DP(double, o_nz_node); d.bias_node = DP(double, o_bias_node);
   d.tr_kind = DP(int, o_kind); d.tr_inv_growth = DP(int, o_inv); d.tr_ia = DP(int, o_ia); d.tr_src = DP(int, o_src);
-  d.tr_delta_ix = DP(int, o_dix); d.tr_delta_t = DP(double, o_dt);
+  d.tr_delta_ix = DP(int, o_dix); d.tr_delta_t = DP(double, o_dt); d.fin_idx = DP(int, o_fin);
   d.tr_m1 = DP(double, o_m1); d.src_tracer = DP(int, o_srct);
   d.ell = DP(double, o_ell); d.ellp5 = DP(double, o_ellp5); d.lnellp5 = DP(double, o_lnellp5);
   d.ellfac = DP(double, o_ellfac); d.covnorm = DP(double, o_covnorm);

@@ -176,13 +176,19 @@ jc_lens_kernel(JcDevPlan pl, Ws ws, int n_cosmo, int s0) {
 
 template <class T>
 __global__ void __launch_bounds__(512) jc_tracer_finish_kernel(JcDevPlan pl, Ws ws) {
-  // One CTA per cosmology; blockDim = rows x T with every thread bound to ONE tracer, so the per-tracer switches
-  // are loop invariant and there is no index division: ncu had 193 warp instructions per element (issue bound,
-  // 15 % FP64 pipe) with a flat (node, tracer) index.
+  // One CTA per cosmology; blockDim = rows x n_fin with every thread bound to ONE of the n_fin tracers that need all
+  // nodes (number counts, delta planes, IA-enabled sources), so the per-tracer switches are loop invariant and there is no
+  // index division: ncu had 193 warp instructions per element (issue bound, 15 % FP64 pipe) with a flat (node, tracer)
+  // index.  Plain extended sources are complete after the lens kernel's epilogue except node 512 (a = 1: chi = 0 -> 0).
   const int c = blockIdx.x;
   const ptrdiff_t doff = ws.doff;
+  for (int t2 = threadIdx.x; t2 < pl.T; t2 += blockDim.x)
+    if (pl.tr_kind[t2] == JC_TRACER_WEAK_LENSING && pl.tr_delta_ix[t2] < 0 && !pl.tr_ia[t2])
+      JxMem<T>::st(ws.rker + ((size_t)c * JC_NA_PAD + JC_NLENS_COLS) * pl.TS + t2, doff, T(0.0));
+  const int nf = pl.n_fin;
+  if (nf > 0 && (int)threadIdx.x < (int)(blockDim.x / nf) * nf) {
   const T Om = JxMem<T>::ld(ws.scal + (size_t)c * JC_SCAL_FIELDS + JC_SCAL_OMEGA_M, doff);
-  const int t = threadIdx.x % pl.T, rows = blockDim.x / pl.T;
+  const int t = pl.fin_idx[threadIdx.x % nf], rows = blockDim.x / nf;
   const bool is_wl = pl.tr_kind[t] == JC_TRACER_WEAK_LENSING, inv_growth = pl.tr_inv_growth[t], ia = pl.tr_ia[t];
   const int dix = pl.tr_delta_ix[t];
   const double m1 = pl.tr_m1[t];
@@ -197,16 +203,13 @@ __global__ void __launch_bounds__(512) jc_tracer_finish_kernel(JcDevPlan pl, Ws 
     inv_chis = 1.0 / jx_floor1(chis);
   }
   const T wl_amp = (3.0 * JC_H0 * JC_H0 / 2.0 / JC_C_LIGHT) * Om * m1;
-  // extended weak-lensing sources are finished by the lens kernel's epilogue for nodes 0..511; here only node 512
-  // (a = 1: chi = 0, so the lensing term vanishes and the NLA term remains)
-  const bool staged = is_wl && dix < 0;
-  for (int n = (staged && !ia) ? JC_NLENS_COLS + threadIdx.x / pl.T : threadIdx.x / pl.T;
-       n < JC_NA && (int)threadIdx.x < rows * pl.T; n += rows) {
+  const bool staged = is_wl && dix < 0;  // IA source: lensing term in place for nodes 0..511, NLA term added here
+  for (int n = threadIdx.x / nf; n < JC_NA; n += rows) {
     double* out = ws.rker + ((size_t)c * JC_NA_PAD + n) * pl.TS + t;
     const T H = JxMem<T>::ld(Hn + n, doff);
     T r;
     if (is_wl) {
-      if (staged) {  // lensing term already in place for nodes 0..511 (lens kernel epilogue); node 512: chi = 0
+      if (staged) {  // node 512: chi = 0
         r = n < JC_NLENS_COLS ? JxMem<T>::ld(out, doff) : T(0.0);
       } else {
         const T chi = JxMem<T>::ld(Cn + n, doff);
@@ -224,6 +227,7 @@ __global__ void __launch_bounds__(512) jc_tracer_finish_kernel(JcDevPlan pl, Ws 
       r = pl.nz_node[(size_t)n * pl.TS + t] * b * H;
     }
     JxMem<T>::st(out, doff, r);
+  }
   }
   // pad rows 513..519: the TMA contraction reads R in whole 12-row blocks (up to row 515) and relies on zeros
   for (int idx = threadIdx.x; idx < (JC_NA_PAD - JC_NA) * pl.TS; idx += blockDim.x)
@@ -274,9 +278,14 @@ int jc_launch_tracers(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t
 int jc_launch_tracers_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s) {
   return launch_all_lens<Dual, 2, 4>(pl, ws, chunk, s);
 }
+static int finish_threads(const JcDevPlan& pl) {  // rows x n_fin threads, at least one thread per tracer
+  const int nf = pl.n_fin > 0 ? pl.n_fin : 1;
+  const int n = (512 / nf) * nf;
+  return n < pl.T ? ((pl.T + 31) / 32) * 32 : n;
+}
 void jc_launch_finish(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s) {
-  jc_tracer_finish_kernel<double><<<chunk, (512 / pl.T) * pl.T, 0, s>>>(pl, ws);
+  jc_tracer_finish_kernel<double><<<chunk, finish_threads(pl), 0, s>>>(pl, ws);
 }
 void jc_launch_finish_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s) {
-  jc_tracer_finish_kernel<Dual><<<chunk, (512 / pl.T) * pl.T, 0, s>>>(pl, ws);
+  jc_tracer_finish_kernel<Dual><<<chunk, finish_threads(pl), 0, s>>>(pl, ws);
 }
