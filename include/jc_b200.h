@@ -298,6 +298,28 @@ int jc_grid_plan_create(int32_t transfer, int32_t nonlinear, int32_t growth, con
 int jc_grid_eval_f64(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo, double* pk_dev, double* chi_dev,
                      double* chi_transverse_dev, double* growth_dev, double* hubble_dev, double* transfer_dev,
                      double* kernels_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
+/* The other public functions of background.py on a grid plan's scale factors (n_a <= 512):
+ * aux_dev [B, JC_BG_FIELDS, n_a], rows JC_BG_*:
+ *   growth_rate  dlnD/dlna: ODE plans -> a D'/D of the growth solution, interpolated like growth_factor
+ *                (background.py:478-483, 491-512); gamma plans -> Omega_m(a)^gamma (background.py:551-584)
+ *   Omega_m_a, Omega_de_a (background.py:145-196), dchioverda [Mpc/h] (background.py:270-294), w, f_de (background.py:25-90) */
+enum { JC_BG_GROWTH_RATE = 0, JC_BG_OMEGA_M_A, JC_BG_OMEGA_DE_A, JC_BG_DCHIOVERDA, JC_BG_W, JC_BG_F_DE, JC_BG_FIELDS };
+int jc_grid_background_f64(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo, double* aux_dev, void* ws_dev,
+                           size_t ws_bytes, void* stream);
+
+/* background.a_of_chi (background.py:245-267): scale factor at comoving distance chi [Mpc/h] by the reference's interp()
+ * on the cosmology's (decreasing) 256-point chi table, neighbour rule as written in scipy/interpolate.py:25-37.
+ * chi_dev [n_chi] is shared by all cosmologies, a_dev [B, n_chi].  Any plan (its growth mode fixes the row width). */
+int jc_a_of_chi_f64(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo, const double* chi_dev, int64_t n_chi,
+                    double* a_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
+/* power.sigmasqr (power.py:56-78): sigma^2(R) of the UNNORMALISED spectrum T(k)^2 k^n_s (primordial_matter_power,
+ * power.py:14-18) with a top-hat window, Romberg over 129 points (divmax = 7) between log10(kmin) and log10(kmax) with
+ * k = e^x (the reference's limits as written).  R_dev [n_R] in Mpc/h (shared by all cosmologies), out_dev [B, n_R].  Only the reference's default
+ * kmin = 1e-4, kmax = 1e3 are tabulated: other limits return JC_ERR_UNSUPPORTED.  The plan's transfer fit is used. */
+int jc_sigmasqr_f64(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo, const double* R_dev, int32_t n_R,
+                    double kmin, double kmax, double* out_dev, void* ws_dev, size_t ws_bytes, void* stream);
 int jc_grid_plan_create_probes(const jc_problem* problem, const double* a_host, int32_t n_a, int32_t device,
                                jc_plan** plan_out);
 

@@ -31,7 +31,7 @@ SCAL_FIELDS = ["LN13KEQ", "INV13KEQ", "BETA_C", "C14_ALPHA_C", "SH_D", "LNKSILK"
 # every symbol include/jc_b200.h declares
 EXPORTS = ["jc_plan_create", "jc_plan_destroy", "jc_plan_n_tracers", "jc_plan_n_cls", "jc_plan_n_ell", "jc_plan_n_cosmo_params",
            "jc_workspace_bytes", "jc_workspace_layout", "jc_angular_cl_f64", "jc_angular_cl_host_f64",
-           "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64", "jc_gaussian_loglike_f64", "jc_fisher_f64", "jc_vjp_f64", "jc_sparse_bmm_f64", "jc_sparse_inv_f64", "jc_debug_stages_f64", "jc_grid_plan_create", "jc_grid_plan_create_probes", "jc_grid_eval_f64", "jc_nz_eval_f64",
+           "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64", "jc_gaussian_loglike_f64", "jc_fisher_f64", "jc_vjp_f64", "jc_sparse_bmm_f64", "jc_sparse_inv_f64", "jc_debug_stages_f64", "jc_grid_plan_create", "jc_grid_plan_create_probes", "jc_grid_eval_f64", "jc_grid_background_f64", "jc_a_of_chi_f64", "jc_sigmasqr_f64", "jc_nz_eval_f64",
            "jc_noise_f64", "jc_gaussian_cov_f64", "jc_profile_enable", "jc_profile_read",
            "jc_fp64_peak_tflops", "jc_debug_math_f64", "jc_status_string",
            "jc_last_cuda_error", "jc_abi_version"]
@@ -113,6 +113,12 @@ def load_library():
         lib.jc_grid_plan_create_probes.argtypes = [C.POINTER(jc_problem), dp, i32, i32, C.POINTER(C.c_void_p)]
         lib.jc_grid_plan_create_probes.restype = C.c_int
         lib.jc_grid_eval_f64.restype = C.c_int
+        lib.jc_grid_background_f64.argtypes = [vp, vp, i64, vp, vp, C.c_size_t, vp]
+        lib.jc_grid_background_f64.restype = C.c_int
+        lib.jc_a_of_chi_f64.argtypes = [vp, vp, i64, vp, i64, vp, vp, C.c_size_t, vp]
+        lib.jc_a_of_chi_f64.restype = C.c_int
+        lib.jc_sigmasqr_f64.argtypes = [vp, vp, i64, vp, i32, C.c_double, C.c_double, vp, vp, C.c_size_t, vp]
+        lib.jc_sigmasqr_f64.restype = C.c_int
         lib.jc_debug_stages_f64.argtypes = [vp, i32, vp, i64, vp, vp, C.c_size_t, vp]
         lib.jc_debug_stages_f64.restype = C.c_int
         lib.jc_nz_eval_f64.argtypes = [C.POINTER(jc_nz), dp, i64, dp]
@@ -520,6 +526,47 @@ class GridPlan(Plan):
                                              ptr("growth"), ptr("hubble"), ptr("transfer"), ptr("kernels"), ws.data_ptr(), ws.numel() * 8,
                                              torch.cuda.current_stream(cosmo_dev.device).cuda_stream)
         check(st, "jc_grid_eval_f64")
+        return out
+
+    BG_FIELDS = ("growth_rate", "Omega_m_a", "Omega_de_a", "dchioverda", "w", "f_de")  # JC_BG_* of jc_b200.h
+
+    def _cosmo_check(self, cosmo_dev):
+        import torch
+
+        assert cosmo_dev.is_cuda and cosmo_dev.dtype == torch.float64 and cosmo_dev.is_contiguous()
+        self._check_rows(cosmo_dev)
+        return cosmo_dev.shape[0], self.workspace(cosmo_dev.shape[0]), torch.cuda.current_stream(cosmo_dev.device).cuda_stream
+
+    def background(self, cosmo_dev):
+        """jc_grid_background_f64: cosmo_dev CUDA [B, ncp] -> CUDA [B, 6, n_a], rows BG_FIELDS."""
+        import torch
+
+        B, ws, stream = self._cosmo_check(cosmo_dev)
+        aux = torch.empty((B, len(self.BG_FIELDS), len(self.a)), dtype=torch.float64, device=cosmo_dev.device)
+        check(load_library().jc_grid_background_f64(self._h, cosmo_dev.data_ptr(), B, aux.data_ptr(), ws.data_ptr(), ws.numel() * 8,
+                                                    stream), "jc_grid_background_f64")
+        return aux
+
+    def a_of_chi(self, cosmo_dev, chi_dev):
+        """jc_a_of_chi_f64: chi_dev CUDA [n_chi] (shared) -> CUDA [B, n_chi]."""
+        import torch
+
+        B, ws, stream = self._cosmo_check(cosmo_dev)
+        assert chi_dev.is_cuda and chi_dev.dtype == torch.float64 and chi_dev.is_contiguous() and chi_dev.dim() == 1
+        out = torch.empty((B, chi_dev.numel()), dtype=torch.float64, device=cosmo_dev.device)
+        check(load_library().jc_a_of_chi_f64(self._h, cosmo_dev.data_ptr(), B, chi_dev.data_ptr(), chi_dev.numel(), out.data_ptr(),
+                                             ws.data_ptr(), ws.numel() * 8, stream), "jc_a_of_chi_f64")
+        return out
+
+    def sigmasqr(self, cosmo_dev, R_dev, kmin=0.0001, kmax=1000.0):
+        """jc_sigmasqr_f64: R_dev CUDA [n_R] (shared) -> CUDA [B, n_R]."""
+        import torch
+
+        B, ws, stream = self._cosmo_check(cosmo_dev)
+        assert R_dev.is_cuda and R_dev.dtype == torch.float64 and R_dev.is_contiguous() and R_dev.dim() == 1
+        out = torch.empty((B, R_dev.numel()), dtype=torch.float64, device=cosmo_dev.device)
+        check(load_library().jc_sigmasqr_f64(self._h, cosmo_dev.data_ptr(), B, R_dev.data_ptr(), R_dev.numel(), float(kmin), float(kmax),
+                                             out.data_ptr(), ws.data_ptr(), ws.numel() * 8, stream), "jc_sigmasqr_f64")
         return out
 
 

@@ -66,6 +66,7 @@ struct JcDevPlan {
   const double* romb_k;      // [129]
   const double* romb_lnk;    // [129]
   const double* romb_f;      // [129] w_i (b-a) k (k W(8k))^2 / (2 pi^2)
+  const double* romb_w;      // [129] w_i (b-a)
   // halofit grids
   const double* hf_k;        // [257]
   const double* hf_lnk;      // [257]
@@ -166,6 +167,8 @@ __device__ __forceinline__ double jc_rcp(double x) {
 // per-stage launchers (one translation unit per kernel)
 void jc_launch_setup(const JcDevPlan& pl, const double* cosmo, const Ws& ws, int chunk, cudaStream_t s);
 void jc_launch_contract_1cta(const JcDevPlan& pl, const Ws& ws, double* cl, int chunk, cudaStream_t s);
+void jc_launch_sigmasqr(const JcDevPlan& pl, const Ws& ws, const double* cosmo, int chunk, const double* R_dev, int n_R, double* out,
+                        cudaStream_t s);
 void jc_launch_transfer(const JcDevPlan& pl, const Ws& ws, int chunk, double* tk, cudaStream_t s);
 // JVP (Dual) variants: same kernels instantiated on value+tangent; `tangent` = direction [8] in parameter space
 void jc_launch_setup_jvp(const JcDevPlan& pl, const double* cosmo, const double* tangent, const Ws& ws, int chunk,

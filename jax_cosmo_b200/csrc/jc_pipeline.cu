@@ -200,6 +200,118 @@ extern "C" int jc_grid_eval_f64(const jc_plan* plan, const double* cosmo_dev, in
   return JC_OK;
 }
 
+// The remaining background.py functions on a grid plan's scale factors: aux[c][f][n], f = JC_BG_* (jc_b200.h).
+// growth_rate comes from K1 (node slot JC_NODE_GEOM of grid plans), the others are closed forms of the cosmology row and
+// K1's E^2(a_n) (background.py:52, 90, 168, 196, 294).
+namespace {
+__global__ void __launch_bounds__(256) jc_grid_background_kernel(JcDevPlan pl, Ws ws, const double* __restrict__ cosmo,
+                                                                 double* __restrict__ aux) {
+  const int c = blockIdx.y, na = pl.grid_na, n = blockIdx.x * 256 + threadIdx.x;
+  if (n >= na) return;
+  const double* row = cosmo + (size_t)c * pl.ncp;
+  const double Om = row[0] + row[1], Ok = row[5], w0 = row[6], wa = row[7];
+  const double Ode = (1.0 - Ok) - Om;                               // core.py:95-96
+  const double a = pl.limb_a[n];
+  const double hub = node_ptr(ws, c, JC_NODE_HUBBLE)[n] / JC_H0;     // sqrt(E^2)
+  const double e2 = hub * hub;
+  const double fde = -3.0 * (1.0 + w0 + wa) * pl.limb_lna[n] + 3.0 * wa * (a - 1.0);
+  double* o = aux + (size_t)c * JC_BG_FIELDS * na + n;
+  o[(size_t)JC_BG_GROWTH_RATE * na] = node_ptr(ws, c, JC_NODE_GEOM)[n];
+  o[(size_t)JC_BG_OMEGA_M_A * na] = Om / (a * a * a) / e2;
+  o[(size_t)JC_BG_OMEGA_DE_A * na] = Ode * exp(fde) / e2;
+  o[(size_t)JC_BG_DCHIOVERDA * na] = JC_RH / (a * a * hub);
+  o[(size_t)JC_BG_W * na] = w0 + (1.0 - a) * wa;
+  o[(size_t)JC_BG_F_DE * na] = fde;
+}
+
+// background.a_of_chi (background.py:245-267): interp(chi, chitab, atab) on K1's DECREASING chi table with the
+// reference's rule as written (scipy/interpolate.py:25-37): nearest node by squared distance (first minimum), clipped to
+// [1, n-2]; neighbour = sign(clip(x, xp[1], xp[-2]) - xp[ind]) with clip(x, lo, hi) = min(max(x, lo), hi) and lo > hi
+// here, i.e. always xp[-2] - xp[ind] <= 0: the left neighbour, except ind = n-2 (sign 0 -> +1).
+__global__ void __launch_bounds__(256) jc_a_of_chi_kernel(JcDevPlan pl, Ws ws, const double* __restrict__ chi, int n_chi,
+                                                          double* __restrict__ out) {
+  const int c = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n_chi) return;
+  const double* xp = ws.chitab + (size_t)c * JC_NCHI;
+  const double x = chi[i];
+  int lo = 0, hi = JC_NCHI - 1;  // xp[lo] >= x >= xp[hi] once inside the table
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (xp[mid] >= x) lo = mid; else hi = mid;
+  }
+  const double dl = (x - xp[lo]) * (x - xp[lo]), dr = (x - xp[hi]) * (x - xp[hi]);
+  int ind = dl <= dr ? lo : hi;
+  while (ind > 0 && (x - xp[ind - 1]) * (x - xp[ind - 1]) <= (x - xp[ind]) * (x - xp[ind])) --ind;  // ties / plateaus: first minimum
+  ind = ind < 1 ? 1 : (ind > JC_NCHI - 2 ? JC_NCHI - 2 : ind);
+  const double sgn = xp[JC_NCHI - 2] - xp[ind];
+  const int nb = sgn < 0.0 ? ind - 1 : ind + 1;
+  const double slope = (pl.chi_pt_a[2 * nb] - pl.chi_pt_a[2 * ind]) / (xp[nb] - xp[ind]);
+  const double b = pl.chi_pt_a[2 * ind] - slope * xp[ind];
+  out[(size_t)c * n_chi + i] = slope * x + b;
+}
+}  // namespace
+
+extern "C" int jc_grid_background_f64(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo, double* aux_dev,
+                                      void* ws_dev, size_t ws_bytes, void* stream) {
+  if (!plan || !plan->d.grid_mode || !cosmo_dev || !aux_dev || !ws_dev || n_cosmo < 1) return JC_ERR_INVALID;
+  jc_ws_layout lo;
+  int st = jc_workspace_layout(plan, ws_bytes, &lo);
+  if (st != JC_OK) return st;
+  const JcDevPlan& pl = plan->d;
+  cudaStream_t s = (cudaStream_t)stream;
+  Ws ws;
+  resolve(lo, (double*)ws_dev, 0, &ws);
+  const int na = pl.grid_na;
+  for (int64_t c0 = 0; c0 < n_cosmo; c0 += lo.chunk) {
+    const int chunk = (int)((n_cosmo - c0) < lo.chunk ? (n_cosmo - c0) : lo.chunk);
+    jc_launch_setup(pl, cosmo_dev + c0 * pl.ncp, ws, chunk, s);
+    jc_grid_background_kernel<<<dim3((na + 255) / 256, chunk), 256, 0, s>>>(pl, ws, cosmo_dev + c0 * pl.ncp,
+                                                                           aux_dev + (size_t)c0 * JC_BG_FIELDS * na);
+  }
+  JC_CUDA_TRY(cudaGetLastError());
+  return JC_OK;
+}
+
+extern "C" int jc_a_of_chi_f64(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo, const double* chi_dev,
+                               int64_t n_chi, double* a_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+  if (!plan || !cosmo_dev || !chi_dev || !a_dev || !ws_dev || n_cosmo < 1 || n_chi < 1 || n_chi > (1 << 30)) return JC_ERR_INVALID;
+  jc_ws_layout lo;
+  int st = jc_workspace_layout(plan, ws_bytes, &lo);
+  if (st != JC_OK) return st;
+  const JcDevPlan& pl = plan->d;
+  cudaStream_t s = (cudaStream_t)stream;
+  Ws ws;
+  resolve(lo, (double*)ws_dev, 0, &ws);
+  for (int64_t c0 = 0; c0 < n_cosmo; c0 += lo.chunk) {
+    const int chunk = (int)((n_cosmo - c0) < lo.chunk ? (n_cosmo - c0) : lo.chunk);
+    jc_launch_setup(pl, cosmo_dev + c0 * pl.ncp, ws, chunk, s);
+    jc_a_of_chi_kernel<<<dim3((unsigned)((n_chi + 255) / 256), chunk), 256, 0, s>>>(pl, ws, chi_dev, (int)n_chi,
+                                                                                     a_dev + (size_t)c0 * n_chi);
+  }
+  JC_CUDA_TRY(cudaGetLastError());
+  return JC_OK;
+}
+
+extern "C" int jc_sigmasqr_f64(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo, const double* R_dev, int32_t n_R,
+                               double kmin, double kmax, double* out_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+  if (!plan || !cosmo_dev || !R_dev || !out_dev || !ws_dev || n_cosmo < 1 || n_R < 1) return JC_ERR_INVALID;
+  if (kmin != 0.0001 || kmax != 1000.0) return JC_ERR_UNSUPPORTED;  // the plan tabulates the reference's default limits
+  jc_ws_layout lo;
+  int st = jc_workspace_layout(plan, ws_bytes, &lo);
+  if (st != JC_OK) return st;
+  const JcDevPlan& pl = plan->d;
+  cudaStream_t s = (cudaStream_t)stream;
+  Ws ws;
+  resolve(lo, (double*)ws_dev, 0, &ws);
+  for (int64_t c0 = 0; c0 < n_cosmo; c0 += lo.chunk) {
+    const int chunk = (int)((n_cosmo - c0) < lo.chunk ? (n_cosmo - c0) : lo.chunk);
+    jc_launch_setup(pl, cosmo_dev + c0 * pl.ncp, ws, chunk, s);
+    jc_launch_sigmasqr(pl, ws, cosmo_dev + c0 * pl.ncp, chunk, R_dev, n_R, out_dev + (size_t)c0 * n_R, s);
+  }
+  JC_CUDA_TRY(cudaGetLastError());
+  return JC_OK;
+}
+
 // Experiment support: run a subset of the pipeline stages of ONE chunk on `stream` (bit 0 setup, 1 lens, 2 finish, 3 power,
 // 4 contraction (persistent TMA kernel), 5 contraction (8-warp cp.async kernel, one CTA per SM)).  scripts/overlap_probe.py
 // uses it to time the power kernel of one chunk against the contraction of another on two streams.

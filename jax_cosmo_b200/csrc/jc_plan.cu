@@ -339,7 +339,7 @@ static int create_plan(const jc_problem* pb, const double* ell_host, int32_t n_e
     lgix[n] = (uint16_t)(i0 | (i1 << 8)); lgt[n] = t;
   }
   // ---- sigma8 Romberg functional ----------------------------------------------------------------
-  std::vector<double> rw = romberg_weights(7), rk(JC_NROMB), rlnk(JC_NROMB), rf(JC_NROMB);
+  std::vector<double> rw = romberg_weights(7), rk(JC_NROMB), rlnk(JC_NROMB), rf(JC_NROMB), rwn(JC_NROMB);
   {
     double lo = std::log10(0.0001), hi = std::log10(1000.0);
     std::vector<double> x = linspace(lo, hi, JC_NROMB);
@@ -349,6 +349,7 @@ static int create_plan(const jc_problem* pb, const double* ell_host, int32_t n_e
       double w = 3.0 * (std::sin(xr) - xr * std::cos(xr)) / (xr * xr * xr);
       rk[i] = k; rlnk[i] = x[i];
       rf[i] = rw[i] * (hi - lo) * (k * (k * w) * (k * w)) / (2.0 * M_PI * M_PI);
+      rwn[i] = rw[i] * (hi - lo);  // jc_sigmasqr_f64: any R
     }
   }
   // ---- halofit grids ------------------------------------------------------------------------------
@@ -423,7 +424,7 @@ static int create_plan(const jc_problem* pb, const double* ell_host, int32_t n_e
   size_t o_gr_pt_a = B.add(gr_pt_a), o_gr_pt_lna = B.add(gr_pt_lna), o_gr_h = B.add(gr_h);
   size_t o_la = B.add(la), o_llna = B.add(llna), o_lz = B.add(lz), o_lw = B.add(lw);
   size_t o_lct = B.add(lct), o_lgt = B.add(lgt), o_lcix = B.add(lcix), o_lgix = B.add(lgix);
-  size_t o_rk = B.add(rk), o_rlnk = B.add(rlnk), o_rf = B.add(rf);
+  size_t o_rk = B.add(rk), o_rlnk = B.add(rlnk), o_rf = B.add(rf), o_rwn = B.add(rwn);
   size_t o_hk = B.add(hk), o_hlnk = B.add(hlnk), o_hwk = B.add(hwk), o_hr = B.add(hr), o_hlogr = B.add(hlogr);
   size_t o_lens_t = B.add(lens_t), o_lens_ix = B.add(lens_ix), o_lens_z = B.add(lens_z);
   size_t o_lens_nw = B.reserve((size_t)(n_src ? n_src : 1) * nl * sizeof(double));
@@ -468,7 +469,7 @@ static int create_plan(const jc_problem* pb, const double* ell_host, int32_t n_e
   d.limb_a = DP(double, o_la); d.limb_lna = DP(double, o_llna); d.limb_z = DP(double, o_lz); d.limb_w = DP(double, o_lw);
   d.limb_chi_t = DP(double, o_lct); d.limb_gr_t = DP(double, o_lgt);
   d.limb_chi_ix = DP(uint16_t, o_lcix); d.limb_gr_ix = DP(uint16_t, o_lgix);
-  d.romb_k = DP(double, o_rk); d.romb_lnk = DP(double, o_rlnk); d.romb_f = DP(double, o_rf);
+  d.romb_k = DP(double, o_rk); d.romb_lnk = DP(double, o_rlnk); d.romb_f = DP(double, o_rf); d.romb_w = DP(double, o_rwn);
   d.hf_k = DP(double, o_hk); d.hf_lnk = DP(double, o_hlnk); d.hf_wk = DP(double, o_hwk);
   d.hf_r = DP(double, o_hr); d.hf_logr = DP(double, o_hlogr);
   d.lens_t = DP(double, o_lens_t); d.lens_ix = DP(uint16_t, o_lens_ix); d.lens_nw = DP(double, o_lens_nw);

@@ -253,6 +253,10 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
     const T g = S.gtab[tid] / S.gtab[127];  // background.py:480
     put(ws.gtab + (size_t)c * JC_NGROW + tid, g);
     S.f[tid] = g;  // normalised copy (S.f is free now)
+    // grid plans, ODE growth: growth-rate table f = a D'/D of the same RK4 solution (background.py:478-483)
+    if (pl.grid_mode && pl.growth != JC_GROWTH_GAMMA)
+      S.f[128 + tid] = tid == 0 ? T(1.0)
+                                : (S.M[4 * (tid - 1) + 2] * pl.gr_pt_a[0] + S.M[4 * (tid - 1) + 3]) * pl.gr_pt_a[2 * tid] / S.gtab[tid];
   }
   __syncthreads();
 
@@ -276,7 +280,13 @@ __global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const doubl
     put(node(JC_NODE_CHI, n), chi);
     put(node(JC_NODE_INVCHIC, n), 1.0 / chic);
     put(node(JC_NODE_LNCHIC, n), lnchic);
-    put(node(JC_NODE_GEOM, n), geom);
+    if (pl.grid_mode) {  // grid plans have no Limber weight: the slot carries growth_rate(a_n) (background.py:401-440)
+      const T om_a = bg.Om / (a * a * a) / e2;
+      const T fa = S.f[128 + (ix & 255)], fb = S.f[128 + (ix >> 8)];
+      put(node(JC_NODE_GEOM, n), pl.growth == JC_GROWTH_GAMMA ? jx_pow(om_a, gam) : fa + (fb - fa) * pl.limb_gr_t[n]);
+    } else {
+      put(node(JC_NODE_GEOM, n), geom);
+    }
     put(node(JC_NODE_GK, n), pl.grid_mode ? T(JC_TWO_PI_SQ) : geom * JC_TWO_PI_SQ * (chic * chic * chic));  // grid plan: V = P(k, a)
     S.rnl[n] = lnchic;  // scratch until the halofit root phase
     put(node(JC_NODE_GROWTH, n), D);
@@ -488,7 +498,37 @@ __global__ void __launch_bounds__(256) jc_transfer_kernel(JcDevPlan pl, Ws ws, d
   tk[(size_t)c * pl.L + l] = eh_transfer<double>(ws.scal + (size_t)c * JC_SCAL_FIELDS, pl.ellp5[l], pl.lnellp5[l], pl.transfer);
 }
 
+// power.sigmasqr (power.py:56-78) for any R: one CTA per cosmology, thread = Romberg node (129 of 160), T(k) from K1's constants,
+// fixed-order block reduction per R
+__global__ void __launch_bounds__(160) jc_sigmasqr_kernel(JcDevPlan pl, Ws ws, const double* __restrict__ cosmo,
+                                                          const double* __restrict__ R, int n_R, double* __restrict__ out) {
+  __shared__ double red[5];
+  const int c = blockIdx.x, tid = threadIdx.x;
+  double base = 0.0, k = 1.0;
+  if (tid < JC_NROMB) {
+    k = pl.romb_k[tid];
+    const double lnk = pl.romb_lnk[tid];
+    const double Tk = eh_transfer<double>(ws.scal + (size_t)c * JC_SCAL_FIELDS, k, lnk, pl.transfer);
+    base = pl.romb_w[tid] * (Tk * Tk) * exp(cosmo[(size_t)c * pl.ncp + 3] * lnk);  // pk = T^2 k^n_s (power.py:14-18, 74)
+  }
+  for (int r = 0; r < n_R; ++r) {
+    const double x = k * R[r];
+    const double w = 3.0 * (sin(x) - x * cos(x)) / (x * x * x);
+    double v = base * (k * (k * w) * (k * w));
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    if (tid == 0) out[(size_t)c * n_R + r] = (((red[0] + red[1]) + (red[2] + red[3])) + red[4]) / JC_TWO_PI_SQ;
+  }
+}
+
 }  // namespace
+
+void jc_launch_sigmasqr(const JcDevPlan& pl, const Ws& ws, const double* cosmo, int chunk, const double* R_dev, int n_R, double* out,
+                        cudaStream_t s) {
+  jc_sigmasqr_kernel<<<chunk, 160, 0, s>>>(pl, ws, cosmo, R_dev, n_R, out);
+}
 
 void jc_launch_transfer(const JcDevPlan& pl, const Ws& ws, int chunk, double* tk, cudaStream_t s) {
   jc_transfer_kernel<<<dim3((pl.L + 255) / 256, chunk), 256, 0, s>>>(pl, ws, tk);

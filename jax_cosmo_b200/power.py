@@ -9,6 +9,7 @@ Romberg normalisation, growth table, halofit sigma(R) tables and quirk root as i
     linear_matter_power(cosmo, k, a=1.0, transfer_fn=Eisenstein_Hu)                          power.py:19-53
     nonlinear_matter_power(cosmo, k, a=1.0, transfer_fn=Eisenstein_Hu, nonlinear_fn=halofit)   power.py:265-272
     primordial_matter_power(cosmo, k)                                                          power.py:14-18
+    sigmasqr(cosmo, R, transfer_fn)                                                            power.py:56-78
 
 k [h/Mpc] and a broadcast against each other like NumPy arrays (the reference's semantics); the result is squeezed.
 No CPU fallback.
@@ -20,7 +21,7 @@ import numpy as np
 from jax_cosmo_b200 import _native
 from jax_cosmo_b200 import transfer as tklib
 
-__all__ = ["halofit", "linear", "linear_matter_power", "nonlinear_matter_power", "primordial_matter_power"]
+__all__ = ["halofit", "linear", "linear_matter_power", "nonlinear_matter_power", "primordial_matter_power", "sigmasqr"]
 
 _MAX_GRID_POINTS = 50_000_000
 
@@ -87,3 +88,19 @@ def halofit(cosmo, k, a, transfer_fn, prescription="takahashi2012"):
 def nonlinear_matter_power(cosmo, k, a=1.0, transfer_fn=tklib.Eisenstein_Hu, nonlinear_fn=halofit):
     """power.py:265-272: nonlinear_fn(cosmo, k, a, transfer_fn=transfer_fn)."""
     return nonlinear_fn(cosmo, k, a, transfer_fn=transfer_fn)
+
+
+def sigmasqr(cosmo, R, transfer_fn, kmin=0.0001, kmax=1000.0, ksteps=5, **kwargs):
+    """sigma^2(R) of the unnormalised spectrum T(k)^2 k^n_s (power.py:56-78; `ksteps` is unused there as well).  Limits other
+    than the reference's defaults raise NotImplementedError (JC_ERR_UNSUPPORTED)."""
+    import torch
+
+    if kwargs:
+        transfer_fn = functools.partial(transfer_fn, **kwargs)
+    row = cosmo.to_row() if hasattr(cosmo, "to_row") else np.asarray(cosmo, dtype=np.float64)
+    plan = _native.get_grid_plan([1.0], [1.0], transfer=_transfer_code(transfer_fn), nonlinear=_native.JC_PK_LINEAR,
+                                 growth=1 if len(row) == 9 else 0)
+    dev = "cuda:%d" % plan.device
+    R_arr = np.ascontiguousarray(np.atleast_1d(np.asarray(R, dtype=np.float64)).reshape(-1))
+    out = plan.sigmasqr(torch.as_tensor(row[None], device=dev), torch.as_tensor(R_arr, device=dev), kmin, kmax)[0].cpu().numpy()
+    return float(out[0]) if np.ndim(R) == 0 else out.reshape(np.shape(R))

@@ -220,6 +220,31 @@ def growth_table(c):
     return atab, D / D[-1]
 
 
+def growth_rate_table(c):
+    """background.py:478-483: ftab = y[:, 1] / y1[-1] * atab / gtab = a D'(a) / D(a) from the same RK4 solution as growth_table()
+    (same one-step matrices, second component kept)."""
+    atab = np.logspace(-3, 0.0, N_GROWTH)
+
+    def rhs(y, x):  # background.py:465-475
+        om, ode = Omega_m_a(c, x), Omega_de_a(c, x)
+        q = (2.0 - 0.5 * (om + (1.0 + 3.0 * w_de(c, x)) * ode)) / x
+        r = 1.5 * om / x / x
+        return np.array([y[1], -q * y[1] + r * y[0]])
+
+    y = np.array([atab[0], 1.0])
+    ys = [y]
+    for n in range(N_GROWTH - 1):  # scipy/ode.py:6-22
+        t0, h = atab[n], atab[n + 1] - atab[n]
+        k1 = rhs(y, t0)
+        k2 = rhs(y + h * k1 / 2, t0 + h / 2)
+        k3 = rhs(y + h * k2 / 2, t0 + h / 2)
+        k4 = rhs(y + h * k3, t0 + h)
+        y = y + 1.0 / 6.0 * h * (k1 + 2 * k2 + 2 * k3 + k4)
+        ys.append(y)
+    ys = np.array(ys)
+    return atab, ys[:, 1] * atab / ys[:, 0]
+
+
 class Background:
     """Per-cosmology tables + query functions (the reference's cosmo._workspace, core.py:64)."""
 
@@ -235,6 +260,16 @@ class Background:
     def growth(self, a, fast=True):  # background.py:488
         f = interp_fast if fast else interp
         return np.clip(f(np.atleast_1d(a), self.ag, self.gtab), 0.0, 1.0)
+
+    def growth_rate(self, a):  # background.py:401-440, 491-512, 551-584
+        a = np.atleast_1d(np.asarray(a, dtype=np.float64))
+        if getattr(self.c, "gamma", None) is not None:
+            return Omega_m_a(self.c, a) ** self.c.gamma
+        atab, ftab = growth_rate_table(self.c)
+        return interp(a, atab, ftab)
+
+    def a_of_chi(self, chi):  # background.py:245-267: interp() on the DECREASING chi table (its neighbour rule as written)
+        return interp(np.atleast_1d(np.asarray(chi, dtype=np.float64)), self.chitab, self.atab)
 
 
 # ----------------------------------------------------------------------------------------------

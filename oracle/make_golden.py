@@ -179,14 +179,44 @@ def run_grid_functions():
     return out
 
 
+def run_background_extra():
+    """The remaining public functions of background.py (w, f_de, Omega_m_a, Omega_de_a, dchioverda, growth_rate, a_of_chi)
+    and power.sigmasqr, same four cosmologies as run_grid_functions()."""
+    from functools import partial
+
+    import jax_cosmo.background as bk
+    import jax_cosmo.power as pw
+    import jax_cosmo.transfer as tk
+
+    a = np.array([0.02, 0.09090909090909091, 0.15, 0.25, 0.4, 0.5, 0.62, 0.75, 0.9, 0.97, 1.0])
+    chi = np.array([0.0, 3.0, 50.0, 400.0, 1234.5, 2500.0, 4000.0, 6000.0, 9000.0])
+    R = np.array([1.0, 8.0, 20.0])
+    cosmos = {"planck15": sc.PLANCK15, "open_wcdm": dict(sc.WCDM, Omega_k=0.04), "closed_wcdm": dict(sc.WCDM, Omega_k=-0.03),
+              "gamma": dict(sc.WCDM, gamma=0.55)}
+    out = dict(a=a, chi=chi, R=R, names=np.array(json.dumps(list(cosmos))))
+    for name, cdict in cosmos.items():
+        cosmo = jc.Cosmology(**cdict)
+        out[name + "_row"] = sc.cosmo_row(cdict)
+        for fn in ("w", "f_de", "Omega_m_a", "Omega_de_a", "dchioverda", "growth_rate"):
+            out[name + "_" + fn] = np.asarray(getattr(bk, fn)(cosmo, a))
+        out[name + "_a_of_chi"] = np.asarray(bk.a_of_chi(cosmo, chi))
+        out[name + "_sigmasqr"] = np.array([float(pw.sigmasqr(cosmo, r, tk.Eisenstein_Hu)) for r in R])
+        out[name + "_sigmasqr_nowiggle"] = np.array([float(pw.sigmasqr(cosmo, r, partial(tk.Eisenstein_Hu, type="eisenhu"))) for r in R])
+    return out
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
     ap.add_argument("--stages", action="store_true")
     ap.add_argument("--likelihood", action="store_true")
     ap.add_argument("--grid", action="store_true")
+    ap.add_argument("--background", action="store_true")
     args = ap.parse_args()
     os.makedirs(OUT, exist_ok=True)
+    if args.background:
+        np.savez(os.path.join(OUT, "background_extra.npz"), **run_background_extra())
+        sys.exit(0)
     if args.grid or (args.only is None and not args.stages and not args.likelihood):
         np.savez(os.path.join(OUT, "grid_functions.npz"), **run_grid_functions())
         if args.grid:
