@@ -3,7 +3,7 @@ import numpy as np
 
 from jax_cosmo_b200.jax_utils import container
 
-__all__ = ["WeakLensing", "NumberCounts"]
+__all__ = ["WeakLensing", "NumberCounts", "weak_lensing_kernel", "density_kernel", "nla_kernel"]
 
 
 def _radial_kernels(probe, cosmo, z):
@@ -91,3 +91,19 @@ class NumberCounts(container):
         """1 / n_gal per bin (probes.py:274-281)."""
         pzs = self.params[0]
         return 1.0 / np.array([pz.gals_per_steradian for pz in pzs])
+
+
+def weak_lensing_kernel(cosmo, pzs, z, ell):
+    """probes.py:17-75: lensing kernels of the bins `pzs` (extended or delta_nz), shape (n_bins, n_z), ell factor included."""
+    return WeakLensing(pzs).kernel(cosmo, z, ell)
+
+
+def density_kernel(cosmo, pzs, bias, z, ell):
+    """probes.py:78-100: number-count kernels n(z) b(z) H(z); one bias object or one per bin."""
+    return NumberCounts(pzs, bias).kernel(cosmo, z, ell)
+
+
+def nla_kernel(cosmo, pzs, bias, z, ell):
+    """probes.py:103-129: the intrinsic-alignment term alone.  The tracer kernel K2b adds it to the lensing term in place, so
+    it is returned as the difference of the two kernel evaluations (both on the GPU path)."""
+    return WeakLensing(pzs, ia_bias=bias).kernel(cosmo, z, ell) - WeakLensing(pzs).kernel(cosmo, z, ell)

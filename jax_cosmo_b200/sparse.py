@@ -171,3 +171,22 @@ def det(sparse):
     if _is_tensor(sign):
         return sign * logdet.exp()
     return sign * float(np.exp(logdet))
+
+
+def _named(kinds, name):
+    def fn(*args):
+        if [_ndim(a) for a in args] != kinds:
+            raise ValueError("%s: expected operands of dimension %s" % (name, kinds))
+        return dot(*args)
+    fn.__name__ = name
+    fn.__doc__ = "sparse.py: %s, one strided per-ell product kernel (jc_sparse_bmm_f64) like dot()." % name
+    return fn
+
+
+# the reference's named special cases of dot() (sparse.py:141-292)
+sparse_dot_vec = _named([3, 1], "sparse_dot_vec")
+sparse_dot_dense = _named([3, 2], "sparse_dot_dense")
+vec_dot_sparse = _named([1, 3], "vec_dot_sparse")
+dense_dot_sparse = _named([2, 3], "dense_dot_sparse")
+sparse_dot_sparse = _named([3, 3], "sparse_dot_sparse")
+dense_dot_sparse_dot_dense = _named([2, 3, 2], "dense_dot_sparse_dot_dense")

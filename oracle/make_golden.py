@@ -202,6 +202,17 @@ def run_background_extra():
         out[name + "_a_of_chi"] = np.asarray(bk.a_of_chi(cosmo, chi))
         out[name + "_sigmasqr"] = np.array([float(pw.sigmasqr(cosmo, r, tk.Eisenstein_Hu)) for r in R])
         out[name + "_sigmasqr_nowiggle"] = np.array([float(pw.sigmasqr(cosmo, r, partial(tk.Eisenstein_Hu, type="eisenhu"))) for r in R])
+    # module-level kernel functions of probes.py (17-129) on the open wCDM cosmology of the kernel scenario
+    import jax_cosmo.probes as pr
+    nz1, nz2 = sc.smail(1.0, 2.0, 1.0, 2.0), sc.smail(1.0, 2.0, 0.5, 3.0, shift=0.02)
+    pzs = [sc.build_nz(nz1, jc), sc.build_nz(nz2, jc)]
+    kc = dict(sc.WCDM, Omega_k=0.04)
+    zk = np.concatenate([[0.0, 0.01], np.linspace(0.05, 3.0, 30)])
+    out["pk_z"], out["pk_row"] = zk, sc.cosmo_row(kc)
+    out["pk_nz"] = np.array(json.dumps([nz1, nz2]))
+    out["pk_wl"] = np.asarray(pr.weak_lensing_kernel(jc.Cosmology(**kc), pzs, zk, 50.0))
+    out["pk_density"] = np.asarray(pr.density_kernel(jc.Cosmology(**kc), pzs, jc.bias.constant_linear_bias(1.3), zk, 50.0))
+    out["pk_nla"] = np.asarray(pr.nla_kernel(jc.Cosmology(**kc), pzs, jc.bias.des_y1_ia_bias(0.5, 0.1, 0.62), zk, 50.0))
     return out
 
 

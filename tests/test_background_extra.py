@@ -41,6 +41,63 @@ def test_oracle_background_extra_vs_reference_golden():
             assert relerr(got, g[name + key]) < 1e-13
 
 
+def _ell_factor(ell):
+    return np.sqrt((ell - 1) * ell * (ell + 1) * (ell + 2)) / (ell + 0.5) ** 2
+
+
+def test_oracle_probe_kernel_functions_vs_reference_golden():
+    """probes.weak_lensing_kernel / density_kernel / nla_kernel (probes.py:17-129)."""
+    from oracle import scenarios as sc
+    g, _ = _golden()
+    nzs = json.loads(str(g["pk_nz"]))
+    z = g["pk_z"]
+    bg = o.Background(o.Cosmo(g["pk_row"]))
+
+    def kernels(probe):
+        scn = sc.scenario("k", dict(zip(sc.COSMO_KEYS, g["pk_row"])), [50.0], [probe])
+        return o.radial_kernels(bg, sc.flatten_spec(scn)["tracers"], z)[0]
+
+    wl = kernels(sc.wl(nzs)) * _ell_factor(50.0)
+    assert np.max(np.abs(wl - g["pk_wl"])) < 1e-12 * np.abs(g["pk_wl"]).max()
+    dens = kernels(sc.nc(nzs, [sc.bias("constant", 1.3)] * 2))
+    assert np.max(np.abs(dens - g["pk_density"])) < 1e-12 * np.abs(g["pk_density"]).max()
+    nla = kernels(sc.wl(nzs, ia=sc.bias("des_y1_ia", 0.5, 0.1, 0.62))) * _ell_factor(50.0) - wl
+    assert np.max(np.abs(nla - g["pk_nla"])) < 1e-11 * np.abs(g["pk_nla"]).max()
+
+
+@pytest.mark.gpu
+def test_gpu_probe_kernel_functions_and_named_sparse_products(jc):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import scenarios as sc
+    g, _ = _golden()
+    z = g["pk_z"]
+    pzs = [sc.build_nz(s, jc) for s in json.loads(str(g["pk_nz"]))]
+    row = g["pk_row"]
+    cosmo = jc.Cosmology(*row[:8])
+    for key, got in (("pk_wl", jc.probes.weak_lensing_kernel(cosmo, pzs, z, 50.0)),
+                     ("pk_density", jc.probes.density_kernel(cosmo, pzs, jc.bias.constant_linear_bias(1.3), z, 50.0)),
+                     ("pk_nla", jc.probes.nla_kernel(cosmo, pzs, jc.bias.des_y1_ia_bias(0.5, 0.1, 0.62), z, 50.0))):
+        assert got.shape == g[key].shape
+        assert np.max(np.abs(got - g[key])) < RTOL * np.abs(g[key]).max(), (key, np.max(np.abs(got - g[key])))
+    # the named special cases of sparse.dot (sparse.py:141-292) against dense NumPy products
+    rng = np.random.default_rng(2)
+    S, S2 = rng.standard_normal((3, 4, 5)), rng.standard_normal((4, 2, 5))
+    v4, v3 = rng.standard_normal(20), rng.standard_normal(15)
+    D4, D3 = rng.standard_normal((20, 6)), rng.standard_normal((7, 15))
+    sp = jc.sparse
+    dS, dS2 = sp.to_dense(S), sp.to_dense(S2)
+    assert np.allclose(sp.sparse_dot_vec(S, v4), dS @ v4, rtol=1e-13, atol=1e-13)
+    assert np.allclose(sp.sparse_dot_dense(S, D4), dS @ D4, rtol=1e-13, atol=1e-13)
+    assert np.allclose(sp.vec_dot_sparse(v3, S), v3 @ dS, rtol=1e-13, atol=1e-13)
+    assert np.allclose(sp.dense_dot_sparse(D3, S), D3 @ dS, rtol=1e-13, atol=1e-13)
+    assert np.allclose(sp.to_dense(sp.sparse_dot_sparse(S, S2)), dS @ dS2, rtol=1e-13, atol=1e-13)
+    assert np.allclose(sp.dense_dot_sparse_dot_dense(D3, S, D4), D3 @ dS @ D4, rtol=1e-13, atol=1e-12)
+    with pytest.raises(ValueError):
+        sp.sparse_dot_vec(S, D4)
+
+
 @pytest.mark.gpu
 def test_gpu_background_extra_vs_reference_golden(jc):
     import torch
