@@ -288,8 +288,8 @@ def main():
     # instructions per (ell, node) point x 64 flop for K3; DMMA m8n8k4 count x 512 flop for K4
     sass_flops = {"power": 186.0 * 2 * N_ELL * A, "contract": 45279.0 * 512}
     # DRAM bytes per launch of `chunk` cosmologies, scaled from the ncu --set full captures at 592 cosmologies
-    # (prof_r01_v9; profiles/r01_ncu_summary.md section 8)
-    ncu_dram_per_cosmo = {"power": (42.55e6 + 194.5e6) / 592, "contract": (297.4e6 + 77.71e6) / 592}
+    # (final build: profiles/r01_ncu_v14_metrics.csv, r01_ncu_summary.md section 13)
+    ncu_dram_per_cosmo = {"power": (42.55e6 + 193.52e6) / 592, "contract": (297.02e6 + 77.66e6) / 592}
     step_tflops = 2.0 * slots["total"] * B * args.steps / (ms * 1e-3) / 1e12
     roofline = {"bound": "fp64", "kernel": kernels[dom], "achieved": achieved, "peak": peak_sustained,
                 "unit": "TFLOP/s", "frac": achieved / peak_sustained,
