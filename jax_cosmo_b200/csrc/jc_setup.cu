@@ -77,8 +77,11 @@ template <class T> struct SetupSmem {
 //   sigma8 norm    power.py:47,56-78 (Romberg as a fixed functional)
 //   halofit        power.py:86-141 (sigma^2(R,a) = D(a)^2 S(R); quirky interp root), :199-224
 // =================================================================================================
+#ifndef JC_SETUP_MINB
+#define JC_SETUP_MINB 4  // resident CTAs per SM asked of ptxas: 64 registers (80 B spill) and 4 x 47 KB smem; 3 CTAs at 80 registers is 6 % slower
+#endif
 template <class T>
-__global__ void __launch_bounds__(256) jc_setup_kernel(JcDevPlan pl, const double* __restrict__ cosmo,
+__global__ void __launch_bounds__(256, sizeof(T) == sizeof(double) ? JC_SETUP_MINB : 2) jc_setup_kernel(JcDevPlan pl, const double* __restrict__ cosmo,
                                                        const double* __restrict__ tangent, Ws ws) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SetupSmem<T>& S = *reinterpret_cast<SetupSmem<T>*>(smem_raw);
