@@ -168,6 +168,8 @@ void jc_launch_power(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t 
     case 13: launch_power_cfg<double, 16, 4>(pl, ws, chunk, 2, s); break;
     case 14: launch_power_cfg<double, 16, 4>(pl, ws, chunk, 8, s); break;
     case 15: launch_power_cfg<double, 4, 4>(pl, ws, chunk, 8, s); break;  // the round's earlier default: 6.34 ms
+    case 16: launch_power_cfg<double, 16, 3>(pl, ws, chunk, 8, s); break;  // 80 registers, no spills
+    case 17: launch_power_cfg<double, 16, 5>(pl, ws, chunk, 8, s); break;  // 48 registers
     // fastest (profiles/r01_tuning.md): 16 nodes per thread (the ell-side loads and index arithmetic amortise over 16
     // points), 64 registers, 8 CTAs per cosmology: 6.13 ms
     default: launch_power_cfg<double, 16, 4>(pl, ws, chunk, 8, s); break;
