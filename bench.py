@@ -291,7 +291,9 @@ def main():
     # (final build: profiles/r01_ncu_v14_metrics.csv, r01_ncu_summary.md section 13)
     ncu_dram_per_cosmo = {"power": (42.55e6 + 193.52e6) / 592, "contract": (297.02e6 + 77.66e6) / 592}
     step_tflops = 2.0 * slots["total"] * B * args.steps / (ms * 1e-3) / 1e12
-    roofline = {"bound": "fp64", "kernel": kernels[dom], "achieved": achieved, "peak": peak_sustained,
+    # "tensor": the dominant kernels are arithmetic bound -- the contraction issues FP64 tensor-core MMAs (DMMA.8x8x4), the power
+    # kernel DFMAs on the same FP64 datapath; the denominator is that datapath's measured peak, not the bf16 tensor figure
+    roofline = {"bound": "tensor", "bound_detail": "fp64", "kernel": kernels[dom], "achieved": achieved, "peak": peak_sustained,
                 "unit": "TFLOP/s", "frac": achieved / peak_sustained,
                 "traffic": ncu_dram_per_cosmo[dom] * cosmo_per_launch if dom in ncu_dram_per_cosmo else None,
                 "traffic_note": "dram__bytes_read+write per launch from profiles/r01_ncu_summary.md, scaled to the launch size; "
