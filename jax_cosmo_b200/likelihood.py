@@ -19,10 +19,10 @@ def gaussian_log_likelihood(data, mu, C, include_logdet=True, inverse_method="in
     import torch
 
     C = np.asarray(C, dtype=np.float64)
+    if C.ndim == 2:
+        return _dense_log_likelihood(data, mu, C, include_logdet, inverse_method)
     if C.ndim != 3 or C.shape[0] != C.shape[1]:
-        raise NotImplementedError(
-            "only the sparse block layout [n_cls, n_cls, n_ell] is on the B200 path (use sparse=True in "
-            "gaussian_cl_covariance_and_mean); dense covariances are not accelerated and there is no CPU fallback")
+        raise ValueError("C must be a dense [N, N] or a sparse [n_cls, n_cls, n_ell] covariance")
     P, _, L = C.shape
     mu = np.asarray(mu, dtype=np.float64).reshape(-1)
     data = np.asarray(data, dtype=np.float64).reshape(-1)
@@ -34,6 +34,30 @@ def gaussian_log_likelihood(data, mu, C, include_logdet=True, inverse_method="in
                                           torch.as_tensor(mu[None], device="cuda"),
                                           torch.as_tensor(np.ascontiguousarray(C)[None], device="cuda"), include_logdet)
     return float(out[0].item())
+
+
+def _dense_log_likelihood(data, mu, C, include_logdet, inverse_method):
+    """Dense [N, N] covariance (likelihood.py:44-65): not a kernel of this library -- the factorisations are cuSOLVER's through
+    torch.linalg on the GPU (library calls off the hot path; the sparse layout above is the accelerated one).  Same conventions
+    as the reference: r = mu - data, result -0.5 (r^T C^-1 r - logdet C)."""
+    import torch
+
+    if not torch.cuda.is_available():
+        raise _native.JcError("jax_cosmo_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    r = torch.as_tensor(np.asarray(mu, dtype=np.float64).reshape(-1) - np.asarray(data, dtype=np.float64).reshape(-1), device="cuda")
+    if C.shape != (r.numel(), r.numel()):
+        raise ValueError("dense covariance must be [%d, %d]" % (r.numel(), r.numel()))
+    Cd = torch.as_tensor(np.ascontiguousarray(C), device="cuda")
+    if inverse_method == "inverse":
+        y = torch.linalg.inv(Cd) @ r
+    elif inverse_method == "cholesky":
+        y = torch.cholesky_solve(r[:, None], torch.linalg.cholesky(Cd))[:, 0]
+    else:
+        raise NotImplementedError("inverse_method %r" % (inverse_method,))
+    chi2 = torch.dot(r, y)
+    if not include_logdet:
+        return float((-0.5 * chi2).item())
+    return float((-0.5 * (chi2 - torch.linalg.slogdet(Cd)[1])).item())
 
 
 def fisher_matrix(jac, C):

@@ -326,8 +326,18 @@ def test_likelihood_golden_and_config3(jc, torch_cuda):
         for key, inc in (("loglike_logdet", True), ("loglike_nologdet", False)):
             v = jc.likelihood.gaussian_log_likelihood(g[tag + "_data"], g[tag + "_mu"], g[tag + "_cov"], include_logdet=inc)
             assert abs(v / float(g[tag + "_" + key]) - 1) < RTOL, (tag, key, v)
+    # dense [N, N] covariance (likelihood.py:44-65), both inverse methods: the same golden values through to_dense
+    for tag in ("reftest", "3x2pt"):
+        dense = jc.sparse.to_dense(g[tag + "_cov"])
+        for method in ("inverse", "cholesky"):
+            for key, inc in (("loglike_logdet", True), ("loglike_nologdet", False)):
+                v = jc.likelihood.gaussian_log_likelihood(g[tag + "_data"], g[tag + "_mu"], dense, include_logdet=inc,
+                                                         inverse_method=method)
+                assert abs(v / float(g[tag + "_" + key]) - 1) < 1e-7, (tag, method, key, v)
     with pytest.raises(NotImplementedError):
-        jc.likelihood.gaussian_log_likelihood(np.zeros(4), np.zeros(4), np.eye(4))
+        jc.likelihood.gaussian_log_likelihood(np.zeros(4), np.zeros(4), np.eye(4), inverse_method="svd")
+    with pytest.raises(ValueError):
+        jc.likelihood.gaussian_log_likelihood(np.zeros(4), np.zeros(4), np.eye(5))
     # full config 3 on the device: mean + covariance + likelihood for 3 cosmologies, shared data vector
     scn = sc.scenario("c3", sc.PLANCK15, sc.ELL_CFG2, [sc.sources(10, 1.0), sc.lenses(10, 1.0)])
     plan, probes = _plan(jc, scn)
