@@ -288,7 +288,7 @@ def main():
     # instructions per (ell, node) point x 64 flop for K3; DMMA m8n8k4 count x 512 flop for K4
     sass_flops = {"power": 186.0 * 2 * N_ELL * A, "contract": 45279.0 * 512}
     # DRAM bytes per launch of `chunk` cosmologies, scaled from the ncu --set full captures at 592 cosmologies
-    # (final build: profiles/r01_ncu_v14_metrics.csv, r01_ncu_summary.md section 13)
+    # (profiles/r01_ncu_v14_metrics.csv / r01_ncu_v15_metrics.csv, r01_ncu_summary.md sections 13-14)
     ncu_dram_per_cosmo = {"power": (42.55e6 + 193.52e6) / 592, "contract": (297.02e6 + 77.66e6) / 592}
     step_tflops = 2.0 * slots["total"] * B * args.steps / (ms * 1e-3) / 1e12
     # "tensor": the dominant kernels are arithmetic bound -- the contraction issues FP64 tensor-core MMAs (DMMA.8x8x4), the power
