@@ -16,6 +16,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
 
 
+def pytest_sessionstart(session):
+    """The C-ABI library is a build artefact (git-ignored): build it once if a fresh checkout has none (nvcc cross-compiles
+    sm_100a without a GPU; a few minutes).  The product itself never builds or falls back at import time."""
+    lib = os.path.join(ROOT, "jax_cosmo_b200", "libjc_b200.so")
+    if not os.path.exists(lib):
+        import subprocess
+        subprocess.run(["bash", os.path.join(ROOT, "jax_cosmo_b200", "csrc", "build.sh")], check=True, cwd=ROOT)
+
+
 def golden_cl_files():
     return sorted(glob.glob(os.path.join(GOLDEN, "cl_*.npz")))
 
