@@ -647,9 +647,10 @@ def gaussian_loglike_device(data_dev, mu_dev, cov_dev, include_logdet=True):
     assert data_dev.shape[-1] == P * L
     out = torch.empty(B, dtype=torch.float64, device=cov_dev.device)
     scratch = torch.empty((B, L, 2), dtype=torch.float64, device=cov_dev.device)
-    st = load_library().jc_gaussian_loglike_f64(data_dev.data_ptr(), stride, mu_dev.data_ptr(), cov_dev.data_ptr(), B, P, L,
-                                                1 if include_logdet else 0, out.data_ptr(), scratch.data_ptr(),
-                                                torch.cuda.current_stream(cov_dev.device).cuda_stream)
+    with torch.cuda.device(cov_dev.device):  # a null stream handle means the current device's default stream
+        st = load_library().jc_gaussian_loglike_f64(data_dev.data_ptr(), stride, mu_dev.data_ptr(), cov_dev.data_ptr(), B, P, L,
+                                                    1 if include_logdet else 0, out.data_ptr(), scratch.data_ptr(),
+                                                    torch.cuda.current_stream(cov_dev.device).cuda_stream)
     check(st, "jc_gaussian_loglike_f64")
     return out
 
@@ -663,8 +664,9 @@ def fisher_device(jac_dev, cov_dev):
     jac_dev = jac_dev.reshape(B, K, P * L).contiguous()
     out = torch.empty((B, K, K), dtype=torch.float64, device=cov_dev.device)
     scratch = torch.empty((B, L, K * K + 1), dtype=torch.float64, device=cov_dev.device)
-    st = load_library().jc_fisher_f64(jac_dev.data_ptr(), cov_dev.contiguous().data_ptr(), B, K, P, L, out.data_ptr(),
-                                      scratch.data_ptr(), torch.cuda.current_stream(cov_dev.device).cuda_stream)
+    with torch.cuda.device(cov_dev.device):
+        st = load_library().jc_fisher_f64(jac_dev.data_ptr(), cov_dev.contiguous().data_ptr(), B, K, P, L, out.data_ptr(),
+                                          scratch.data_ptr(), torch.cuda.current_stream(cov_dev.device).cuda_stream)
     check(st, "jc_fisher_f64")
     return out
 
@@ -684,8 +686,9 @@ def vjp_device(jac_dev, cot_dev):
     else:
         raise ValueError("cotangent has %d elements, expected %d or %d" % (cot_dev.numel(), N, B * N))
     out = torch.empty((B, K), dtype=torch.float64, device=jac_dev.device)
-    st = load_library().jc_vjp_f64(jac_dev.data_ptr(), cot_dev.data_ptr(), stride, B, K, N, out.data_ptr(),
-                                   torch.cuda.current_stream(jac_dev.device).cuda_stream)
+    with torch.cuda.device(jac_dev.device):
+        st = load_library().jc_vjp_f64(jac_dev.data_ptr(), cot_dev.data_ptr(), stride, B, K, N, out.data_ptr(),
+                                       torch.cuda.current_stream(jac_dev.device).cuda_stream)
     check(st, "jc_vjp_f64")
     return out
 

@@ -50,7 +50,8 @@ static int ensure(void** p, size_t* have, size_t need) {
 extern "C" int jc_angular_cl_host_f64(jc_plan* plan, const double* cosmo_host, int64_t n_cosmo,
                                       double* cl_host) {
   if (!plan || !cosmo_host || !cl_host || n_cosmo < 1) return JC_ERR_INVALID;
-  JC_CUDA_TRY(cudaSetDevice(plan->device));
+  JcDeviceGuard guard(plan->device);
+  JC_CUDA_TRY(guard.status);
   if (!plan->s_compute) {
     JC_CUDA_TRY(cudaStreamCreateWithFlags(&plan->s_compute, cudaStreamNonBlocking));
     JC_CUDA_TRY(cudaStreamCreateWithFlags(&plan->s_copy, cudaStreamNonBlocking));
@@ -139,6 +140,7 @@ extern "C" int jc_gaussian_cov_f64(const jc_plan* plan, const double* cl_dev, co
                                    int64_t n_cosmo, double f_sky, double* cov_dev, void* stream) {
   if (!plan || !cl_dev || !noise_dev || !cov_dev || n_cosmo < 1) return JC_ERR_INVALID;
   if (plan->d.L < 2) return JC_ERR_INVALID;  // np.gradient needs >= 2 points
+  JcDeviceGuard guard(plan->device);
   size_t total = (size_t)n_cosmo * plan->d.P * plan->d.P * plan->d.L;
   size_t blocks = (total + 255) / 256;
   if (blocks > 0x7fffffffu) return JC_ERR_INVALID;
@@ -190,7 +192,8 @@ extern "C" int jc_debug_math_f64(int32_t fn, const double* x_dev, double* y_dev,
 // ---------------------------------------------------------------------------------------------
 extern "C" int jc_profile_enable(jc_plan* plan, int32_t enable) {
   if (!plan) return JC_ERR_INVALID;
-  JC_CUDA_TRY(cudaSetDevice(plan->device));
+  JcDeviceGuard guard(plan->device);
+  JC_CUDA_TRY(guard.status);
   if (enable && !plan->prof) {
     plan->prof = new JcProf();
     memset(plan->prof, 0, sizeof(JcProf));

@@ -386,14 +386,15 @@ jc_contract_tma_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64
 template <int KC, int TMA_STAGES, bool JVP>
 void launch_tma(const JcDevPlan& pl, const Ws& ws, double* out, int64_t stride, int chunk, cudaStream_t s) {
   const size_t smem = (size_t)(JVP ? 2 : 1) * TMA_STAGES * KC * (pl.TS + LSV) * sizeof(double) + 2 * TMA_STAGES * sizeof(uint64_t);
-  static int sms = 0;  // idempotent; racing writers set the same values
-  if (!sms) {
+  static int sms = 0;  // idempotent; racing writers set the same values (every device of a box is the same part)
+  static unsigned long long attr_done = 0;
+  JC_ONCE_PER_DEVICE(attr_done, {
     int dev = 0, n = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(jc_contract_tma_kernel<KC, TMA_STAGES, JVP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     sms = n > 0 ? n : 148;
-  }
+  });
   jc_contract_tma_kernel<KC, TMA_STAGES, JVP><<<chunk < sms ? chunk : sms, TMA_CW * 32, smem, s>>>(pl, ws, out, stride, chunk);
 }
 
@@ -407,11 +408,9 @@ template <int KC, int WARPS, int MINB, bool JVP>
 void launch_cfg(const JcDevPlan& pl, const Ws& ws, double* out, int64_t stride, int chunk, int msplit, cudaStream_t s) {
   const int ngroups = (pl.L + NCOLS - 1) / NCOLS;
   const size_t smem = (size_t)(JVP ? 2 : 1) * STAGES * KC * (pl.TS + LSV) * sizeof(double);
-  static bool attr_done = false;  // idempotent attribute; racing writers set the same value
-  if (!attr_done) {
-    cudaFuncSetAttribute(jc_contract_kernel<KC, WARPS, MINB, JVP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    attr_done = true;
-  }
+  static unsigned long long attr_done = 0;
+  JC_ONCE_PER_DEVICE(attr_done, cudaFuncSetAttribute(jc_contract_kernel<KC, WARPS, MINB, JVP>,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   jc_contract_kernel<KC, WARPS, MINB, JVP><<<dim3(ngroups * msplit, chunk), WARPS * 32, smem, s>>>(pl, ws, out, stride, msplit);
 }
 
@@ -450,11 +449,9 @@ void jc_launch_contract_1cta(const JcDevPlan& pl, const Ws& ws, double* cl, int 
   const int mtiles = (pl.P + 7) / 8;
   const int msplit = mtiles > 16 ? 2 : 1;
   const int ngroups = (pl.L + NCOLS - 1) / NCOLS;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(jc_contract_kernel<12, 8, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    attr_done = true;
-  }
+  static unsigned long long attr_done = 0;
+  JC_ONCE_PER_DEVICE(attr_done, cudaFuncSetAttribute(jc_contract_kernel<12, 8, 2, false>,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   // <.., 2, ..>: the 128-register build; the 120 KB request keeps it at one CTA per SM
   jc_contract_kernel<12, 8, 2, false><<<dim3(ngroups * msplit, chunk), 256, 120 * 1024, s>>>(pl, ws, cl, (int64_t)pl.P * pl.L, msplit);
 }

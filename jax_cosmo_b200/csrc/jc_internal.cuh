@@ -132,6 +132,35 @@ struct jc_plan {
   cudaEvent_t ev_done[2], ev_copied[2];
 };
 
+// Function attributes (dynamic shared-memory opt-in) belong to the device's context: run the statement(s) the first time the call site is reached on
+// the CURRENT device (`flag`: one bit per device ordinal, racing callers repeat an idempotent call).
+#define JC_ONCE_PER_DEVICE(flag, ...)                                           \
+  do {                                                                          \
+    int jc_d_ = 0;                                                              \
+    cudaGetDevice(&jc_d_);                                                      \
+    const unsigned long long jc_b_ = 1ull << (jc_d_ & 63);                      \
+    if (!(__atomic_load_n(&(flag), __ATOMIC_ACQUIRE) & jc_b_)) {                \
+      __VA_ARGS__;                                                              \
+      __atomic_fetch_or(&(flag), jc_b_, __ATOMIC_RELEASE);                      \
+    }                                                                           \
+  } while (0)
+
+// Entry points that own a device (plan creation / destruction, the host-buffer calls) switch to the plan's device and put the caller's
+// current device back on every return path.
+struct JcDeviceGuard {
+  int prev = -1;
+  cudaError_t status;
+  explicit JcDeviceGuard(int device) {
+    cudaGetDevice(&prev);
+    status = cudaSetDevice(device);
+  }
+  ~JcDeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  JcDeviceGuard(const JcDeviceGuard&) = delete;
+  JcDeviceGuard& operator=(const JcDeviceGuard&) = delete;
+};
+
 void jc_set_cuda_error(cudaError_t e, const char* where);
 void jc_math_table(double* out288);  // host: tables of the table-driven exp / log (jc_math.cuh)
 int jc_pipeline_init();  // one-time function attributes (dynamic shared memory opt-in)

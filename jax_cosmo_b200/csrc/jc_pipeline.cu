@@ -54,6 +54,7 @@ extern "C" int jc_angular_cl_jvp_f64(const jc_plan* plan, const double* cosmo_de
                                      void* ws_dev, size_t ws_bytes, void* stream) {
   if (!plan || plan->d.grid_mode || !cosmo_dev || !tangents_dev || !dcl_dev || !ws_dev || n_cosmo < 1 || n_tangents < 1)
     return JC_ERR_INVALID;
+  JcDeviceGuard guard(plan->device);  // a null stream handle means the CURRENT device's default stream
   jc_ws_layout lo;
   int st = jc_workspace_layout(plan, ws_bytes / 2, &lo);
   if (st != JC_OK) return st;
@@ -97,6 +98,7 @@ extern "C" int jc_workspace_layout(const jc_plan* plan, size_t ws_bytes, jc_ws_l
 extern "C" int jc_angular_cl_f64(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo,
                                  double* cl_dev, void* ws_dev, size_t ws_bytes, void* stream) {
   if (!plan || plan->d.grid_mode || !cosmo_dev || !cl_dev || !ws_dev || n_cosmo < 1) return JC_ERR_INVALID;
+  JcDeviceGuard guard(plan->device);  // a null stream handle means the CURRENT device's default stream
   jc_ws_layout lo;
   int st = jc_workspace_layout(plan, ws_bytes, &lo);
   if (st != JC_OK) return st;
@@ -171,6 +173,7 @@ extern "C" int jc_grid_eval_f64(const jc_plan* plan, const double* cosmo_dev, in
                                 double* chi_dev, double* chi_transverse_dev, double* growth_dev, double* hubble_dev,
                                 double* transfer_dev, double* kernels_dev, void* ws_dev, size_t ws_bytes, void* stream) {
   if (!plan || !plan->d.grid_mode || !cosmo_dev || !ws_dev || n_cosmo < 1) return JC_ERR_INVALID;
+  JcDeviceGuard guard(plan->device);  // a null stream handle means the CURRENT device's default stream
   jc_ws_layout lo;
   int st = jc_workspace_layout(plan, ws_bytes, &lo);
   if (st != JC_OK) return st;
@@ -254,6 +257,7 @@ __global__ void __launch_bounds__(256) jc_a_of_chi_kernel(JcDevPlan pl, Ws ws, c
 extern "C" int jc_grid_background_f64(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo, double* aux_dev,
                                       void* ws_dev, size_t ws_bytes, void* stream) {
   if (!plan || !plan->d.grid_mode || !cosmo_dev || !aux_dev || !ws_dev || n_cosmo < 1) return JC_ERR_INVALID;
+  JcDeviceGuard guard(plan->device);  // a null stream handle means the CURRENT device's default stream
   jc_ws_layout lo;
   int st = jc_workspace_layout(plan, ws_bytes, &lo);
   if (st != JC_OK) return st;
@@ -275,6 +279,7 @@ extern "C" int jc_grid_background_f64(const jc_plan* plan, const double* cosmo_d
 extern "C" int jc_a_of_chi_f64(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo, const double* chi_dev,
                                int64_t n_chi, double* a_dev, void* ws_dev, size_t ws_bytes, void* stream) {
   if (!plan || !cosmo_dev || !chi_dev || !a_dev || !ws_dev || n_cosmo < 1 || n_chi < 1 || n_chi > (1 << 30)) return JC_ERR_INVALID;
+  JcDeviceGuard guard(plan->device);  // a null stream handle means the CURRENT device's default stream
   jc_ws_layout lo;
   int st = jc_workspace_layout(plan, ws_bytes, &lo);
   if (st != JC_OK) return st;
@@ -296,6 +301,7 @@ extern "C" int jc_sigmasqr_f64(const jc_plan* plan, const double* cosmo_dev, int
                                double kmin, double kmax, double* out_dev, void* ws_dev, size_t ws_bytes, void* stream) {
   if (!plan || !cosmo_dev || !R_dev || !out_dev || !ws_dev || n_cosmo < 1 || n_R < 1) return JC_ERR_INVALID;
   if (kmin != 0.0001 || kmax != 1000.0) return JC_ERR_UNSUPPORTED;  // the plan tabulates the reference's default limits
+  JcDeviceGuard guard(plan->device);  // a null stream handle means the CURRENT device's default stream
   jc_ws_layout lo;
   int st = jc_workspace_layout(plan, ws_bytes, &lo);
   if (st != JC_OK) return st;
@@ -318,6 +324,7 @@ extern "C" int jc_sigmasqr_f64(const jc_plan* plan, const double* cosmo_dev, int
 extern "C" int jc_debug_stages_f64(const jc_plan* plan, int32_t stage_mask, const double* cosmo_dev, int64_t n_cosmo,
                                    double* cl_dev, void* ws_dev, size_t ws_bytes, void* stream) {
   if (!plan || plan->d.grid_mode || !cosmo_dev || !cl_dev || !ws_dev || n_cosmo < 1) return JC_ERR_INVALID;
+  JcDeviceGuard guard(plan->device);  // a null stream handle means the CURRENT device's default stream
   jc_ws_layout lo;
   int st = jc_workspace_layout(plan, ws_bytes, &lo);
   if (st != JC_OK) return st;

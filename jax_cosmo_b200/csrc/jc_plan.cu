@@ -243,7 +243,8 @@ static int create_plan(const jc_problem* pb, const double* ell_host, int32_t n_e
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return JC_ERR_NO_DEVICE;
   if (device < 0 || device >= ndev) return JC_ERR_INVALID;
-  JC_CUDA_TRY(cudaSetDevice(device));
+  JcDeviceGuard guard(device);
+  JC_CUDA_TRY(guard.status);
   st = jc_pipeline_init();
   if (st != JC_OK) return st;
 
@@ -591,7 +592,7 @@ extern "C" int jc_grid_plan_create_probes(const jc_problem* pb, const double* a_
 
 extern "C" void jc_plan_destroy(jc_plan* plan) {
   if (!plan) return;
-  cudaSetDevice(plan->device);
+  JcDeviceGuard guard(plan->device);
   if (plan->prof) {
     for (int i = 0; i < JC_PROF_SLOTS; ++i)
       for (int j = 0; j <= JC_N_STAGES; ++j) if (plan->prof->ev[i][j]) cudaEventDestroy(plan->prof->ev[i][j]);

@@ -239,11 +239,9 @@ void launch_lens(const JcDevPlan& pl, const Ws& ws, int chunk, int s0, cudaStrea
   constexpr int CTA_COSMO = NCOS * LENS_CGROUPS;
   dim3 grid(JC_NLENS_COLS / LENS_NODES, (chunk + CTA_COSMO - 1) / CTA_COSMO);
   constexpr int smem = LENS_STAGES * LENS_MR * (LENS_NODES * 8 * (1 + NS) + LENS_NODES * 2);
-  static bool attr_done = false;  // idempotent attribute; racing writers set the same value
-  if (!attr_done) {
-    cudaFuncSetAttribute(jc_lens_kernel<T, NS, NCOS, LENS_CGROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr_done = true;
-  }
+  static unsigned long long attr_done = 0;
+  JC_ONCE_PER_DEVICE(attr_done, cudaFuncSetAttribute(jc_lens_kernel<T, NS, NCOS, LENS_CGROUPS>,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   jc_lens_kernel<T, NS, NCOS, LENS_CGROUPS><<<grid, LENS_NODES * LENS_CGROUPS, smem, st>>>(pl, ws, chunk, s0);
 }
 

@@ -72,9 +72,10 @@ def _bmm(A, sA, B, sB, out_shape, sC, I, J, K, L):
     import torch
 
     out = torch.empty(out_shape, dtype=torch.float64, device=A.device)
-    st = _native.load_library().jc_sparse_bmm_f64(
-        A.data_ptr(), sA[0], sA[1], sA[2], B.data_ptr(), sB[0], sB[1], sB[2], out.data_ptr(), sC[0], sC[1], sC[2],
-        I, J, K, L, torch.cuda.current_stream(A.device).cuda_stream)
+    with torch.cuda.device(A.device):
+        st = _native.load_library().jc_sparse_bmm_f64(
+            A.data_ptr(), sA[0], sA[1], sA[2], B.data_ptr(), sB[0], sB[1], sB[2], out.data_ptr(), sC[0], sC[1], sC[2],
+            I, J, K, L, torch.cuda.current_stream(A.device).cuda_stream)
     _native.check(st, "jc_sparse_bmm_f64")
     return out
 
@@ -144,9 +145,10 @@ def _inv_core(sparse, want_inv):
     sign = torch.empty(L, dtype=torch.float64, device=S.device)
     logdet = torch.empty(L, dtype=torch.float64, device=S.device)
     scratch = torch.empty((L, P, 2 * P), dtype=torch.float64, device=S.device)
-    st = _native.load_library().jc_sparse_inv_f64(
-        S.data_ptr(), P, L, inv_t.data_ptr() if want_inv else None, sign.data_ptr(), logdet.data_ptr(),
-        scratch.data_ptr(), torch.cuda.current_stream(S.device).cuda_stream)
+    with torch.cuda.device(S.device):
+        st = _native.load_library().jc_sparse_inv_f64(
+            S.data_ptr(), P, L, inv_t.data_ptr() if want_inv else None, sign.data_ptr(), logdet.data_ptr(),
+            scratch.data_ptr(), torch.cuda.current_stream(S.device).cuda_stream)
     _native.check(st, "jc_sparse_inv_f64")
     return inv_t, sign, logdet, was_tensor
 

@@ -419,6 +419,29 @@ def test_sharded_single_process(jc, torch_cuda):
     assert np.array_equal(cl.cpu().numpy(), jc.cl.angular_cl_batch(rows, scn["ell"], probes))
 
 
+def test_two_devices_in_one_process(jc, torch_cuda):
+    """One process driving two GPUs (plans on cuda:0 and cuda:1): kernel attributes such as the dynamic shared-memory opt-in belong to each
+    device's context, so the second device must get them too.  Results are bitwise equal across devices."""
+    torch = torch_cuda
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from jax_cosmo_b200 import _native
+    scn = sc.scenario("d2", sc.PLANCK15, sc.ELL_CFG2[::4], [sc.sources(10, 1.0), sc.lenses(10, 1.0)])
+    probes = sc.build_probes(scn, jc)
+    rows = sc.config5_cosmologies(40)
+    outs = []
+    for dev in (0, 1):
+        with torch.cuda.device(dev):
+            plan = _native.get_plan(probes, scn["ell"], None, None, device=dev)
+            outs.append(plan.angular_cl_device(torch.as_tensor(rows, device="cuda:%d" % dev)).cpu().numpy())
+            tang = torch.zeros((1, 8), dtype=torch.float64, device="cuda:%d" % dev)
+            tang[0, 4] = 1.0
+            _, dcl = plan.angular_cl_jvp_device(torch.as_tensor(rows[:3], device="cuda:%d" % dev), tang)
+            outs.append(dcl.cpu().numpy())
+    assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[3])
+    assert np.isfinite(outs[0]).all() and np.isfinite(outs[1]).all()
+
+
 def test_device_math(torch_cuda):
     """The kernels' own exp/log/sin/rcbrt/rcp (csrc/jc_math.cuh) against NumPy on the argument
     ranges the pipeline produces.  Stated bound: 4 ulp-ish relative (2e-15); sin: absolute."""
