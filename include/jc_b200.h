@@ -233,7 +233,10 @@ int jc_angular_cl_f64(const jc_plan* plan, const double* cosmo_dev, int64_t n_co
  * directional derivative of cl[b] along it -- the derivative of the discretised program with
  * interpolation / root indices and clip branches frozen at the evaluation point.  cl_dev may be NULL.
  * cosmo_dev [B,8], tangents_dev [K,8], cl_dev [B,P,L], dcl_dev [B,K,P,L]; the workspace holds a value
- * plane and a tangent plane: jc_workspace_bytes_jvp() = 2 x jc_workspace_bytes(). */
+ * plane and a tangent plane: jc_workspace_bytes_jvp() = 2 x jc_workspace_bytes().
+ * Small batches: when the workspace has room for B*K entries (ask jc_workspace_bytes_jvp(plan, B*K)), all K directions of
+ * every cosmology run in ONE pass over B*K entries instead of K latency-bound passes (a Jacobian at one cosmology: 0.58 ms
+ * instead of 2.5 ms); the results are bitwise the same either way. */
 int jc_workspace_bytes_jvp(const jc_plan* plan, int64_t n_cosmo, size_t* bytes_out);
 int jc_angular_cl_jvp_f64(const jc_plan* plan, const double* cosmo_dev, const double* tangents_dev,
                           int32_t n_tangents, int64_t n_cosmo, double* cl_dev, double* dcl_dev,

@@ -414,7 +414,9 @@ class Plan:
         self._check_rows(tangents_dev, "tangents")
         B, K = cosmo_dev.shape[0], tangents_dev.shape[0]
         need = C.c_size_t()
-        check(load_library().jc_workspace_bytes_jvp(self._h, B, C.byref(need)), "jc_workspace_bytes_jvp")
+        # small batches: room for B*K workspace entries lets the library run all K directions in one pass
+        entries = B * K if B * K <= 1024 else B
+        check(load_library().jc_workspace_bytes_jvp(self._h, entries, C.byref(need)), "jc_workspace_bytes_jvp")
         ws = torch.empty(need.value // 8, dtype=torch.float64, device=cosmo_dev.device)
         cl = torch.empty((B, self.P, self.L), dtype=torch.float64, device=cosmo_dev.device)
         dcl = torch.empty((B, K, self.P, self.L), dtype=torch.float64, device=cosmo_dev.device)

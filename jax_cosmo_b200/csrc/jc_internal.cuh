@@ -200,7 +200,7 @@ void jc_launch_sigmasqr(const JcDevPlan& pl, const Ws& ws, const double* cosmo, 
                         cudaStream_t s);
 void jc_launch_transfer(const JcDevPlan& pl, const Ws& ws, int chunk, double* tk, cudaStream_t s);
 // JVP (Dual) variants: same kernels instantiated on value+tangent; `tangent` = direction [8] in parameter space
-void jc_launch_setup_jvp(const JcDevPlan& pl, const double* cosmo, const double* tangent, const Ws& ws, int chunk,
+void jc_launch_setup_jvp(const JcDevPlan& pl, const double* cosmo, const double* tangent, const Ws& ws, int chunk, int kdiv,
                          cudaStream_t s);
 int jc_launch_tracers_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s);
 void jc_launch_finish_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s);

@@ -63,10 +63,30 @@ extern "C" int jc_angular_cl_jvp_f64(const jc_plan* plan, const double* cosmo_de
   Ws ws;
   resolve(lo, (double*)ws_dev, (ptrdiff_t)((lo.total + 1) & ~(int64_t)1), &ws);
   const int64_t PL = (int64_t)pl.P * pl.L;
+  if (n_tangents > 1 && n_cosmo * n_tangents <= lo.chunk) {
+    // Small batches (a Fisher forecast at one cosmology): all K directions of every cosmology in ONE pass over B*K workspace
+    // entries (entry b*K + k = cosmology b, direction k, which is also the layout of dcl) instead of K latency-bound passes.
+    // Needs a workspace for B*K entries (jc_workspace_bytes_jvp(plan, B*K)); per-entry arithmetic is the same, results are
+    // bitwise those of the pass-per-direction path.  The value plane of entry b*K is C_l of cosmology b: it is contracted into the
+    // dcl buffer first (same size), its rows b*K copied out to cl, then the tangent contraction overwrites dcl.
+    const int entries = (int)(n_cosmo * n_tangents);
+    jc_launch_setup_jvp(pl, cosmo_dev, tangents_dev, ws, entries, n_tangents, s);
+    jc_launch_tracers_jvp(pl, ws, entries, s);
+    jc_launch_finish_jvp(pl, ws, entries, s);
+    jc_launch_power_jvp(pl, ws, entries, s);
+    if (cl_dev) {
+      jc_launch_contract(pl, ws, dcl_dev, entries, s);
+      JC_CUDA_TRY(cudaMemcpy2DAsync(cl_dev, (size_t)PL * sizeof(double), dcl_dev, (size_t)n_tangents * PL * sizeof(double),
+                                    (size_t)PL * sizeof(double), (size_t)n_cosmo, cudaMemcpyDeviceToDevice, s));
+    }
+    jc_launch_contract_jvp(pl, ws, dcl_dev, PL, entries, s);
+    JC_CUDA_TRY(cudaGetLastError());
+    return JC_OK;
+  }
   for (int64_t c0 = 0; c0 < n_cosmo; c0 += lo.chunk) {
     const int chunk = (int)((n_cosmo - c0) < lo.chunk ? (n_cosmo - c0) : lo.chunk);
     for (int k = 0; k < n_tangents; ++k) {
-      jc_launch_setup_jvp(pl, cosmo_dev + c0 * pl.ncp, tangents_dev + (size_t)k * pl.ncp, ws, chunk, s);
+      jc_launch_setup_jvp(pl, cosmo_dev + c0 * pl.ncp, tangents_dev + (size_t)k * pl.ncp, ws, chunk, 1, s);
       jc_launch_tracers_jvp(pl, ws, chunk, s);
       jc_launch_finish_jvp(pl, ws, chunk, s);
       jc_launch_power_jvp(pl, ws, chunk, s);

@@ -82,7 +82,7 @@ template <class T> struct SetupSmem {
 #endif
 template <class T>
 __global__ void __launch_bounds__(256, sizeof(T) == sizeof(double) ? JC_SETUP_MINB : 2) jc_setup_kernel(JcDevPlan pl, const double* __restrict__ cosmo,
-                                                       const double* __restrict__ tangent, Ws ws) {
+                                                       const double* __restrict__ tangent, Ws ws, int kdiv) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SetupSmem<T>& S = *reinterpret_cast<SetupSmem<T>*>(smem_raw);
   double* const s_hfk = reinterpret_cast<double*>(S.f);  // halofit k nodes (S.f is free by then)
@@ -93,7 +93,10 @@ __global__ void __launch_bounds__(256, sizeof(T) == sizeof(double) ? JC_SETUP_MI
   auto put = [&](double* p, T x) { JxMem<T>::st(p, doff, x); };
   auto node = [&](int field, int n) { return node_ptr(ws, c, field) + n; };
 
-  const double* cp = cosmo + (size_t)c * pl.ncp;
+  // JVP passes: workspace entry c carries cosmology c / kdiv with tangent direction c % kdiv (kdiv = 1: one direction for the whole
+  // pass; kdiv = K: all K directions of every cosmology in one pass).  Forward passes: kdiv = 1, tangent = nullptr.
+  const double* cp = cosmo + (size_t)(c / kdiv) * pl.ncp;
+  if constexpr (sizeof(T) != sizeof(double)) tangent += (size_t)(c % kdiv) * pl.ncp;
   T par[JC_N_COSMO_PARAMS];
 #pragma unroll
   for (int i = 0; i < JC_N_COSMO_PARAMS; ++i) {
@@ -544,10 +547,10 @@ int jc_setup_init() {
 }
 
 void jc_launch_setup(const JcDevPlan& pl, const double* cosmo, const Ws& ws, int chunk, cudaStream_t s) {
-  jc_setup_kernel<double><<<chunk, 256, sizeof(SetupSmem<double>), s>>>(pl, cosmo, nullptr, ws);
+  jc_setup_kernel<double><<<chunk, 256, sizeof(SetupSmem<double>), s>>>(pl, cosmo, nullptr, ws, 1);
 }
 
-void jc_launch_setup_jvp(const JcDevPlan& pl, const double* cosmo, const double* tangent, const Ws& ws, int chunk,
+void jc_launch_setup_jvp(const JcDevPlan& pl, const double* cosmo, const double* tangent, const Ws& ws, int chunk, int kdiv,
                          cudaStream_t s) {
-  jc_setup_kernel<Dual><<<chunk, 256, sizeof(SetupSmem<Dual>), s>>>(pl, cosmo, tangent, ws);
+  jc_setup_kernel<Dual><<<chunk, 256, sizeof(SetupSmem<Dual>), s>>>(pl, cosmo, tangent, ws, kdiv);
 }
