@@ -419,6 +419,24 @@ def test_sharded_single_process(jc, torch_cuda):
     assert np.array_equal(cl.cpu().numpy(), jc.cl.angular_cl_batch(rows, scn["ell"], probes))
 
 
+def test_jvp_fused_directions_bitwise(jc, torch_cuda):
+    """jc_angular_cl_jvp_f64 runs all K directions in one pass when the workspace holds B*K entries (small batches) and one pass per
+    direction otherwise: both give bitwise the same spectra and derivatives."""
+    torch = torch_cuda
+    from jax_cosmo_b200 import _native
+    scn = sc.scenario("jf", sc.PLANCK15, sc.ELL_CFG2[::7], [sc.sources(5, 2.0), sc.lenses(5, 2.0)])
+    plan = _native.get_plan(sc.build_probes(scn, jc), scn["ell"], None, None)
+    rows = torch.as_tensor(sc.config5_cosmologies(3), device="cuda")
+    tang = torch.zeros((7, 8), dtype=torch.float64, device="cuda")
+    tang[torch.arange(7), torch.tensor([0, 1, 2, 3, 4, 6, 7])] = 1.0
+    tang[2, 0] = 0.5  # a mixed direction
+    cl, dcl = plan.angular_cl_jvp_device(rows, tang)          # 21 entries: fused
+    for k in range(7):
+        cl1, d1 = plan.angular_cl_jvp_device(rows, tang[k:k + 1].contiguous())  # K = 1: one pass per direction
+        assert torch.equal(cl1, cl) and torch.equal(d1[:, 0], dcl[:, k]), k
+    assert torch.isfinite(dcl).all() and float(dcl.abs().max()) > 0
+
+
 def test_two_devices_in_one_process(jc, torch_cuda):
     """One process driving two GPUs (plans on cuda:0 and cuda:1): kernel attributes such as the dynamic shared-memory opt-in belong to each
     device's context, so the second device must get them too.  Results are bitwise equal across devices."""
