@@ -24,6 +24,13 @@ import sys
 import threading
 import time
 
+# The CPU arm runs one single-threaded NumPy worker per host core.  BLAS/OpenMP pools must be pinned to one thread
+# BEFORE NumPy is imported (the workers are forked from this process): unpinned, every worker starts its own
+# cpu_count()-wide pool and the arm runs 5-10x slower than the cores allow (round-1 finding; torchrun exports
+# OMP_NUM_THREADS=1 itself, which is why the N>1 reference runs were faster than N=1).
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+    os.environ[_v] = "1"
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -35,6 +42,7 @@ N_ELL, N_SRC, N_LENS = 100, 10, 10
 T = N_SRC + N_LENS
 P = T * (T + 1) // 2
 A = 513
+WORKLOAD = "config5: 3x2pt 10+10 Smail bins (T=20, P=210), 100 ell, halofit, wCDM box seed 20240607"
 
 
 def v0_slots(L, n_src, Pn, halofit=True):
@@ -105,71 +113,152 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------
-def _oracle_worker(args):
-    rows, = args
+def _oracle_init():
+    try:  # belt and braces: pools that ignore the environment variables
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
     from oracle import cl_oracle as o
     from oracle import scenarios as sc
     scn = scenario()
-    prob = sc.flatten_spec(scn)
-    ell = np.array(scn["ell"])
+    _oracle_init.ctx = (o, sc.flatten_spec(scn), np.array(scn["ell"]))
+
+
+def _oracle_worker(rows):
+    o, prob, ell = _oracle_init.ctx
     for row in rows:
         o.angular_cl(row, ell, prob)
     return len(rows)
 
 
-def cpu_oracle_rate(n_cosmo, cores):
-    """Time the oracle port over n_cosmo cosmologies of the bench workload on `cores` processes."""
-    import multiprocessing as mp
-    from oracle import scenarios as sc
-    rows = sc.config5_cosmologies(65536)[:n_cosmo]
-    parts = [rows[i::cores] for i in range(cores)]
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
-        pool.map(_oracle_worker, [(p[:1],) for p in parts])  # warm-up (imports, caches)
+class CpuArm:
+    """The reference's CPU path for the bench workload: the NumPy oracle port (oracle/cl_oracle.py; the reference is
+    pure Python on JAX and JAX is not installable here) on one single-threaded process per host core.  One persistent
+    pool; every timed pass runs `sample` cosmologies of the config-5 box dealt round-robin to the workers."""
+
+    def __init__(self, sample):
+        import multiprocessing as mp
+        from oracle import scenarios as sc
+        self.cores = os.cpu_count() or 1
+        self.sample = max(self.cores, int(sample))
+        self.rows = sc.config5_cosmologies(65536)[:self.sample]
+        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_oracle_init)
+        self.pool.map(_oracle_worker, [self.rows[i:i + 1] for i in range(self.cores)])  # imports + caches
+
+    def run(self):
+        """-> (C_ell/s, seconds) of one pass over the sample."""
+        parts = [self.rows[i::self.cores] for i in range(self.cores)]
         t0 = time.perf_counter()
-        pool.map(_oracle_worker, [(p,) for p in parts])
+        self.pool.map(_oracle_worker, parts)
         dt = time.perf_counter() - t0
-    return n_cosmo * P * N_ELL / dt, dt
+        return self.sample * P * N_ELL / dt, dt
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+    def describe(self, rate):
+        return {"value": rate, "unit": UNIT, "cores": self.cores, "kind": "port",
+                "per_core": rate / self.cores, "blas_threads_per_worker": 1,
+                "sample": "%d cosmologies x 210 x 100 per pass, NumPy oracle port of the reference on %d single-threaded "
+                          "processes (JAX not installable: the reference itself cannot run)" % (self.sample, self.cores),
+                "footnote": "reference source executed unmodified on the NumPy jax shim: ~5 s per ell per cosmology "
+                            "(BASELINE.md section 2 item 3; un-jitted interpreter cost, parity use only)"}
+
+
+def default_cpu_sample():
+    return 16 * (os.cpu_count() or 1)
 
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path for this workload (oracle port, all host cores)."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    sample = max(cores, min(args.cpu_sample, 8 * cores))
-    for _ in range(args.warmup):
-        cpu_oracle_rate(cores, cores)
-    t_tot, n_tot = 0.0, 0
+    arm = CpuArm(args.cpu_sample or default_cpu_sample())
+    for _ in range(min(args.warmup, 1)):
+        arm.run()
+    t_tot = 0.0
     for _ in range(args.steps):
-        rate, dt = cpu_oracle_rate(sample, cores)
+        _, dt = arm.run()
         t_tot += dt
-        n_tot += sample
-    value = n_tot * P * N_ELL / t_tot
+    arm.close()
+    value = args.steps * arm.sample * P * N_ELL / t_tot
     line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "config5: 3x2pt 10+10 Smail bins, 100 ell, halofit, wCDM box seed 20240607",
-                       "cosmologies_per_step": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d cosmologies x 210 x 100 per step, NumPy oracle port of the reference "
-                                       "(JAX not installable: reference itself cannot run)" % sample},
+            "config": {"workload": WORKLOAD, "cosmologies_per_step": arm.sample},
+            "cpu_baseline": arm.describe(value),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------
+def git_head():
+    try:
+        return subprocess.run(["git", "-C", ROOT, "rev-parse", "--short=12", "HEAD"], capture_output=True, text=True,
+                              timeout=5).stdout.strip() or None
+    except Exception:
+        return None
+
+
+def ncu_current():
+    """profiles/ncu_current.json: per-kernel figures read from the committed ncu --set full capture (DRAM bytes and
+    executed FP64 / DMMA instruction counts per cosmology), stamped with the hash of the kernel sources they were
+    captured from.  Stale (sources changed since) -> None: the bench then prints no traffic / executed-work figure
+    instead of an outdated one."""
+    path = os.path.join(ROOT, "profiles", "ncu_current.json")
+    try:
+        rec = json.load(open(path))
+    except Exception:
+        return None, "profiles/ncu_current.json missing"
+    if rec.get("csrc_sha256") != csrc_hash():
+        return None, "profiles/ncu_current.json is stale (kernel sources changed since the capture)"
+    return rec, "profiles/ncu_current.json (%s)" % rec.get("capture", "?")
+
+
+def csrc_hash():
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "jax_cosmo_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()
+
+
+def d2h_probe(torch, dev, nbytes=1 << 30, reps=3):
+    """Plain pinned cudaMemcpy device->host rate on this box (GB/s): the ceiling of the e2e leg."""
+    src = torch.empty(nbytes // 8, dtype=torch.float64, device=dev)
+    dst = torch.empty(nbytes // 8, dtype=torch.float64).pin_memory()
+    dst.copy_(src)
+    torch.cuda.synchronize()
+    best = 0.0
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        best = max(best, nbytes / (time.perf_counter() - t0) / 1e9)
+    return best
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cosmologies-per-gpu", type=int, default=8192)
-    ap.add_argument("--cpu-sample", type=int, default=256)
+    ap.add_argument("--workload", default="config5", choices=["config5", "config3", "config4"])
+    ap.add_argument("--cosmologies-per-gpu", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="cosmologies per CPU pass (default 16 per host core, the same for cpu_baseline and --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="N > 1: time the sharded compute only (no exchange)")
+    ap.add_argument("--gather-mode", default="peer", choices=["peer", "nccl", "collective"])
+    ap.add_argument("--sub-chunk", type=int, default=0, help="cosmologies per compute/push step of the gather pipeline")
     ap.add_argument("--peak-tflops", type=float, default=0.0,
                     help="use this FP64 peak instead of probing (for runs under ncu)")
     args = ap.parse_args()
@@ -180,12 +269,17 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    if args.workload != "config5":
+        import bench_workloads
+        bench_workloads.run(args, rank, world, local)
+        return
 
     import torch
     import torch.distributed as dist
 
     import jax_cosmo_b200 as jc
     from jax_cosmo_b200 import _native
+    from jax_cosmo_b200.distributed import DEFAULT_SUB_CHUNK, ShardedAngularCl
     from oracle import scenarios as sc
 
     if not torch.cuda.is_available():
@@ -201,17 +295,27 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     scn = scenario()
     probes = sc.build_probes(scn, jc)
     plan = _native.get_plan(probes, scn["ell"], None, None, device=local)
-    B = args.cosmologies_per_gpu
+    B = args.cosmologies_per_gpu or 8192
     box = sc.config5_cosmologies(65536)
-    rows = box[(rank * B) % 65536:][:B] if (rank * B) % 65536 + B <= 65536 else box[:B]
-    rows = np.ascontiguousarray(rows)
+    if world * B <= 65536:
+        rows_all = box[:world * B]
+    else:
+        rows_all = np.concatenate([box] * (-(-world * B // 65536)))[:world * B]
+    rows = np.ascontiguousarray(rows_all[rank * B:(rank + 1) * B])
     cos = torch.as_tensor(rows, device=dev)
     out = torch.empty((B, P, N_ELL), dtype=torch.float64, device=dev)
     ws = plan.workspace(B)
     ws_bytes = ws.numel() * 8
+    steps, warmup = args.steps, max(args.warmup, 3)
 
     # FP64 roofline denominator (not in MEASURED_PEAKS.json): DFMA probe, burst and sustained
     if args.peak_tflops > 0:  # profiler runs: skip the probe launches
@@ -224,7 +328,8 @@ def main():
         peak_src = ("measured live: jc_fp64_peak_tflops DFMA probe, 2 s sustained "
                     "(MEASURED_PEAKS.json holds no FP64 figure)")
 
-    for _ in range(max(args.warmup, 3)):
+    # ---- sharded compute, results resident on the owning GPU (no exchange) ----------------------------------------
+    for _ in range(warmup):
         plan.angular_cl_device(cos, out=out, workspace=ws)
     barrier()
     plan.profile_enable(True)
@@ -233,20 +338,74 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         plan.angular_cl_device(cos, out=out, workspace=ws)
     e1.record()
     barrier()
-    clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
+    ms_compute = max_over_ranks(e0.elapsed_time(e1))
     stage_ms, stage_n = plan.profile_read()
     plan.profile_enable(False)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
     evals_per_step = world * B * P * N_ELL
-    value = evals_per_step * args.steps / (ms * 1e-3)
+    value_compute = evals_per_step * steps / (ms_compute * 1e-3)
+    n_launches = int(sum(stage_n.values()))
+
+    # ---- N > 1: the same step including the path's one exchange, the gather of the shards on every rank ------------
+    gather = None
+    ms = ms_compute
+    if world > 1 and not args.no_gather:
+        sub = args.sub_chunk or DEFAULT_SUB_CHUNK
+        sh = ShardedAngularCl(world * B, scn["ell"], probes, gather_mode=args.gather_mode, sub_chunk=sub)
+        rows_dev = torch.as_tensor(np.ascontiguousarray(rows_all), device=dev)
+        for _ in range(warmup):
+            sh(rows_dev)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        g0.record()
+        for _ in range(steps):
+            sh(rows_dev)
+        g1.record()
+        barrier()
+        ms = max_over_ranks(g0.elapsed_time(g1))
+        # correctness on the hardware: the gathered buffer equals the resident result (own rows) and a fresh local
+        # evaluation of rows another rank computed and pushed, bitwise
+        nb = (rank + 1) % world
+        probe_rows = torch.as_tensor(np.ascontiguousarray(rows_all[nb * B:nb * B + 64]), device=dev)
+        same = bool(torch.equal(sh.full[rank * B:(rank + 1) * B], out)) and bool(
+            torch.equal(sh.full[nb * B:nb * B + 64], plan.angular_cl_device(probe_rows)))
+        same = max_over_ranks(0.0 if same else 1.0) == 0.0
+        # the exchange alone (no compute): NVLink leg by itself
+        ms_x = None
+        if sh.mode == "peer":
+            for _ in range(2):
+                sh._peer.push(rank * B, B)
+                sh.barrier()
+            barrier()
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x0.record()
+            for _ in range(steps):
+                sh._peer.push(rank * B, B)
+                sh.barrier()
+            x1.record()
+            barrier()
+            ms_x = max_over_ranks(x0.elapsed_time(x1)) / steps
+        bytes_in = (world - 1) * B * P * N_ELL * 8
+        n_chunks = -(-B // sub)
+        gather = {"mode": sh.mode, "sub_chunk": sub, "ms_per_step": ms / steps, "ms_per_step_compute_only": ms_compute / steps,
+                  "exposed_ms": (ms - ms_compute) / steps, "ratio_vs_compute_only": ms / ms_compute,
+                  "bytes_in_per_gpu_per_step": bytes_in, "bytes_out_per_gpu_per_step": bytes_in,
+                  "nvlink_in_gbs_overlapped": bytes_in / (ms / steps * 1e-3) / 1e9,
+                  "exchange_alone_ms": ms_x, "nvlink_in_gbs_alone": (bytes_in / (ms_x * 1e-3) / 1e9) if ms_x else None,
+                  "value_compute_only": value_compute, "bitwise_equal_to_local": same,
+                  "note": "every rank ends the step holding the full [%d, %d, %d] result; pushes by the copy engines over "
+                          "NVLink peer memory overlapped with the next sub-chunk's kernels, closed by a stream-ordered "
+                          "one-element NCCL all-reduce" % (world * B, P, N_ELL)}
+        passes = steps * max(-(-B // int(plan.workspace_layout(ws_bytes).chunk)), 1)
+        n_launches = (n_launches // passes) * n_chunks * steps  # kernels per chunk pass x passes of the gather loop
+        gather["copies_per_step"] = n_chunks * (world - 1)
+        sh.close()
+    clocks = sampler.stop()
+    value = evals_per_step * steps / (ms * 1e-3)
 
     # ---- end to end through the drop-in host API (pinned host buffers) ----------------------------
     e2e = None
@@ -257,17 +416,25 @@ def main():
             jc.cl.angular_cl_batch(rows_pin, scn["ell"], probes, out=out_pin)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             jc.cl.angular_cl_batch(rows_pin, scn["ell"], probes, out=out_pin)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": evals_per_step * args.steps / float(tt.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(rows.nbytes), "d2h_bytes_per_step": int(out_pin.numel() * 8)}
-        chk = float((out_pin[:4].to(dev) - out[:4]).abs().max().item())
-        e2e["max_abs_diff_vs_device_path"] = chk
+        dt = max_over_ranks(time.perf_counter() - t0)
+        d2h_bytes = int(out_pin.numel() * 8)
+        e2e = {"value": evals_per_step * steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(rows.nbytes), "d2h_bytes_per_step": d2h_bytes}
+        # every row of the host result against the device-resident result of the same rows
+        diff = 0.0
+        for r0 in range(0, B, 1024):
+            diff = max(diff, float((out_pin[r0:r0 + 1024].to(dev) - out[r0:r0 + 1024]).abs().max().item()))
+        e2e["max_abs_diff_vs_device_path"] = diff
+        e2e["rows_compared"] = B
+        e2e["d2h_gbs"] = d2h_bytes * steps / dt / 1e9
+        if world == 1:
+            peak_d2h = d2h_probe(torch, dev)
+            e2e["d2h_peak_gbs"] = peak_d2h
+            e2e["frac_of_d2h_peak"] = e2e["d2h_gbs"] / peak_d2h
+            e2e["bound"] = "device->host copy of the [B, 210, 100] f64 result over PCIe, compute hidden behind it"
 
     if rank != 0:
         if world > 1:
@@ -282,56 +449,66 @@ def main():
     dom = max(("power", "contract", "setup", "lens"), key=lambda k: stage_ms[k])  # dominant kernel of the step
     n_launch = max(stage_n[dom], 1)
     launch_ms = stage_ms[dom] / n_launch              # average launch duration (CUDA events on the launch stream)
-    cosmo_per_launch = B * args.steps / n_launch
+    cosmo_per_launch = B * steps / n_launch
     achieved = 2.0 * slots[dom] * cosmo_per_launch / (launch_ms * 1e-3) / 1e12
-    # FP64 work the compiled kernels actually execute (ncu, profiles/r01_ncu_summary.md): FP64-pipe warp
-    # instructions per (ell, node) point x 64 flop for K3; DMMA m8n8k4 count x 512 flop for K4
-    sass_flops = {"power": 186.0 * 2 * N_ELL * A, "contract": 45279.0 * 512}
-    # DRAM bytes per launch of `chunk` cosmologies, scaled from the ncu --set full captures at 592 cosmologies
-    # (profiles/r01_ncu_v14_metrics.csv / r01_ncu_v15_metrics.csv, r01_ncu_summary.md sections 13-14)
-    ncu_dram_per_cosmo = {"power": (42.55e6 + 193.52e6) / 592, "contract": (297.02e6 + 77.66e6) / 592}
-    step_tflops = 2.0 * slots["total"] * B * args.steps / (ms * 1e-3) / 1e12
+    step_tflops = 2.0 * slots["total"] * B * steps / (ms_compute * 1e-3) / 1e12
+    # executed FP64-pipe work and DRAM traffic: read from the committed ncu capture, refused when stale
+    ncu, ncu_src = ncu_current()
+    pipe = {}
+    traffic = None
+    if ncu:
+        k = ncu["kernels"]
+        # pipe_frac = FP64-datapath busy time at 100 % issue (executed DFMA-class warp instructions x 64 flop, DMMA x 512 flop) / elapsed
+        for st in ("setup", "lens", "power", "contract"):
+            fl = k[st]["fp64_flops_per_cosmology"]
+            pipe[st] = fl * B * steps / (stage_ms[st] * 1e-3) / 1e12 / peak_sustained
+        tot = sum(k[st]["fp64_flops_per_cosmology"] for st in ("setup", "lens", "finish", "power", "contract") if st in k)
+        pipe["step"] = tot * B * steps / (ms_compute * 1e-3) / 1e12 / peak_sustained
+        traffic = k[dom]["dram_bytes_per_cosmology"] * cosmo_per_launch
+    alg_bytes = (8.0 * A * N_ELL if dom == "power" else 8.0 * (A * N_ELL + A * T + P * N_ELL)) * cosmo_per_launch
     # "tensor": the dominant kernels are arithmetic bound -- the contraction issues FP64 tensor-core MMAs (DMMA.8x8x4), the power
     # kernel DFMAs on the same FP64 datapath; the denominator is that datapath's measured peak, not the bf16 tensor figure
     roofline = {"bound": "tensor", "bound_detail": "fp64", "kernel": kernels[dom], "achieved": achieved, "peak": peak_sustained,
-                "unit": "TFLOP/s", "frac": achieved / peak_sustained,
-                "traffic": ncu_dram_per_cosmo[dom] * cosmo_per_launch if dom in ncu_dram_per_cosmo else None,
-                "traffic_note": "dram__bytes_read+write per launch from profiles/r01_ncu_summary.md, scaled to the launch size; "
-                                "algorithmic bytes per launch: %.3e" % (
-                                    (8.0 * A * N_ELL if dom == "power" else 8.0 * (A * N_ELL + A * T + P * N_ELL)) * cosmo_per_launch),
+                "unit": "TFLOP/s", "frac": achieved / peak_sustained, "traffic": traffic,
+                "traffic_source": ncu_src, "algorithmic_bytes_per_launch": alg_bytes,
+                "pipe_frac": pipe.get(dom), "pipe_frac_step": pipe.get("step"),
+                "pipe_frac_setup": pipe.get("setup"), "pipe_frac_lens": pipe.get("lens"),
+                "pipe_frac_power": pipe.get("power"), "pipe_frac_contract": pipe.get("contract"),
+                "pipe_frac_note": "executed FP64-datapath work (ncu instruction counts of the committed capture: DFMA-class warp "
+                                  "instructions x 64 flop + DMMA.8x8x4 x 512 flop) / live stage time / measured FP64 peak -- the pipe "
+                                  "utilisation; `frac` follows the SURVEY 8(d) v0 flop convention, which books 500 issue slots per P(k) "
+                                  "point and therefore is not a utilisation for the power kernel or the whole step",
                 "bound_note": "FP64 arithmetic pipe (DFMA and DMMA share one datapath: jc_fp64_peak_tflops mode 2); "
                               "~550 flop/B, HBM and bf16 tensor peaks of MEASURED_PEAKS.json do not bound this path",
                 "peak_source": peak_src, "peak_burst": peak_burst, "peak_dmma": peak_dmma,
                 "flops_convention": "SURVEY 8(d) v0 (2 x issue slots): power 500 slots/point, contraction 1 slot/(ell,node,pair)",
-                "achieved_sass": (sass_flops[dom] * cosmo_per_launch / (launch_ms * 1e-3) / 1e12) if dom in sass_flops else None,
-                "frac_sass": (sass_flops[dom] * cosmo_per_launch / (launch_ms * 1e-3) / 1e12 / peak_sustained) if dom in sass_flops else None,
-                "frac_note": "frac follows the SURVEY 8(d) v0 convention and can exceed 1 for jc_power_kernel: v0 books 500 issue "
-                             "slots per P(k) point, the compiled kernel needs 186 FP64 instructions (separable power laws, merged "
-                             "divisions, table-driven exp/log); frac_sass = executed FP64 flops / peak is the pipe utilisation",
                 "launch_ms": launch_ms, "cosmologies_per_launch": cosmo_per_launch,
-                "step": {"achieved": step_tflops, "frac": step_tflops / peak_sustained,
-                         "slots_per_cosmology": slots["total"]},
-                "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
-                "stage_share": {k: v / max(sum(stage_ms.values()), 1e-9) for k, v in stage_ms.items()},
-                "stage_v0_frac": {k: (2.0 * slots[k] * B * args.steps / (stage_ms[k] * 1e-3) / 1e12 / peak_sustained)
+                "frac_v0_step": step_tflops / peak_sustained,
+                "ms_setup": stage_ms["setup"] / steps, "ms_lens": stage_ms["lens"] / steps, "ms_finish": stage_ms["finish"] / steps,
+                "ms_power": stage_ms["power"] / steps, "ms_contract": stage_ms["contract"] / steps,
+                "stage_v0_frac": {k: (2.0 * slots[k] * B * steps / (stage_ms[k] * 1e-3) / 1e12 / peak_sustained)
                                   for k in ("setup", "lens", "power", "contract")}}
     cpu = None
     if not args.no_cpu_baseline and world == 1:  # the CPU arm is timed beside the N = 1 run only
-        cores = os.cpu_count() or 1
-        sample = max(cores, min(args.cpu_sample, 8 * cores))
-        rate, dt = cpu_oracle_rate(sample, cores)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d cosmologies x 210 x 100 (%.1f s wall), NumPy oracle port on %d processes" % (sample, dt, cores)}
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        arm = CpuArm(args.cpu_sample or default_cpu_sample())
+        rate, dt = arm.run()
+        arm.close()
+        cpu = arm.describe(rate)
+        cpu["wall_s"] = dt
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "config5: 3x2pt 10+10 Smail bins (T=20, P=210), 100 ell, halofit, wCDM box seed 20240607",
+            "config": {"workload": WORKLOAD,
                        "cosmologies_per_gpu": B, "global_cosmologies": world * B, "chunk": chunk,
                        "l2": "per-step working set (workspace %.1f GB + output %.1f GB) exceeds L2; no flush needed"
                              % (ws_bytes / 1e9, out.numel() * 8 / 1e9),
-                       "parallelism": "cosmology shards, one rank per GPU, no data-path collective"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(sum(stage_n.values())),
-            "roofline": roofline, "cpu_baseline": cpu}
+                       "parallelism": ("cosmology shards, one rank per GPU; the timed step ends with the gather of all shards on every "
+                                       "rank (%s)" % gather["mode"]) if gather else
+                                      "cosmology shards, one rank per GPU, results resident on the owning GPU (no exchange)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": n_launches,
+            "roofline": roofline, "cpu_baseline": cpu, "git_head": git_head()}
+    if gather:
+        line["gather"] = gather
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

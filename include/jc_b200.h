@@ -353,6 +353,33 @@ int jc_sparse_bmm_f64(const double* A_dev, int64_t sAi, int64_t sAj, int64_t sAl
 int jc_sparse_inv_f64(const double* sparse_dev, int32_t P, int32_t L, double* inv_dev, double* sign_dev,
                       double* logdet_dev, double* scratch_dev, void* stream);
 
+/* ---- multi-GPU: the final gather of the per-rank [B/G, P, L] blocks over NVLink (the path's one exchange) --------
+ * The reference has no multi-device code (no pmap / shard_map / psum); a batch of cosmologies is the
+ * data-parallel axis this path adds, and a gather of the shards is what `jax.vmap(angular_cl)` over a sharded batch
+ * would end with.  One rank per GPU.  Every rank owns a FULL-size result buffer [rows_total, P, L] in device memory
+ * (jc_gather_create allocates it and exports a CUDA IPC handle); after the handles have been exchanged
+ * (jc_gather_connect_ipc: other processes of the box; jc_gather_connect_local: other devices of this process) a rank
+ * computes its rows in sub-chunks straight into its own buffer and the copy engines push each finished sub-chunk into
+ * the same rows of every peer's buffer while the next sub-chunk computes (cudaMemcpyAsync over NVLink peer memory on
+ * side streams -- no SM is taken from the FP64 kernels).  On return `stream` is ordered after this rank's OUTGOING
+ * pushes; the rows the peers write are complete once every rank has got there: close the step with a stream-ordered
+ * cross-rank barrier (e.g. a one-element NCCL all-reduce).  Results are bitwise those of jc_angular_cl_f64. */
+#define JC_IPC_HANDLE_BYTES 64
+#define JC_MAX_RANKS 16
+typedef struct jc_gather jc_gather;
+int jc_gather_create(int32_t rank, int32_t world, int32_t device, size_t bytes, jc_gather** gather_out,
+                     unsigned char* ipc_handle_out /* [JC_IPC_HANDLE_BYTES] or NULL */);
+void* jc_gather_buffer(const jc_gather* gather); /* this rank's device buffer */
+int jc_gather_connect_ipc(jc_gather* gather, const unsigned char* ipc_handles /* [world][JC_IPC_HANDLE_BYTES] */);
+int jc_gather_connect_local(jc_gather* gather, void* const* buffers /* [world] */, const int32_t* devices /* [world] */);
+int jc_gather_destroy(jc_gather* gather);
+/* cosmo_dev [n_cosmo, 8|9] = this rank's rows, which land in rows [row_offset, row_offset + n_cosmo) of every buffer;
+ * sub_chunk = cosmologies per compute/push step (< 1: one step); ws as for jc_angular_cl_f64. */
+int jc_angular_cl_gather_f64(const jc_plan* plan, jc_gather* gather, const double* cosmo_dev, int64_t n_cosmo,
+                             int64_t row_offset, int64_t sub_chunk, void* ws_dev, size_t ws_bytes, void* stream);
+/* the exchange alone: push rows [row_offset, row_offset + rows) (row_bytes each) of the local buffer to every peer */
+int jc_gather_push_f64(jc_gather* gather, size_t row_bytes, int64_t row_offset, int64_t rows, void* stream);
+
 /* Per-stage device timing (CUDA events recorded on the launch stream between the stages of
  * jc_angular_cl_f64).  Stages: 0 setup, 1 lensing efficiency, 2 tracer finish, 3 power, 4 pair
  * contraction.  While enabled the plan is not re-entrant.  jc_profile_read synchronises the

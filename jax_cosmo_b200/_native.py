@@ -32,7 +32,8 @@ SCAL_FIELDS = ["LN13KEQ", "INV13KEQ", "BETA_C", "C14_ALPHA_C", "SH_D", "LNKSILK"
 EXPORTS = ["jc_plan_create", "jc_plan_destroy", "jc_plan_n_tracers", "jc_plan_n_cls", "jc_plan_n_ell", "jc_plan_n_cosmo_params",
            "jc_workspace_bytes", "jc_workspace_layout", "jc_angular_cl_f64", "jc_angular_cl_host_f64",
            "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64", "jc_gaussian_loglike_f64", "jc_fisher_f64", "jc_vjp_f64", "jc_sparse_bmm_f64", "jc_sparse_inv_f64", "jc_debug_stages_f64", "jc_grid_plan_create", "jc_grid_plan_create_probes", "jc_grid_eval_f64", "jc_grid_background_f64", "jc_a_of_chi_f64", "jc_sigmasqr_f64", "jc_nz_eval_f64",
-           "jc_noise_f64", "jc_gaussian_cov_f64", "jc_profile_enable", "jc_profile_read",
+           "jc_noise_f64", "jc_gaussian_cov_f64", "jc_gather_create", "jc_gather_buffer", "jc_gather_connect_ipc",
+           "jc_gather_connect_local", "jc_gather_destroy", "jc_angular_cl_gather_f64", "jc_gather_push_f64", "jc_profile_enable", "jc_profile_read",
            "jc_fp64_peak_tflops", "jc_debug_math_f64", "jc_status_string",
            "jc_last_cuda_error", "jc_abi_version"]
 
@@ -129,6 +130,20 @@ def load_library():
         lib.jc_noise_f64.restype = C.c_int
         lib.jc_gaussian_cov_f64.argtypes = [vp, vp, vp, i64, C.c_double, vp, vp]
         lib.jc_gaussian_cov_f64.restype = C.c_int
+        lib.jc_gather_create.argtypes = [i32, i32, i32, C.c_size_t, C.POINTER(vp), C.c_char_p]
+        lib.jc_gather_create.restype = C.c_int
+        lib.jc_gather_buffer.argtypes = [vp]
+        lib.jc_gather_buffer.restype = vp
+        lib.jc_gather_connect_ipc.argtypes = [vp, C.c_char_p]
+        lib.jc_gather_connect_ipc.restype = C.c_int
+        lib.jc_gather_connect_local.argtypes = [vp, C.POINTER(vp), C.POINTER(i32)]
+        lib.jc_gather_connect_local.restype = C.c_int
+        lib.jc_gather_destroy.argtypes = [vp]
+        lib.jc_gather_destroy.restype = C.c_int
+        lib.jc_angular_cl_gather_f64.argtypes = [vp, vp, vp, i64, i64, i64, vp, C.c_size_t, vp]
+        lib.jc_angular_cl_gather_f64.restype = C.c_int
+        lib.jc_gather_push_f64.argtypes = [vp, C.c_size_t, i64, i64, vp]
+        lib.jc_gather_push_f64.restype = C.c_int
         lib.jc_profile_enable.argtypes = [vp, i32]
         lib.jc_profile_enable.restype = C.c_int
         lib.jc_profile_read.argtypes = [vp, dp, C.POINTER(C.c_int64)]
@@ -374,13 +389,43 @@ class Plan:
         check(load_library().jc_workspace_layout(self._h, int(ws_bytes), C.byref(lo)), "jc_workspace_layout")
         return lo
 
-    def workspace(self, n_cosmo):
+    def workspace(self, n_cosmo, jvp_entries=None):
+        """Scratch for `n_cosmo` cosmologies, cached per CUDA stream: the device entry points are asynchronous on
+        torch's current stream, so callers that overlap batches of one problem on several streams (or threads with
+        their own current stream) must not share the K1..K4 tables."""
         import torch
 
-        need = self.workspace_bytes(n_cosmo)
-        if self._ws is None or self._ws.numel() * 8 < need:
-            self._ws = torch.empty(need // 8, dtype=torch.float64, device="cuda:%d" % self.device)
-        return self._ws
+        if jvp_entries is None:
+            need = self.workspace_bytes(n_cosmo)
+        else:
+            out = C.c_size_t()
+            check(load_library().jc_workspace_bytes_jvp(self._h, int(jvp_entries), C.byref(out)), "jc_workspace_bytes_jvp")
+            need = out.value
+        if self._ws is None:
+            self._ws = {}
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() * 8 < need:
+            if ws is None and len(self._ws) >= 8:  # streams come and go: keep the cache bounded
+                self._ws.pop(next(iter(self._ws)))
+            ws = torch.empty(need // 8, dtype=torch.float64, device="cuda:%d" % self.device)
+            self._ws[key] = ws
+        return ws
+
+    def _check_dev(self, t, what, shape=None):
+        """Real exceptions (not asserts, which -O strips): CUDA float64 contiguous tensor on the plan's device."""
+        import torch
+
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise ValueError("%s must be a CUDA tensor" % what)
+        if t.dtype != torch.float64:
+            raise ValueError("%s must be float64 (jax_enable_x64 semantics), got %s" % (what, t.dtype))
+        if not t.is_contiguous():
+            raise ValueError("%s must be contiguous" % what)
+        if t.device.index != self.device:
+            raise ValueError("%s lives on cuda:%s, the plan on cuda:%d" % (what, t.device.index, self.device))
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError("%s must have shape %s, got %s" % (what, tuple(shape), tuple(t.shape)))
 
     def _check_rows(self, rows, what="cosmology rows"):
         if rows.ndim != 2 or rows.shape[1] != self.ncp:
@@ -392,12 +437,16 @@ class Plan:
         """cosmo_dev: CUDA float64 tensor [B,8] -> CUDA tensor [B,P,L]; async on torch's current stream."""
         import torch
 
-        assert cosmo_dev.is_cuda and cosmo_dev.dtype == torch.float64 and cosmo_dev.is_contiguous()
+        self._check_dev(cosmo_dev, "cosmology rows")
         self._check_rows(cosmo_dev)
         B = cosmo_dev.shape[0]
         if out is None:
             out = torch.empty((B, self.P, self.L), dtype=torch.float64, device=cosmo_dev.device)
+        else:
+            self._check_dev(out, "out", (B, self.P, self.L))
         ws = self.workspace(B) if workspace is None else workspace
+        if workspace is not None:
+            self._check_dev(workspace, "workspace")
         stream = torch.cuda.current_stream(cosmo_dev.device).cuda_stream
         st = load_library().jc_angular_cl_f64(self._h, cosmo_dev.data_ptr(), B, out.data_ptr(), ws.data_ptr(),
                                               ws.numel() * 8, stream)
@@ -408,8 +457,8 @@ class Plan:
         """cosmo_dev [B,8], tangents_dev [K,8] (CUDA float64) -> (cl [B,P,L], dcl [B,K,P,L]) on the device."""
         import torch
 
-        assert cosmo_dev.is_cuda and cosmo_dev.dtype == torch.float64 and cosmo_dev.is_contiguous()
-        assert tangents_dev.is_cuda and tangents_dev.dtype == torch.float64 and tangents_dev.is_contiguous()
+        self._check_dev(cosmo_dev, "cosmology rows")
+        self._check_dev(tangents_dev, "tangents")
         self._check_rows(cosmo_dev)
         self._check_rows(tangents_dev, "tangents")
         B, K = cosmo_dev.shape[0], tangents_dev.shape[0]
@@ -431,12 +480,25 @@ class Plan:
         import torch
 
         is_t = isinstance(cosmo_rows, torch.Tensor)
-        rows = cosmo_rows if is_t else np.ascontiguousarray(cosmo_rows, dtype=np.float64)
+        if is_t:
+            if cosmo_rows.is_cuda:
+                raise ValueError("angular_cl_host takes host rows; use angular_cl_device for CUDA tensors")
+            # torch.tensor(python_floats) is float32: the C side reads doubles, so coerce instead of reinterpreting
+            rows = cosmo_rows.to(torch.float64).contiguous()
+        else:
+            rows = np.ascontiguousarray(cosmo_rows, dtype=np.float64)
         self._check_rows(rows)
         B = rows.shape[0]
+        shape = (B, self.P, self.L)
         if out is None:
-            out = (torch.empty((B, self.P, self.L), dtype=torch.float64, pin_memory=True) if is_t
-                   else np.empty((B, self.P, self.L), dtype=np.float64))
+            out = (torch.empty(shape, dtype=torch.float64, pin_memory=True) if is_t
+                   else np.empty(shape, dtype=np.float64))
+        elif isinstance(out, torch.Tensor):
+            if out.is_cuda or out.dtype != torch.float64 or not out.is_contiguous() or tuple(out.shape) != shape:
+                raise ValueError("out must be a contiguous float64 CPU tensor of shape %s" % (shape,))
+        elif not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous
+                  and out.flags.writeable and out.shape == shape):
+            raise ValueError("out must be a writeable C-contiguous float64 array of shape %s" % (shape,))
         src = rows.data_ptr() if is_t else rows.ctypes.data
         dst = out.data_ptr() if isinstance(out, torch.Tensor) else out.ctypes.data
         with torch.cuda.device(self.device):
@@ -514,7 +576,7 @@ class GridPlan(Plan):
         """cosmo_dev CUDA [B, ncp] -> dict of CUDA tensors: pk [B, n_a, n_k], the others [B, n_a]."""
         import torch
 
-        assert cosmo_dev.is_cuda and cosmo_dev.dtype == torch.float64 and cosmo_dev.is_contiguous()
+        self._check_dev(cosmo_dev, "cosmology rows")
         self._check_rows(cosmo_dev)
         B, na, nk = cosmo_dev.shape[0], len(self.a), len(self.k)
         out = {}
@@ -535,7 +597,7 @@ class GridPlan(Plan):
     def _cosmo_check(self, cosmo_dev):
         import torch
 
-        assert cosmo_dev.is_cuda and cosmo_dev.dtype == torch.float64 and cosmo_dev.is_contiguous()
+        self._check_dev(cosmo_dev, "cosmology rows")
         self._check_rows(cosmo_dev)
         return cosmo_dev.shape[0], self.workspace(cosmo_dev.shape[0]), torch.cuda.current_stream(cosmo_dev.device).cuda_stream
 
@@ -554,7 +616,9 @@ class GridPlan(Plan):
         import torch
 
         B, ws, stream = self._cosmo_check(cosmo_dev)
-        assert chi_dev.is_cuda and chi_dev.dtype == torch.float64 and chi_dev.is_contiguous() and chi_dev.dim() == 1
+        self._check_dev(chi_dev, "chi")
+        if chi_dev.dim() != 1:
+            raise ValueError("chi must be one-dimensional")
         out = torch.empty((B, chi_dev.numel()), dtype=torch.float64, device=cosmo_dev.device)
         check(load_library().jc_a_of_chi_f64(self._h, cosmo_dev.data_ptr(), B, chi_dev.data_ptr(), chi_dev.numel(), out.data_ptr(),
                                              ws.data_ptr(), ws.numel() * 8, stream), "jc_a_of_chi_f64")
@@ -565,7 +629,9 @@ class GridPlan(Plan):
         import torch
 
         B, ws, stream = self._cosmo_check(cosmo_dev)
-        assert R_dev.is_cuda and R_dev.dtype == torch.float64 and R_dev.is_contiguous() and R_dev.dim() == 1
+        self._check_dev(R_dev, "R")
+        if R_dev.dim() != 1:
+            raise ValueError("R must be one-dimensional")
         out = torch.empty((B, R_dev.numel()), dtype=torch.float64, device=cosmo_dev.device)
         check(load_library().jc_sigmasqr_f64(self._h, cosmo_dev.data_ptr(), B, R_dev.data_ptr(), R_dev.numel(), float(kmin), float(kmax),
                                              out.data_ptr(), ws.data_ptr(), ws.numel() * 8, stream), "jc_sigmasqr_f64")
@@ -592,6 +658,7 @@ def get_grid_plan(k, a, transfer=JC_TF_EH_OSC, nonlinear=JC_PK_HALOFIT, growth=0
 
 
 _pinned = {}
+_PINNED_CAP_DOUBLES = (128 << 20) // 8  # 128 MB of page-locked staging per device at most
 
 
 def to_host(t):
@@ -603,15 +670,112 @@ def to_host(t):
     n = t.numel()
     if not t.is_cuda or n * t.element_size() < (1 << 20) or t.dtype != torch.float64:
         return t.cpu().numpy()
+    # the staging buffer is capped (a dense (P L)^2 covariance is 3.5 GB at the bench configuration: page-locking
+    # that much for the life of the process is not acceptable); larger tensors go through it in pieces, two
+    # halves alternating so that the device copy of one piece overlaps the host copy of the previous one
+    cap = _PINNED_CAP_DOUBLES
     key = t.device.index
     buf = _pinned.get(key)
-    if buf is None or buf.numel() < n:
-        buf = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    want = min(n, cap)
+    if buf is None or buf.numel() < want:
+        buf = torch.empty(want, dtype=torch.float64, pin_memory=True)
         _pinned[key] = buf
-    buf[:n].copy_(t.reshape(-1))
     out = np.empty(tuple(t.shape), dtype=np.float64)
-    np.copyto(out.reshape(-1), buf[:n].numpy())
+    flat_out, flat_t = out.reshape(-1), t.reshape(-1)
+    if n <= buf.numel():
+        buf[:n].copy_(flat_t)
+        np.copyto(flat_out, buf[:n].numpy())
+        return out
+    half = buf.numel() // 2
+    ev = [torch.cuda.Event(), torch.cuda.Event()]
+    pieces = [(o, min(half, n - o)) for o in range(0, n, half)]
+    with torch.cuda.device(t.device):
+        for i, (o, m) in enumerate(pieces):
+            b = i & 1
+            buf[b * half:b * half + m].copy_(flat_t[o:o + m], non_blocking=True)
+            ev[b].record()
+            if i >= 1:
+                po, pm = pieces[i - 1]
+                ev[1 - b].synchronize()
+                np.copyto(flat_out[po:po + pm], buf[(1 - b) * half:(1 - b) * half + pm].numpy())
+        po, pm = pieces[-1]
+        b = (len(pieces) - 1) & 1
+        ev[b].synchronize()
+        np.copyto(flat_out[po:po + pm], buf[b * half:b * half + pm].numpy())
     return out
+
+
+class _DevArray:
+    """Zero-copy view of library-owned device memory for torch.as_tensor (__cuda_array_interface__)."""
+
+    def __init__(self, ptr, shape, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+        self._owner = owner
+
+
+class PeerGather:
+    """jc_gather: this rank's full-size result buffer [rows_total, P, L], mapped into every peer (see jc_b200.h).
+    `handle` is the CUDA IPC handle to exchange; call connect_ipc(all handles in rank order) or connect_local(...)."""
+
+    def __init__(self, plan, rows_total, rank, world):
+        import torch
+
+        self.plan, self.rank, self.world, self.rows_total = plan, int(rank), int(world), int(rows_total)
+        nbytes = self.rows_total * plan.P * plan.L * 8
+        h = C.c_void_p()
+        buf = C.create_string_buffer(64)
+        check(load_library().jc_gather_create(self.rank, self.world, plan.device, nbytes, C.byref(h), buf), "jc_gather_create")
+        self._h = h
+        self.handle = bytes(buf.raw)
+        self.ptr = load_library().jc_gather_buffer(h)
+        self.full = torch.as_tensor(_DevArray(self.ptr, (self.rows_total, plan.P, plan.L), self),
+                                    device="cuda:%d" % plan.device)
+
+    def connect_ipc(self, handles):
+        if len(handles) != self.world:
+            raise ValueError("need one IPC handle per rank")
+        check(load_library().jc_gather_connect_ipc(self._h, b"".join(handles)), "jc_gather_connect_ipc")
+
+    def connect_local(self, peers):
+        """peers: the PeerGather objects of all ranks (same process, one per device), in rank order."""
+        ptrs = (C.c_void_p * self.world)(*[p.ptr for p in peers])
+        devs = (C.c_int32 * self.world)(*[p.plan.device for p in peers])
+        check(load_library().jc_gather_connect_local(self._h, ptrs, devs), "jc_gather_connect_local")
+
+    def compute_and_push(self, cosmo_dev, row_offset, sub_chunk, workspace=None):
+        """K1..K4 of this rank's rows into rows [row_offset, ...) of the local buffer, every finished sub-chunk pushed
+        to the peers meanwhile.  Asynchronous on torch's current stream (ordered after the outgoing pushes)."""
+        import torch
+
+        n = int(cosmo_dev.shape[0])
+        if n:
+            self.plan._check_dev(cosmo_dev, "cosmology rows")
+            self.plan._check_rows(cosmo_dev)
+        ws = self.plan.workspace(max(min(n, int(sub_chunk) if sub_chunk > 0 else n), 1)) if workspace is None else workspace
+        stream = torch.cuda.current_stream(self.plan.device).cuda_stream
+        check(load_library().jc_angular_cl_gather_f64(self.plan._h, self._h, cosmo_dev.data_ptr() if n else None, n,
+                                                      int(row_offset), int(sub_chunk), ws.data_ptr(), ws.numel() * 8, stream),
+              "jc_angular_cl_gather_f64")
+
+    def push(self, row_offset, rows):
+        import torch
+
+        stream = torch.cuda.current_stream(self.plan.device).cuda_stream
+        check(load_library().jc_gather_push_f64(self._h, self.plan.P * self.plan.L * 8, int(row_offset), int(rows), stream),
+              "jc_gather_push_f64")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.full = None
+            load_library().jc_gather_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 _plan_cache = {}

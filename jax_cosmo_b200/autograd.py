@@ -34,8 +34,11 @@ def _make_function():
     class AngularCl(torch.autograd.Function):
         @staticmethod
         def forward(ctx, rows, plan, cols):
+            # grad mode is off inside forward(): a .contiguous() copy of a non-contiguous view would read
+            # requires_grad=False, so decide from the autograd context, not from the tensor
+            needs_grad = ctx.needs_input_grad[0]
             rows = rows.contiguous()
-            if not rows.requires_grad:
+            if not needs_grad:
                 return plan.angular_cl_device(rows)
             tang = torch.zeros((len(cols), rows.shape[1]), dtype=torch.float64, device=rows.device)
             tang[torch.arange(len(cols)), torch.as_tensor(cols)] = 1.0

@@ -377,22 +377,35 @@ def _nccl_worker(rank, world, port, out_dir):
     import torch.distributed as dist
 
     import jax_cosmo_b200 as jcm
-    from jax_cosmo_b200.distributed import angular_cl_sharded
+    from jax_cosmo_b200.distributed import ShardedAngularCl, angular_cl_sharded
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         scn = sc.scenario("d", sc.PLANCK15, sc.ELL_CFG2[::10], [sc.sources(5, 2.0), sc.lenses(5, 2.0)])
-        rows = sc.config5_cosmologies(37)
-        cl, (lo, hi) = angular_cl_sharded(rows, scn["ell"], sc.build_probes(scn, jcm), gather=True)
-        np.save(os.path.join(out_dir, "g%d.npy" % rank), cl.cpu().numpy())
+        probes = sc.build_probes(scn, jcm)
+        rows = sc.config5_cosmologies(37)  # ragged: 19 + 18 rows
+        for mode in ("peer", "nccl", "collective"):
+            cl, (lo, hi) = angular_cl_sharded(rows, scn["ell"], probes, gather=True, gather_mode=mode, sub_chunk=7)
+            np.save(os.path.join(out_dir, "g_%s_%d.npy" % (mode, rank)), cl.cpu().numpy())
+        # persistent evaluator, called twice on different batches (buffer reuse, second step after the barrier)
+        sh = ShardedAngularCl(37, scn["ell"], probes, gather_mode="peer", sub_chunk=5)
+        sh(rows[::-1].copy())
+        full = sh(rows).clone()
+        torch.cuda.synchronize()
+        np.save(os.path.join(out_dir, "g_again_%d.npy" % rank), full.cpu().numpy())
+        sh.close()
+        # more ranks than rows
+        cl1, b1 = angular_cl_sharded(rows[:1], scn["ell"], probes, gather=True, gather_mode="peer")
+        np.save(os.path.join(out_dir, "g_one_%d.npy" % rank), cl1.cpu().numpy())
     finally:
         dist.destroy_process_group()
 
 
 def test_sharded_nccl_two_gpus(jc, torch_cuda, tmp_path):
-    """2 ranks x NCCL: sharded compute + final all-gather equals the single-GPU batch bitwise."""
+    """2 ranks: sharded compute + the final gather (NVLink peer pushes / grouped NCCL send-recv / plain all_gather)
+    equals the single-GPU batch bitwise on every rank."""
     torch = torch_cuda
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -406,7 +419,37 @@ def test_sharded_nccl_two_gpus(jc, torch_cuda, tmp_path):
     scn = sc.scenario("d", sc.PLANCK15, sc.ELL_CFG2[::10], [sc.sources(5, 2.0), sc.lenses(5, 2.0)])
     ref = jc.cl.angular_cl_batch(sc.config5_cosmologies(37), scn["ell"], sc.build_probes(scn, jc))
     for r in range(2):
-        assert np.array_equal(np.load(tmp_path / ("g%d.npy" % r)), ref)
+        for tag in ("peer", "nccl", "collective", "again"):
+            assert np.array_equal(np.load(tmp_path / ("g_%s_%d.npy" % (tag, r))), ref), (tag, r)
+        assert np.array_equal(np.load(tmp_path / ("g_one_%d.npy" % r)), ref[:1]), r
+
+
+def test_peer_gather_two_devices_one_process(jc, torch_cuda):
+    """jc_gather with plain peer pointers (one process, two devices): each device computes its rows and pushes them into
+    the other's buffer over NVLink; both buffers then hold the full batch, bitwise the single-GPU result."""
+    torch = torch_cuda
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from jax_cosmo_b200 import _native
+    scn = sc.scenario("d", sc.PLANCK15, sc.ELL_CFG2[::10], [sc.sources(5, 2.0), sc.lenses(5, 2.0)])
+    probes = sc.build_probes(scn, jc)
+    rows = sc.config5_cosmologies(21)
+    ref = jc.cl.angular_cl_batch(rows, scn["ell"], probes)
+    plans = [_native.get_plan(probes, scn["ell"], None, None, device=d) for d in range(2)]
+    per = 11
+    gathers = [_native.PeerGather(plans[d], 2 * per, d, 2) for d in range(2)]
+    for g in gathers:
+        g.connect_local(gathers)
+    for d in range(2):
+        lo, hi = d * per, min((d + 1) * per, len(rows))
+        with torch.cuda.device(d):
+            gathers[d].compute_and_push(torch.as_tensor(rows[lo:hi], device="cuda:%d" % d), lo, 4)
+    for d in range(2):
+        torch.cuda.synchronize(d)
+    for d in range(2):
+        assert np.array_equal(gathers[d].full[:len(rows)].cpu().numpy(), ref), d
+    for g in gathers:
+        g.close()
 
 
 def test_sharded_single_process(jc, torch_cuda):
