@@ -258,7 +258,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="N > 1: time the sharded compute only (no exchange)")
     ap.add_argument("--gather-mode", default="peer", choices=["peer", "nccl", "collective"])
-    ap.add_argument("--sub-chunk", type=int, default=0, help="cosmologies per compute/push step of the gather pipeline")
+    ap.add_argument("--sub-chunk", type=int, default=0, help="cosmologies per compute chunk (K1..K3) of the gather pipeline")
+    ap.add_argument("--push-rows", type=int, default=0, help="cosmologies per contraction launch + NVLink push")
     ap.add_argument("--peak-tflops", type=float, default=0.0,
                     help="use this FP64 peak instead of probing (for runs under ncu)")
     args = ap.parse_args()
@@ -279,7 +280,7 @@ def main():
 
     import jax_cosmo_b200 as jc
     from jax_cosmo_b200 import _native
-    from jax_cosmo_b200.distributed import DEFAULT_SUB_CHUNK, ShardedAngularCl
+    from jax_cosmo_b200.distributed import DEFAULT_PUSH_ROWS, DEFAULT_SUB_CHUNK, ShardedAngularCl
     from oracle import scenarios as sc
 
     if not torch.cuda.is_available():
@@ -354,7 +355,10 @@ def main():
     ms = ms_compute
     if world > 1 and not args.no_gather:
         sub = args.sub_chunk or DEFAULT_SUB_CHUNK
-        sh = ShardedAngularCl(world * B, scn["ell"], probes, gather_mode=args.gather_mode, sub_chunk=sub)
+        push = args.push_rows or DEFAULT_PUSH_ROWS
+        if args.gather_mode != "peer":
+            sub = args.sub_chunk or push  # the NCCL pipeline exchanges per compute chunk
+        sh = ShardedAngularCl(world * B, scn["ell"], probes, gather_mode=args.gather_mode, sub_chunk=sub, push_rows=push)
         rows_dev = torch.as_tensor(np.ascontiguousarray(rows_all), device=dev)
         for _ in range(warmup):
             sh(rows_dev)
@@ -391,7 +395,8 @@ def main():
             ms_x = max_over_ranks(x0.elapsed_time(x1)) / steps
         bytes_in = (world - 1) * B * P * N_ELL * 8
         n_chunks = -(-B // sub)
-        gather = {"mode": sh.mode, "sub_chunk": sub, "ms_per_step": ms / steps, "ms_per_step_compute_only": ms_compute / steps,
+        n_push = (-(-B // push) + 1) if sh.mode == "peer" else n_chunks
+        gather = {"mode": sh.mode, "sub_chunk": sub, "push_rows": push if sh.mode == "peer" else sub, "ms_per_step": ms / steps, "ms_per_step_compute_only": ms_compute / steps,
                   "exposed_ms": (ms - ms_compute) / steps, "ratio_vs_compute_only": ms / ms_compute,
                   "bytes_in_per_gpu_per_step": bytes_in, "bytes_out_per_gpu_per_step": bytes_in,
                   "nvlink_in_gbs_overlapped": bytes_in / (ms / steps * 1e-3) / 1e9,
@@ -401,8 +406,9 @@ def main():
                           "NVLink peer memory overlapped with the next sub-chunk's kernels, closed by a stream-ordered "
                           "one-element NCCL all-reduce" % (world * B, P, N_ELL)}
         passes = steps * max(-(-B // int(plan.workspace_layout(ws_bytes).chunk)), 1)
-        n_launches = (n_launches // passes) * n_chunks * steps  # kernels per chunk pass x passes of the gather loop
-        gather["copies_per_step"] = n_chunks * (world - 1)
+        per_pass = n_launches // passes  # kernels per chunk pass of the compute-only loop (one contraction each)
+        n_launches = ((per_pass - 1) * n_chunks + n_push) * steps
+        gather["copies_per_step"] = n_push * (world - 1)
         sh.close()
     clocks = sampler.stop()
     value = evals_per_step * steps / (ms * 1e-3)

@@ -138,9 +138,27 @@ static int push_rows(jc_gather* g, size_t row_bytes, int64_t row0, int64_t rows,
 }
 
 // angular_cl of this rank's n_cosmo cosmologies into rows [row_offset, row_offset + n_cosmo) of the gather buffer
-// (layout [rows_total, P, L]) and, sub-chunk by sub-chunk, into the same rows of every peer's buffer.
+// (layout [rows_total, P, L]) and, slice by slice, into the same rows of every peer's buffer.  K1..K3 run on compute
+// chunks of `sub_chunk` cosmologies (full waves); the contraction of a chunk is launched per `push_rows` cosmologies and
+// each finished slice is pushed while the following slices / the next chunk compute.
+namespace {
+struct PushCtx {
+  jc_gather* g;
+  size_t row_bytes;
+  int64_t row_offset;
+  cudaStream_t s;
+};
+int push_cb(void* p, int64_t first_row, int64_t rows) {
+  PushCtx* c = (PushCtx*)p;
+  if (c->g->world < 2) return JC_OK;
+  JC_CUDA_TRY(cudaEventRecord(c->g->ev_chunk, c->s));
+  return push_rows(c->g, c->row_bytes, c->row_offset + first_row, rows, c->g->ev_chunk);
+}
+}  // namespace
+
 extern "C" int jc_angular_cl_gather_f64(const jc_plan* plan, jc_gather* g, const double* cosmo_dev, int64_t n_cosmo,
-                                        int64_t row_offset, int64_t sub_chunk, void* ws_dev, size_t ws_bytes, void* stream) {
+                                        int64_t row_offset, int64_t sub_chunk, int64_t push_rows_n, void* ws_dev,
+                                        size_t ws_bytes, void* stream) {
   if (!plan || !g || plan->d.grid_mode || n_cosmo < 0 || row_offset < 0 || (n_cosmo > 0 && (!cosmo_dev || !ws_dev)))
     return JC_ERR_INVALID;
   if (g->world > 1 && !g->connected) return JC_ERR_INVALID;
@@ -150,17 +168,11 @@ extern "C" int jc_angular_cl_gather_f64(const jc_plan* plan, jc_gather* g, const
   JcDeviceGuard guard(plan->device);
   JC_CUDA_TRY(guard.status);
   cudaStream_t s = (cudaStream_t)stream;
-  if (sub_chunk < 1) sub_chunk = n_cosmo > 0 ? n_cosmo : 1;
-  double* out = (double*)g->local + (size_t)row_offset * plan->d.P * plan->d.L;
-  for (int64_t c0 = 0; c0 < n_cosmo; c0 += sub_chunk) {
-    const int64_t nc = (n_cosmo - c0) < sub_chunk ? (n_cosmo - c0) : sub_chunk;
-    int st = jc_angular_cl_f64(plan, cosmo_dev + c0 * plan->d.ncp, nc, out + (size_t)c0 * plan->d.P * plan->d.L, ws_dev,
-                               ws_bytes, s);
+  if (n_cosmo > 0) {
+    PushCtx ctx{g, row_bytes, row_offset, s};
+    double* out = (double*)g->local + (size_t)row_offset * plan->d.P * plan->d.L;
+    int st = jc_run_pipeline(plan, cosmo_dev, n_cosmo, out, ws_dev, ws_bytes, s, sub_chunk, push_rows_n, push_cb, &ctx);
     if (st != JC_OK) return st;
-    if (g->world > 1) {
-      JC_CUDA_TRY(cudaEventRecord(g->ev_chunk, s));
-      if ((st = push_rows(g, row_bytes, row_offset + c0, nc, g->ev_chunk)) != JC_OK) return st;
-    }
   }
   if (g->world > 1)
     for (int i = 0; i < g->n_streams; ++i) {  // `stream` continues after this rank's pushes

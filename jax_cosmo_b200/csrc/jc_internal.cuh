@@ -162,6 +162,9 @@ struct JcDeviceGuard {
 };
 
 void jc_set_cuda_error(cudaError_t e, const char* where);
+typedef int (*jc_slice_cb)(void* ctx, int64_t first_row, int64_t rows);
+int jc_run_pipeline(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo, double* cl_dev, void* ws_dev,
+                    size_t ws_bytes, cudaStream_t s, int64_t chunk_cap, int64_t slice, jc_slice_cb cb, void* ctx);
 void jc_math_table(double* out288);  // host: tables of the table-driven exp / log (jc_math.cuh)
 int jc_pipeline_init();  // one-time function attributes (dynamic shared memory opt-in)
 

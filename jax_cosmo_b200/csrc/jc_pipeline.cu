@@ -115,22 +115,28 @@ extern "C" int jc_workspace_layout(const jc_plan* plan, size_t ws_bytes, jc_ws_l
   return JC_OK;
 }
 
-extern "C" int jc_angular_cl_f64(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo,
-                                 double* cl_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+// K1..K4 over n_cosmo cosmologies in chunks of <= chunk_cap (and <= what the workspace holds).  With slice > 0 the
+// contraction of a chunk is launched per slice of cosmologies and `cb(ctx, first_row, rows)` is called after each slice's
+// launch (the gather records an event there and starts the peer copies of those rows): the exchange granularity is
+// then independent of the compute chunk, whose K1..K3 keep full waves.  The last slice of the batch is halved so that
+// the copy left exposed at the end of the step is short.
+int jc_run_pipeline(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo, double* cl_dev, void* ws_dev,
+                    size_t ws_bytes, cudaStream_t s, int64_t chunk_cap, int64_t slice, jc_slice_cb cb, void* ctx) {
   if (!plan || plan->d.grid_mode || !cosmo_dev || !cl_dev || !ws_dev || n_cosmo < 1) return JC_ERR_INVALID;
   JcDeviceGuard guard(plan->device);  // a null stream handle means the CURRENT device's default stream
   jc_ws_layout lo;
   int st = jc_workspace_layout(plan, ws_bytes, &lo);
   if (st != JC_OK) return st;
   const JcDevPlan& pl = plan->d;
-  cudaStream_t s = (cudaStream_t)stream;
   double* base = (double*)ws_dev;
   Ws ws;
   resolve(lo, base, 0, &ws);
+  const int64_t cap = (chunk_cap > 0 && chunk_cap < lo.chunk) ? chunk_cap : lo.chunk;
+  const size_t PL = (size_t)pl.P * pl.L;
 
   JcProf* prof = (plan->prof && plan->prof->enabled) ? plan->prof : nullptr;
-  for (int64_t c0 = 0; c0 < n_cosmo; c0 += lo.chunk) {
-    const int chunk = (int)((n_cosmo - c0) < lo.chunk ? (n_cosmo - c0) : lo.chunk);
+  for (int64_t c0 = 0; c0 < n_cosmo; c0 += cap) {
+    const int chunk = (int)((n_cosmo - c0) < cap ? (n_cosmo - c0) : cap);
     cudaEvent_t* ev = nullptr;
     int* nl = nullptr;
     if (prof && prof->used < JC_PROF_SLOTS) { ev = prof->ev[prof->used]; nl = prof->launches[prof->used]; ++prof->used; }
@@ -144,13 +150,36 @@ extern "C" int jc_angular_cl_f64(const jc_plan* plan, const double* cosmo_dev, i
     JC_MARK(3);
     jc_launch_power(pl, ws, chunk, s);
     JC_MARK(4);
-    jc_launch_contract(pl, ws, cl_dev + (size_t)c0 * pl.P * pl.L, chunk, s);
+    int n_contract = 0;
+    if (slice <= 0) {
+      jc_launch_contract(pl, ws, cl_dev + (size_t)c0 * PL, chunk, s);
+      n_contract = 1;
+      if (cb && (st = cb(ctx, c0, chunk)) != JC_OK) return st;
+    } else {
+      const bool last_chunk = c0 + chunk >= n_cosmo;
+      for (int s0 = 0; s0 < chunk;) {
+        int ns = (int)((chunk - s0) < slice ? (chunk - s0) : slice);
+        if (last_chunk && s0 + ns >= chunk && ns > slice / 2 && ns >= 2) ns = (ns + 1) / 2;  // halve the batch's final slice
+        Ws w = ws;  // the contraction reads R and V of the slice's cosmologies only
+        w.rker += (size_t)s0 * JC_NA_PAD * pl.TS;
+        w.vtab += (size_t)s0 * JC_NA * pl.Lpad;
+        jc_launch_contract(pl, w, cl_dev + (size_t)(c0 + s0) * PL, ns, s);
+        ++n_contract;
+        if (cb && (st = cb(ctx, c0 + s0, ns)) != JC_OK) return st;
+        s0 += ns;
+      }
+    }
     JC_MARK(5);
 #undef JC_MARK
-    if (nl) { nl[0] = 1; nl[1] = n_lens; nl[2] = 1; nl[3] = 1; nl[4] = 1; }
+    if (nl) { nl[0] = 1; nl[1] = n_lens; nl[2] = 1; nl[3] = 1; nl[4] = n_contract; }
   }
   JC_CUDA_TRY(cudaGetLastError());
   return JC_OK;
+}
+
+extern "C" int jc_angular_cl_f64(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo,
+                                 double* cl_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+  return jc_run_pipeline(plan, cosmo_dev, n_cosmo, cl_dev, ws_dev, ws_bytes, (cudaStream_t)stream, 0, 0, nullptr, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -28,6 +28,67 @@ struct PowerK {
 static __constant__ PowerK PK = {2.718281828459045 /* np.exp(1.0) */, 69.9, 14.2, 386.0, 1.8,
                                  1.0 / 5.4, 1.0 / 5.2, 0.125, 0.25, 0.43, 2.0 * 2.718281828459045, 62.5, 731.0};
 
+// Per-cosmology constants of the transfer function (transfer.py:47-136), loaded once per thread.
+template <class T> struct EhK {
+  T inv13keq, c14ac, b18, shd, alpha_b, fb, fc, bnode3, bb3, alpha_g, omh_t27;
+};
+template <class T> __device__ __forceinline__ EhK<T> eh_load(const double* scp, ptrdiff_t doff) {
+  auto SC = [&](int f) { return JxMem<T>::ld(scp + f, doff); };
+  EhK<T> E;
+  E.inv13keq = SC(JC_SCAL_INV13KEQ); E.c14ac = SC(JC_SCAL_C14_ALPHA_C); E.b18 = PK.c18 * SC(JC_SCAL_BETA_C);
+  E.shd = SC(JC_SCAL_SH_D); E.alpha_b = SC(JC_SCAL_ALPHA_B); E.fb = SC(JC_SCAL_FB); E.fc = SC(JC_SCAL_FC);
+  const T bnode = SC(JC_SCAL_BETA_NODE), bb = SC(JC_SCAL_BETA_B);
+  E.bnode3 = bnode * bnode * bnode; E.bb3 = bb * bb * bb;
+  E.alpha_g = SC(JC_SCAL_ALPHA_GAMMA); E.omh_t27 = SC(JC_SCAL_OMH_T27);  // no-wiggle fit only
+  return E;
+}
+
+// T(k): Eisenstein & Hu with wiggles (transfer.py:113-153) or the no-wiggle fit (transfer.py:92-105).
+// q108 = q^1.08 and ks14 = (k / k_silk)^1.4 come from the caller (separable tables in the point kernel, exp in the
+// table build); the ~14 divisions are merged into one reciprocal.
+template <class T, bool NOWIG>
+__device__ __forceinline__ T eh_point(const EhK<T>& E, T k, T q108, T ks14, const double* __restrict__ s_tab) {
+  if constexpr (NOWIG) {
+    const T ks43 = PK.c043 * (k * E.shd);
+    const T k2 = ks43 * ks43;
+    const T q = k * jx_rcp(E.omh_t27 * (E.alpha_g + (JCK.one - E.alpha_g) * jx_rcp(k2 * k2 + JCK.one)));
+    const T L = jx_log_t(PK.c18 * q + PK.two_e1, s_tab);
+    const T Wn = PK.c625 * q + JCK.one;                  // C = 14.2 + 731/Wn
+    const T LW = L * Wn;
+    return LW * jx_rcp(LW + (PK.c142 * Wn + PK.c731) * (q * q));
+  } else {
+    const T q = k * E.inv13keq;
+    const T q2 = q * q;
+    const T W = PK.c699 * q108 + JCK.one;  // 1 + 69.9 q^1.08
+    const T U1 = PK.c142 * W + PK.c386;    // C(alpha=1) W
+    const T U2 = E.c14ac * W + PK.c386;    // C(alpha_c) W
+    const T L1 = jx_log_t(E.b18 * q + PK.e1, s_tab);
+    const T L2 = jx_log_t(PK.c18 * q + PK.e1, s_tab);
+    const T L1W = L1 * W, L2W = L2 * W;
+    const T N1 = U1 * q2 + L1W;  // T~(k,1,beta_c)       = L1W / N1
+    const T N2 = U2 * q2 + L1W;  // T~(k,alpha_c,beta_c) = L1W / N2
+    const T N3 = U1 * q2 + L2W;  // T~(k,1,1)            = L2W / N3
+    const T ks = k * E.shd;
+    const T x54 = ks * PK.inv54;
+    const T x54_2 = x54 * x54;
+    const T Fm1 = x54_2 * x54_2;  // f = 1/(1+Fm1)
+    // Tc = f T1 + (1-f) T2 = L1W (N2 + Fm1 N1) / ((1+Fm1) N1 N2)
+    const T numC = L1W * (Fm1 * N1 + N2);
+    const T denC = (JCK.one + Fm1) * (N1 * N2);
+    const T ks2 = ks * ks, ks3 = ks2 * ks;
+    const T arg = ks2 * jx_rcbrt(ks3 + E.bnode3);  // k s~ = ks^2 / cbrt(ks^3 + beta_node^3)
+    const T x52 = ks * PK.inv52;
+    const T X52 = x52 * x52 + JCK.one;
+    const T BB = ks3 + E.bb3;  // 1/(1+(beta_b/ks)^3) = ks^3 / BB
+    const T silk = jx_exp_t(-ks14, s_tab);  // exp(-(k/k_silk)^1.4)
+    // Tb = [T3/X52 + alpha_b ks^3/BB silk] sin(arg)/arg
+    const T N3X = N3 * X52;
+    const T numB = (L2W * BB + E.alpha_b * ks3 * silk * N3X) * jx_sin(arg);
+    const T denB = N3X * BB * arg;
+    return ((E.fb * numB) * denC + E.fc * numC * denB) * jx_rcp(denB * denC);
+  }
+}
+
 // NPT: Limber nodes per thread; MINB: CTAs per SM the register allocation must allow; NOWIG: the
 // no-wiggle Eisenstein-Hu fit (transfer.py:99-105) instead of the default "eisenhu_osc".
 template <class T, int NPT, int MINB, bool NOWIG>
@@ -39,13 +100,7 @@ __global__ void __launch_bounds__(256, MINB) jc_power_kernel(JcDevPlan pl, Ws ws
   const ptrdiff_t doff = ws.doff;
   const int c = blockIdx.y;
   const double* scp = ws.scal + (size_t)c * JC_SCAL_FIELDS;
-  auto SC = [&](int f) { return JxMem<T>::ld(scp + f, doff); };
-  // cosmology side (transfer.py:47-136)
-  const T inv13keq = SC(JC_SCAL_INV13KEQ), c14ac = SC(JC_SCAL_C14_ALPHA_C), b18 = PK.c18 * SC(JC_SCAL_BETA_C);
-  const T shd = SC(JC_SCAL_SH_D), alpha_b = SC(JC_SCAL_ALPHA_B), fb = SC(JC_SCAL_FB), fc = SC(JC_SCAL_FC);
-  const T bnode = SC(JC_SCAL_BETA_NODE), bb = SC(JC_SCAL_BETA_B);
-  const T bnode3 = bnode * bnode * bnode, bb3 = bb * bb * bb;
-  const T alpha_g = SC(JC_SCAL_ALPHA_GAMMA), omh_t27 = SC(JC_SCAL_OMH_T27);  // no-wiggle fit only
+  const EhK<T> E = eh_load<T>(scp, doff);  // cosmology side (transfer.py:47-136)
   const double* nd = ws.node + (size_t)c * JC_NODE_FIELDS * JC_NA_PAD;
 #define NODE(f) JxMem<T>::ld(nd + (f)*JC_NA_PAD + n, doff)
 
@@ -64,47 +119,7 @@ __global__ void __launch_bounds__(256, MINB) jc_power_kernel(JcDevPlan pl, Ws ws
     for (int n = n0; n < n1; ++n) {
       const T lnk = lnl - NODE(JC_NODE_LNCHIC);
       const T k = lp5 * NODE(JC_NODE_INVCHIC);  // angular_cl.py:73
-      T Tk;
-      if constexpr (NOWIG) {  // no-wiggle fit (transfer.py:92-105)
-        const T ks43 = PK.c043 * (k * shd);
-        const T k2 = ks43 * ks43;
-        const T q = k * jx_rcp(omh_t27 * (alpha_g + (JCK.one - alpha_g) * jx_rcp(k2 * k2 + JCK.one)));
-        const T L = jx_log_t(PK.c18 * q + PK.two_e1, s_tab);
-        const T Wn = PK.c625 * q + JCK.one;                  // C = 14.2 + 731/Wn
-        const T LW = L * Wn;
-        Tk = LW * jx_rcp(LW + (PK.c142 * Wn + PK.c731) * (q * q));
-      } else {
-      // ---- Eisenstein & Hu (transfer.py:113-153) ------------------------------------------------
-      const T q = k * inv13keq;
-      const T q2 = q * q;
-      const T W = PK.c699 * (l108 * NODE(JC_NODE_NQ108)) + JCK.one;  // 1 + 69.9 q^1.08
-      const T U1 = PK.c142 * W + PK.c386;                            // C(alpha=1) W
-      const T U2 = c14ac * W + PK.c386;                              // C(alpha_c) W
-      const T L1 = jx_log_t(b18 * q + PK.e1, s_tab);
-      const T L2 = jx_log_t(PK.c18 * q + PK.e1, s_tab);
-      const T L1W = L1 * W, L2W = L2 * W;
-      const T N1 = U1 * q2 + L1W;  // T~(k,1,beta_c)       = L1W / N1
-      const T N2 = U2 * q2 + L1W;  // T~(k,alpha_c,beta_c) = L1W / N2
-      const T N3 = U1 * q2 + L2W;  // T~(k,1,1)            = L2W / N3
-      const T ks = k * shd;
-      const T x54 = ks * PK.inv54;
-      const T x54_2 = x54 * x54;
-      const T Fm1 = x54_2 * x54_2;  // f = 1/(1+Fm1)
-      // Tc = f T1 + (1-f) T2 = L1W (N2 + Fm1 N1) / ((1+Fm1) N1 N2)
-      const T numC = L1W * (Fm1 * N1 + N2);
-      const T denC = (JCK.one + Fm1) * (N1 * N2);
-      const T ks2 = ks * ks, ks3 = ks2 * ks;
-      const T arg = ks2 * jx_rcbrt(ks3 + bnode3);  // k s~ = ks^2 / cbrt(ks^3 + beta_node^3)
-      const T x52 = ks * PK.inv52;
-      const T X52 = x52 * x52 + JCK.one;
-      const T BB = ks3 + bb3;  // 1/(1+(beta_b/ks)^3) = ks^3 / BB
-      const T silk = jx_exp_t(-(l14 * NODE(JC_NODE_NSILK)), s_tab);  // exp(-(k/k_silk)^1.4)
-      // Tb = [T3/X52 + alpha_b ks^3/BB silk] sin(arg)/arg
-      const T N3X = N3 * X52;
-      const T numB = (L2W * BB + alpha_b * ks3 * silk * N3X) * jx_sin(arg);
-      const T denB = N3X * BB * arg;
-      Tk = ((fb * numB) * denC + fc * numC * denB) * jx_rcp(denB * denC);
-      }
+      const T Tk = eh_point<T, NOWIG>(E, k, NOWIG ? T(0.0) : T(l108 * NODE(JC_NODE_NQ108)), NOWIG ? T(0.0) : T(l14 * NODE(JC_NODE_NSILK)), s_tab);
       // ---- Delta^2_L = k^3 P_lin / (2 pi^2)  (power.py:49-52, :250) -----------------------------------
       const T d2l = lpns * NODE(JC_NODE_NAMP) * (Tk * Tk);
       T d2;

@@ -9,9 +9,10 @@ Results do not depend on the sharding (no cross-cosmology reduction) and are bit
 Gather modes (`gather_mode`):
 
   "peer"        every rank owns a full-size `[B, P, L]` buffer mapped into all ranks (CUDA IPC); the rank computes its
-                rows in sub-chunks straight into the final layout and the copy engines push each finished sub-chunk
-                into the peers' buffers over NVLink while the next one computes (csrc/jc_gather.cu).  No SM is taken
-                from the FP64 kernels; only the last sub-chunk's push is exposed.  Default on CUDA.
+                rows straight into the final layout -- K1..K3 on chunks of `sub_chunk` cosmologies, the contraction per
+                `push_rows` cosmologies -- and the copy engines push each finished slice into the peers' buffers over
+                NVLink while the following slices compute (csrc/jc_gather.cu).  No SM is taken from the FP64 kernels;
+                only the last (halved) slice's push is exposed.  Default on CUDA.
   "nccl"        the same sub-chunk pipeline with one grouped NCCL send/recv per sub-chunk on a side stream, received
                 straight into the final layout (the library baseline the peer path is measured against).
   "collective"  one `all_gather` after the compute (any backend; what the CPU / gloo tests exercise).
@@ -20,7 +21,8 @@ Gather modes (`gather_mode`):
 """
 import numpy as np
 
-DEFAULT_SUB_CHUNK = 592  # = 148 SMs x 4: one full wave of the setup kernel, 4 cosmologies per contraction CTA
+DEFAULT_SUB_CHUNK = 1184  # compute chunk of K1..K3: 2 x 592 = two full waves of the setup kernel (148 SMs x 4 CTAs)
+DEFAULT_PUSH_ROWS = 592   # cosmologies per contraction launch + NVLink push: 4 per persistent contraction CTA
 
 
 def shard_bounds(n_rows, world_size, rank):
@@ -49,7 +51,7 @@ class ShardedAngularCl:
     overwritten by the next call."""
 
     def __init__(self, n_rows, ell, probes, transfer_fn=None, nonlinear_fn=None, group=None, gather_mode="auto",
-                 sub_chunk=DEFAULT_SUB_CHUNK, growth=0):
+                 sub_chunk=DEFAULT_SUB_CHUNK, growth=0, push_rows=DEFAULT_PUSH_ROWS):
         import torch
         import torch.distributed as dist
 
@@ -61,6 +63,7 @@ class ShardedAngularCl:
         self.per = -(-self.n_rows // self.world)
         self.lo, self.hi = shard_bounds(self.n_rows, self.world, self.rank)
         self.sub_chunk = int(sub_chunk) if sub_chunk and sub_chunk > 0 else max(self.per, 1)
+        self.push_rows = int(push_rows) if push_rows and push_rows > 0 else 0
         if not torch.cuda.is_available():
             raise _native.JcError("jax_cosmo_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.plan = _native.get_plan(probes, ell, transfer_fn, nonlinear_fn, growth=growth)
@@ -123,7 +126,7 @@ class ShardedAngularCl:
         if self.mode == "none":
             self.compute_shard(shard)
         elif self.mode == "peer":
-            self._peer.compute_and_push(shard, self.lo, self.sub_chunk)
+            self._peer.compute_and_push(shard, self.lo, self.sub_chunk, self.push_rows)
             self.barrier()
         elif self.mode == "collective":
             self.compute_shard(shard)
@@ -164,7 +167,8 @@ class ShardedAngularCl:
 
 
 def angular_cl_sharded(cosmo_rows, ell, probes, transfer_fn=None, nonlinear_fn=None, group=None,
-                       gather=False, compute=None, gather_mode="auto", sub_chunk=DEFAULT_SUB_CHUNK):
+                       gather=False, compute=None, gather_mode="auto", sub_chunk=DEFAULT_SUB_CHUNK,
+                       push_rows=DEFAULT_PUSH_ROWS):
     """Compute C_ell for the rows owned by this rank (one-shot form).
 
     cosmo_rows : [B, 8] array ([B, 9] with the growth index gamma), identical on every rank (cheap: 64 B per cosmology).
@@ -188,7 +192,7 @@ def angular_cl_sharded(cosmo_rows, ell, probes, transfer_fn=None, nonlinear_fn=N
         nl = power.halofit if nonlinear_fn is None else nonlinear_fn
         mode = gather_mode if (gather and world > 1) else "none"
         sh = ShardedAngularCl(len(rows), ell, probes, tf, nl, group=group, gather_mode=mode, sub_chunk=sub_chunk,
-                              growth=1 if rows.shape[1] == 9 else 0)
+                              growth=1 if rows.shape[1] == 9 else 0, push_rows=push_rows)
         full = sh(rows)
         torch.cuda.current_stream(sh.device).synchronize()
         out = (full if mode != "none" else full[lo:hi]).clone()  # the buffer belongs to `sh`

@@ -390,7 +390,7 @@ def _nccl_worker(rank, world, port, out_dir):
             cl, (lo, hi) = angular_cl_sharded(rows, scn["ell"], probes, gather=True, gather_mode=mode, sub_chunk=7)
             np.save(os.path.join(out_dir, "g_%s_%d.npy" % (mode, rank)), cl.cpu().numpy())
         # persistent evaluator, called twice on different batches (buffer reuse, second step after the barrier)
-        sh = ShardedAngularCl(37, scn["ell"], probes, gather_mode="peer", sub_chunk=5)
+        sh = ShardedAngularCl(37, scn["ell"], probes, gather_mode="peer", sub_chunk=5, push_rows=2)
         sh(rows[::-1].copy())
         full = sh(rows).clone()
         torch.cuda.synchronize()
@@ -443,7 +443,7 @@ def test_peer_gather_two_devices_one_process(jc, torch_cuda):
     for d in range(2):
         lo, hi = d * per, min((d + 1) * per, len(rows))
         with torch.cuda.device(d):
-            gathers[d].compute_and_push(torch.as_tensor(rows[lo:hi], device="cuda:%d" % d), lo, 4)
+            gathers[d].compute_and_push(torch.as_tensor(rows[lo:hi], device="cuda:%d" % d), lo, 4, 3)
     for d in range(2):
         torch.cuda.synchronize(d)
     for d in range(2):
