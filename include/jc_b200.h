@@ -402,6 +402,17 @@ int jc_fp64_peak_tflops(int32_t mode, double seconds, double* tflops_out);
  * 6 table-driven log (x >= 1).  Synchronises the stream. */
 int jc_debug_math_f64(int32_t fn, const double* x_dev, double* y_dev, int64_t n, void* stream);
 
+/* Process-wide options (diagnostics / A-B runs; defaults are the hot path):
+ *   "power_exact"   0 | 1   1: the power kernel evaluates the Eisenstein-Hu formula at every (ell, node) point instead of
+ *                           interpolating the per-cosmology T(k) table (default 0; also env JC_POWER_EXACT);
+ *   "contract_eps"  >= 0    relative threshold below which a number-counts n(z_n) counts as zero when the contraction's
+ *                           node ranges are planned; 0 = exact zeros only (bitwise the full sum); read by jc_plan_create
+ *                           (default 1e-20; also env JC_CONTRACT_EPS);
+ *   "contract_kernel" 0..3  0: persistent TMA contraction where it applies (>= 17 pair tiles), 3: the cp.async kernel
+ *                           everywhere (all node stages, the reference's pair order) -- the A/B partner of the tests. */
+int jc_set_option(const char* name, double value);
+int jc_get_option(const char* name, double* value_out);
+
 const char* jc_status_string(int status);
 const char* jc_last_cuda_error(void);
 int32_t jc_abi_version(void);

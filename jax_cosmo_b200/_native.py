@@ -33,7 +33,7 @@ EXPORTS = ["jc_plan_create", "jc_plan_destroy", "jc_plan_n_tracers", "jc_plan_n_
            "jc_workspace_bytes", "jc_workspace_layout", "jc_angular_cl_f64", "jc_angular_cl_host_f64",
            "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64", "jc_gaussian_loglike_f64", "jc_fisher_f64", "jc_vjp_f64", "jc_sparse_bmm_f64", "jc_sparse_inv_f64", "jc_debug_stages_f64", "jc_grid_plan_create", "jc_grid_plan_create_probes", "jc_grid_eval_f64", "jc_grid_background_f64", "jc_a_of_chi_f64", "jc_sigmasqr_f64", "jc_nz_eval_f64",
            "jc_noise_f64", "jc_gaussian_cov_f64", "jc_gather_create", "jc_gather_buffer", "jc_gather_connect_ipc",
-           "jc_gather_connect_local", "jc_gather_destroy", "jc_angular_cl_gather_f64", "jc_gather_push_f64", "jc_profile_enable", "jc_profile_read",
+           "jc_gather_connect_local", "jc_gather_destroy", "jc_angular_cl_gather_f64", "jc_gather_push_f64", "jc_set_option", "jc_get_option", "jc_profile_enable", "jc_profile_read",
            "jc_fp64_peak_tflops", "jc_debug_math_f64", "jc_status_string",
            "jc_last_cuda_error", "jc_abi_version"]
 
@@ -144,6 +144,10 @@ def load_library():
         lib.jc_angular_cl_gather_f64.restype = C.c_int
         lib.jc_gather_push_f64.argtypes = [vp, C.c_size_t, i64, i64, vp]
         lib.jc_gather_push_f64.restype = C.c_int
+        lib.jc_set_option.argtypes = [C.c_char_p, C.c_double]
+        lib.jc_set_option.restype = C.c_int
+        lib.jc_get_option.argtypes = [C.c_char_p, dp]
+        lib.jc_get_option.restype = C.c_int
         lib.jc_profile_enable.argtypes = [vp, i32]
         lib.jc_profile_enable.restype = C.c_int
         lib.jc_profile_read.argtypes = [vp, dp, C.POINTER(C.c_int64)]
@@ -872,6 +876,19 @@ def debug_math(fn, x):
                                           torch.cuda.current_stream(x.device).cuda_stream)
     check(st, "jc_debug_math_f64")
     return y
+
+
+def set_option(name, value):
+    """jc_set_option: "power_exact" (0 | 1), "contract_eps" (>= 0; read when a plan is created -- cached plans keep theirs)."""
+    check(load_library().jc_set_option(name.encode(), float(value)), "jc_set_option(%s)" % name)
+    if name == "contract_eps":
+        _plan_cache.clear()
+
+
+def get_option(name):
+    out = C.c_double()
+    check(load_library().jc_get_option(name.encode(), C.byref(out)), "jc_get_option(%s)" % name)
+    return out.value
 
 
 def fp64_peak_tflops(mode=0, seconds=0.5):

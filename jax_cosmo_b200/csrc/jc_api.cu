@@ -15,6 +15,27 @@ void jc_set_cuda_error(cudaError_t e, const char* where) {
 }
 
 extern "C" const char* jc_last_cuda_error(void) { return g_cuda_err; }
+
+// ---- process-wide options (jc_set_option) -------------------------------------------------------------------------
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+static double env_double(const char* name, double dflt) { const char* e = getenv(name); return e ? atof(e) : dflt; }
+int g_jc_power_exact = env_int("JC_POWER_EXACT", 0);
+double g_jc_contract_eps = env_double("JC_CONTRACT_EPS", 1e-20);
+
+extern "C" int jc_set_option(const char* name, double value) {
+  if (!name) return JC_ERR_INVALID;
+  if (!strcmp(name, "power_exact")) { g_jc_power_exact = value != 0.0; return JC_OK; }
+  if (!strcmp(name, "contract_eps")) { if (!(value >= 0.0) || value > 1e-6) return JC_ERR_INVALID; g_jc_contract_eps = value; return JC_OK; }
+  if (!strcmp(name, "contract_kernel")) { const int v = (int)value; if (v < 0 || v > 3) return JC_ERR_INVALID; g_contract_cfg = v; return JC_OK; }
+  return JC_ERR_INVALID;
+}
+extern "C" int jc_get_option(const char* name, double* value_out) {
+  if (!name || !value_out) return JC_ERR_INVALID;
+  if (!strcmp(name, "power_exact")) { *value_out = g_jc_power_exact; return JC_OK; }
+  if (!strcmp(name, "contract_eps")) { *value_out = g_jc_contract_eps; return JC_OK; }
+  if (!strcmp(name, "contract_kernel")) { *value_out = g_contract_cfg < 0 ? 0 : g_contract_cfg; return JC_OK; }
+  return JC_ERR_INVALID;
+}
 extern "C" int32_t jc_abi_version(void) { return JC_ABI_VERSION; }
 
 extern "C" const char* jc_status_string(int status) {

@@ -49,7 +49,7 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 
 // One pipeline stage (KC/4 k-steps) of a warp's CNT x NT accumulator tiles.  `half` = doubles from the
 // value image [R | V] of a stage to its tangent image (JVP only).
-template <int KC, int CNT, int NT, bool JVP>
+template <int KC, int CNT, int NT, bool JVP, int M0 = 0>
 __device__ __forceinline__ void mma_stage(const double* __restrict__ Rs, const double* __restrict__ Vs,
                                           int TS, int half, int g, int tig, const int (&ti)[2], const int (&tj)[2],
                                           double (&acc)[2][NTW][2]) {
@@ -59,44 +59,75 @@ __device__ __forceinline__ void mma_stage(const double* __restrict__ Rs, const d
     const double* vr = Vs + (ks * 4 + tig) * LSV + g;
     double a[CNT], b[NT];
 #pragma unroll
-    for (int mt = 0; mt < CNT; ++mt) a[mt] = rr[ti[mt]] * rr[tj[mt]];
+    for (int mt = 0; mt < CNT; ++mt) a[mt] = rr[ti[M0 + mt]] * rr[tj[M0 + mt]];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) b[nt] = vr[nt * 8];
     if (!JVP) {
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-        for (int mt = 0; mt < CNT; ++mt) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+        for (int mt = 0; mt < CNT; ++mt) dmma(acc[M0 + mt][nt][0], acc[M0 + mt][nt][1], a[mt], b[nt]);
     } else {
       double ad[CNT], bd[NT];
 #pragma unroll
       for (int mt = 0; mt < CNT; ++mt)
-        ad[mt] = fma(rr[half + ti[mt]], rr[tj[mt]], rr[ti[mt]] * rr[half + tj[mt]]);  // dR_i R_j + R_i dR_j
+        ad[mt] = fma(rr[half + ti[M0 + mt]], rr[tj[M0 + mt]], rr[ti[M0 + mt]] * rr[half + tj[M0 + mt]]);  // dR_i R_j + R_i dR_j
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) bd[nt] = vr[half + nt * 8];
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int mt = 0; mt < CNT; ++mt) {
-          dmma(acc[mt][nt][0], acc[mt][nt][1], ad[mt], b[nt]);
-          dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], bd[nt]);
+          dmma(acc[M0 + mt][nt][0], acc[M0 + mt][nt][1], ad[mt], b[nt]);
+          dmma(acc[M0 + mt][nt][0], acc[M0 + mt][nt][1], a[mt], bd[nt]);
         }
     }
   }
 }
 
-template <int KC, int CNT, bool JVP>
+template <int KC, int CNT, bool JVP, int M0 = 0>
 __device__ __forceinline__ void mma_stage_nt(int ntw, const double* Rs, const double* Vs, int TS, int half, int g,
                                              int tig, const int (&ti)[2], const int (&tj)[2],
                                              double (&acc)[2][NTW][2]) {
   switch (ntw) {  // warp-uniform
-    case 7: mma_stage<KC, CNT, 7, JVP>(Rs, Vs, TS, half, g, tig, ti, tj, acc); break;
-    case 6: mma_stage<KC, CNT, 6, JVP>(Rs, Vs, TS, half, g, tig, ti, tj, acc); break;
-    case 5: mma_stage<KC, CNT, 5, JVP>(Rs, Vs, TS, half, g, tig, ti, tj, acc); break;
-    case 4: mma_stage<KC, CNT, 4, JVP>(Rs, Vs, TS, half, g, tig, ti, tj, acc); break;
-    case 3: mma_stage<KC, CNT, 3, JVP>(Rs, Vs, TS, half, g, tig, ti, tj, acc); break;
-    case 2: mma_stage<KC, CNT, 2, JVP>(Rs, Vs, TS, half, g, tig, ti, tj, acc); break;
-    default: mma_stage<KC, CNT, 1, JVP>(Rs, Vs, TS, half, g, tig, ti, tj, acc); break;
+    case 7: mma_stage<KC, CNT, 7, JVP, M0>(Rs, Vs, TS, half, g, tig, ti, tj, acc); break;
+    case 6: mma_stage<KC, CNT, 6, JVP, M0>(Rs, Vs, TS, half, g, tig, ti, tj, acc); break;
+    case 5: mma_stage<KC, CNT, 5, JVP, M0>(Rs, Vs, TS, half, g, tig, ti, tj, acc); break;
+    case 4: mma_stage<KC, CNT, 4, JVP, M0>(Rs, Vs, TS, half, g, tig, ti, tj, acc); break;
+    case 3: mma_stage<KC, CNT, 3, JVP, M0>(Rs, Vs, TS, half, g, tig, ti, tj, acc); break;
+    case 2: mma_stage<KC, CNT, 2, JVP, M0>(Rs, Vs, TS, half, g, tig, ti, tj, acc); break;
+    default: mma_stage<KC, CNT, 1, JVP, M0>(Rs, Vs, TS, half, g, tig, ti, tj, acc); break;
+  }
+}
+
+// Epilogue of the TMA kernel: tiles follow the plan's contraction order (pl.cpair_*): sorted pair q = tile * 8 + g is row
+// cpair_out[q] of the output.
+__device__ __forceinline__ void store_tiles_ord(const JcDevPlan& pl, const double (&acc)[2][NTW][2], const int (&mtile)[2],
+                                                const bool (&has)[2], const int (&ti)[2], const int (&tj)[2], int l0, int g,
+                                                int tig, bool vec2, double* __restrict__ out_cosmo) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const int q = mtile[mt] * 8 + g;
+    if (!has[mt] || q >= pl.P) continue;
+    const bool wi = pl.tr_kind[ti[mt]] == JC_TRACER_WEAK_LENSING;
+    const bool wj = pl.tr_kind[tj[mt]] == JC_TRACER_WEAK_LENSING;
+    double* out = out_cosmo + (size_t)pl.cpair_out[q] * pl.L;
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt) {
+      const int l = l0 + nt * 8 + 2 * tig;
+      double v[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const double ef = (l + h < pl.L) ? pl.ellfac[l + h] : 1.0;
+        v[h] = acc[mt][nt][h] * ((wi ? ef : 1.0) * (wj ? ef : 1.0));  // probes.py:73
+      }
+      if (vec2 && l + 1 < pl.L) {
+        *reinterpret_cast<double2*>(out + l) = make_double2(v[0], v[1]);
+      } else {
+        if (l < pl.L) out[l] = v[0];
+        if (l + 1 < pl.L) out[l + 1] = v[1];
+      }
+    }
   }
 }
 
@@ -270,7 +301,7 @@ jc_contract_tma_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64
   // the last stage holds <= 12 valid nodes: it is consumed as a 12-node stage (3 k-steps) and only the R rows inside
   // the padded table are copied
   constexpr int TAIL_NODES = JC_NA - (NKC - 1) * KC;
-  static_assert(KC % 12 == 0 && TAIL_NODES <= 12 && (NKC - 1) * KC + 12 <= JC_NA_PAD, "tail stage = one 12-node block");
+  static_assert(KC == 12 && TAIL_NODES <= 12 && (NKC - 1) * KC + 12 <= JC_NA_PAD, "12-node stages: the plan's tile ranges (ctile_lo / ctile_hi) are in units of 12 nodes");
   static_assert(KC < 31, "one lane per V row + lane 31 for R");
   static_assert((TMA_STAGES & (TMA_STAGES - 1)) == 0, "ring index by mask");
   extern __shared__ __align__(16) double smem[];
@@ -336,19 +367,22 @@ jc_contract_tma_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64
       const int l0 = grp * NCOLS;
       const int ntw = (min(pl.L - l0, NCOLS) + 7) >> 3;
       for (int m_base = 0; m_base < mtiles_all; m_base += 2 * TMA_CW, ++rot) {
-        // deal the round's pair tiles: `base` or base+1 per warp, the extras to the lowest virtual warps; the
-        // virtual index rotates so that the sub-partition (= warp % 4) holding the fewest tiles moves on
+        // deal the round's pair tiles: the tiles are sorted by the first stage of their node range (plan: ctile_lo),
+        // virtual warp v takes tiles v and v + 16, so every prefix of the sorted list -- the tiles active at a given
+        // stage -- is spread evenly over the four sub-partitions (= warp % 4); v rotates from item to item so that the
+        // sub-partition holding the fewest tiles moves on
         const int m_round = min(2 * TMA_CW, mtiles_all - m_base);
-        const int base = m_round / TMA_CW, extra = m_round - base * TMA_CW;
         const int v = (warp + rot) & (TMA_CW - 1);
-        const int cnt = base + (v < extra ? 1 : 0);
-        const int m_first = m_base + v * base + min(v, extra);
-        int ti[2], tj[2];
+        const int mtile[2] = {m_base + v, m_base + v + TMA_CW};
+        const bool has[2] = {v < m_round, v + TMA_CW < m_round};
+        int ti[2], tj[2], s_lo[2], s_hi[2];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
-          const int p = min((m_first + mt) * 8 + g, pl.P - 1);  // clamped rows are never stored
-          ti[mt] = pl.pair_i[p];
-          tj[mt] = pl.pair_j[p];
+          const int qp = min(mtile[mt] * 8 + g, ((pl.P + 7) & ~7) - 1);  // pad rows repeat the last pair, never stored
+          ti[mt] = pl.cpair_i[qp];
+          tj[mt] = pl.cpair_j[qp];
+          s_lo[mt] = has[mt] ? pl.ctile_lo[mtile[mt]] : 1;
+          s_hi[mt] = has[mt] ? pl.ctile_hi[mtile[mt]] : 0;
         }
         double acc[2][NTW][2];
 #pragma unroll
@@ -361,23 +395,21 @@ jc_contract_tma_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64
           mbar_wait(full + sb, (q / TMA_STAGES) & 1);
           const double* Rs = smem + (size_t)sb * stage_doubles;
           const double* Vs = Rs + KC * TS;
-          if (KC > 12 && kc == NKC - 1) {  // tail stage: nodes beyond the first 12 are stale
-            if (cnt == 2) mma_stage_nt<12, 2, JVP>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
-            else if (cnt == 1) mma_stage_nt<12, 1, JVP>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
-          } else {
-            if (cnt == 2) mma_stage_nt<KC, 2, JVP>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
-            else if (cnt == 1) mma_stage_nt<KC, 1, JVP>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
-          }
+          // stages outside a tile's range hold exact zeros (or values below the plan's threshold) of R_i R_j: skipped
+          const bool a0 = kc >= s_lo[0] && kc <= s_hi[0], a1 = kc >= s_lo[1] && kc <= s_hi[1];
+          if (a0 && a1) mma_stage_nt<KC, 2, JVP, 0>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+          else if (a0) mma_stage_nt<KC, 1, JVP, 0>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+          else if (a1) mma_stage_nt<KC, 1, JVP, 1>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
           __syncwarp();
           if (lane == 0) mbar_arrive(empty + sb);
-          // the lightest-loaded warp of the item (v = 15 holds `base` tiles) doubles as the producer: once all 16
+          // the lightest-loaded warp of the item (v = 15 holds one tile at most) doubles as the producer: once all 16
           // warps have left the stage it refills the buffer with the stage 8 ahead -- off the critical path
           if (v == TMA_CW - 1 && q + TMA_STAGES < total_stages) {
             mbar_wait(empty + sb, (q / TMA_STAGES) & 1);
             issue_stage(q + TMA_STAGES);
           }
         }
-        store_tiles(pl, acc, cnt, m_first, ti, tj, l0, g, tig, vec2, out_base + (size_t)c * out_cosmo_stride);
+        store_tiles_ord(pl, acc, mtile, has, ti, tj, l0, g, tig, vec2, out_base + (size_t)c * out_cosmo_stride);
       }
     }
   }
@@ -414,13 +446,15 @@ void launch_cfg(const JcDevPlan& pl, const Ws& ws, double* out, int64_t stride, 
   jc_contract_kernel<KC, WARPS, MINB, JVP><<<dim3(ngroups * msplit, chunk), WARPS * 32, smem, s>>>(pl, ws, out, stride, msplit);
 }
 
-int g_contract_cfg = -1;
-
 }  // namespace
+
+// jc_set_option("contract_kernel") / env JC_CONTRACT_CFG: 0 = persistent TMA kernel where it applies (default),
+// 3 = the 8-warp cp.async kernel everywhere, 1 / 2 = its 16-warp variants (profiles/r01_tuning.md)
+int g_contract_cfg = -1;
 
 int jc_contract_init() {
   if (g_contract_cfg < 0) {
-    const char* e = getenv("JC_CONTRACT_CFG");  // tuning knob (profiles/r01_tuning.md)
+    const char* e = getenv("JC_CONTRACT_CFG");
     g_contract_cfg = e ? atoi(e) : 0;
   }
   return JC_OK;
@@ -436,8 +470,6 @@ void jc_launch_contract(const JcDevPlan& pl, const Ws& ws, double* cl, int chunk
     case 3: launch_cfg<12, 8, 2, false>(pl, ws, cl, stride, chunk, mtiles > 16 ? 2 : 1, s); break;
     default:
       if (!tma_ok(pl, ws)) launch_cfg<12, 8, 2, false>(pl, ws, cl, stride, chunk, mtiles > 16 ? 2 : 1, s);
-      else if (g_contract_cfg == 4) launch_tma<24, 4, false>(pl, ws, cl, stride, chunk, s);  // 24 nodes per stage: 6.30 ms, no gain
-      else if (g_contract_cfg == 5) launch_tma<24, 8, false>(pl, ws, cl, stride, chunk, s);  // 6.31 ms
       else launch_tma<12, 8, false>(pl, ws, cl, stride, chunk, s);
       break;
   }

@@ -91,6 +91,7 @@ struct JcDevPlan {
   const double* tr_delta_t;  // [T] its interpolation weight
   const double* tr_m1;       // [T] 1 + m
   // ell
+  double lnl_min, lnl_max;   // min / max of ln(ell + 1/2): the ln k range of the tabulated transfer function
   const double* ell;         // [L]
   const double* ellp5;       // [L] ell + 0.5
   const double* lnellp5;     // [L]
@@ -103,6 +104,13 @@ struct JcDevPlan {
   // pairs
   const uint8_t* pair_i;     // [P]
   const uint8_t* pair_j;     // [P]
+  // contraction order of the persistent TMA kernel: pairs sorted by the first 12-node stage their product can be
+  // non-zero at (number-count kernels vanish where n(z) does), in tiles of 8
+  const uint8_t* cpair_i;    // [Ppad8] tracer i of sorted pair q
+  const uint8_t* cpair_j;    // [Ppad8]
+  const uint16_t* cpair_out; // [Ppad8] output row (index into the reference's pair order)
+  const uint8_t* ctile_lo;   // [Ppad8 / 8] first stage of the tile's range
+  const uint8_t* ctile_hi;   // [Ppad8 / 8] last stage (lo > hi: nothing to do, the rows are zero)
 };
 
 #define JC_PROF_SLOTS 2048
@@ -162,6 +170,9 @@ struct JcDeviceGuard {
 };
 
 void jc_set_cuda_error(cudaError_t e, const char* where);
+extern int g_jc_power_exact;      // jc_set_option("power_exact"): exact-formula power kernel everywhere
+extern int g_contract_cfg;        // jc_set_option("contract_kernel")
+extern double g_jc_contract_eps;  // jc_set_option("contract_eps"): support threshold of the contraction, read at plan creation
 typedef int (*jc_slice_cb)(void* ctx, int64_t first_row, int64_t rows);
 int jc_run_pipeline(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo, double* cl_dev, void* ws_dev,
                     size_t ws_bytes, cudaStream_t s, int64_t chunk_cap, int64_t slice, jc_slice_cb cb, void* ctx);

@@ -143,6 +143,35 @@ __device__ __forceinline__ double jcm_log_t(double x, const double* __restrict__
   return fma(de, JCK.ln2_hi, cl.y) + fma(de, JCK.ln2_lo, p);
 }
 
+// Reduced-degree variants for the tabulated power kernel (error budget 1e-10 per factor against a 1e-6 parity bar):
+// exp: degree-3 Taylor on |r| <= ln2/512 (truncation r^4/24 < 1.4e-13) and a one-word ln2/N (|x| 1.1e-16 absolute);
+// log: degree-4 series on |r| <= 1/256 (truncation r^5/5 < 1.9e-13) and a one-word ln2.
+template <bool CLAMP = true>
+__device__ __forceinline__ double jcm_exp_t3(double x, const double* __restrict__ tab) {
+  if (CLAMP) x = jcm_clamp_exp_arg(x);
+  const double kd = fma(x, JCT.k32, JCT.magic);
+  const int k = __double2loint(kd);
+  const double kf = kd - JCT.magic;
+  const double r = fma(kf, -JCT.l32_hi, x);
+  double p = fma(JCT.e[1], r, JCT.e[0]);
+  p = fma(p, r, JCK.one);
+  p = fma(p, r, JCK.one);
+  p *= tab[JCM_TAB_EXP + (k & (JCM_EXP_N - 1))];
+  return __hiloint2double(__double2hiint(p) + ((k >> JCM_EXP_BITS) << 20), __double2loint(p));
+}
+__device__ __forceinline__ double jcm_log_t4(double x, const double* __restrict__ tab) {
+  const int hx = __double2hiint(x);
+  const int e = (hx >> 20) - 1023;
+  const int j = (hx >> 13) & 127;
+  const double m = __hiloint2double((hx & 0x000fffff) | 0x3ff00000, __double2loint(x));
+  const double2 cl = *reinterpret_cast<const double2*>(tab + JCM_TAB_LOG + 2 * j);
+  const double r = fma(m, cl.x, -JCK.one);
+  double p = fma(JCT.l[2], r, JCT.l[1]);
+  p = fma(p, r, JCT.l[0]);
+  p = fma(p * r, r, r);  // r - r^2/2 + r^3/3 - r^4/4
+  return fma((double)e, JCK.ln2_hi, cl.y) + p;
+}
+
 // sin(x) for 0 <= x < ~1e6 (3-term Cody-Waite reduction; error grows linearly with x beyond 2^20*pi/2,
 // where this path's integrand is already suppressed by > 1e-12).
 __device__ __forceinline__ double jcm_sin(double x) {

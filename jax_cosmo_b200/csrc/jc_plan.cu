@@ -15,6 +15,8 @@
 #include <cstring>
 #include <vector>
 
+#include <algorithm>
+
 #include "jc_internal.cuh"
 #include "jc_math.cuh"
 
@@ -452,6 +454,11 @@ static int create_plan(const jc_problem* pb, const double* ell_host, int32_t n_e
   size_t o_ellfac = B.add(ellfac), o_covnorm = B.add(covnorm);
   size_t o_ell108 = B.add(ell108), o_ell14 = B.add(ell14), o_ellm3 = B.add(ellm3);
   size_t o_pi = B.add(pi), o_pj = B.add(pj);
+  // contraction order (filled after the n(z) kernels below): pairs sorted by the first Limber stage their kernel
+  // product can be non-zero at, tiles of 8 pairs with the stage range each tile has to visit
+  const int Ppad8 = (P + 7) & ~7, mtiles = Ppad8 / 8;
+  size_t o_cpi = B.reserve(Ppad8), o_cpj = B.reserve(Ppad8), o_cpo = B.reserve((size_t)Ppad8 * sizeof(uint16_t));
+  size_t o_tlo = B.reserve(mtiles), o_thi = B.reserve(mtiles);
   // tables of the kernels' table-driven exp / log (jc_math.cuh): 2^(j/256); {c_j, -ln c_j}
   std::vector<double> math_tab(JCM_TAB_DOUBLES);
   jc_math_table(math_tab.data());
@@ -479,9 +486,13 @@ static int create_plan(const jc_problem* pb, const double* ell_host, int32_t n_e
   d.tr_delta_ix = DP(int, o_dix); d.tr_delta_t = DP(double, o_dt); d.fin_idx = DP(int, o_fin);
   d.tr_m1 = DP(double, o_m1); d.src_tracer = DP(int, o_srct);
   d.ell = DP(double, o_ell); d.ellp5 = DP(double, o_ellp5); d.lnellp5 = DP(double, o_lnellp5);
+  d.lnl_min = *std::min_element(lnellp5.begin(), lnellp5.end());
+  d.lnl_max = *std::max_element(lnellp5.begin(), lnellp5.end());
   d.ellfac = DP(double, o_ellfac); d.covnorm = DP(double, o_covnorm);
   d.ell108 = DP(double, o_ell108); d.ell14 = DP(double, o_ell14); d.ellm3 = DP(double, o_ellm3);
   d.pair_i = DP(uint8_t, o_pi); d.pair_j = DP(uint8_t, o_pj);
+  d.cpair_i = DP(uint8_t, o_cpi); d.cpair_j = DP(uint8_t, o_cpj); d.cpair_out = DP(uint16_t, o_cpo);
+  d.ctile_lo = DP(uint8_t, o_tlo); d.ctile_hi = DP(uint8_t, o_thi);
   d.math_tab = DP(double, o_math);
   plan->d = d;
 
@@ -509,6 +520,58 @@ static int create_plan(const jc_problem* pb, const double* ell_host, int32_t n_e
   ce = cudaDeviceSynchronize();
   if (ce == cudaSuccess) ce = cudaGetLastError();
   if (ce != cudaSuccess) { jc_set_cuda_error(ce, "plan n(z) kernels"); cudaFree(base); delete plan; return JC_ERR_CUDA; }
+  // ---- contraction supports --------------------------------------------------------------------------------
+  // A number-counts kernel is n_i(z_n) b_i H (probes.py:77-99): zero wherever the cosmology-independent n_i(z_n) is.
+  // Per tracer the node range outside of which |n_i| <= eps * max|n_i| (eps = 0: exactly zero -> bitwise the full sum;
+  // the default 1e-20 drops contributions below 1e-20 of the bin's peak, far under one ulp of the sum); lensing
+  // tracers keep every node.  K4 visits, per tile of 8 pairs, only the 12-node stages inside the tile's range.
+  {
+    std::vector<double> nzh((size_t)JC_NA_PAD * d.TS);
+    ce = cudaMemcpy(nzh.data(), base + o_nz_node, nzh.size() * sizeof(double), cudaMemcpyDeviceToHost);
+    if (ce != cudaSuccess) { jc_set_cuda_error(ce, "cudaMemcpy(nz_node)"); cudaFree(base); delete plan; return JC_ERR_CUDA; }
+    const double eps = g_jc_contract_eps;
+    const int n_stage = (JC_NA + 11) / 12;
+    std::vector<int> t_lo(T, 0), t_hi(T, JC_NA - 1);
+    for (int t = 0; t < T && !grid_a; ++t) {
+      if (tr_kind[t] != JC_TRACER_NUMBER_COUNTS) continue;
+      double mx = 0.0;
+      for (int n = 0; n < JC_NA; ++n) mx = std::max(mx, std::fabs(nzh[(size_t)n * d.TS + t]));
+      int lo = JC_NA, hi = -1;
+      for (int n = 0; n < JC_NA; ++n) {
+        const double v = std::fabs(nzh[(size_t)n * d.TS + t]);
+        if (!(v <= eps * mx) || (eps <= 0.0 && v != 0.0) || v != v) { if (n < lo) lo = n; hi = n; }
+      }
+      t_lo[t] = lo; t_hi[t] = hi;  // lo > hi: the kernel vanishes everywhere
+    }
+    std::vector<int> p_lo(P), p_hi(P), order(P);
+    for (int q = 0; q < P; ++q) {
+      const int lo = std::max(t_lo[pi[q]], t_lo[pj[q]]), hi = std::min(t_hi[pi[q]], t_hi[pj[q]]);
+      if (lo > hi) { p_lo[q] = n_stage; p_hi[q] = -1; } else { p_lo[q] = lo / 12; p_hi[q] = hi / 12; }
+      order[q] = q;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      if (p_lo[a] != p_lo[b]) return p_lo[a] < p_lo[b];
+      return p_hi[a] > p_hi[b];
+    });
+    std::vector<uint8_t> cpi(Ppad8), cpj(Ppad8), tlo(mtiles), thi(mtiles);
+    std::vector<uint16_t> cpo(Ppad8);
+    for (int q = 0; q < Ppad8; ++q) {
+      const int src = order[q < P ? q : P - 1];  // pad rows repeat the last pair and are never stored
+      cpi[q] = pi[src]; cpj[q] = pj[src]; cpo[q] = (uint16_t)src;
+    }
+    for (int m = 0; m < mtiles; ++m) {
+      int lo = n_stage, hi = -1;
+      for (int q = 8 * m; q < std::min(8 * m + 8, P); ++q) { lo = std::min(lo, p_lo[order[q]]); hi = std::max(hi, p_hi[order[q]]); }
+      if (hi < lo) { lo = 1; hi = 0; }  // empty: no stage
+      tlo[m] = (uint8_t)lo; thi[m] = (uint8_t)hi;
+    }
+    ce = cudaMemcpy(base + o_cpi, cpi.data(), cpi.size(), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(base + o_cpj, cpj.data(), cpj.size(), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(base + o_cpo, cpo.data(), cpo.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(base + o_tlo, tlo.data(), tlo.size(), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(base + o_thi, thi.data(), thi.size(), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { jc_set_cuda_error(ce, "cudaMemcpy(contraction order)"); cudaFree(base); delete plan; return JC_ERR_CUDA; }
+  }
 #undef DP
   *plan_out = plan;
   return JC_OK;

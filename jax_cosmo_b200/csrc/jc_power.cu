@@ -149,6 +149,143 @@ __global__ void __launch_bounds__(256, MINB) jc_power_kernel(JcDevPlan pl, Ws ws
 #undef NODE
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K3 with the transfer function tabulated per cosmology (the hot-path default for double, non-grid plans with >= 32 ell).
+//
+// T(k) depends on k only, and the 51,300 (ell, node) points of a cosmology sample it densely: ~80 of the exact kernel's
+// 186 FP64 instructions per point re-evaluate the same smooth function.  Here one CTA (512 threads, two per SM) owns a
+// cosmology: it evaluates T(k) with the exact formula at NT nodes uniform in ln k over the cosmology's own range
+// [ln(l_min+1/2) - ln chi_max, ln(l_max+1/2)] (spacing h = range / (NT - 7) = 0.0023 at the bench configuration),
+// derives the node slopes h T'(k_j) by 4th-order central differences, keeps {T, h T'} pairs in shared memory (96 KB) and
+// evaluates every point by cubic Hermite interpolation (2 LDS.128 + 11 FP64 instead of 2 log, 1 exp, 1 sin, 1 rcbrt and
+// ~45 multiply-adds).  The halofit part uses the reduced-degree exp / log of jc_math.cuh.
+// Accuracy: the interpolation error is largest where the baryon wiggles are densest in ln k (k ~ 0.4 h/Mpc: 8e-10 on a single V entry);
+// on C_ell, an integral over 513 nodes, it is <= 6e-11 (oracle experiment over the config-5 box, profiles/r02_power_tab.md) against the
+// path's 1e-6 bar.  The exact kernel above stays the one behind grid plans, JVP passes, L < 32 and JC_POWER_EXACT=1,
+// and a cosmology whose range would need h > 0.004 takes the exact formula inside this kernel (warp-uniform branch).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int TAB_NT = 6144;           // table nodes (3 pad nodes on either side of the range)
+constexpr int TAB_THREADS = 512;
+constexpr double TAB_H_MAX = 0.004;
+
+// The (ell, node) points of one cosmology for the CTA of jc_power_tab_kernel.  TAB: T(k) by cubic Hermite interpolation
+// in the shared-memory table; !TAB: the exact formula (cosmologies whose ln k range is too wide for the table) -- a
+// separate instantiation so that the EH constants are not live in the tabulated loop.
+template <int NPT, bool NOWIG, bool TAB>
+__device__ __forceinline__ void tab_points(const JcDevPlan& pl, const Ws& ws, int c, unsigned inv_L, const EhK<double>& E,
+                                           const double* __restrict__ nd, const double2* __restrict__ tk,
+                                           const double* __restrict__ s_tab, double x0, double inv_h) {
+  constexpr int NGRP = (JC_NA + NPT - 1) / NPT;
+#define NODE(f) nd[(f)*JC_NA_PAD + n]
+  for (unsigned idx = threadIdx.x; idx < (unsigned)(NGRP * pl.L); idx += TAB_THREADS) {
+    const int grp = inv_L ? (int)__umulhi(idx, inv_L) : (int)(idx / (unsigned)pl.L);
+    const int l = (int)idx - grp * pl.L;
+    const double lnl = pl.lnellp5[l], lp5 = pl.ellp5[l], lm3 = pl.ellm3[l];
+    const double lpns = ws.ellpow[(size_t)c * pl.Lpad + l];
+    const int n0 = grp * NPT;
+    const int n1 = min(n0 + NPT, JC_NA);
+    double* vout = ws.vtab + (size_t)c * JC_NA * pl.Lpad + l;
+#pragma unroll 1
+    for (int n = n0; n < n1; ++n) {
+      const double lnk = lnl - NODE(JC_NODE_LNCHIC);
+      const double k = lp5 * NODE(JC_NODE_INVCHIC);  // angular_cl.py:73
+      double Tk;
+      if constexpr (TAB) {
+        const double u = (lnk - x0) * inv_h;
+        int i = __double2int_rz(u);
+        i = max(2, min(i, TAB_NT - 4));
+        const double t = u - (double)i;
+        const double2 a = tk[i], b = tk[i + 1];
+        const double D = b.x - a.x;
+        const double c3 = (a.y + b.y) - (D + D);  // cubic Hermite in t: f0 + t (d0 + t (c2 + t c3))
+        const double c2 = (D - a.y) - c3;
+        Tk = fma(t, fma(t, fma(t, c3, c2), a.y), a.x);
+      } else {
+        Tk = eh_point<double, NOWIG>(E, k, NOWIG ? 0.0 : pl.ell108[l] * NODE(JC_NODE_NQ108), NOWIG ? 0.0 : pl.ell14[l] * NODE(JC_NODE_NSILK), s_tab);
+      }
+      const double d2l = lpns * NODE(JC_NODE_NAMP) * (Tk * Tk);
+      double d2;
+      if (pl.nonlinear) {  // halofit (power.py:246-262), same association as the exact kernel
+        const double y = k * NODE(JC_NODE_RNL);
+        const double lny = lnk - NODE(JC_NODE_LNKNL);
+        const double y2 = y * y;
+        const double Nq = d2l * jcm_exp_t3(NODE(JC_NODE_BETA) * jcm_log_t4(JCK.one + d2l, s_tab) - (y2 * PK.eighth + PK.quarter * y), s_tab);
+        const double Dq = NODE(JC_NODE_ALPHA) * d2l + JCK.one;
+        const double ye1 = jcm_exp_t3<false>(NODE(JC_NODE_E1) * lny, s_tab);
+        const double ye2 = jcm_exp_t3<false>(NODE(JC_NODE_E2) * lny, s_tab);
+        const double cfy = jcm_exp_t3<false>(NODE(JC_NODE_P3) * (NODE(JC_NODE_LNCF) + lny), s_tab);
+        const double Nh = NODE(JC_NODE_AN) * ye1 * y2;
+        double ynu = y2 + NODE(JC_NODE_NU);
+        if (pl.nonlinear == JC_PK_HALOFIT_SMITH2003) ynu = ynu + NODE(JC_NODE_MU) * y;
+        const double Dh = (NODE(JC_NODE_BN) * ye2 + JCK.one + cfy) * ynu;
+        d2 = (Nq * Dh + Nh * Dq) * jcm_rcp(Dq * Dh);
+      } else {
+        d2 = d2l;
+      }
+      vout[(size_t)n * pl.Lpad] = d2 * lm3 * NODE(JC_NODE_GK);
+    }
+  }
+#undef NODE
+}
+
+template <int NPT, bool NOWIG>
+__global__ void __launch_bounds__(TAB_THREADS, 2) jc_power_tab_kernel(JcDevPlan pl, Ws ws, unsigned inv_L, double lnl_min,
+                                                                       double lnl_max) {
+  extern __shared__ __align__(16) double smem_p[];
+  double2* tk = reinterpret_cast<double2*>(smem_p);  // [TAB_NT] {T(k_j), h dT/dlnk(k_j)}
+  double* s_tab = smem_p + 2 * TAB_NT;
+  for (int i = threadIdx.x; i < JCM_TAB_DOUBLES; i += TAB_THREADS) s_tab[i] = pl.math_tab[i];
+  const int c = blockIdx.x;
+  const double* scp = ws.scal + (size_t)c * JC_SCAL_FIELDS;
+  const EhK<double> E = eh_load<double>(scp, 0);
+  const double* nd = ws.node + (size_t)c * JC_NODE_FIELDS * JC_NA_PAD;
+  // ln k range of this cosmology: chi decreases with the node index, node 0 = a_min holds the largest chi
+  const double lo = lnl_min - nd[JC_NODE_LNCHIC * JC_NA_PAD + 0], hi = lnl_max - nd[JC_NODE_LNCHIC * JC_NA_PAD + JC_NA - 1];
+  const double h = (hi - lo) * (1.0 / (TAB_NT - 7));
+  const bool use_tab = h <= TAB_H_MAX;
+  const double x0 = lo - 3.0 * h, inv_h = 1.0 / h;
+  __syncthreads();
+  if (use_tab) {
+    const double ln13keq = scp[JC_SCAL_LN13KEQ], lnksilk = scp[JC_SCAL_LNKSILK];
+    for (int j = threadIdx.x; j < TAB_NT; j += TAB_THREADS) {
+      const double lnk = fma((double)j, h, x0);
+      const double k = jcm_exp_t(lnk, s_tab);
+      double q108 = 0.0, ks14 = 0.0;
+      if (!NOWIG) {
+        q108 = jcm_exp_t(1.08 * (lnk - ln13keq), s_tab);
+        ks14 = jcm_exp_t(1.4 * (lnk - lnksilk), s_tab);
+      }
+      tk[j].x = eh_point<double, NOWIG>(E, k, q108, ks14, s_tab);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < TAB_NT; j += TAB_THREADS) {
+      double d = 0.0;
+      if (j >= 2 && j < TAB_NT - 2)
+        d = (8.0 * (tk[j + 1].x - tk[j - 1].x) - (tk[j + 2].x - tk[j - 2].x)) * (1.0 / 12.0);
+      tk[j].y = d;
+    }
+    __syncthreads();
+  }
+  if (use_tab) tab_points<NPT, NOWIG, true>(pl, ws, c, inv_L, E, nd, tk, s_tab, x0, inv_h);
+  else tab_points<NPT, NOWIG, false>(pl, ws, c, inv_L, E, nd, tk, s_tab, x0, inv_h);
+}
+
+template <int NPT>
+void launch_power_tab(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s) {
+  const unsigned inv_L = (pl.L >= 2 && pl.L <= 2048) ? (unsigned)((0x100000000ull + pl.L - 1) / pl.L) : 0u;
+  const size_t smem = (size_t)(2 * TAB_NT + JCM_TAB_DOUBLES) * sizeof(double);
+  static unsigned long long attr_done = 0;
+  JC_ONCE_PER_DEVICE(attr_done, {
+    cudaFuncSetAttribute(jc_power_tab_kernel<NPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(jc_power_tab_kernel<NPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  });
+  if (pl.transfer == JC_TF_EISENSTEIN_HU_NOWIGGLE)
+    jc_power_tab_kernel<NPT, true><<<chunk, TAB_THREADS, smem, s>>>(pl, ws, inv_L, pl.lnl_min, pl.lnl_max);
+  else
+    jc_power_tab_kernel<NPT, false><<<chunk, TAB_THREADS, smem, s>>>(pl, ws, inv_L, pl.lnl_min, pl.lnl_max);
+}
+
 // split: CTAs per cosmology (each strides over the index space)
 template <class T, int NPT, int MINB>
 void launch_power_cfg(const JcDevPlan& pl, const Ws& ws, int chunk, int split, cudaStream_t s) {
@@ -165,8 +302,22 @@ void launch_power_cfg(const JcDevPlan& pl, const Ws& ws, int chunk, int split, c
 }  // namespace
 
 void jc_launch_power(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s) {
-  static int cfg = -1;
-  if (cfg < 0) { const char* e = getenv("JC_POWER_CFG"); cfg = e ? atoi(e) : 0; }  // tuning knob
+  static int cfg = -1, tab_npt = 0;
+  if (cfg < 0) {  // tuning knobs
+    const char* e = getenv("JC_POWER_CFG");
+    const char* t = getenv("JC_POWER_TAB_NPT");
+    tab_npt = t ? atoi(t) : 0;
+    cfg = e ? atoi(e) : 0;
+  }
+  // jc_set_option("power_exact", 1) / JC_POWER_EXACT=1: the exact-formula kernel everywhere (A/B runs, stage tests)
+  if (!g_jc_power_exact && !pl.grid_mode && pl.L >= 32 && ws.doff == 0) {  // tabulated transfer function (see jc_power_tab_kernel)
+    switch (tab_npt) {
+      case 4: launch_power_tab<4>(pl, ws, chunk, s); break;
+      case 16: launch_power_tab<16>(pl, ws, chunk, s); break;
+      default: launch_power_tab<8>(pl, ws, chunk, s); break;
+    }
+    return;
+  }
   switch (cfg) {
     case 1: launch_power_cfg<double, 4, 1>(pl, ws, chunk, 8, s); break;  // unconstrained registers
     case 2: launch_power_cfg<double, 4, 3>(pl, ws, chunk, 8, s); break;  // 80 registers, 3 CTAs / SM

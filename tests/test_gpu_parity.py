@@ -13,6 +13,13 @@ from oracle import scenarios as sc
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-9  # asserted; project bar is 1e-6
+# >= 32 ell: the power kernel interpolates the per-cosmology T(k) table (csrc/jc_power.cu): observed <= 1.4e-9
+# element-wise (4.5e-11 of a spectrum's maximum over 1152 cosmologies, profiles/r02_power_tab.md), asserted at ~10x that
+RTOL_TAB = 2e-8
+
+
+def tol(n_ell):
+    return RTOL_TAB if n_ell >= 32 else RTOL
 
 
 @pytest.fixture(scope="module")
@@ -73,7 +80,7 @@ def test_cl_vs_golden_and_oracle(jc, torch_cuda, path):
     cl_full = jc.cl.angular_cl(cosmo, ell, probes, transfer_fn=tf, nonlinear_fn=nl)
     ref = o.angular_cl(sc.cosmo_row(scn["cosmo"]), ell, sc.flatten_spec(scn))
     e = relerr(cl_full, ref)
-    assert e < RTOL, "C_ell vs oracle (full ell): %.3e" % e
+    assert e < tol(len(ell)), "C_ell vs oracle (full ell): %.3e" % e
 
 
 @pytest.mark.parametrize("name", ["cfg2_3x2pt_5p5", "cfg2_extended_wcdm", "cfg1_wl4_linear"])
@@ -157,7 +164,7 @@ def test_batch_config5_subset(jc, torch_cuda):
     for i, row in enumerate(rows):
         worst = max(worst, relerr(cl[i], o.angular_cl(row, scn["ell"], prob)))
     print("config5 subset worst rel err %.3e over %d cosmologies" % (worst, len(rows)))
-    assert worst < RTOL, worst
+    assert worst < RTOL_TAB, worst
 
 
 def test_batch_properties_full_size(jc, torch_cuda):
@@ -221,7 +228,7 @@ def test_edge_cases(jc, torch_cuda):
     for ell in ([50.0], np.logspace(1, 3, 33), np.logspace(0.5, 3.9, 7)):
         cl = jc.cl.angular_cl(jc.Planck15(), ell, [jc.probes.WeakLensing([nz])])
         assert cl.shape == (1, len(ell))
-        assert relerr(cl, o.angular_cl(sc.cosmo_row(sc.PLANCK15), ell, prob1)) < RTOL
+        assert relerr(cl, o.angular_cl(sc.cosmo_row(sc.PLANCK15), ell, prob1)) < tol(len(ell))
     # corners of the config-5 prior box
     lo = [0.20, 0.04, 0.60, 0.92, 0.70, 0.0, -1.3, -0.5]
     hi = [0.35, 0.06, 0.80, 1.00, 0.90, 0.0, -0.7, 0.5]
@@ -614,7 +621,7 @@ def test_tma_contraction_shapes(jc, torch_cuda, shape):
     T = n_src + n_lens
     assert cl.shape == (T * (T + 1) // 2, L)
     ref = o.angular_cl(row, ell, prob)
-    assert relerr(cl, ref) < RTOL, relerr(cl, ref)
+    assert relerr(cl, ref) < tol(L), relerr(cl, ref)
     # a batch larger than the SM count (persistent CTAs walk over several cosmologies) equals the single rows bitwise
     torch = torch_cuda
     rows = np.concatenate([row[None], sc.config5_cosmologies(200)])
@@ -630,3 +637,63 @@ def test_tma_contraction_shapes(jc, torch_cuda, shape):
     _, jac_ref, _ = od.fd_jacobian(row, ell[sub], prob, params=params)
     scale = np.abs(jac_ref).max(axis=2, keepdims=True)
     assert (np.abs(jac[:, :, sub] - jac_ref) / scale).max() < 1e-6
+
+
+def test_power_tab_vs_exact_kernel(jc, torch_cuda):
+    """The tabulated-T(k) power kernel (default at >= 32 ell) against the exact-formula kernel (jc_set_option
+    "power_exact") on the bench tracer set: the exact kernel holds the oracle at 1e-9, the table stays within 2e-8
+    element-wise and 1e-9 of each spectrum's maximum; V itself (stage table) within 1e-8."""
+    torch = torch_cuda
+    from jax_cosmo_b200 import _native
+    scn = sc.scenario("cfg5", sc.PLANCK15, sc.ELL_CFG2, [sc.sources(10, 1.0), sc.lenses(10, 1.0)])
+    probes = sc.build_probes(scn, jc)
+    plan = _native.get_plan(probes, scn["ell"], None, None)
+    rows = np.concatenate([sc.cosmo_row(sc.PLANCK15)[None], sc.config5_cosmologies(65536)[[0, 1, 4095, 65535]]])
+    dev = torch.as_tensor(rows, device="cuda")
+    assert _native.get_option("power_exact") == 0.0
+    ws = plan.workspace(len(rows))
+    cl_tab = plan.angular_cl_device(dev, workspace=ws).cpu().numpy()
+    lo = plan.workspace_layout(ws.numel() * 8)
+    v_tab = ws[lo.vtab:lo.vtab + len(rows) * 513 * lo.ell_stride].cpu().numpy().reshape(len(rows), 513, lo.ell_stride)[:, :, :100]
+    try:
+        _native.set_option("power_exact", 1)
+        cl_ex = plan.angular_cl_device(dev, workspace=ws).cpu().numpy()
+        v_ex = ws[lo.vtab:lo.vtab + len(rows) * 513 * lo.ell_stride].cpu().numpy().reshape(len(rows), 513, lo.ell_stride)[:, :, :100]
+    finally:
+        _native.set_option("power_exact", 0)
+    prob = sc.flatten_spec(scn)
+    for i, row in enumerate(rows):
+        ref = o.angular_cl(row, scn["ell"], prob)
+        assert relerr(cl_ex[i], ref) < RTOL
+        assert relerr(cl_tab[i], ref) < RTOL_TAB
+        assert np.max(np.abs(cl_tab[i] - ref) / np.abs(ref).max(axis=1, keepdims=True)) < 1e-9
+    assert np.max(np.abs(v_tab / v_ex - 1)) < 1e-8
+    assert not np.array_equal(cl_tab, cl_ex)  # the two kernels really are different code paths
+
+
+def test_contraction_support_ranges(jc, torch_cuda):
+    """The TMA contraction visits, per tile of 8 sorted pairs, only the node stages where the number-counts n(z) is
+    above the plan's threshold.  contract_eps = 0 (exact zeros only) is bitwise the cp.async kernel, which multiplies
+    every node in the reference's pair order; the default 1e-20 changes nothing above 1e-15."""
+    torch = torch_cuda
+    from jax_cosmo_b200 import _native
+    # narrow lens bins (supports end early) + a bin whose n(z) vanishes nowhere, 10 + 10 tracers -> 27 pair tiles
+    lens = [sc.smail(2.0, 4.0, 0.15 + 0.07 * i, 1.0) for i in range(9)] + [sc.smail(1.0, 1.0, 2.0, 1.0)]
+    scn = sc.scenario("sup", sc.PLANCK15, sc.ELL_CFG2[::3], [sc.sources(10, 1.0), sc.nc(lens, [sc.bias("constant", 1.0 + 0.1 * i) for i in range(10)])])
+    probes = sc.build_probes(scn, jc)
+    rows = torch.as_tensor(np.concatenate([sc.cosmo_row(sc.PLANCK15)[None], sc.config5_cosmologies(300)]), device="cuda")
+    out = {}
+    try:
+        for tag, eps, kern in (("full", 0.0, 3), ("exact0", 0.0, 0), ("eps", 1e-20, 0)):
+            _native.set_option("contract_eps", eps)
+            _native.set_option("contract_kernel", kern)
+            plan = _native.get_plan(probes, scn["ell"], None, None)
+            out[tag] = plan.angular_cl_device(rows).cpu().numpy()
+    finally:
+        _native.set_option("contract_eps", 1e-20)
+        _native.set_option("contract_kernel", 0)
+    assert np.array_equal(out["exact0"], out["full"])
+    scale = np.abs(out["full"]).max(axis=2, keepdims=True)
+    assert np.max(np.abs(out["eps"] - out["full"]) / scale) < 1e-15
+    ref = o.angular_cl(sc.cosmo_row(sc.PLANCK15), scn["ell"], sc.flatten_spec(scn))
+    assert relerr(out["eps"][0], ref) < RTOL_TAB
