@@ -268,6 +268,24 @@ int jc_gaussian_loglike_f64(const double* data_dev, int64_t data_stride, const d
                             const double* cov_dev, int64_t n_cosmo, int32_t P, int32_t L,
                             int32_t include_logdet, double* loglike_dev, double* scratch_dev, void* stream);
 
+/* BASELINE config 3 end to end on the device, without forming the covariance: the Gaussian log-likelihood of a data
+ * vector under the Gaussian covariance OF THE MODEL SPECTRA, i.e. the reference's
+ *     mu, cov = gaussian_cl_covariance_and_mean(cosmo, ell, probes, f_sky=f_sky, sparse=True)     angular_cl.py:166-196
+ *     lnL = gaussian_log_likelihood(data, mu, cov, include_logdet)                                likelihood.py:9-61
+ * for a batch of cosmologies whose signal spectra cl_dev [B, P, L] are already on the device (jc_angular_cl_f64).
+ * cov[(ij),(mn),l] = (C_im C_jn + C_in C_jm) / nu_l is the operator S -> C S C on symmetric T x T matrices in the basis
+ * of the P unique pairs, so r^T cov^-1 r = nu/2 tr(C^-1 R C^-1 R) and log det cov = (T+1) log det C + T log 2 - P log nu
+ * per ell (C = signal + noise, R = residual matrix, nu = (2l+1) gradient(l) f_sky): O(T^3) per slice instead of O(P^3),
+ * 8 P bytes read instead of 8 P^2 (csrc/jc_cl_loglike.cu).  Equal to the two-call form in exact arithmetic.
+ * data_dev [P*L] (data_stride = 0) or [B, P*L] (data_stride = P*L), noise_dev [T] (jc_noise_f64), loglike_dev [B],
+ * scratch_dev [B, L, 2] doubles.  dcl_dev (may be NULL; needs include_logdet = 1): [B, P, L] cotangent d lnL / d cl[b,p,l]
+ * INCLUDING the dependence of the covariance and of its determinant on the spectra -- contracted with the forward-mode
+ * Jacobian by jc_vjp_f64 it is the gradient of the full likelihood, what jax.grad(likelihood) returns for the
+ * reference's README example (README.md:17-27).  n_cosmo <= 65535 per call. */
+int jc_gaussian_cl_loglike_f64(const jc_plan* plan, const double* cl_dev, const double* data_dev, int64_t data_stride,
+                               const double* noise_dev, int64_t n_cosmo, double f_sky, int32_t include_logdet,
+                               double* loglike_dev, double* dcl_dev, double* scratch_dev, void* stream);
+
 /* Fisher matrix F[b] = J^T C^-1 J on the sparse block covariance (the reference's recipe
  * sparse.dot(dmu.T, sparse.inv(cov), dmu), docs/notebooks/jax-cosmo-intro.ipynb cell 51; pairs with
  * jc_angular_cl_jvp_f64): jac_dev [B, K, P*L] (one row per parameter, cls-major), cov_dev [B, P, P, L],

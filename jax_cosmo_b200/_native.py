@@ -31,7 +31,7 @@ SCAL_FIELDS = ["LN13KEQ", "INV13KEQ", "BETA_C", "C14_ALPHA_C", "SH_D", "LNKSILK"
 # every symbol include/jc_b200.h declares
 EXPORTS = ["jc_plan_create", "jc_plan_destroy", "jc_plan_n_tracers", "jc_plan_n_cls", "jc_plan_n_ell", "jc_plan_n_cosmo_params",
            "jc_workspace_bytes", "jc_workspace_layout", "jc_angular_cl_f64", "jc_angular_cl_host_f64",
-           "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64", "jc_gaussian_loglike_f64", "jc_fisher_f64", "jc_vjp_f64", "jc_sparse_bmm_f64", "jc_sparse_inv_f64", "jc_debug_stages_f64", "jc_grid_plan_create", "jc_grid_plan_create_probes", "jc_grid_eval_f64", "jc_grid_background_f64", "jc_a_of_chi_f64", "jc_sigmasqr_f64", "jc_nz_eval_f64",
+           "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64", "jc_gaussian_loglike_f64", "jc_gaussian_cl_loglike_f64", "jc_fisher_f64", "jc_vjp_f64", "jc_sparse_bmm_f64", "jc_sparse_inv_f64", "jc_debug_stages_f64", "jc_grid_plan_create", "jc_grid_plan_create_probes", "jc_grid_eval_f64", "jc_grid_background_f64", "jc_a_of_chi_f64", "jc_sigmasqr_f64", "jc_nz_eval_f64",
            "jc_noise_f64", "jc_gaussian_cov_f64", "jc_gather_create", "jc_gather_buffer", "jc_gather_connect_ipc",
            "jc_gather_connect_local", "jc_gather_destroy", "jc_angular_cl_gather_f64", "jc_gather_push_f64", "jc_set_option", "jc_get_option", "jc_profile_enable", "jc_profile_read",
            "jc_fp64_peak_tflops", "jc_debug_math_f64", "jc_status_string",
@@ -100,6 +100,8 @@ def load_library():
         lib.jc_angular_cl_jvp_f64.restype = C.c_int
         lib.jc_gaussian_loglike_f64.argtypes = [vp, i64, vp, vp, i64, i32, i32, i32, vp, vp, vp]
         lib.jc_gaussian_loglike_f64.restype = C.c_int
+        lib.jc_gaussian_cl_loglike_f64.argtypes = [vp, vp, vp, i64, vp, i64, C.c_double, i32, vp, vp, vp, vp]
+        lib.jc_gaussian_cl_loglike_f64.restype = C.c_int
         lib.jc_fisher_f64.argtypes = [vp, vp, i64, i32, i32, i32, vp, vp, vp]
         lib.jc_fisher_f64.restype = C.c_int
         lib.jc_vjp_f64.argtypes = [vp, vp, i64, i64, i32, i64, vp, vp]
@@ -540,6 +542,45 @@ class Plan:
                                                 cov.data_ptr(), stream)
         check(st, "jc_gaussian_cov_f64")
         return cov
+
+
+    def gaussian_cl_loglike_device(self, cl_dev, data_dev, f_sky=0.25, include_logdet=True, noise=None, want_cotangent=False):
+        """jc_gaussian_cl_loglike_f64: cl_dev CUDA [B, P, L] (signal), data_dev CUDA [P*L] or [B, P*L] -> loglike [B]
+        (and, with want_cotangent, d lnL / d cl [B, P, L]) under the Gaussian covariance of the model spectra, without
+        forming the covariance.  Asynchronous on torch's current stream."""
+        import torch
+
+        self._check_dev(cl_dev, "cl")
+        B = cl_dev.shape[0]
+        if tuple(cl_dev.shape) != (B, self.P, self.L):
+            raise ValueError("cl must have shape [B, %d, %d]" % (self.P, self.L))
+        data_dev = data_dev.reshape(-1, self.P * self.L) if data_dev.dim() > 1 else data_dev
+        self._check_dev(data_dev, "data")
+        if data_dev.dim() == 1 and data_dev.numel() == self.P * self.L:
+            stride = 0
+        elif data_dev.dim() == 2 and tuple(data_dev.shape) == (B, self.P * self.L):
+            stride = self.P * self.L
+        else:
+            raise ValueError("data must have %d elements, or [B, %d]" % (self.P * self.L, self.P * self.L))
+        nv = self.noise() if noise is None else np.asarray(noise, dtype=np.float64)
+        if self._noise_dev is None or noise is not None:
+            noise_dev = torch.as_tensor(nv, device=cl_dev.device)
+            if noise is None:
+                self._noise_dev = noise_dev
+        else:
+            noise_dev = self._noise_dev
+        out = torch.empty(B, dtype=torch.float64, device=cl_dev.device)
+        dcl = torch.empty((B, self.P, self.L), dtype=torch.float64, device=cl_dev.device) if want_cotangent else None
+        scratch = torch.empty((B, self.L, 2), dtype=torch.float64, device=cl_dev.device)
+        stream = torch.cuda.current_stream(cl_dev.device).cuda_stream
+        for b0 in range(0, B, 32768):  # grid.y limit of the kernel
+            b1 = min(B, b0 + 32768)
+            st = load_library().jc_gaussian_cl_loglike_f64(
+                self._h, cl_dev[b0:b1].data_ptr(), (data_dev[b0:b1] if stride else data_dev).data_ptr(), stride,
+                noise_dev.data_ptr(), b1 - b0, float(f_sky), 1 if include_logdet else 0, out[b0:b1].data_ptr(),
+                dcl[b0:b1].data_ptr() if want_cotangent else None, scratch[b0:b1].data_ptr(), stream)
+            check(st, "jc_gaussian_cl_loglike_f64")
+        return (out, dcl) if want_cotangent else out
 
 
 class GridPlan(Plan):

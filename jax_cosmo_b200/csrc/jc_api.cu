@@ -25,7 +25,7 @@ double g_jc_contract_eps = env_double("JC_CONTRACT_EPS", 1e-20);
 extern "C" int jc_set_option(const char* name, double value) {
   if (!name) return JC_ERR_INVALID;
   if (!strcmp(name, "power_exact")) { g_jc_power_exact = value != 0.0; return JC_OK; }
-  if (!strcmp(name, "contract_eps")) { if (!(value >= 0.0) || value > 1e-6) return JC_ERR_INVALID; g_jc_contract_eps = value; return JC_OK; }
+  if (!strcmp(name, "contract_eps")) { if (!(value >= -1.0) || value > 1e-6) return JC_ERR_INVALID; g_jc_contract_eps = value; return JC_OK; }
   if (!strcmp(name, "contract_kernel")) { const int v = (int)value; if (v < 0 || v > 3) return JC_ERR_INVALID; g_contract_cfg = v; return JC_OK; }
   return JC_ERR_INVALID;
 }

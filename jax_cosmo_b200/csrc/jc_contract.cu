@@ -295,7 +295,7 @@ constexpr int TMA_CW = 16;      // warps per CTA
 // KC nodes per stage (12 or 24), TMA_STAGES ring depth (power of two)
 template <int KC, int TMA_STAGES, bool JVP>
 __global__ void __launch_bounds__(TMA_CW * 32, 1)
-jc_contract_tma_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64_t out_cosmo_stride, int chunk) {
+jc_contract_tma_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64_t out_cosmo_stride, int chunk, int pairing) {
   constexpr int NKC = (JC_NA + KC - 1) / KC;
   constexpr int NIMG = JVP ? 2 : 1;
   // the last stage holds <= 12 valid nodes: it is consumed as a 12-node stage (3 k-steps) and only the R rows inside
@@ -373,8 +373,12 @@ jc_contract_tma_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64
         // sub-partition holding the fewest tiles moves on
         const int m_round = min(2 * TMA_CW, mtiles_all - m_base);
         const int v = (warp + rot) & (TMA_CW - 1);
-        const int mtile[2] = {m_base + v, m_base + v + TMA_CW};
-        const bool has[2] = {v < m_round, v + TMA_CW < m_round};
+        // pairing 0: tiles (v, v + 16); 1: (s + 8r, s + 8r + 4) with s = v % 4, r = v / 4 -- the same tiles per
+        // sub-partition, neighbours in the sorted order paired in one warp; 2: (2v, 2v + 1)
+        const int t0 = pairing == 0 ? v : (pairing == 1 ? (v & 3) + 8 * (v >> 2) : 2 * v);
+        const int t1 = pairing == 0 ? v + TMA_CW : (pairing == 1 ? t0 + 4 : t0 + 1);
+        const int mtile[2] = {m_base + t0, m_base + t1};
+        const bool has[2] = {t0 < m_round, t1 < m_round};
         int ti[2], tj[2], s_lo[2], s_hi[2];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
@@ -427,7 +431,9 @@ void launch_tma(const JcDevPlan& pl, const Ws& ws, double* out, int64_t stride, 
     cudaFuncSetAttribute(jc_contract_tma_kernel<KC, TMA_STAGES, JVP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     sms = n > 0 ? n : 148;
   });
-  jc_contract_tma_kernel<KC, TMA_STAGES, JVP><<<chunk < sms ? chunk : sms, TMA_CW * 32, smem, s>>>(pl, ws, out, stride, chunk);
+  static int pairing = -1;
+  if (pairing < 0) { const char* e = getenv("JC_CONTRACT_PAIRING"); pairing = e ? atoi(e) : 0; }  // tuning knob
+  jc_contract_tma_kernel<KC, TMA_STAGES, JVP><<<chunk < sms ? chunk : sms, TMA_CW * 32, smem, s>>>(pl, ws, out, stride, chunk, pairing);
 }
 
 // TMA bulk copies need 16-byte aligned rows on both sides
@@ -465,11 +471,11 @@ void jc_launch_contract(const JcDevPlan& pl, const Ws& ws, double* cl, int chunk
   const int64_t stride = (int64_t)pl.P * pl.L;
   switch (g_contract_cfg) {
     case 1: launch_cfg<12, 16, 1, false>(pl, ws, cl, stride, chunk, 1, s); break;
-    case 2: launch_cfg<24, 16, 1, false>(pl, ws, cl, stride, chunk, 1, s); break;
     // 8 warps, 2 CTAs per SM, pair tiles split over 2 CTAs, cp.async staging (the default up to 16 pair tiles)
     case 3: launch_cfg<12, 8, 2, false>(pl, ws, cl, stride, chunk, mtiles > 16 ? 2 : 1, s); break;
     default:
       if (!tma_ok(pl, ws)) launch_cfg<12, 8, 2, false>(pl, ws, cl, stride, chunk, mtiles > 16 ? 2 : 1, s);
+      else if (g_contract_cfg == 2) launch_tma<12, 16, false>(pl, ws, cl, stride, chunk, s);  // 16-stage ring
       else launch_tma<12, 8, false>(pl, ws, cl, stride, chunk, s);
       break;
   }

@@ -563,6 +563,7 @@ static int create_plan(const jc_problem* pb, const double* ell_host, int32_t n_e
       int lo = n_stage, hi = -1;
       for (int q = 8 * m; q < std::min(8 * m + 8, P); ++q) { lo = std::min(lo, p_lo[order[q]]); hi = std::max(hi, p_hi[order[q]]); }
       if (hi < lo) { lo = 1; hi = 0; }  // empty: no stage
+      if (eps < 0.0) { lo = 0; hi = n_stage - 1; }  // contract_eps < 0: every stage (A/B knob)
       tlo[m] = (uint8_t)lo; thi[m] = (uint8_t)hi;
     }
     ce = cudaMemcpy(base + o_cpi, cpi.data(), cpi.size(), cudaMemcpyHostToDevice);

@@ -10,7 +10,8 @@ import numpy as np
 
 from jax_cosmo_b200 import _native
 
-__all__ = ["gaussian_log_likelihood", "gaussian_log_likelihood_batch", "fisher_matrix", "gaussian_log_likelihood_grad"]
+__all__ = ["gaussian_log_likelihood", "gaussian_log_likelihood_batch", "fisher_matrix", "gaussian_log_likelihood_grad",
+           "gaussian_cl_log_likelihood", "gaussian_cl_log_likelihood_and_grad"]
 
 
 def gaussian_log_likelihood(data, mu, C, include_logdet=True, inverse_method="inverse"):
@@ -104,3 +105,63 @@ def gaussian_log_likelihood_batch(data, mu, C, include_logdet=True):
     """Device form for batches: CUDA tensors data [N] or [B, N], mu [B, N], C [B, P, P, L] -> [B]
     (stream-ordered; pairs with `Plan.angular_cl_device` + `Plan.gaussian_cov_device`)."""
     return _native.gaussian_loglike_device(data, mu, C, include_logdet)
+
+
+def _cl_loglike_setup(cosmo, data, ell, probes, transfer_fn, nonlinear_fn):
+    import torch
+
+    from jax_cosmo_b200 import power, transfer
+    from jax_cosmo_b200.angular_cl import _growth, _rows
+
+    rows = _rows(cosmo)
+    tf = transfer.Eisenstein_Hu if transfer_fn is None else transfer_fn
+    nl = power.halofit if nonlinear_fn is None else nonlinear_fn
+    plan = _native.get_plan(probes, ell, tf, nl, growth=_growth(rows))
+    dev = "cuda:%d" % plan.device
+    data = np.ascontiguousarray(np.asarray(data, dtype=np.float64)).reshape(-1)
+    if data.size != plan.P * plan.L:
+        raise ValueError("data must have %d elements (n_cls * n_ell, cls-major)" % (plan.P * plan.L))
+    return rows, plan, torch.as_tensor(rows, device=dev), torch.as_tensor(data, device=dev)
+
+
+def gaussian_cl_log_likelihood(cosmo, data, ell, probes, f_sky=0.25, include_logdet=True, transfer_fn=None,
+                               nonlinear_fn=None):
+    """The reference's two calls in one device pass (BASELINE config 3):
+
+        mu, cov = gaussian_cl_covariance_and_mean(cosmo, ell, probes, f_sky=f_sky, sparse=True)   # angular_cl.py:166-196
+        lnL = gaussian_log_likelihood(data, mu, cov, include_logdet)                              # likelihood.py:9-61
+
+    without forming the covariance (csrc/jc_cl_loglike.cu: the Gaussian covariance of the spectra is S -> C S C on
+    symmetric T x T matrices, so every ell slice is a T x T Cholesky instead of a P x P one).  `cosmo` is a Cosmology
+    (-> float) or an array of rows [B, 8|9] (-> array [B])."""
+    rows, plan, rows_dev, data_dev = _cl_loglike_setup(cosmo, data, ell, probes, transfer_fn, nonlinear_fn)
+    out = plan.gaussian_cl_loglike_device(plan.angular_cl_device(rows_dev), data_dev, f_sky, include_logdet).cpu().numpy()
+    return float(out[0]) if hasattr(cosmo, "to_row") else out
+
+
+def gaussian_cl_log_likelihood_and_grad(cosmo, data, ell, probes, params=None, f_sky=0.25, transfer_fn=None,
+                                        nonlinear_fn=None):
+    """(lnL, d lnL / d theta) of the likelihood above with BOTH the mean and the covariance (and its determinant)
+    depending on the cosmology -- what `jax.grad(likelihood)` returns for the reference's README example
+    (README.md:17-27).  The likelihood kernel returns the cotangent d lnL / d cl, the forward-mode pipeline the
+    Jacobian d cl / d theta (one fused pass), and `jc_vjp_f64` contracts the two.  `params`: names of the cosmology
+    parameters (default: the 7 wCDM parameters, plus gamma for a gamma-growth cosmology); returns (float, [n_params])
+    for a Cosmology, ([B], [B, n_params]) for rows."""
+    import torch
+
+    from jax_cosmo_b200.angular_cl import _PARAM_INDEX, WCDM_PARAMS
+
+    rows, plan, rows_dev, data_dev = _cl_loglike_setup(cosmo, data, ell, probes, transfer_fn, nonlinear_fn)
+    width = rows.shape[1]
+    if params is None:
+        params = WCDM_PARAMS + (("gamma",) if width == 9 else ())
+    tang = np.zeros((len(params), width))
+    for k, name in enumerate(params):
+        if name not in _PARAM_INDEX or _PARAM_INDEX[name] >= width:
+            raise ValueError("unknown parameter %r" % (name,))
+        tang[k, _PARAM_INDEX[name]] = 1.0
+    cl, dcl = plan.angular_cl_jvp_device(rows_dev, torch.as_tensor(tang, device=rows_dev.device))
+    lnl, cot = plan.gaussian_cl_loglike_device(cl, data_dev, f_sky, True, want_cotangent=True)
+    grad = _native.vjp_device(dcl, cot)
+    lnl, grad = lnl.cpu().numpy(), grad.cpu().numpy()
+    return (float(lnl[0]), grad[0]) if hasattr(cosmo, "to_row") else (lnl, grad)

@@ -95,8 +95,12 @@ def test_stage_tables(jc, torch_cuda, name):
     rows = np.stack([sc.cosmo_row(scn["cosmo"]), sc.config5_cosmologies(3)[2]])
     cos = torch.as_tensor(rows, device="cuda")
     ws = torch.zeros(plan.workspace_bytes(len(rows)) // 8, dtype=torch.float64, device="cuda")
-    cl = plan.angular_cl_device(cos, workspace=ws)
-    torch.cuda.synchronize()
+    _native.set_option("power_exact", 1)  # the stage values of the exact-formula pipeline (V is held to 1e-9 point by point)
+    try:
+        cl = plan.angular_cl_device(cos, workspace=ws)
+        torch.cuda.synchronize()
+    finally:
+        _native.set_option("power_exact", 0)
     lo = plan.workspace_layout(ws.numel() * 8)
     assert lo.chunk == len(rows)
     w = ws.cpu().numpy()
@@ -697,3 +701,66 @@ def test_contraction_support_ranges(jc, torch_cuda):
     assert np.max(np.abs(out["eps"] - out["full"]) / scale) < 1e-15
     ref = o.angular_cl(sc.cosmo_row(sc.PLANCK15), scn["ell"], sc.flatten_spec(scn))
     assert relerr(out["eps"][0], ref) < RTOL_TAB
+
+
+def test_fused_cl_likelihood(jc, torch_cuda):
+    """jc_gaussian_cl_loglike_f64 (T x T identity, no covariance formed) against the reference's two-call form: the
+    oracle's gaussian_cl_covariance + gaussian_log_likelihood (pinned to the reference by tests/golden/likelihood_*.npz)
+    and this package's explicit covariance + per-ell Cholesky kernels; the cotangent d lnL / d cl against central
+    differences of the oracle's likelihood; the full-likelihood gradient against the chain rule through the
+    oracle's Jacobian."""
+    torch = torch_cuda
+    from jax_cosmo_b200 import _native
+    from oracle import derivatives as od
+    nz1, nz2 = sc.smail(1.0, 2.0, 1.0), sc.smail(1.0, 2.0, 0.5)
+    scn = sc.scenario("lk", sc.PLANCK15, [20.0, 50.0, 120.0, 300.0, 700.0],
+                      [sc.wl([nz1, nz2], sigma_e=[0.26, 0.3]), sc.nc([nz1, nz2], sc.bias("constant", 1.2))], f_sky=0.3)
+    probes, prob, ell = sc.build_probes(scn, jc), sc.flatten_spec(scn), np.array(scn["ell"])
+    row = sc.cosmo_row(sc.PLANCK15)
+    cl_ref = o.angular_cl(row, ell, prob)
+    T, (P, L) = len(prob["tracers"]), cl_ref.shape
+    rng = np.random.default_rng(3)
+    data = (cl_ref * (1.0 + 0.02 * rng.standard_normal(cl_ref.shape))).flatten()
+    nl = o.noise_cl(ell, prob)
+
+    def ref_lnl(cl, logdet=True):
+        return o.gaussian_log_likelihood(data, cl.flatten(), o.gaussian_cl_covariance(ell, T, cl, nl, 0.3, True), logdet)
+
+    for logdet in (True, False):
+        got = jc.likelihood.gaussian_cl_log_likelihood(jc.Planck15(), data, ell, probes, f_sky=0.3, include_logdet=logdet)
+        assert abs(got / ref_lnl(cl_ref, logdet) - 1) < 1e-9, (logdet, got, ref_lnl(cl_ref, logdet))
+    # the explicit path of this package (covariance kernel + P x P Cholesky kernel)
+    mu, cov = jc.cl.gaussian_cl_covariance_and_mean(jc.Planck15(), ell, probes, f_sky=0.3, sparse=True)
+    two_call = jc.likelihood.gaussian_log_likelihood(data, mu, cov)
+    assert abs(jc.likelihood.gaussian_cl_log_likelihood(jc.Planck15(), data, ell, probes, f_sky=0.3) / two_call - 1) < 1e-10
+    # cotangent
+    plan = _native.get_plan(probes, ell, None, None)
+    cl_dev = torch.as_tensor(cl_ref[None], device="cuda")
+    lnl, cot = plan.gaussian_cl_loglike_device(cl_dev, torch.as_tensor(data, device="cuda"), 0.3, True, want_cotangent=True)
+    cot = cot[0].cpu().numpy()
+    num = np.zeros_like(cl_ref)
+    for p in range(P):
+        for l in range(L):
+            h = 1e-6 * abs(cl_ref[p, l])
+            up, dn = cl_ref.copy(), cl_ref.copy()
+            up[p, l] += h
+            dn[p, l] -= h
+            num[p, l] = (ref_lnl(up) - ref_lnl(dn)) / (2 * h)
+    assert np.max(np.abs(cot - num)) < 1e-6 * np.abs(num).max(), np.max(np.abs(cot - num)) / np.abs(num).max()
+    # full gradient: cotangent . Jacobian, the Jacobian from the index-checked finite-difference oracle
+    params = ("Omega_c", "sigma8", "w0", "h")
+    _, jac, _ = od.fd_jacobian(row, ell, prob, params=params)
+    ref_grad = np.array([np.sum(num * jac[k]) for k in range(len(params))])
+    lnl2, grad = jc.likelihood.gaussian_cl_log_likelihood_and_grad(jc.Planck15(), data, ell, probes, params=params, f_sky=0.3)
+    assert abs(lnl2 / ref_lnl(cl_ref) - 1) < 1e-9
+    assert np.max(np.abs(grad / ref_grad - 1)) < 1e-5, (grad, ref_grad)
+    # batch of the bench tracer set: fused == two-call kernels on every row
+    scn5 = sc.scenario("lk5", sc.PLANCK15, sc.ELL_CFG2[::4], [sc.sources(10, 1.0), sc.lenses(10, 1.0)])
+    probes5 = sc.build_probes(scn5, jc)
+    plan5 = _native.get_plan(probes5, scn5["ell"], None, None)
+    rows = torch.as_tensor(np.concatenate([row[None], sc.config5_cosmologies(7)]), device="cuda")
+    cl5 = plan5.angular_cl_device(rows)
+    data5 = (cl5[0] * 1.01).reshape(-1).contiguous()
+    fused = plan5.gaussian_cl_loglike_device(cl5, data5, 0.25)
+    explicit = _native.gaussian_loglike_device(data5, cl5.reshape(len(rows), -1), plan5.gaussian_cov_device(cl5, 0.25))
+    assert float(((fused - explicit).abs() / explicit.abs()).max()) < 1e-9
