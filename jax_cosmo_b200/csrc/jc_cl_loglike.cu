@@ -72,15 +72,18 @@ __global__ void __launch_bounds__(LT * 32) jc_cl_loglike_kernel(JcDevPlan pl, co
       }
     }
     __syncwarp();
-    // Cholesky C = L L^T (right-looking, lower triangle in place); an indefinite C gives NaN, as the reference's inverse would
-    double ld = 0.0;
+    // Cholesky C = L L^T (right-looking, lower triangle in place); an indefinite C gives NaN, as the reference's inverse would.
+    // The slice is latency bound (one warp, dependent steps): no division, square root or logarithm inside the loops --
+    // 1/L_kk by rsqrt is kept on the diagonal (the substitutions multiply by it), log det from a running product.
+    double ld = 0.0, prod = 1.0;
     for (int k = 0; k < T; ++k) {
-      const double dk = sqrt(Cm[k * TP + k]);
-      const double inv = 1.0 / dk;
-      ld += log(dk);
+      const double ckk = Cm[k * TP + k];
+      const double inv = rsqrt(ckk);  // 1 / L_kk
+      prod *= ckk;                    // = L_kk^2
+      if ((k & 7) == 7) { ld += log(prod); prod = 1.0; }
       __syncwarp();
       if (row && i > k) Cm[i * TP + k] *= inv;
-      if (i == k) Cm[k * TP + k] = dk;
+      if (i == k) Cm[k * TP + k] = inv;
       __syncwarp();
       if (row && i > k) {
         const double lik = Cm[i * TP + k];
@@ -88,13 +91,19 @@ __global__ void __launch_bounds__(LT * 32) jc_cl_loglike_kernel(JcDevPlan pl, co
       }
       __syncwarp();
     }
-    logdet = (T + 1) * 2.0 * ld + T * 0.6931471805599453 - P * log(nu);
+    ld += log(prod);  // sum_k log L_kk^2
+    logdet = (T + 1) * ld + T * 0.6931471805599453 - P * log(nu);
     // Y^T = R L^-T: lane j forward-substitutes column j of R (= its own row, R is symmetric) in place
     if (row) {
       for (int r = 0; r < T; ++r) {
-        double s = Xm[i * TP + r];
-        for (int m = 0; m < r; ++m) s -= Cm[r * TP + m] * Xm[i * TP + m];
-        Xm[i * TP + r] = s / Cm[r * TP + r];
+        double s0 = Xm[i * TP + r], s1 = 0.0;
+        int m = 0;
+        for (; m + 1 < r; m += 2) {
+          s0 -= Cm[r * TP + m] * Xm[i * TP + m];
+          s1 -= Cm[r * TP + m + 1] * Xm[i * TP + m + 1];
+        }
+        if (m < r) s0 -= Cm[r * TP + m] * Xm[i * TP + m];
+        Xm[i * TP + r] = (s0 + s1) * Cm[r * TP + r];
       }
     }
     __syncwarp();
@@ -102,11 +111,16 @@ __global__ void __launch_bounds__(LT * 32) jc_cl_loglike_kernel(JcDevPlan pl, co
     double ss = 0.0;
     if (row) {
       for (int r = 0; r < T; ++r) {
-        double s = Xm[r * TP + i];
-        for (int m = 0; m < r; ++m) s -= Cm[r * TP + m] * Xm[m * TP + i];
-        s /= Cm[r * TP + r];
-        Xm[r * TP + i] = s;
-        ss += s * s;
+        double s0 = Xm[r * TP + i], s1 = 0.0;
+        int m = 0;
+        for (; m + 1 < r; m += 2) {
+          s0 -= Cm[r * TP + m] * Xm[m * TP + i];
+          s1 -= Cm[r * TP + m + 1] * Xm[(m + 1) * TP + i];
+        }
+        if (m < r) s0 -= Cm[r * TP + m] * Xm[m * TP + i];
+        const double x = (s0 + s1) * Cm[r * TP + r];
+        Xm[r * TP + i] = x;
+        ss += x * x;
       }
     }
 #pragma unroll
@@ -128,7 +142,7 @@ __global__ void __launch_bounds__(LT * 32) jc_cl_loglike_kernel(JcDevPlan pl, co
         for (int r = T - 1; r >= 0; --r) {
           double s = Mm[r * TP + i];
           for (int m = r + 1; m < T; ++m) s -= Cm[m * TP + r] * Mm[m * TP + i];
-          Mm[r * TP + i] = s / Cm[r * TP + r];
+          Mm[r * TP + i] = s * Cm[r * TP + r];  // the diagonal holds 1 / L_rr
         }
       }
       __syncwarp();
@@ -137,7 +151,7 @@ __global__ void __launch_bounds__(LT * 32) jc_cl_loglike_kernel(JcDevPlan pl, co
         for (int r = T - 1; r >= 0; --r) {
           double s = Mm[i * TP + r];
           for (int m = r + 1; m < T; ++m) s -= Cm[m * TP + r] * Mm[i * TP + m];
-          Mm[i * TP + r] = s / Cm[r * TP + r];
+          Mm[i * TP + r] = s * Cm[r * TP + r];
         }
       }
       __syncwarp();

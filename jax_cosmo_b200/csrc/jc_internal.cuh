@@ -92,6 +92,7 @@ struct JcDevPlan {
   const double* tr_m1;       // [T] 1 + m
   // ell
   double lnl_min, lnl_max;   // min / max of ln(ell + 1/2): the ln k range of the tabulated transfer function
+  double lnl_step;           // spacing of ln(ell + 1/2) when it is uniform (np.logspace in ell + 1/2 ... ), else 0
   const double* ell;         // [L]
   const double* ellp5;       // [L] ell + 0.5
   const double* lnellp5;     // [L]

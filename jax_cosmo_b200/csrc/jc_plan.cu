@@ -488,6 +488,17 @@ static int create_plan(const jc_problem* pb, const double* ell_host, int32_t n_e
   d.ell = DP(double, o_ell); d.ellp5 = DP(double, o_ellp5); d.lnellp5 = DP(double, o_lnellp5);
   d.lnl_min = *std::min_element(lnellp5.begin(), lnellp5.end());
   d.lnl_max = *std::max_element(lnellp5.begin(), lnellp5.end());
+  d.lnl_step = 0.0;  // > 0: ln(ell + 1/2) is (nearly) uniformly spaced -- lets the power kernel snap its table spacing
+  if (L >= 8) {      // median spacing, accepted when every spacing is within 10 % of it (np.logspace in ell: ell + 1/2 is not exactly log-uniform)
+    std::vector<double> dl(L - 1);
+    for (int l = 0; l + 1 < L; ++l) dl[l] = lnellp5[l + 1] - lnellp5[l];
+    std::vector<double> sorted(dl);
+    std::sort(sorted.begin(), sorted.end());
+    const double med = sorted[(L - 1) / 2];
+    bool uniform = med > 0.0;
+    for (int l = 0; l + 1 < L && uniform; ++l) uniform = std::fabs(dl[l] - med) < 0.1 * med;
+    if (uniform) d.lnl_step = med;
+  }
   d.ellfac = DP(double, o_ellfac); d.covnorm = DP(double, o_covnorm);
   d.ell108 = DP(double, o_ell108); d.ell14 = DP(double, o_ell14); d.ellm3 = DP(double, o_ellm3);
   d.pair_i = DP(uint8_t, o_pi); d.pair_j = DP(uint8_t, o_pj);

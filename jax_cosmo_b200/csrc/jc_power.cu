@@ -172,13 +172,13 @@ constexpr double TAB_H_MAX = 0.004;
 // The (ell, node) points of one cosmology for the CTA of jc_power_tab_kernel.  TAB: T(k) by cubic Hermite interpolation
 // in the shared-memory table; !TAB: the exact formula (cosmologies whose ln k range is too wide for the table) -- a
 // separate instantiation so that the EH constants are not live in the tabulated loop.
-template <int NPT, bool NOWIG, bool TAB>
+template <int NPT, bool NOWIG, bool TAB, int NTHREADS = 512>
 __device__ __forceinline__ void tab_points(const JcDevPlan& pl, const Ws& ws, int c, unsigned inv_L, const EhK<double>& E,
                                            const double* __restrict__ nd, const double2* __restrict__ tk,
                                            const double* __restrict__ s_tab, double x0, double inv_h) {
   constexpr int NGRP = (JC_NA + NPT - 1) / NPT;
 #define NODE(f) nd[(f)*JC_NA_PAD + n]
-  for (unsigned idx = threadIdx.x; idx < (unsigned)(NGRP * pl.L); idx += TAB_THREADS) {
+  for (unsigned idx = threadIdx.x; idx < (unsigned)(NGRP * pl.L); idx += NTHREADS) {
     const int grp = inv_L ? (int)__umulhi(idx, inv_L) : (int)(idx / (unsigned)pl.L);
     const int l = (int)idx - grp * pl.L;
     const double lnl = pl.lnellp5[l], lp5 = pl.ellp5[l], lm3 = pl.ellm3[l];
@@ -271,6 +271,220 @@ __global__ void __launch_bounds__(TAB_THREADS, 2) jc_power_tab_kernel(JcDevPlan 
   else tab_points<NPT, NOWIG, false>(pl, ws, c, inv_L, E, nd, tk, s_tab, x0, inv_h);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K3, tabulated, second form: one CTA of 1024 threads per cosmology with EVERYTHING the point loop touches in shared
+// memory.  ncu on jc_power_tab_kernel (profiles/r02_ncu_summary.md): issue slots 48 % busy, 1.0 eligible warp per
+// scheduler; stalls = long scoreboard 6.1 warps per issue (the ~17 per-node table entries a point reads come from L2: with
+// 2 x 102 KB of shared memory carved out, 28 KB of L1 are left), wait 3.1, short scoreboard 2.8; shared-memory wavefronts
+// 59 per warp-point, 60 % of them bank conflicts of the random table gathers.  Here
+//   * a thread owns ONE ell for the whole kernel (row r = tid / L of floor(1024 / L) rows): its five ell-side values sit
+//     in registers;
+//   * the Limber nodes are walked in blocks of nb <= 64; the 15 per-node values of a block, already combined into the
+//     forms the point needs (table coordinate offset, y / (l+1/2), ln y offset, ...), are staged in shared memory one
+//     block ahead (loads at the top of a block, stores after its points, one __syncthreads per block): warp-uniform LDS
+//     instead of L2 round trips;
+//   * the exp / log tables are replicated per lane slot ("lane-private banks": entry j of slot c at word j * 16 + c), so
+//     a gather with 32 different indices is conflict free: 2 wavefronts per LDS.64 instead of ~6, 4 per LDS.128 instead
+//     of ~10; exp uses 128 entries per octave with the degree-3 polynomial (|r| <= ln2/256, truncation 2e-12);
+//   * when ln(ell + 1/2) is uniformly spaced (plan: lnl_step > 0, e.g. np.logspace) the table spacing h is snapped so that
+//     neighbouring lanes are an ODD number of entries apart: the two LDS.128 of the Hermite gather then touch every
+//     16-byte bank group once per quarter warp (4 wavefronts each instead of ~10).
+// Used when floor(1024 / L) * L >= 0.9 * 1024 (else jc_power_tab_kernel).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int T2_THREADS = 1024;
+constexpr int T2_NB = 64;   // nodes per block (<=)
+constexpr int T2_NF = 15;   // staged values per node
+constexpr int T2_EXPN = 128;
+enum { F_UOFF = 0, F_YF, F_LNY0, F_NAMP, F_BETA, F_ALPHA, F_E1, F_E2, F_P3, F_P3LNCF, F_AN, F_NU, F_BN, F_GK, F_MU };
+
+struct JcMathL {
+  double k128, magic, l128;  // 128/ln2, 1.5*2^52, ln2/128
+};
+static __constant__ JcMathL JCL = {1.4426950408889634074 * T2_EXPN, 6755399441055744.0, 6.93147180559945309417e-01 / T2_EXPN};
+
+// exp(x), |x| < 700 unless CLAMP; lane-private table: entry j of slot c at e[j * 16 + c]
+template <bool CLAMP>
+__device__ __forceinline__ double exp_lane(double x, const double* __restrict__ e_slot) {
+  if (CLAMP) x = jcm_clamp_exp_arg(x);
+  const double kd = fma(x, JCL.k128, JCL.magic);
+  const int k = __double2loint(kd);
+  const double kf = kd - JCL.magic;
+  const double r = fma(kf, -JCL.l128, x);
+  double p = fma(JCT.e[1], r, JCT.e[0]);
+  p = fma(p, r, JCK.one);
+  p = fma(p, r, JCK.one);
+  p *= e_slot[(k & (T2_EXPN - 1)) * 16];
+  return __hiloint2double(__double2hiint(p) + ((k >> 7) << 20), __double2loint(p));
+}
+// log(x), x >= 1 normal; lane-private table of {c_j, -ln c_j}: entry j of slot c at l[(j * 8 + c)]
+__device__ __forceinline__ double log_lane(double x, const double2* __restrict__ l_slot) {
+  const int hx = __double2hiint(x);
+  const int e = (hx >> 20) - 1023;
+  const int j = (hx >> 13) & 127;
+  const double m = __hiloint2double((hx & 0x000fffff) | 0x3ff00000, __double2loint(x));
+  const double2 cl = l_slot[j * 8];
+  const double r = fma(m, cl.x, -JCK.one);
+  double p = fma(JCT.l[2], r, JCT.l[1]);
+  p = fma(p, r, JCT.l[0]);
+  p = fma(p * r, r, r);
+  return fma((double)e, JCK.ln2_hi, cl.y) + p;
+}
+
+template <bool NOWIG>
+__global__ void __launch_bounds__(T2_THREADS, 1) jc_power_tab2_kernel(JcDevPlan pl, Ws ws, int nb, int rows) {
+  extern __shared__ __align__(16) double smem_p[];
+  double2* tk = reinterpret_cast<double2*>(smem_p);                 // [TAB_NT] {T(k_j), h dT/dlnk(k_j)}
+  double* s_tab = smem_p + 2 * TAB_NT;                               // build phase: jc_math tables
+  double* e_l = s_tab + JCM_TAB_DOUBLES;                             // [128][16]
+  double2* l_l = reinterpret_cast<double2*>(e_l + T2_EXPN * 16);     // [128][8]
+  double* nf = e_l + T2_EXPN * 16 + 128 * 8 * 2;                     // [2][T2_NF][T2_NB]
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < JCM_TAB_DOUBLES; i += T2_THREADS) s_tab[i] = pl.math_tab[i];
+  for (int i = tid; i < T2_EXPN * 16; i += T2_THREADS) e_l[i] = pl.math_tab[JCM_TAB_EXP + (i >> 4) * (JCM_EXP_N / T2_EXPN)];
+  for (int i = tid; i < 128 * 8; i += T2_THREADS)
+    l_l[i] = make_double2(pl.math_tab[JCM_TAB_LOG + 2 * (i >> 3)], pl.math_tab[JCM_TAB_LOG + 2 * (i >> 3) + 1]);
+  const int c = blockIdx.x;
+  const double* scp = ws.scal + (size_t)c * JC_SCAL_FIELDS;
+  const double* nd = ws.node + (size_t)c * JC_NODE_FIELDS * JC_NA_PAD;
+  const double lo = pl.lnl_min - nd[JC_NODE_LNCHIC * JC_NA_PAD + 0], hi = pl.lnl_max - nd[JC_NODE_LNCHIC * JC_NA_PAD + JC_NA - 1];
+  double h = (hi - lo) * (1.0 / (TAB_NT - 7));
+  if (pl.lnl_step > 0.0) {  // snap: neighbouring ell an odd number of table entries apart
+    int m = (int)(pl.lnl_step / h);
+    m -= 1 - (m & 1);
+    if (m >= 1) h = pl.lnl_step / (double)m;
+  }
+  const bool use_tab = h <= TAB_H_MAX;
+  const double x0 = lo - 3.0 * h, inv_h = 1.0 / h;
+  __syncthreads();
+  if (use_tab) {
+    const EhK<double> E = eh_load<double>(scp, 0);
+    const double ln13keq = scp[JC_SCAL_LN13KEQ], lnksilk = scp[JC_SCAL_LNKSILK];
+    for (int j = tid; j < TAB_NT; j += T2_THREADS) {
+      const double lnk = fma((double)j, h, x0);
+      const double k = jcm_exp_t(lnk, s_tab);
+      double q108 = 0.0, ks14 = 0.0;
+      if (!NOWIG) {
+        q108 = jcm_exp_t(1.08 * (lnk - ln13keq), s_tab);
+        ks14 = jcm_exp_t(1.4 * (lnk - lnksilk), s_tab);
+      }
+      tk[j].x = eh_point<double, NOWIG>(E, k, q108, ks14, s_tab);
+    }
+    __syncthreads();
+    for (int j = tid; j < TAB_NT; j += T2_THREADS) {
+      double d = 0.0;
+      if (j >= 2 && j < TAB_NT - 2)
+        d = (8.0 * (tk[j + 1].x - tk[j - 1].x) - (tk[j + 2].x - tk[j - 2].x)) * (1.0 / 12.0);
+      tk[j].y = d;
+    }
+  } else {  // ln k range too wide for the table: exact formula at every point (global-memory node tables)
+    const EhK<double> E = eh_load<double>(scp, 0);
+    const unsigned inv_L = (pl.L >= 2 && pl.L <= 2048) ? (unsigned)((0x100000000ull + pl.L - 1) / pl.L) : 0u;
+    tab_points<8, NOWIG, false, T2_THREADS>(pl, ws, c, inv_L, E, nd, tk, s_tab, x0, inv_h);
+    return;
+  }
+  // ---- point loop -------------------------------------------------------------------------------------------------
+  const int L = pl.L;
+  const int row = tid / L, l = tid - row * L;
+  const bool active = row < rows;
+  double lnl = 0.0, lnl_ih = 0.0, lp5 = 0.0, lpns = 0.0, lm3 = 0.0;
+  if (active) {
+    lnl = pl.lnellp5[l]; lp5 = pl.ellp5[l]; lm3 = pl.ellm3[l];
+    lpns = ws.ellpow[(size_t)c * pl.Lpad + l];
+    lnl_ih = lnl * inv_h;
+  }
+  const double* e_slot = e_l + (lane & 15);
+  const double2* l_slot = l_l + (lane & 7);
+  const bool smith = pl.nonlinear == JC_PK_HALOFIT_SMITH2003;
+  const bool halofit = pl.nonlinear != 0;
+  double* vbase = ws.vtab + (size_t)c * JC_NA * pl.Lpad + l;
+  // staging of a node block: thread t < nb * T2_NF loads and combines one value (field f = t / nb, node j = t % nb)
+  auto stage_load = [&](int blk) -> double {
+    const int f = tid / nb, j = tid - f * nb, n = blk * nb + j;
+    if (f >= T2_NF || n >= JC_NA) return 0.0;
+    auto N = [&](int fld) { return nd[fld * JC_NA_PAD + n]; };
+    switch (f) {
+      case F_UOFF: return -(N(JC_NODE_LNCHIC) + x0) * inv_h;
+      case F_YF: return N(JC_NODE_INVCHIC) * N(JC_NODE_RNL);
+      case F_LNY0: return N(JC_NODE_LNCHIC) + N(JC_NODE_LNKNL);
+      case F_NAMP: return N(JC_NODE_NAMP);
+      case F_BETA: return N(JC_NODE_BETA);
+      case F_ALPHA: return N(JC_NODE_ALPHA);
+      case F_E1: return N(JC_NODE_E1);
+      case F_E2: return N(JC_NODE_E2);
+      case F_P3: return N(JC_NODE_P3);
+      case F_P3LNCF: return N(JC_NODE_P3) * N(JC_NODE_LNCF);
+      case F_AN: return N(JC_NODE_AN);
+      case F_NU: return N(JC_NODE_NU);
+      case F_BN: return N(JC_NODE_BN);
+      case F_GK: return N(JC_NODE_GK);
+      default: return N(JC_NODE_MU);
+    }
+  };
+  const int nblk = (JC_NA + nb - 1) / nb;
+  if (tid < nb * T2_NF) nf[(tid / nb) * T2_NB + (tid % nb)] = stage_load(0);
+  __syncthreads();  // table slopes + block 0
+  for (int blk = 0; blk < nblk; ++blk) {
+    const double* F = nf + (blk & 1) * (T2_NF * T2_NB);
+    double staged = 0.0;
+    if (blk + 1 < nblk) staged = stage_load(blk + 1);
+    const int n_lo = blk * nb, n_cnt = min(nb, JC_NA - n_lo);
+    if (active) {
+      double* vp = vbase + (size_t)(n_lo + row) * pl.Lpad;
+      const size_t vstep = (size_t)rows * pl.Lpad;
+#pragma unroll 1
+      for (int j = row; j < n_cnt; j += rows, vp += vstep) {
+        const double u = lnl_ih + F[F_UOFF * T2_NB + j];
+        int i = __double2int_rz(u);
+        i = max(2, min(i, TAB_NT - 4));
+        const double t = u - (double)i;
+        const double2 a = tk[i], b = tk[i + 1];
+        const double D = b.x - a.x;
+        const double c3 = (a.y + b.y) - (D + D);
+        const double c2 = (D - a.y) - c3;
+        const double Tk = fma(t, fma(t, fma(t, c3, c2), a.y), a.x);
+        const double d2l = lpns * F[F_NAMP * T2_NB + j] * (Tk * Tk);
+        double d2 = d2l;
+        if (halofit) {  // power.py:246-262, same association as the exact kernel
+          const double y = lp5 * F[F_YF * T2_NB + j];
+          const double lny = lnl - F[F_LNY0 * T2_NB + j];
+          const double y2 = y * y;
+          const double Nq = d2l * exp_lane<true>(F[F_BETA * T2_NB + j] * log_lane(JCK.one + d2l, l_slot) - (y2 * PK.eighth + PK.quarter * y), e_slot);
+          const double Dq = F[F_ALPHA * T2_NB + j] * d2l + JCK.one;
+          const double ye1 = exp_lane<false>(F[F_E1 * T2_NB + j] * lny, e_slot);
+          const double ye2 = exp_lane<false>(F[F_E2 * T2_NB + j] * lny, e_slot);
+          const double cfy = exp_lane<false>(fma(F[F_P3 * T2_NB + j], lny, F[F_P3LNCF * T2_NB + j]), e_slot);
+          const double Nh = F[F_AN * T2_NB + j] * ye1 * y2;
+          double ynu = y2 + F[F_NU * T2_NB + j];
+          if (smith) ynu = fma(F[F_MU * T2_NB + j], y, ynu);
+          const double Dh = (F[F_BN * T2_NB + j] * ye2 + JCK.one + cfy) * ynu;
+          d2 = (Nq * Dh + Nh * Dq) * jcm_rcp(Dq * Dh);
+        }
+        *vp = d2 * lm3 * F[F_GK * T2_NB + j];
+      }
+    }
+    if (blk + 1 < nblk && tid < nb * T2_NF) nf[((blk + 1) & 1) * (T2_NF * T2_NB) + (tid / nb) * T2_NB + (tid % nb)] = staged;
+    __syncthreads();
+  }
+}
+
+template <int NPT>
+void launch_power_tab(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s);
+
+void launch_power_tab2(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s) {
+  const size_t smem = (size_t)(2 * TAB_NT + JCM_TAB_DOUBLES + T2_EXPN * 16 + 128 * 8 * 2 + 2 * T2_NF * T2_NB) * sizeof(double);
+  static unsigned long long attr_done = 0;
+  JC_ONCE_PER_DEVICE(attr_done, {
+    cudaFuncSetAttribute(jc_power_tab2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(jc_power_tab2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  });
+  const int rows = T2_THREADS / pl.L;
+  int nb = (T2_NB / rows) * rows;  // whole rounds of `rows` nodes per block
+  if (nb < rows) nb = rows;
+  if (pl.transfer == JC_TF_EISENSTEIN_HU_NOWIGGLE) jc_power_tab2_kernel<true><<<chunk, T2_THREADS, smem, s>>>(pl, ws, nb, rows);
+  else jc_power_tab2_kernel<false><<<chunk, T2_THREADS, smem, s>>>(pl, ws, nb, rows);
+}
+
 template <int NPT>
 void launch_power_tab(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s) {
   const unsigned inv_L = (pl.L >= 2 && pl.L <= 2048) ? (unsigned)((0x100000000ull + pl.L - 1) / pl.L) : 0u;
@@ -311,6 +525,10 @@ void jc_launch_power(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t 
   }
   // jc_set_option("power_exact", 1) / JC_POWER_EXACT=1: the exact-formula kernel everywhere (A/B runs, stage tests)
   if (!g_jc_power_exact && !pl.grid_mode && pl.L >= 32 && ws.doff == 0) {  // tabulated transfer function (see jc_power_tab_kernel)
+    const int rows = T2_THREADS / pl.L;
+    if (tab_npt >= 0 && rows >= 1 && rows * pl.L * 10 >= T2_THREADS * 9 && pl.L <= T2_THREADS) {  // JC_POWER_TAB_NPT=-1: first form only
+      if (tab_npt == 0) { launch_power_tab2(pl, ws, chunk, s); return; }
+    }
     switch (tab_npt) {
       case 4: launch_power_tab<4>(pl, ws, chunk, s); break;
       case 16: launch_power_tab<16>(pl, ws, chunk, s); break;

@@ -637,7 +637,8 @@ def test_tma_contraction_shapes(jc, torch_cuda, shape):
     sub = slice(None, None, max(1, L // 6))
     params = ("Omega_c", "sigma8")
     cl_j, jac = jc.cl.angular_cl_jacobian(cosmo, ell, probes, params=params)
-    assert relerr(cl_j, cl) < 1e-12
+    # the JVP pass carries the exact-formula power kernel, the forward pass interpolates T(k) from >= 32 ell on
+    assert relerr(cl_j, cl) < (RTOL_TAB if L >= 32 else 1e-12)
     _, jac_ref, _ = od.fd_jacobian(row, ell[sub], prob, params=params)
     scale = np.abs(jac_ref).max(axis=2, keepdims=True)
     assert (np.abs(jac[:, :, sub] - jac_ref) / scale).max() < 1e-6
