@@ -1,9 +1,12 @@
 // jc_xla_ffi.cc -- XLA FFI custom-call handlers over the C ABI of include/jc_b200.h (north_star: "Python host code
 // calls hand-written sm_100a CUDA kernels through a thin XLA-FFI custom call").
 //
-// NOT built in this repository: the image has neither jax/jaxlib nor the xla/ffi/api headers, so this file cannot
-// be compiled or tested here.  It is the ~100-line shim a maintainer adds next to
-// libjc_b200.so; it only unpacks buffers and forwards to the extern "C" entry points -- no arithmetic lives here.
+// The image has neither jax/jaxlib nor the xla/ffi/api headers, so the real jax.ffi registration cannot run here.
+// What CI does instead (tests/test_ffi_shim.py): compile and link this file against libjc_b200.so with the minimal
+// stand-in header tests/ffi_stub/xla/ffi/api/ffi.h (the Bind() chains are type-checked against the Impl
+// signatures), and -- with -DJC_FFI_TEST_HOOKS -- drive AngularClImpl / AngularClJvpImpl / VjpImpl / GaussianCovImpl
+// through fake buffers on the GPU, comparing with the direct C-ABI calls.  It is the ~100-line shim a maintainer
+// adds next to libjc_b200.so; it only unpacks buffers and forwards to the extern "C" entry points.
 //
 //   g++ -O2 -fPIC -shared -std=c++17 -I$(python -c "import jax; print(jax.ffi.include_dir())") -Iinclude \
 //       integration/jc_xla_ffi.cc -Ljax_cosmo_b200 -ljc_b200 -lcudart -o jax_cosmo_b200/libjc_xla_ffi.so
@@ -12,6 +15,7 @@
 #include <cuda_runtime_api.h>
 
 #include <cstdint>
+#include <string>
 
 #include "jc_b200.h"
 #include "xla/ffi/api/ffi.h"
@@ -77,3 +81,45 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(JcGaussianCov, GaussianCovImpl,
                               ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::Buffer<ffi::F64>>()
                                   .Arg<ffi::Buffer<ffi::F64>>().Attr<int64_t>("plan").Attr<double>("f_sky")
                                   .Ret<ffi::Buffer<ffi::F64>>());
+
+#ifdef JC_FFI_TEST_HOOKS
+// Test hooks (tests/test_ffi_shim.py): call the handlers' Impl functions with buffers built from raw device pointers.
+// Return 0 on success, else the ffi::ErrorCode.
+extern "C" int jc_ffi_test_angular_cl(void* stream, double* cosmo, int64_t B, int64_t ncp, int64_t plan, double* cl, int64_t P,
+                                      int64_t L, uint8_t* ws, int64_t ws_bytes) {
+  ffi::Error e = AngularClImpl(static_cast<cudaStream_t>(stream), ffi::Buffer<ffi::F64>(cosmo, {B, ncp}), plan,
+                               ffi::ResultBuffer<ffi::F64>(ffi::Buffer<ffi::F64>(cl, {B, P, L})),
+                               ffi::ResultBuffer<ffi::U8>(ffi::Buffer<ffi::U8>(ws, {ws_bytes})));
+  return static_cast<int>(e.code());
+}
+extern "C" int jc_ffi_test_angular_cl_jvp(void* stream, double* cosmo, int64_t B, int64_t ncp, double* tangents, int64_t K,
+                                          int64_t plan, double* cl, double* dcl, int64_t P, int64_t L, uint8_t* ws,
+                                          int64_t ws_bytes) {
+  ffi::Error e = AngularClJvpImpl(static_cast<cudaStream_t>(stream), ffi::Buffer<ffi::F64>(cosmo, {B, ncp}),
+                                  ffi::Buffer<ffi::F64>(tangents, {K, ncp}), plan,
+                                  ffi::ResultBuffer<ffi::F64>(ffi::Buffer<ffi::F64>(cl, {B, P, L})),
+                                  ffi::ResultBuffer<ffi::F64>(ffi::Buffer<ffi::F64>(dcl, {B, K, P, L})),
+                                  ffi::ResultBuffer<ffi::U8>(ffi::Buffer<ffi::U8>(ws, {ws_bytes})));
+  return static_cast<int>(e.code());
+}
+extern "C" int jc_ffi_test_vjp(void* stream, double* jac, int64_t B, int64_t K, int64_t P, int64_t L, double* cot, double* grad) {
+  ffi::Error e = VjpImpl(static_cast<cudaStream_t>(stream), ffi::Buffer<ffi::F64>(jac, {B, K, P, L}),
+                         ffi::Buffer<ffi::F64>(cot, {B, P, L}), ffi::ResultBuffer<ffi::F64>(ffi::Buffer<ffi::F64>(grad, {B, K})));
+  return static_cast<int>(e.code());
+}
+extern "C" int jc_ffi_test_gaussian_cov(void* stream, double* cl, int64_t B, int64_t P, int64_t L, double* noise, int64_t T,
+                                        int64_t plan, double f_sky, double* cov) {
+  ffi::Error e = GaussianCovImpl(static_cast<cudaStream_t>(stream), ffi::Buffer<ffi::F64>(cl, {B, P, L}),
+                                 ffi::Buffer<ffi::F64>(noise, {T}), plan, f_sky,
+                                 ffi::ResultBuffer<ffi::F64>(ffi::Buffer<ffi::F64>(cov, {B, P, P, L})));
+  return static_cast<int>(e.code());
+}
+// an invalid plan handle must come back as an ffi::Error, not a crash
+extern "C" int jc_ffi_test_error_path(void) {
+  double x = 0.0;
+  uint8_t w = 0;
+  ffi::Error e = AngularClImpl(nullptr, ffi::Buffer<ffi::F64>(&x, {1, 8}), 0, ffi::ResultBuffer<ffi::F64>(ffi::Buffer<ffi::F64>(&x, {1, 1, 1})),
+                               ffi::ResultBuffer<ffi::U8>(ffi::Buffer<ffi::U8>(&w, {1})));
+  return e.success() ? 0 : (e.message().empty() ? -1 : static_cast<int>(e.code()));
+}
+#endif

@@ -14,8 +14,8 @@
 // becomes a 2 % epilogue of its spectra.  Identical in exact arithmetic to the reference's expression; tests hold it to
 // the reference-generated golden (tests/golden/likelihood_*.npz) and to the explicit-covariance kernel (jc_loglike.cu).
 //
-// One warp per (cosmology, ell) slice, lane = matrix row; the CTA stages 8 consecutive ell of the [P, L] spectra so
-// that global reads are 64-byte segments.  Optionally the same pass returns the cotangent d lnL / d cl[p, l] INCLUDING
+// One warp per (cosmology, ell) slice, matrices in registers (lane = row / column, shuffles for the rest); the CTA
+// stages 8 consecutive ell of the [P, L] spectra so that global reads are 64-byte segments.  Optionally the same pass returns the cotangent d lnL / d cl[p, l] INCLUDING
 // the dependence of the covariance and of its determinant on the spectra,
 //     dlnL/dS = L^-T [ -1/2 (nu X - nu X^2 - (T+1) I) ] L^-1,   X = L^-1 R L^-T,
 // which jc_vjp_f64 contracts with the forward-mode Jacobian: the gradient of the full likelihood that
@@ -30,23 +30,31 @@ __device__ __forceinline__ int pair_idx(int i, int j, int T) {  // angular_cl.py
   return i * T - (i * (i - 1)) / 2 + (j - i);
 }
 
-template <bool GRAD>
+// One warp per (cosmology, ell) slice, TM = T rounded up to 8 / 16 / 24 / 32, every loop fully unrolled.  Lane i keeps
+// ROW i of C (Cholesky) and COLUMN i of the right-hand sides (substitutions) in registers; what a step needs from the
+// other lanes -- column k of L -- is written once to a column-major shared-memory tile and read back by all lanes as
+// broadcast LDS.128 (two entries per instruction).  History: matrices in shared memory with one dependent load-FMA-store
+// per step: 66 k cycles per slice, 45 % of the config-3 step; registers + one 64-bit shuffle per L entry: shuffle bound
+// (2 SHFL per entry, one warp-shuffle per clock and SM), 36 %.  All eliminations are right-looking / column oriented so
+// that the T^2/2 FMAs of a phase are independent; rows and columns beyond T are identity / zero padding.
+template <int TM, bool GRAD>
 __global__ void __launch_bounds__(LT * 32) jc_cl_loglike_kernel(JcDevPlan pl, const double* __restrict__ cl,
                                                                 const double* __restrict__ data, int64_t data_stride,
                                                                 const double* __restrict__ noise, double f_sky,
                                                                 double* __restrict__ partial /* [B, L, 2] */,
                                                                 double* __restrict__ dcl /* [B, P, L] or null */) {
   extern __shared__ __align__(16) double sm[];
-  const int T = pl.T, P = pl.P, L = pl.L, TP = T + 1;
+  const int T = pl.T, P = pl.P, L = pl.L;
+  constexpr int TP = TM + 2;   // column stride of the L tile (even: LDS.128 pairs stay 16-byte aligned)
+  constexpr int TQ = TM + 1;   // row stride of the transpose tile
+  constexpr int PER_WARP = TM * TP + TM + TM * TQ;
   const int b = blockIdx.y, l0 = blockIdx.x * LT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* s_cl = sm;                       // [P][LT] signal
-  double* s_r = s_cl + (size_t)P * LT;     // [P][LT] residual mu - data; later the cotangent tile
-  double* mats = s_r + (size_t)P * LT;
-  const int nmat = GRAD ? 3 : 2;
-  double* Cm = mats + (size_t)warp * nmat * T * TP;  // [T][T+1] C -> L (lower triangle)
-  double* Xm = Cm + (size_t)T * TP;                  // [T][T+1] R -> X
-  double* Mm = Xm + (size_t)T * TP;                  // [T][T+1] (GRAD) M -> dlnL/dS
+  double* s_cl = sm;                    // [P][LT] signal
+  double* s_r = s_cl + (size_t)P * LT;  // [P][LT] residual mu - data; later the cotangent tile
+  double* Lc = s_r + (size_t)P * LT + (size_t)warp * PER_WARP;  // [TM][TP] column-major: Lc[k * TP + j] = L_jk (j > k)
+  double* invd = Lc + TM * TP;                                  // [TM] 1 / L_kk
+  double* St = invd + TM;                                       // [TM][TQ] transpose tile
   const double* clb = cl + (size_t)b * P * L;
   const double* db = data + (size_t)b * data_stride;
   for (int q = threadIdx.x; q < P * LT; q += LT * 32) {
@@ -60,112 +68,127 @@ __global__ void __launch_bounds__(LT * 32) jc_cl_loglike_kernel(JcDevPlan pl, co
   const int l = l0 + warp;
   const bool live = l < L;  // warps past the last ell idle through the CTA barriers below
   const int i = lane;
-  const bool row = live && i < T;
-  double chi2 = 0.0, logdet = 0.0, nu = 1.0;
+  const bool rowl = i < TM;
+  double g[GRAD ? TM : 1];  // (GRAD) column i of d lnL / dS at the end
   if (live) {
-    nu = pl.covnorm[l] * f_sky;  // (2l+1) gradient(l) f_sky, angular_cl.py:139
-    if (row) {
-      for (int j = 0; j < T; ++j) {
-        const int p = i <= j ? pair_idx(i, j, T) : pair_idx(j, i, T);
-        Cm[i * TP + j] = s_cl[p * LT + warp] + (i == j ? noise[i] : 0.0);
-        Xm[i * TP + j] = s_r[p * LT + warp];
+    const double nu = pl.covnorm[l] * f_sky;  // (2l+1) gradient(l) f_sky, angular_cl.py:139
+    double x[TM];
+    double logdet;
+    {
+      double c[TM];
+#pragma unroll
+      for (int j = 0; j < TM; ++j) {
+        const bool in = i < T && j < T;
+        const int p = in ? (i <= j ? pair_idx(i, j, T) : pair_idx(j, i, T)) : 0;
+        const double sv = s_cl[p * LT + warp], rv = s_r[p * LT + warp];
+        c[j] = in ? sv + (i == j ? noise[i] : 0.0) : (i == j ? 1.0 : 0.0);
+        x[j] = in ? rv : 0.0;
       }
-    }
-    __syncwarp();
-    // Cholesky C = L L^T (right-looking, lower triangle in place); an indefinite C gives NaN, as the reference's inverse would.
-    // The slice is latency bound (one warp, dependent steps): no division, square root or logarithm inside the loops --
-    // 1/L_kk by rsqrt is kept on the diagonal (the substitutions multiply by it), log det from a running product.
-    double ld = 0.0, prod = 1.0;
-    for (int k = 0; k < T; ++k) {
-      const double ckk = Cm[k * TP + k];
-      const double inv = rsqrt(ckk);  // 1 / L_kk
-      prod *= ckk;                    // = L_kk^2
-      if ((k & 7) == 7) { ld += log(prod); prod = 1.0; }
-      __syncwarp();
-      if (row && i > k) Cm[i * TP + k] *= inv;
-      if (i == k) Cm[k * TP + k] = inv;
-      __syncwarp();
-      if (row && i > k) {
-        const double lik = Cm[i * TP + k];
-        for (int j = k + 1; j <= i; ++j) Cm[i * TP + j] -= lik * Cm[j * TP + k];
-      }
-      __syncwarp();
-    }
-    ld += log(prod);  // sum_k log L_kk^2
-    logdet = (T + 1) * ld + T * 0.6931471805599453 - P * log(nu);
-    // Y^T = R L^-T: lane j forward-substitutes column j of R (= its own row, R is symmetric) in place
-    if (row) {
-      for (int r = 0; r < T; ++r) {
-        double s0 = Xm[i * TP + r], s1 = 0.0;
-        int m = 0;
-        for (; m + 1 < r; m += 2) {
-          s0 -= Cm[r * TP + m] * Xm[i * TP + m];
-          s1 -= Cm[r * TP + m + 1] * Xm[i * TP + m + 1];
+      // Cholesky C = L L^T, right-looking.  Step k: every lane publishes its (unscaled) entry of column k, all lanes read the
+      // pivot and the entries below it; with t = C_ik / C_kk the update is C_ij -= t C_jk.  An indefinite C gives NaN, as the
+      // reference's inverse would.  log det from the running product of the pivots.
+      double prod = 1.0, ld = 0.0;
+#pragma unroll
+      for (int k = 0; k < TM; ++k) {
+        if (rowl) Lc[k * TP + i] = c[k];
+        __syncwarp();
+        const double dkk = Lc[k * TP + k];
+        const double inv = rsqrt(dkk);
+        prod *= dkk;
+        if ((k & 7) == 7) { ld += log(prod); prod = 1.0; }
+        if (i == 0) invd[k] = inv;
+        const double t = c[k] * (inv * inv);
+        if (((k + 1) & 1) && k + 1 < TM) c[k + 1] = fma(-t, Lc[k * TP + k + 1], c[k + 1]);  // odd first row: one LDS.64
+#pragma unroll
+        for (int j = (k + 2) & ~1; j < TM; j += 2) {  // TM is even: aligned pairs to the end
+          const double2 pr = *reinterpret_cast<const double2*>(Lc + k * TP + j);
+          c[j] = fma(-t, pr.x, c[j]);
+          c[j + 1] = fma(-t, pr.y, c[j + 1]);
         }
-        if (m < r) s0 -= Cm[r * TP + m] * Xm[i * TP + m];
-        Xm[i * TP + r] = (s0 + s1) * Cm[r * TP + r];
       }
+      logdet = (T + 1) * (ld + log(prod)) + T * 0.6931471805599453 - P * log(nu);
+    }
+    // scale the stored columns: Lc[k][i] = L_ik = C_ik^(k) / L_kk (lane i owns row i of the tile)
+    __syncwarp();
+    if (rowl) {
+#pragma unroll
+      for (int k = 0; k < TM; ++k)
+        if (k < i) Lc[k * TP + i] *= invd[k];
     }
     __syncwarp();
-    // X = L^-1 Y^T: lane c forward-substitutes column c in place; X is symmetric
+    // forward substitution L y = v (lane i: its own right-hand side), column oriented
+    auto forward = [&](double (&v)[TM]) {
+#pragma unroll
+      for (int m = 0; m < TM; ++m) {
+        v[m] *= invd[m];
+        if (((m + 1) & 1) && m + 1 < TM) v[m + 1] = fma(-Lc[m * TP + m + 1], v[m], v[m + 1]);
+#pragma unroll
+        for (int r = (m + 2) & ~1; r < TM; r += 2) {
+          const double2 pr = *reinterpret_cast<const double2*>(Lc + m * TP + r);
+          v[r] = fma(-pr.x, v[m], v[r]);
+          v[r + 1] = fma(-pr.y, v[m], v[r + 1]);
+        }
+      }
+    };
+    auto backward = [&](double (&v)[TM]) {  // L^T q = v: q_m final, then eliminated from the rows above with L_mr = Lc[r][m]
+#pragma unroll
+      for (int m = TM - 1; m >= 0; --m) {
+        v[m] *= invd[m];
+#pragma unroll
+        for (int r = 0; r < m; ++r) v[r] = fma(-Lc[r * TP + m], v[m], v[r]);
+      }
+    };
+    auto transpose = [&](double (&v)[TM]) {  // lane i: v[r] = M[r][i]  ->  v[r] = M[i][r]
+      __syncwarp();
+      if (rowl) {
+#pragma unroll
+        for (int r = 0; r < TM; ++r) St[r * TQ + i] = v[r];
+      }
+      __syncwarp();
+      if (rowl) {
+#pragma unroll
+        for (int r = 0; r < TM; ++r) v[r] = St[i * TQ + r];
+      }
+    };
+    forward(x);    // column i of Y = L^-1 R
+    transpose(x);  // column i of Y^T
+    forward(x);    // column i of X = L^-1 R L^-T (symmetric)
     double ss = 0.0;
-    if (row) {
-      for (int r = 0; r < T; ++r) {
-        double s0 = Xm[r * TP + i], s1 = 0.0;
-        int m = 0;
-        for (; m + 1 < r; m += 2) {
-          s0 -= Cm[r * TP + m] * Xm[m * TP + i];
-          s1 -= Cm[r * TP + m + 1] * Xm[(m + 1) * TP + i];
-        }
-        if (m < r) s0 -= Cm[r * TP + m] * Xm[m * TP + i];
-        const double x = (s0 + s1) * Cm[r * TP + r];
-        Xm[r * TP + i] = x;
-        ss += x * x;
-      }
-    }
+#pragma unroll
+    for (int r = 0; r < TM; ++r) ss = fma(x[r], x[r], ss);
+    if (!rowl) ss = 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    chi2 = 0.5 * nu * ss;
-    __syncwarp();
-    if (GRAD) {
-      // M = -1/2 (nu X - nu X^2 - (T+1) I); lane i forms row i
-      if (row) {
-        for (int j = 0; j < T; ++j) {
-          double x2 = 0.0;
-          for (int m = 0; m < T; ++m) x2 += Xm[i * TP + m] * Xm[m * TP + j];
-          Mm[i * TP + j] = -0.5 * (nu * (Xm[i * TP + j] - x2) - (i == j ? (double)(T + 1) : 0.0));
-        }
-      }
-      __syncwarp();
-      // Q = L^-T M: lane c back-substitutes column c in place
-      if (row) {
-        for (int r = T - 1; r >= 0; --r) {
-          double s = Mm[r * TP + i];
-          for (int m = r + 1; m < T; ++m) s -= Cm[m * TP + r] * Mm[m * TP + i];
-          Mm[r * TP + i] = s * Cm[r * TP + r];  // the diagonal holds 1 / L_rr
-        }
-      }
-      __syncwarp();
-      // G = Q L^-1 (symmetric) = L^-T Q^T: lane c back-substitutes row c of Q in place
-      if (row) {
-        for (int r = T - 1; r >= 0; --r) {
-          double s = Mm[i * TP + r];
-          for (int m = r + 1; m < T; ++m) s -= Cm[m * TP + r] * Mm[i * TP + m];
-          Mm[i * TP + r] = s * Cm[r * TP + r];
-        }
-      }
-      __syncwarp();
-    }
     if (lane == 0) {
-      partial[((size_t)b * L + l) * 2 + 0] = chi2;
+      partial[((size_t)b * L + l) * 2 + 0] = 0.5 * nu * ss;
       partial[((size_t)b * L + l) * 2 + 1] = logdet;
     }
+    if constexpr (GRAD) {
+      // column i of M = -1/2 (nu X - nu X^2 - (T+1) I) inside the T x T block, 0 in the padding; X through the tile
+      __syncwarp();
+      if (rowl) {
+#pragma unroll
+        for (int r = 0; r < TM; ++r) St[r * TQ + i] = x[r];  // St[r][i] = X[r][i]
+      }
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < TM; ++r) {
+        double x2 = 0.0;
+#pragma unroll
+        for (int m = 0; m < TM; ++m) x2 = fma(St[r * TQ + m], x[m], x2);  // sum_m X[r][m] X[m][i]
+        g[r] = (i < T && r < T) ? -0.5 * (nu * (x[r] - x2) - (i == r ? (double)(T + 1) : 0.0)) : 0.0;
+      }
+      backward(g);   // column i of Q = L^-T M
+      transpose(g);  // column i of Q^T
+      backward(g);   // column i of dlnL/dS = L^-T M L^-1 (symmetric)
+    }
   }
-  if (GRAD) {
+  if constexpr (GRAD) {
     __syncthreads();  // every warp has read its residual column of s_r: reuse the tile for the cotangent
-    if (row) {
-      for (int j = i; j < T; ++j)  // d lnL / d cl[(i,j)] : both S_ij and S_ji move with an off-diagonal spectrum
-        s_r[pair_idx(i, j, T) * LT + warp] = (i == j ? 1.0 : 2.0) * Mm[i * TP + j];
+    if (live && i < T) {
+#pragma unroll
+      for (int r = 0; r < TM; ++r)  // d lnL / d cl[(r,i)], r <= i: both S_ri and S_ir move with an off-diagonal spectrum
+        if (r <= i && r < T) s_r[pair_idx(r, i, T) * LT + warp] = (r == i ? 1.0 : 2.0) * g[r];
     }
     __syncthreads();
     double* ob = dcl + (size_t)b * P * L;
@@ -205,19 +228,26 @@ extern "C" int jc_gaussian_cl_loglike_f64(const jc_plan* plan, const double* cl_
   JcDeviceGuard guard(plan->device);
   JC_CUDA_TRY(guard.status);
   cudaStream_t s = (cudaStream_t)stream;
-  const int nmat = dcl_dev ? 3 : 2;
-  const size_t smem = ((size_t)2 * pl.P * LT + (size_t)LT * nmat * pl.T * (pl.T + 1)) * sizeof(double);
-  static unsigned long long attr_done = 0;
-  JC_ONCE_PER_DEVICE(attr_done, {
-    cudaFuncSetAttribute(jc_cl_loglike_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(jc_cl_loglike_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  });
+  const int TM = (pl.T + 7) & ~7;
+  const size_t smem = ((size_t)2 * pl.P * LT + (size_t)LT * (TM * (TM + 2) + TM + TM * (TM + 1))) * sizeof(double);
   if (smem > 200 * 1024) return JC_ERR_UNSUPPORTED;
   const dim3 grid((pl.L + LT - 1) / LT, (unsigned)n_cosmo);
-  if (dcl_dev)
-    jc_cl_loglike_kernel<true><<<grid, LT * 32, smem, s>>>(pl, cl_dev, data_dev, data_stride, noise_dev, f_sky, scratch_dev, dcl_dev);
-  else
-    jc_cl_loglike_kernel<false><<<grid, LT * 32, smem, s>>>(pl, cl_dev, data_dev, data_stride, noise_dev, f_sky, scratch_dev, nullptr);
+#define JC_LL_LAUNCH(TM_, GRAD_)                                                                                              \
+  do {                                                                                                                        \
+    static unsigned long long done_ = 0;                                                                                      \
+    JC_ONCE_PER_DEVICE(done_, cudaFuncSetAttribute(jc_cl_loglike_kernel<TM_, GRAD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                   200 * 1024));                                                              \
+    jc_cl_loglike_kernel<TM_, GRAD_><<<grid, LT * 32, smem, s>>>(pl, cl_dev, data_dev, data_stride, noise_dev, f_sky, scratch_dev, \
+                                                                 dcl_dev);                                                    \
+  } while (0)
+  if (dcl_dev) {
+    switch (TM) { case 8: JC_LL_LAUNCH(8, true); break; case 16: JC_LL_LAUNCH(16, true); break;
+                  case 24: JC_LL_LAUNCH(24, true); break; default: JC_LL_LAUNCH(32, true); break; }
+  } else {
+    switch (TM) { case 8: JC_LL_LAUNCH(8, false); break; case 16: JC_LL_LAUNCH(16, false); break;
+                  case 24: JC_LL_LAUNCH(24, false); break; default: JC_LL_LAUNCH(32, false); break; }
+  }
+#undef JC_LL_LAUNCH
   jc_cl_loglike_sum_kernel<<<(unsigned)((n_cosmo + 127) / 128), 128, 0, s>>>(scratch_dev, n_cosmo, pl.L, include_logdet, loglike_dev);
   JC_CUDA_TRY(cudaGetLastError());
   return JC_OK;
