@@ -38,6 +38,36 @@ N_HF_R = 256  # power.py:93
 
 
 # ----------------------------------------------------------------------------------------------
+# complex-step support (oracle/derivatives.py::cs_jacobian)
+# ----------------------------------------------------------------------------------------------
+# The derivative oracle evaluates this module at theta + i h e_k (h = 1e-30): every analytic operation carries the
+# directional derivative in the imaginary part to machine precision, and every DECISION -- nearest-node / bracket
+# indices, clips, abs, sign -- is taken on the real part with the derivative following the selected branch, which is
+# exactly the "frozen-index" derivative jax.jacfwd returns for the reference.  For real input the helpers
+# below are numpy's own functions, so the real path (pinned by tests/golden/) is unchanged.
+def _clip(x, lo, hi):
+    if not np.iscomplexobj(x):
+        return np.clip(x, lo, hi)
+    xr = np.real(x)
+    out = np.array(x, dtype=np.complex128, copy=True)
+    if lo is not None:
+        out = np.where(xr < np.real(lo), lo, out)
+    if hi is not None:
+        out = np.where(xr > np.real(hi), hi, out)
+    return out
+
+
+def _abs(x):
+    if not np.iscomplexobj(x):
+        return np.abs(x)
+    return np.where(np.real(x) < 0, -x, x)
+
+
+def _scalar(v):
+    return complex(v) if np.iscomplexobj(v) and np.imag(v) != 0 else float(np.real(v))
+
+
+# ----------------------------------------------------------------------------------------------
 # scipy/ helpers
 # ----------------------------------------------------------------------------------------------
 def simps_weights(N):
@@ -70,18 +100,20 @@ def romb_weights(divmax=7):
 def interp(x, xp, fp):
     """scipy/interpolate.py:12-37 verbatim semantics (nearest node, neighbour by sign rule,
     linear inter/extrapolation anchored at the nearest node).  Brute-force argmin in chunks."""
-    x = np.atleast_1d(np.asarray(x, dtype=np.float64))
+    x = np.atleast_1d(np.asarray(x))
     shp = x.shape
     x = x.ravel()
     n = len(xp)
-    out = np.empty_like(x)
+    out = np.empty(x.shape, dtype=np.result_type(x, xp, fp, np.float64))
     step = 1 << 15
+    xpr = np.real(xp)  # decisions on real parts (complex-step mode); identity for real tables
     for s in range(0, x.size, step):
         xs = x[s:s + step]
-        ind = np.argmin((xs[:, None] - xp[None, :]) ** 2, axis=1)
+        xsr = np.real(xs)
+        ind = np.argmin((xsr[:, None] - xpr[None, :]) ** 2, axis=1)
         ind = np.clip(ind, 1, n - 2)
         xi = xp[ind]
-        sgn = np.sign(np.clip(xs, xp[1], xp[-2]) - xi)
+        sgn = np.sign(np.clip(xsr, xpr[1], xpr[-2]) - xpr[ind])
         d = np.where(sgn >= 0, 1, -1)  # copysign(1, s) with s integer: s==0 -> +1
         a = (fp[ind + d] - fp[ind]) / (xp[ind + d] - xp[ind])
         b = fp[ind] - a * xp[ind]
@@ -119,8 +151,8 @@ class Cosmo:
 
     def __init__(self, row):
         (self.Omega_c, self.Omega_b, self.h, self.n_s, self.sigma8, self.Omega_k, self.w0,
-         self.wa) = [float(v) for v in row[:8]]
-        self.gamma = float(row[8]) if len(row) > 8 else None
+         self.wa) = [_scalar(v) for v in row[:8]]
+        self.gamma = _scalar(row[8]) if len(row) > 8 else None
         self.Omega_m = self.Omega_b + self.Omega_c
         self.Omega_de = (1.0 - self.Omega_k) - self.Omega_m
 
@@ -195,7 +227,7 @@ def growth_table(c):
         om, ode = Omega_m_a(c, x), Omega_de_a(c, x)
         q = (2.0 - 0.5 * (om + (1.0 + 3.0 * w_de(c, x)) * ode)) / x
         r = 1.5 * om / x / x
-        M = np.zeros(x.shape + (2, 2))
+        M = np.zeros(x.shape + (2, 2), dtype=np.result_type(r, np.float64))
         M[..., 0, 1] = 1.0
         M[..., 1, 0] = r
         M[..., 1, 1] = -q
@@ -255,11 +287,11 @@ class Background:
 
     def chi(self, a, fast=True):  # background.py:240-242
         f = interp_fast if fast else interp
-        return np.clip(f(np.atleast_1d(a), self.atab, self.chitab), 0.0, None)
+        return _clip(f(np.atleast_1d(a), self.atab, self.chitab), 0.0, None)
 
     def growth(self, a, fast=True):  # background.py:488
         f = interp_fast if fast else interp
-        return np.clip(f(np.atleast_1d(a), self.ag, self.gtab), 0.0, 1.0)
+        return _clip(f(np.atleast_1d(a), self.ag, self.gtab), 0.0, 1.0)
 
     def growth_rate(self, a):  # background.py:401-440, 491-512, 551-584
         a = np.atleast_1d(np.asarray(a, dtype=np.float64))
@@ -269,7 +301,7 @@ class Background:
         return interp(a, atab, ftab)
 
     def a_of_chi(self, chi):  # background.py:245-267: interp() on the DECREASING chi table (its neighbour rule as written)
-        return interp(np.atleast_1d(np.asarray(chi, dtype=np.float64)), self.chitab, self.atab)
+        return interp(np.atleast_1d(np.asarray(chi)), self.chitab, self.atab)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -382,14 +414,15 @@ class Power:
         sig = g2[:, None] * S[None, :]  # decreasing in r
         n = N_HF_R
         # interp(1.0, xp=sig, fp=logr), scipy/interpolate.py:25-37, per a (quirk A.9-1)
-        ind = np.clip(np.argmin((1.0 - sig) ** 2, axis=1), 1, n - 2)
+        sigr = np.real(sig)  # root index and neighbour are decided on values (complex-step: real parts)
+        ind = np.clip(np.argmin((1.0 - sigr) ** 2, axis=1), 1, n - 2)
         rows = np.arange(len(a))
         xi = sig[rows, ind]
-        xq = np.minimum(np.maximum(1.0, sig[:, 1]), sig[:, n - 2])  # clip(x, xp[1], xp[-2])
-        d = np.where(np.sign(xq - xi) >= 0, 1, -1)
+        xq = np.minimum(np.maximum(1.0, sigr[:, 1]), sigr[:, n - 2])  # clip(x, xp[1], xp[-2])
+        d = np.where(np.sign(xq - np.real(xi)) >= 0, 1, -1)
         m = (logr[ind + d] - logr[ind]) / (sig[rows, ind + d] - xi)
         root = m * 1.0 + (logr[ind] - m * xi)
-        k_nl = 1.0 / np.clip(np.exp(root), 1e-6, None)
+        k_nl = 1.0 / _clip(np.exp(root), 1e-6, None)
         y = np.outer(k, 1.0 / k_nl)  # [257, na]
         res = (wk * d2)[:, None] * np.exp(-(y ** 2)) * g2[None, :]
         r0 = np.sum(2 * res * y ** 2, axis=0)
@@ -425,7 +458,7 @@ class Power:
                            + 0.2279 * om_de * (1 + w))
         co["c_n"] = 10 ** (0.3698 + 2.0404 * n + 0.8161 * n ** 2 + 0.5869 * C)
         co["gamma_n"] = 0.1971 - 0.0843 * n + 0.8460 * C
-        co["alpha_n"] = np.abs(6.0835 + 1.3373 * n - 0.1959 * n ** 2 - 5.5274 * C)
+        co["alpha_n"] = _abs(6.0835 + 1.3373 * n - 0.1959 * n ** 2 - 5.5274 * C)
         co["beta_n"] = (2.0379 - 0.7354 * n + 0.3157 * n ** 2 + 1.2490 * n ** 3
                         + 0.3980 * n ** 4 - 0.1682 * C)
         co["nu_n"] = 10 ** (5.2105 + 3.6902 * n)
@@ -500,7 +533,7 @@ def lensing_efficiency(bg, nzs, z, zmax):
     chi = bg.chi(1.0 / (1.0 + z))
     zp = np.linspace(z, zmax, N_LENS + 1)  # [257, nz]
     chip = bg.chi(1.0 / (1.0 + zp))
-    g = np.clip(chip - chi, 0, None) / np.clip(chip, 1.0, None)
+    g = _clip(chip - chi, 0, None) / _clip(chip, 1.0, None)
     dx = (zmax - z) / N_LENS
     w = simps_weights(N_LENS)[:, None]
     out = []
@@ -519,7 +552,7 @@ def radial_kernels(bg, tracers, z):
     c = bg.c
     a = 1.0 / (1.0 + z)
     Hz = H0 * np.sqrt(Esqr(c, a))
-    R = np.zeros((len(tracers), len(z)))
+    R = np.zeros((len(tracers), len(z)), dtype=np.result_type(Hz, np.float64))
     is_wl = np.zeros(len(tracers), dtype=bool)
     wl_idx = [i for i, t in enumerate(tracers) if t["kind"] == "wl"]
     # lensing efficiency is computed per probe in the reference; all WL tracers sharing the same
@@ -534,7 +567,7 @@ def radial_kernels(bg, tracers, z):
     for i in wl_idx:  # delta_nz source planes (probes.py:53-64): no integral
         if tracers[i]["nz"]["family"] == "delta":
             chis = bg.chi(1.0 / (1.0 + np.array([tracers[i]["nz"]["params"][0]])))
-            R[i] = np.clip(chis - chi, 0, None) / np.clip(chis, 1.0, None) * (1.0 + z) * chi * (
+            R[i] = _clip(chis - chi, 0, None) / _clip(chis, 1.0, None) * (1.0 + z) * chi * (
                 3.0 * H0 ** 2 * c.Omega_m / 2.0 / C_LIGHT)
     for i, t in enumerate(tracers):
         if t["kind"] == "wl":
@@ -577,8 +610,8 @@ def angular_cl(cosmo_row, ell, problem, stages=None):
     z = 1.0 / a - 1.0
     chi = bg.chi(a)
     R, is_wl = radial_kernels(bg, tracers, z)
-    geom = wa * dchioverda(c, a) / np.clip(chi ** 2, 1.0, None) / C_LIGHT ** 2
-    kk = (ell[:, None] + 0.5) / np.clip(chi, 1.0, None)[None, :]  # [L, A]
+    geom = wa * dchioverda(c, a) / _clip(chi ** 2, 1.0, None) / C_LIGHT ** 2
+    kk = (ell[:, None] + 0.5) / _clip(chi, 1.0, None)[None, :]  # [L, A]
     aa = np.broadcast_to(a[None, :], kk.shape)
     if problem["nonlinear"]:
         co = pw.halofit_coeffs(a)

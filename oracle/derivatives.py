@@ -18,9 +18,32 @@ import numpy as np
 
 from oracle import cl_oracle as o
 
+
 PARAM_INDEX = {"Omega_c": 0, "Omega_b": 1, "h": 2, "n_s": 3, "sigma8": 4, "Omega_k": 5, "w0": 6, "wa": 7, "gamma": 8}
 WCDM_PARAMS = ("Omega_c", "Omega_b", "h", "n_s", "sigma8", "w0", "wa")
 
+
+
+def cs_jacobian(cosmo_row, ell, problem, params=None, h=1e-30):
+    """Complex-step derivative of the restatement: d cl / d theta_k = Im cl(theta + i h e_k) / h, exact to rounding (no
+    subtraction, h = 1e-30), with every index / clip / abs decision of oracle/cl_oracle.py taken on real parts --
+    the derivative of the discretised program with its indices frozen, which is what jax.jacfwd gives for the reference
+    (docs/notebooks/jax-cosmo-intro.ipynb:989) and what the CUDA JVP kernels compute.  This is the primary derivative
+    oracle (element-wise, ~1e-13); fd_jacobian below is the independent cross-check.
+    -> (cl [P, L], jac [n_params, P, L])."""
+    row = np.asarray(cosmo_row, dtype=np.float64)
+    if params is None:
+        params = WCDM_PARAMS + (("gamma",) if len(row) > 8 else ())
+    cl0 = o.angular_cl(row, ell, problem)
+    jac = np.empty((len(params),) + cl0.shape)
+    for k, name in enumerate(params):
+        r = row.astype(np.complex128)
+        r[PARAM_INDEX[name]] += 1j * h
+        out = o.angular_cl(r, ell, problem)
+        if np.max(np.abs(out.real - cl0)) > 1e-13 * np.max(np.abs(cl0)):
+            raise RuntimeError("complex-step evaluation changed the real part: a decision was not taken on real parts")
+        jac[k] = out.imag / h
+    return cl0, jac
 
 def _eval(row, ell, problem):
     st = {}
