@@ -257,7 +257,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="N > 1: time the sharded compute only (no exchange)")
-    ap.add_argument("--gather-mode", default="peer", choices=["peer", "nccl", "collective"])
+    ap.add_argument("--gather-mode", default="peer", choices=["peer", "peer_ce", "nccl", "collective"])
+    ap.add_argument("--push-sms", type=int, default=-1, help="SMs of the pusher kernel (gather mode peer)")
     ap.add_argument("--sub-chunk", type=int, default=0, help="cosmologies per compute chunk (K1..K3) of the gather pipeline")
     ap.add_argument("--push-rows", type=int, default=0, help="cosmologies per contraction launch + NVLink push")
     ap.add_argument("--peak-tflops", type=float, default=0.0,
@@ -356,9 +357,12 @@ def main():
     if world > 1 and not args.no_gather:
         sub = args.sub_chunk or DEFAULT_SUB_CHUNK
         push = args.push_rows or DEFAULT_PUSH_ROWS
-        if args.gather_mode != "peer":
+        if args.gather_mode not in ("peer", "peer_ce"):
             sub = args.sub_chunk or push  # the NCCL pipeline exchanges per compute chunk
-        sh = ShardedAngularCl(world * B, scn["ell"], probes, gather_mode=args.gather_mode, sub_chunk=sub, push_rows=push)
+        from jax_cosmo_b200.distributed import DEFAULT_PUSH_SMS
+        push_sms = args.push_sms if args.push_sms >= 0 else DEFAULT_PUSH_SMS
+        sh = ShardedAngularCl(world * B, scn["ell"], probes, gather_mode=args.gather_mode, sub_chunk=sub, push_rows=push,
+                              push_sms=push_sms)
         rows_dev = torch.as_tensor(np.ascontiguousarray(rows_all), device=dev)
         for _ in range(warmup):
             sh(rows_dev)
@@ -380,7 +384,7 @@ def main():
         same = max_over_ranks(0.0 if same else 1.0) == 0.0
         # the exchange alone (no compute): NVLink leg by itself
         ms_x = None
-        if sh.mode == "peer":
+        if sh.mode in ("peer", "peer_ce"):
             for _ in range(2):
                 sh._peer.push(rank * B, B)
                 sh.barrier()
@@ -395,8 +399,13 @@ def main():
             ms_x = max_over_ranks(x0.elapsed_time(x1)) / steps
         bytes_in = (world - 1) * B * P * N_ELL * 8
         n_chunks = -(-B // sub)
-        n_push = (-(-B // push) + 1) if sh.mode == "peer" else n_chunks
-        gather = {"mode": sh.mode, "sub_chunk": sub, "push_rows": push if sh.mode == "peer" else sub, "ms_per_step": ms / steps, "ms_per_step_compute_only": ms_compute / steps,
+        n_push = (-(-B // push) + 1) if sh.mode in ("peer", "peer_ce") else n_chunks
+        aborted = sh._peer.pusher_aborted() if sh._peer is not None else False
+        sub, push = sh.sub_chunk, (sh.push_rows if sh.mode in ("peer", "peer_ce") else sh.sub_chunk)
+        n_chunks = -(-B // sub)
+        n_push = (-(-B // push) + 1) if sh.mode in ("peer", "peer_ce") else n_chunks
+        gather = {"mode": sh.mode, "sub_chunk": sub, "push_rows": push,
+                  "push_sms": sh.push_sms, "pusher_aborted": aborted, "ms_per_step": ms / steps, "ms_per_step_compute_only": ms_compute / steps,
                   "exposed_ms": (ms - ms_compute) / steps, "ratio_vs_compute_only": ms / ms_compute,
                   "bytes_in_per_gpu_per_step": bytes_in, "bytes_out_per_gpu_per_step": bytes_in,
                   "nvlink_in_gbs_overlapped": bytes_in / (ms / steps * 1e-3) / 1e9,

@@ -385,8 +385,13 @@ int jc_sparse_inv_f64(const double* sparse_dev, int32_t P, int32_t L, double* in
 #define JC_IPC_HANDLE_BYTES 64
 #define JC_MAX_RANKS 16
 typedef struct jc_gather jc_gather;
-int jc_gather_create(int32_t rank, int32_t world, int32_t device, size_t bytes, jc_gather** gather_out,
+/* push_sms: 0 = copy-engine transport (cudaMemcpyAsync per slice and peer); > 0 = a persistent pusher kernel on that many
+ * SMs stores every finished slice to all peers with the destinations interleaved (uniform all-to-all NVLink traffic; needed
+ * at 8 GPUs, where many medium-sized copy-engine copies lose 40 % of the link rate); the contraction then leaves those SMs
+ * out of its persistent grid. */
+int jc_gather_create(int32_t rank, int32_t world, int32_t device, size_t bytes, int32_t push_sms, jc_gather** gather_out,
                      unsigned char* ipc_handle_out /* [JC_IPC_HANDLE_BYTES] or NULL */);
+int jc_gather_status(jc_gather* gather, int32_t* pusher_aborted_out); /* synchronous; 1: the pusher timed out waiting */
 void* jc_gather_buffer(const jc_gather* gather); /* this rank's device buffer */
 int jc_gather_connect_ipc(jc_gather* gather, const unsigned char* ipc_handles /* [world][JC_IPC_HANDLE_BYTES] */);
 int jc_gather_connect_local(jc_gather* gather, void* const* buffers /* [world] */, const int32_t* devices /* [world] */);

@@ -32,7 +32,7 @@ SCAL_FIELDS = ["LN13KEQ", "INV13KEQ", "BETA_C", "C14_ALPHA_C", "SH_D", "LNKSILK"
 EXPORTS = ["jc_plan_create", "jc_plan_destroy", "jc_plan_n_tracers", "jc_plan_n_cls", "jc_plan_n_ell", "jc_plan_n_cosmo_params",
            "jc_workspace_bytes", "jc_workspace_layout", "jc_angular_cl_f64", "jc_angular_cl_host_f64",
            "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64", "jc_gaussian_loglike_f64", "jc_gaussian_cl_loglike_f64", "jc_fisher_f64", "jc_vjp_f64", "jc_sparse_bmm_f64", "jc_sparse_inv_f64", "jc_debug_stages_f64", "jc_grid_plan_create", "jc_grid_plan_create_probes", "jc_grid_eval_f64", "jc_grid_background_f64", "jc_a_of_chi_f64", "jc_sigmasqr_f64", "jc_nz_eval_f64",
-           "jc_noise_f64", "jc_gaussian_cov_f64", "jc_gather_create", "jc_gather_buffer", "jc_gather_connect_ipc",
+           "jc_noise_f64", "jc_gaussian_cov_f64", "jc_gather_create", "jc_gather_status", "jc_gather_buffer", "jc_gather_connect_ipc",
            "jc_gather_connect_local", "jc_gather_destroy", "jc_angular_cl_gather_f64", "jc_gather_push_f64", "jc_set_option", "jc_get_option", "jc_profile_enable", "jc_profile_read",
            "jc_fp64_peak_tflops", "jc_debug_math_f64", "jc_status_string",
            "jc_last_cuda_error", "jc_abi_version"]
@@ -132,7 +132,9 @@ def load_library():
         lib.jc_noise_f64.restype = C.c_int
         lib.jc_gaussian_cov_f64.argtypes = [vp, vp, vp, i64, C.c_double, vp, vp]
         lib.jc_gaussian_cov_f64.restype = C.c_int
-        lib.jc_gather_create.argtypes = [i32, i32, i32, C.c_size_t, C.POINTER(vp), C.c_char_p]
+        lib.jc_gather_create.argtypes = [i32, i32, i32, C.c_size_t, i32, C.POINTER(vp), C.c_char_p]
+        lib.jc_gather_status.argtypes = [vp, C.POINTER(i32)]
+        lib.jc_gather_status.restype = C.c_int
         lib.jc_gather_create.restype = C.c_int
         lib.jc_gather_buffer.argtypes = [vp]
         lib.jc_gather_buffer.restype = vp
@@ -763,14 +765,16 @@ class PeerGather:
     """jc_gather: this rank's full-size result buffer [rows_total, P, L], mapped into every peer (see jc_b200.h).
     `handle` is the CUDA IPC handle to exchange; call connect_ipc(all handles in rank order) or connect_local(...)."""
 
-    def __init__(self, plan, rows_total, rank, world):
+    def __init__(self, plan, rows_total, rank, world, push_sms=0):
         import torch
 
         self.plan, self.rank, self.world, self.rows_total = plan, int(rank), int(world), int(rows_total)
+        self.push_sms = int(push_sms)
         nbytes = self.rows_total * plan.P * plan.L * 8
         h = C.c_void_p()
         buf = C.create_string_buffer(64)
-        check(load_library().jc_gather_create(self.rank, self.world, plan.device, nbytes, C.byref(h), buf), "jc_gather_create")
+        check(load_library().jc_gather_create(self.rank, self.world, plan.device, nbytes, self.push_sms, C.byref(h), buf),
+              "jc_gather_create")
         self._h = h
         self.handle = bytes(buf.raw)
         self.ptr = load_library().jc_gather_buffer(h)
@@ -803,6 +807,12 @@ class PeerGather:
         check(load_library().jc_angular_cl_gather_f64(self.plan._h, self._h, cosmo_dev.data_ptr() if n else None, n,
                                                       int(row_offset), int(sub_chunk), int(push_rows), ws.data_ptr(), ws.numel() * 8, stream),
               "jc_angular_cl_gather_f64")
+
+    def pusher_aborted(self):
+        """True if the pusher kernel of the last step timed out waiting for the compute stream (synchronises)."""
+        out = C.c_int32()
+        check(load_library().jc_gather_status(self._h, C.byref(out)), "jc_gather_status")
+        return bool(out.value)
 
     def push(self, row_offset, rows):
         import torch

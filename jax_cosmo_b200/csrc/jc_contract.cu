@@ -433,7 +433,8 @@ void launch_tma(const JcDevPlan& pl, const Ws& ws, double* out, int64_t stride, 
   });
   static int pairing = -1;
   if (pairing < 0) { const char* e = getenv("JC_CONTRACT_PAIRING"); pairing = e ? atoi(e) : 1; }  // tuning knob; measured 5.67 / 5.17 / 5.55 ms for 0 / 1 / 2
-  jc_contract_tma_kernel<KC, TMA_STAGES, JVP><<<chunk < sms ? chunk : sms, TMA_CW * 32, smem, s>>>(pl, ws, out, stride, chunk, pairing);
+  const int avail = sms - pl.reserved_sms > 8 ? sms - pl.reserved_sms : 8;
+  jc_contract_tma_kernel<KC, TMA_STAGES, JVP><<<chunk < avail ? chunk : avail, TMA_CW * 32, smem, s>>>(pl, ws, out, stride, chunk, pairing);
 }
 
 // TMA bulk copies need 16-byte aligned rows on both sides

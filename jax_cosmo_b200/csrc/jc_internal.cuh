@@ -48,6 +48,7 @@ struct JcDevPlan {
   const double* chi_pt_lna;  // [511]
   const double* chi_h6;      // [255]  h_i / 6
   int growth, ncp;           // JC_GROWTH_*; doubles per cosmology / tangent row (8 or 9)
+  int reserved_sms;          // SMs occupied by a concurrent kernel (gather pusher): persistent kernels size their grid without them
   int grid_mode, grid_na;    // grid plan (jc_grid_plan_create): nodes = caller's scale factors, "ell + 1/2" = caller's k
   // growth table quadrature: points p = 2i (node), 2i+1 (a_i + h_i/2; JC_GROWTH_GAMMA: ln a_i + h_i/2 with h in ln a)
   const double* gr_pt_a;     // [255]
@@ -176,7 +177,8 @@ extern int g_contract_cfg;        // jc_set_option("contract_kernel")
 extern double g_jc_contract_eps;  // jc_set_option("contract_eps"): support threshold of the contraction, read at plan creation
 typedef int (*jc_slice_cb)(void* ctx, int64_t first_row, int64_t rows);
 int jc_run_pipeline(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo, double* cl_dev, void* ws_dev,
-                    size_t ws_bytes, cudaStream_t s, int64_t chunk_cap, int64_t slice, jc_slice_cb cb, void* ctx);
+                    size_t ws_bytes, cudaStream_t s, int64_t chunk_cap, int64_t slice, jc_slice_cb cb, void* ctx,
+                    int reserved_sms);
 void jc_math_table(double* out288);  // host: tables of the table-driven exp / log (jc_math.cuh)
 int jc_pipeline_init();  // one-time function attributes (dynamic shared memory opt-in)
 

@@ -1,5 +1,8 @@
 // jc_pipeline.cu -- workspace layout and the stream-ordered launcher of the K1..K4 pipeline
 // (kernels: jc_setup.cu, jc_tracers.cu, jc_power.cu, jc_contract.cu; overview in jc_internal.cuh).
+#include <utility>
+#include <vector>
+
 #include "jc_internal.cuh"
 
 namespace {
@@ -120,14 +123,37 @@ extern "C" int jc_workspace_layout(const jc_plan* plan, size_t ws_bytes, jc_ws_l
 // launch (the gather records an event there and starts the peer copies of those rows): the exchange granularity is
 // then independent of the compute chunk, whose K1..K3 keep full waves.  The last slice of the batch is halved so that
 // the copy left exposed at the end of the step is short.
+// The (first row, rows) slices jc_run_pipeline will launch the contraction for, in order (same rule as below).
+int jc_pipeline_slices(const jc_plan* plan, int64_t n_cosmo, size_t ws_bytes, int64_t chunk_cap, int64_t slice,
+                       std::vector<std::pair<int64_t, int64_t>>* out) {
+  jc_ws_layout lo;
+  int st = jc_workspace_layout(plan, ws_bytes, &lo);
+  if (st != JC_OK) return st;
+  const int64_t cap = (chunk_cap > 0 && chunk_cap < lo.chunk) ? chunk_cap : lo.chunk;
+  for (int64_t c0 = 0; c0 < n_cosmo; c0 += cap) {
+    const int64_t chunk = (n_cosmo - c0) < cap ? (n_cosmo - c0) : cap;
+    if (slice <= 0) { out->push_back({c0, chunk}); continue; }
+    const bool last_chunk = c0 + chunk >= n_cosmo;
+    for (int64_t s0 = 0; s0 < chunk;) {
+      int64_t ns = (chunk - s0) < slice ? (chunk - s0) : slice;
+      if (last_chunk && s0 + ns >= chunk && ns > slice / 2 && ns >= 2) ns = (ns + 1) / 2;
+      out->push_back({c0 + s0, ns});
+      s0 += ns;
+    }
+  }
+  return JC_OK;
+}
+
 int jc_run_pipeline(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo, double* cl_dev, void* ws_dev,
-                    size_t ws_bytes, cudaStream_t s, int64_t chunk_cap, int64_t slice, jc_slice_cb cb, void* ctx) {
+                    size_t ws_bytes, cudaStream_t s, int64_t chunk_cap, int64_t slice, jc_slice_cb cb, void* ctx,
+                    int reserved_sms) {
   if (!plan || plan->d.grid_mode || !cosmo_dev || !cl_dev || !ws_dev || n_cosmo < 1) return JC_ERR_INVALID;
   JcDeviceGuard guard(plan->device);  // a null stream handle means the CURRENT device's default stream
   jc_ws_layout lo;
   int st = jc_workspace_layout(plan, ws_bytes, &lo);
   if (st != JC_OK) return st;
-  const JcDevPlan& pl = plan->d;
+  JcDevPlan pl = plan->d;
+  pl.reserved_sms = reserved_sms;  // SMs held by a concurrently running kernel (the gather's pusher): persistent grids leave them out
   double* base = (double*)ws_dev;
   Ws ws;
   resolve(lo, base, 0, &ws);
@@ -179,7 +205,7 @@ int jc_run_pipeline(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosm
 
 extern "C" int jc_angular_cl_f64(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo,
                                  double* cl_dev, void* ws_dev, size_t ws_bytes, void* stream) {
-  return jc_run_pipeline(plan, cosmo_dev, n_cosmo, cl_dev, ws_dev, ws_bytes, (cudaStream_t)stream, 0, 0, nullptr, nullptr);
+  return jc_run_pipeline(plan, cosmo_dev, n_cosmo, cl_dev, ws_dev, ws_bytes, (cudaStream_t)stream, 0, 0, nullptr, nullptr, 0);
 }
 
 // ---------------------------------------------------------------------------------------------------

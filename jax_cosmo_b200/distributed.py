@@ -10,9 +10,13 @@ Gather modes (`gather_mode`):
 
   "peer"        every rank owns a full-size `[B, P, L]` buffer mapped into all ranks (CUDA IPC); the rank computes its
                 rows straight into the final layout -- K1..K3 on chunks of `sub_chunk` cosmologies, the contraction per
-                `push_rows` cosmologies -- and the copy engines push each finished slice into the peers' buffers over
-                NVLink while the following slices compute (csrc/jc_gather.cu).  No SM is taken from the FP64 kernels;
-                only the last (halved) slice's push is exposed.  Default on CUDA.
+                `push_rows` cosmologies -- and a persistent pusher kernel on `push_sms` SMs stores each finished slice
+                into all peers' buffers over NVLink (st.global on the mapped peer pointers, destinations interleaved)
+                while the following slices compute (csrc/jc_gather.cu).  Only the last (halved) slice's push is
+                exposed.  Default on CUDA.
+  "peer_ce"     the same pipeline with the copy engines doing the pushes (one cudaMemcpyAsync per slice and peer): no
+                SM is taken from the FP64 kernels; fully hidden at 2 and 4 GPUs, but at 8 GPUs the ~100 medium-sized
+                copies per step only reach 58 % of the NVLink rate.
   "nccl"        the same sub-chunk pipeline with one grouped NCCL send/recv per sub-chunk on a side stream, received
                 straight into the final layout (the library baseline the peer path is measured against).
   "collective"  one `all_gather` after the compute (any backend; what the CPU / gloo tests exercise).
@@ -23,6 +27,7 @@ import numpy as np
 
 DEFAULT_SUB_CHUNK = 1184  # compute chunk of K1..K3: 2 x 592 = two full waves of the setup kernel (148 SMs x 4 CTAs)
 DEFAULT_PUSH_ROWS = 592   # cosmologies per contraction launch + NVLink push: 4 per persistent contraction CTA
+DEFAULT_PUSH_SMS = 12     # SMs of the pusher kernel ("peer" mode); "peer_ce" uses the copy engines instead
 
 
 def shard_bounds(n_rows, world_size, rank):
@@ -51,7 +56,7 @@ class ShardedAngularCl:
     overwritten by the next call."""
 
     def __init__(self, n_rows, ell, probes, transfer_fn=None, nonlinear_fn=None, group=None, gather_mode="auto",
-                 sub_chunk=DEFAULT_SUB_CHUNK, growth=0, push_rows=DEFAULT_PUSH_ROWS):
+                 sub_chunk=DEFAULT_SUB_CHUNK, growth=0, push_rows=DEFAULT_PUSH_ROWS, push_sms=DEFAULT_PUSH_SMS):
         import torch
         import torch.distributed as dist
 
@@ -72,15 +77,24 @@ class ShardedAngularCl:
             gather_mode = "peer" if self.world > 1 else "none"
         if self.world == 1:
             gather_mode = "none"
-        if gather_mode not in ("peer", "nccl", "collective", "none"):
+        if gather_mode not in ("peer", "peer_ce", "nccl", "collective", "none"):
             raise ValueError("gather_mode %r" % (gather_mode,))
         self.mode = gather_mode
+        self.push_sms = int(push_sms) if gather_mode == "peer" else 0
+        if self.push_sms > 0:
+            # the pusher kernel holds `push_sms` SMs for the whole step: size the contraction slices and the compute chunks in
+            # whole waves of the remaining SMs (4 cosmologies per persistent contraction CTA, 8 per compute chunk)
+            avail = max(torch.cuda.get_device_properties(self.device).multi_processor_count - self.push_sms, 8)
+            if push_rows == DEFAULT_PUSH_ROWS:
+                self.push_rows = 4 * avail
+            if sub_chunk == DEFAULT_SUB_CHUNK:
+                self.sub_chunk = 8 * avail
         self._flag = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._peer = None
         self._side = None
         shape = (self.world * self.per, self.plan.P, self.plan.L)
-        if self.mode == "peer":
-            self._peer = _native.PeerGather(self.plan, shape[0], self.rank, self.world)
+        if self.mode in ("peer", "peer_ce"):
+            self._peer = _native.PeerGather(self.plan, shape[0], self.rank, self.world, push_sms=self.push_sms)
             handles = [None] * self.world
             dist.all_gather_object(handles, self._peer.handle, group=group)
             self._peer.connect_ipc(handles)
@@ -125,7 +139,7 @@ class ShardedAngularCl:
         n = shard.shape[0]
         if self.mode == "none":
             self.compute_shard(shard)
-        elif self.mode == "peer":
+        elif self.mode in ("peer", "peer_ce"):
             self._peer.compute_and_push(shard, self.lo, self.sub_chunk, self.push_rows)
             self.barrier()
         elif self.mode == "collective":

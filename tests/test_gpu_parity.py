@@ -404,7 +404,7 @@ def _nccl_worker(rank, world, port, out_dir):
         scn = sc.scenario("d", sc.PLANCK15, sc.ELL_CFG2[::10], [sc.sources(5, 2.0), sc.lenses(5, 2.0)])
         probes = sc.build_probes(scn, jcm)
         rows = sc.config5_cosmologies(37)  # ragged: 19 + 18 rows
-        for mode in ("peer", "nccl", "collective"):
+        for mode in ("peer", "peer_ce", "nccl", "collective"):
             cl, (lo, hi) = angular_cl_sharded(rows, scn["ell"], probes, gather=True, gather_mode=mode, sub_chunk=7)
             np.save(os.path.join(out_dir, "g_%s_%d.npy" % (mode, rank)), cl.cpu().numpy())
         # persistent evaluator, called twice on different batches (buffer reuse, second step after the barrier)
@@ -437,7 +437,7 @@ def test_sharded_nccl_two_gpus(jc, torch_cuda, tmp_path):
     scn = sc.scenario("d", sc.PLANCK15, sc.ELL_CFG2[::10], [sc.sources(5, 2.0), sc.lenses(5, 2.0)])
     ref = jc.cl.angular_cl_batch(sc.config5_cosmologies(37), scn["ell"], sc.build_probes(scn, jc))
     for r in range(2):
-        for tag in ("peer", "nccl", "collective", "again"):
+        for tag in ("peer", "peer_ce", "nccl", "collective", "again"):
             assert np.array_equal(np.load(tmp_path / ("g_%s_%d.npy" % (tag, r))), ref), (tag, r)
         assert np.array_equal(np.load(tmp_path / ("g_one_%d.npy" % r)), ref[:1]), r
 
@@ -455,19 +455,21 @@ def test_peer_gather_two_devices_one_process(jc, torch_cuda):
     ref = jc.cl.angular_cl_batch(rows, scn["ell"], probes)
     plans = [_native.get_plan(probes, scn["ell"], None, None, device=d) for d in range(2)]
     per = 11
-    gathers = [_native.PeerGather(plans[d], 2 * per, d, 2) for d in range(2)]
-    for g in gathers:
-        g.connect_local(gathers)
-    for d in range(2):
-        lo, hi = d * per, min((d + 1) * per, len(rows))
-        with torch.cuda.device(d):
-            gathers[d].compute_and_push(torch.as_tensor(rows[lo:hi], device="cuda:%d" % d), lo, 4, 3)
-    for d in range(2):
-        torch.cuda.synchronize(d)
-    for d in range(2):
-        assert np.array_equal(gathers[d].full[:len(rows)].cpu().numpy(), ref), d
-    for g in gathers:
-        g.close()
+    for push_sms in (0, 4):  # copy engines / pusher kernel (st.global on the peer's mapped buffer)
+        gathers = [_native.PeerGather(plans[d], 2 * per, d, 2, push_sms=push_sms) for d in range(2)]
+        for g in gathers:
+            g.connect_local(gathers)
+        for d in range(2):
+            lo, hi = d * per, min((d + 1) * per, len(rows))
+            with torch.cuda.device(d):
+                gathers[d].compute_and_push(torch.as_tensor(rows[lo:hi], device="cuda:%d" % d), lo, 4, 3)
+        for d in range(2):
+            torch.cuda.synchronize(d)
+        for d in range(2):
+            assert np.array_equal(gathers[d].full[:len(rows)].cpu().numpy(), ref), (push_sms, d)
+            assert not gathers[d].pusher_aborted()
+        for g in gathers:
+            g.close()
 
 
 def test_sharded_single_process(jc, torch_cuda):
