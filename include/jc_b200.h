@@ -398,10 +398,13 @@ int jc_gather_connect_local(jc_gather* gather, void* const* buffers /* [world] *
 int jc_gather_destroy(jc_gather* gather);
 /* cosmo_dev [n_cosmo, 8|9] = this rank's rows, which land in rows [row_offset, row_offset + n_cosmo) of every buffer;
  * sub_chunk = cosmologies per compute chunk of K1..K3 (< 1: as many as the workspace holds), push_rows = cosmologies per
- * contraction launch + push (< 1: the whole chunk); ws as for jc_angular_cl_f64. */
+ * contraction launch + push (< 1: the whole chunk); ws as for jc_angular_cl_f64.  equal_shards != 0: every rank calls with
+ * the same n_cosmo / sub_chunk / push_rows (B divisible by the number of ranks) -- the copy-engine transport then
+ * runs the pushes of a slice in lockstep on all ranks (a flag barrier per slice by stream memory operations; every
+ * rank MUST make the call, a missing one blocks the others' copy streams). */
 int jc_angular_cl_gather_f64(const jc_plan* plan, jc_gather* gather, const double* cosmo_dev, int64_t n_cosmo,
-                             int64_t row_offset, int64_t sub_chunk, int64_t push_rows, void* ws_dev, size_t ws_bytes,
-                             void* stream);
+                             int64_t row_offset, int64_t sub_chunk, int64_t push_rows, int32_t equal_shards, void* ws_dev,
+                             size_t ws_bytes, void* stream);
 /* the exchange alone: push rows [row_offset, row_offset + rows) (row_bytes each) of the local buffer to every peer */
 int jc_gather_push_f64(jc_gather* gather, size_t row_bytes, int64_t row_offset, int64_t rows, void* stream);
 

@@ -144,7 +144,7 @@ def load_library():
         lib.jc_gather_connect_local.restype = C.c_int
         lib.jc_gather_destroy.argtypes = [vp]
         lib.jc_gather_destroy.restype = C.c_int
-        lib.jc_angular_cl_gather_f64.argtypes = [vp, vp, vp, i64, i64, i64, i64, vp, C.c_size_t, vp]
+        lib.jc_angular_cl_gather_f64.argtypes = [vp, vp, vp, i64, i64, i64, i64, i32, vp, C.c_size_t, vp]
         lib.jc_angular_cl_gather_f64.restype = C.c_int
         lib.jc_gather_push_f64.argtypes = [vp, C.c_size_t, i64, i64, vp]
         lib.jc_gather_push_f64.restype = C.c_int
@@ -792,7 +792,7 @@ class PeerGather:
         devs = (C.c_int32 * self.world)(*[p.plan.device for p in peers])
         check(load_library().jc_gather_connect_local(self._h, ptrs, devs), "jc_gather_connect_local")
 
-    def compute_and_push(self, cosmo_dev, row_offset, sub_chunk, push_rows=0, workspace=None):
+    def compute_and_push(self, cosmo_dev, row_offset, sub_chunk, push_rows=0, workspace=None, equal_shards=False):
         """K1..K4 of this rank's rows into rows [row_offset, ...) of the local buffer: K1..K3 on chunks of `sub_chunk`
         cosmologies, the contraction per `push_rows` cosmologies, every finished slice pushed to the peers meanwhile.
         Asynchronous on torch's current stream (ordered after the outgoing pushes)."""
@@ -805,7 +805,8 @@ class PeerGather:
         ws = self.plan.workspace(max(min(n, int(sub_chunk) if sub_chunk > 0 else n), 1)) if workspace is None else workspace
         stream = torch.cuda.current_stream(self.plan.device).cuda_stream
         check(load_library().jc_angular_cl_gather_f64(self.plan._h, self._h, cosmo_dev.data_ptr() if n else None, n,
-                                                      int(row_offset), int(sub_chunk), int(push_rows), ws.data_ptr(), ws.numel() * 8, stream),
+                                                      int(row_offset), int(sub_chunk), int(push_rows), 1 if equal_shards else 0, ws.data_ptr(),
+                                                      ws.numel() * 8, stream),
               "jc_angular_cl_gather_f64")
 
     def pusher_aborted(self):

@@ -57,7 +57,36 @@ struct jc_gather {
   int push_sms;        // > 0: pusher-kernel transport on that many SMs
   unsigned* flag_dev;  // [0] slices whose contraction has finished, [1] pusher gave up waiting (error)
   bool warmed;         // the pipeline's kernels are loaded on this device (see jc_angular_cl_gather_f64)
+  // copy-engine transport in lockstep: per slice a flag barrier over all ranks (stream memory operations, no kernel)
+  bool lockstep_ok;    // stream memops available and enabled (JC_GATHER_LOCKSTEP, default 1)
+  int lockstep_min_world;
+  unsigned epoch;      // slices signalled so far (identical on every rank: equal shards, same schedule)
+  unsigned* stage_dev; // [JC_STAGE_WORDS] local words the signal values are copied from
 };
+
+#define JC_SYNC_BYTES 4096  // flag words behind the result buffer: flags[src rank] = slices src has finished computing
+#define JC_STAGE_WORDS 256
+
+typedef int (*jc_memop32_fn)(cudaStream_t, unsigned long long /*CUdeviceptr*/, unsigned, unsigned);
+static jc_memop32_fn g_wait32 = nullptr, g_write32 = nullptr;
+static bool load_memops() {
+  static int state = 0;  // 0 unknown, 1 ok, -1 unavailable
+  if (state == 0) {
+    void *w = nullptr, *r = nullptr;
+    cudaDriverEntryPointQueryResult q1, q2;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &w, cudaEnableDefault, &q1) == cudaSuccess && w &&
+        cudaGetDriverEntryPoint("cuStreamWriteValue32", &r, cudaEnableDefault, &q2) == cudaSuccess && r &&
+        q1 == cudaDriverEntryPointSuccess && q2 == cudaDriverEntryPointSuccess) {
+      g_wait32 = (jc_memop32_fn)w;
+      g_write32 = (jc_memop32_fn)r;
+      state = 1;
+    } else {
+      cudaGetLastError();
+      state = -1;
+    }
+  }
+  return state == 1;
+}
 
 extern "C" int jc_gather_create(int32_t rank, int32_t world, int32_t device, size_t bytes, int32_t push_sms, jc_gather** out,
                                 unsigned char* handle_out) {
@@ -69,8 +98,16 @@ extern "C" int jc_gather_create(int32_t rank, int32_t world, int32_t device, siz
   jc_gather* g = new jc_gather();
   memset(g, 0, sizeof(*g));
   g->rank = rank; g->world = world; g->device = device; g->bytes = bytes;
-  cudaError_t e = cudaMalloc(&g->local, bytes);
+  cudaError_t e = cudaMalloc(&g->local, bytes + JC_SYNC_BYTES);
   if (e != cudaSuccess) { delete g; jc_set_cuda_error(e, "cudaMalloc(gather buffer)"); return JC_ERR_CUDA; }
+  e = cudaMemset((char*)g->local + bytes, 0, JC_SYNC_BYTES);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&g->stage_dev, JC_STAGE_WORDS * sizeof(unsigned));
+  if (e != cudaSuccess) { jc_set_cuda_error(e, "gather sync words"); jc_gather_destroy(g); return JC_ERR_CUDA; }
+  {
+    const char* ls = getenv("JC_GATHER_LOCKSTEP");
+    g->lockstep_ok = (ls ? atoi(ls) != 0 : true) && load_memops();
+    g->lockstep_min_world = (ls && atoi(ls) == 2) ? 2 : 3;  // 2: also with a single peer (tests)
+  }
   g->peer[rank] = g->local;
   g->push_sms = push_sms;
   e = cudaMalloc((void**)&g->flag_dev, 2 * sizeof(unsigned));
@@ -151,6 +188,7 @@ extern "C" int jc_gather_destroy(jc_gather* g) {
   }
   if (g->ev_chunk) cudaEventDestroy(g->ev_chunk);
   if (g->flag_dev) cudaFree(g->flag_dev);
+  if (g->stage_dev) cudaFree(g->stage_dev);
   if (g->local) cudaFree(g->local);
   delete g;
   return JC_OK;
@@ -179,11 +217,41 @@ struct PushCtx {
   int64_t row_offset;
   cudaStream_t s;
   int n_done;
+  bool lockstep;
 };
+// Flag barrier over all ranks on copy stream 0, without a kernel: the value travels as a 4-byte copy-engine copy from a
+// local word (written by cuStreamWriteValue32) into flags[my rank] of every peer, cuStreamWaitValue32 then holds the
+// stream until every peer's word has arrived here.  Equal shards: slice k is the same rows on every rank.
+int lockstep_barrier(jc_gather* g, cudaStream_t st) {
+  const unsigned v = ++g->epoch;
+  unsigned* stage = g->stage_dev + (v % JC_STAGE_WORDS);
+  if (g_write32(st, (unsigned long long)(uintptr_t)stage, v, 0) != 0) return JC_ERR_CUDA;
+  for (int i = 1; i < g->world; ++i) {
+    const int r = (g->rank + i) % g->world;
+    JC_CUDA_TRY(cudaMemcpyAsync((char*)g->peer[r] + g->bytes + 4 * g->rank, stage, 4, cudaMemcpyDeviceToDevice, st));
+  }
+  unsigned* mine = (unsigned*)((char*)g->local + g->bytes);
+  for (int i = 1; i < g->world; ++i) {
+    const int r = (g->rank + i) % g->world;
+    if (g_wait32(st, (unsigned long long)(uintptr_t)(mine + r), v, 1 /* CU_STREAM_WAIT_VALUE_GEQ */) != 0) return JC_ERR_CUDA;
+  }
+  return JC_OK;
+}
 int push_cb(void* p, int64_t first_row, int64_t rows) {
   PushCtx* c = (PushCtx*)p;
   if (c->g->world < 2) return JC_OK;
   JC_CUDA_TRY(cudaEventRecord(c->g->ev_chunk, c->s));
+  if (c->lockstep) {
+    // every rank has finished this slice before anyone pushes it: the 7 copies of the slice then run as the permutations
+    // r -> r+1, r -> r+2, ... on all ranks at once (one sender per receiver at any time) instead of drifting into each other
+    JC_CUDA_TRY(cudaStreamWaitEvent(c->g->copy[0], c->g->ev_chunk, 0));
+    int st = lockstep_barrier(c->g, c->g->copy[0]);
+    if (st != JC_OK) return st;
+    if (c->g->n_streams > 1) {
+      JC_CUDA_TRY(cudaEventRecord(c->g->ev_tail[0], c->g->copy[0]));
+      return push_rows(c->g, c->row_bytes, c->row_offset + first_row, rows, c->g->ev_tail[0]);
+    }
+  }
   return push_rows(c->g, c->row_bytes, c->row_offset + first_row, rows, c->g->ev_chunk);
 }
 
@@ -333,8 +401,8 @@ static int launch_pusher(jc_gather* g, const PushArgs& a, cudaStream_t st) {
 }
 
 extern "C" int jc_angular_cl_gather_f64(const jc_plan* plan, jc_gather* g, const double* cosmo_dev, int64_t n_cosmo,
-                                        int64_t row_offset, int64_t sub_chunk, int64_t push_rows_n, void* ws_dev,
-                                        size_t ws_bytes, void* stream) {
+                                        int64_t row_offset, int64_t sub_chunk, int64_t push_rows_n, int32_t equal_shards,
+                                        void* ws_dev, size_t ws_bytes, void* stream) {
   if (!plan || !g || plan->d.grid_mode || n_cosmo < 0 || row_offset < 0 || (n_cosmo > 0 && (!cosmo_dev || !ws_dev)))
     return JC_ERR_INVALID;
   if (g->world > 1 && !g->connected) return JC_ERR_INVALID;
@@ -379,7 +447,7 @@ extern "C" int jc_angular_cl_gather_f64(const jc_plan* plan, jc_gather* g, const
     JC_CUDA_TRY(cudaStreamWaitEvent(g->copy[0], g->ev_chunk, 0));
     int stp = launch_pusher(g, a, g->copy[0]);
     if (stp != JC_OK) return stp;
-    PushCtx ctx{g, row_bytes, row_offset, s, 0};
+    PushCtx ctx{g, row_bytes, row_offset, s, 0, false};
     int st = jc_run_pipeline(plan, cosmo_dev, n_cosmo, out, ws_dev, ws_bytes, s, sub_chunk, push_rows_n, flag_cb, &ctx, g->push_sms);
     if (st != JC_OK) return st;
     JC_CUDA_TRY(cudaEventRecord(g->ev_tail[0], g->copy[0]));
@@ -387,7 +455,7 @@ extern "C" int jc_angular_cl_gather_f64(const jc_plan* plan, jc_gather* g, const
     return JC_OK;
   }
   if (n_cosmo > 0) {
-    PushCtx ctx{g, row_bytes, row_offset, s, 0};
+    PushCtx ctx{g, row_bytes, row_offset, s, 0, equal_shards != 0 && g->lockstep_ok && g->world >= g->lockstep_min_world};
     int st = jc_run_pipeline(plan, cosmo_dev, n_cosmo, out, ws_dev, ws_bytes, s, sub_chunk, push_rows_n, push_cb, &ctx, 0);
     if (st != JC_OK) return st;
   }

@@ -140,7 +140,8 @@ class ShardedAngularCl:
         if self.mode == "none":
             self.compute_shard(shard)
         elif self.mode in ("peer", "peer_ce"):
-            self._peer.compute_and_push(shard, self.lo, self.sub_chunk, self.push_rows)
+            self._peer.compute_and_push(shard, self.lo, self.sub_chunk, self.push_rows,
+                                        equal_shards=self.n_rows % self.world == 0)
             self.barrier()
         elif self.mode == "collective":
             self.compute_shard(shard)
