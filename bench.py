@@ -257,8 +257,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="N > 1: time the sharded compute only (no exchange)")
-    ap.add_argument("--gather-mode", default="peer", choices=["peer", "peer_ce", "nccl", "collective"])
-    ap.add_argument("--push-sms", type=int, default=-1, help="SMs of the pusher kernel (gather mode peer)")
+    ap.add_argument("--gather-mode", default="peer", choices=["peer", "peer_sm", "nccl", "collective"])
+    ap.add_argument("--push-sms", type=int, default=-1, help="SMs of the pusher kernel (gather mode peer_sm)")
     ap.add_argument("--sub-chunk", type=int, default=0, help="cosmologies per compute chunk (K1..K3) of the gather pipeline")
     ap.add_argument("--push-rows", type=int, default=0, help="cosmologies per contraction launch + NVLink push")
     ap.add_argument("--peak-tflops", type=float, default=0.0,
@@ -357,7 +357,7 @@ def main():
     if world > 1 and not args.no_gather:
         sub = args.sub_chunk or DEFAULT_SUB_CHUNK
         push = args.push_rows or DEFAULT_PUSH_ROWS
-        if args.gather_mode not in ("peer", "peer_ce"):
+        if args.gather_mode not in ("peer", "peer_sm"):
             sub = args.sub_chunk or push  # the NCCL pipeline exchanges per compute chunk
         from jax_cosmo_b200.distributed import DEFAULT_PUSH_SMS
         push_sms = args.push_sms if args.push_sms >= 0 else DEFAULT_PUSH_SMS
@@ -384,7 +384,7 @@ def main():
         same = max_over_ranks(0.0 if same else 1.0) == 0.0
         # the exchange alone (no compute): NVLink leg by itself
         ms_x = None
-        if sh.mode in ("peer", "peer_ce"):
+        if sh.mode in ("peer", "peer_sm"):
             for _ in range(2):
                 sh._peer.push(rank * B, B)
                 sh.barrier()
@@ -399,11 +399,11 @@ def main():
             ms_x = max_over_ranks(x0.elapsed_time(x1)) / steps
         bytes_in = (world - 1) * B * P * N_ELL * 8
         n_chunks = -(-B // sub)
-        n_push = (-(-B // push) + 1) if sh.mode in ("peer", "peer_ce") else n_chunks
+        n_push = (-(-B // push) + 1) if sh.mode in ("peer", "peer_sm") else n_chunks
         aborted = sh._peer.pusher_aborted() if sh._peer is not None else False
-        sub, push = sh.sub_chunk, (sh.push_rows if sh.mode in ("peer", "peer_ce") else sh.sub_chunk)
+        sub, push = sh.sub_chunk, (sh.push_rows if sh.mode in ("peer", "peer_sm") else sh.sub_chunk)
         n_chunks = -(-B // sub)
-        n_push = (-(-B // push) + 1) if sh.mode in ("peer", "peer_ce") else n_chunks
+        n_push = (-(-B // push) + 1) if sh.mode in ("peer", "peer_sm") else n_chunks
         gather = {"mode": sh.mode, "sub_chunk": sub, "push_rows": push,
                   "push_sms": sh.push_sms, "pusher_aborted": aborted, "ms_per_step": ms / steps, "ms_per_step_compute_only": ms_compute / steps,
                   "exposed_ms": (ms - ms_compute) / steps, "ratio_vs_compute_only": ms / ms_compute,
@@ -411,9 +411,11 @@ def main():
                   "nvlink_in_gbs_overlapped": bytes_in / (ms / steps * 1e-3) / 1e9,
                   "exchange_alone_ms": ms_x, "nvlink_in_gbs_alone": (bytes_in / (ms_x * 1e-3) / 1e9) if ms_x else None,
                   "value_compute_only": value_compute, "bitwise_equal_to_local": same,
-                  "note": "every rank ends the step holding the full [%d, %d, %d] result; pushes by the copy engines over "
-                          "NVLink peer memory overlapped with the next sub-chunk's kernels, closed by a stream-ordered "
-                          "one-element NCCL all-reduce" % (world * B, P, N_ELL)}
+                  "lockstep": bool(sh.mode == "peer" and world > 2 and (world * B) % world == 0),
+                  "link_time_over_compute_time": (ms_x / (ms_compute / steps)) if ms_x else None,
+                  "note": "every rank ends the step holding the full [%d, %d, %d] result; each finished slice of the contraction "
+                          "is pushed into every peer's buffer over NVLink peer memory (copy engines, in lockstep across ranks) while "
+                          "the following slices compute; closed by a stream-ordered one-element NCCL all-reduce" % (world * B, P, N_ELL)}
         passes = steps * max(-(-B // int(plan.workspace_layout(ws_bytes).chunk)), 1)
         per_pass = n_launches // passes  # kernels per chunk pass of the compute-only loop (one contraction each)
         n_launches = ((per_pass - 1) * n_chunks + n_push) * steps

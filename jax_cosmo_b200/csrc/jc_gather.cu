@@ -98,7 +98,10 @@ extern "C" int jc_gather_create(int32_t rank, int32_t world, int32_t device, siz
   jc_gather* g = new jc_gather();
   memset(g, 0, sizeof(*g));
   g->rank = rank; g->world = world; g->device = device; g->bytes = bytes;
-  cudaError_t e = cudaMalloc(&g->local, bytes + JC_SYNC_BYTES);
+  // One allocation = result buffer + flag words, rounded up to 2 MiB: with an odd size (bytes + 4096) the peer copies of the
+  // whole buffer ran at 544 instead of 770 GB/s (the mapping then falls back to small pages).
+  const size_t alloc = (bytes + JC_SYNC_BYTES + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+  cudaError_t e = cudaMalloc(&g->local, alloc);
   if (e != cudaSuccess) { delete g; jc_set_cuda_error(e, "cudaMalloc(gather buffer)"); return JC_ERR_CUDA; }
   e = cudaMemset((char*)g->local + bytes, 0, JC_SYNC_BYTES);
   if (e == cudaSuccess) e = cudaMalloc((void**)&g->stage_dev, JC_STAGE_WORDS * sizeof(unsigned));

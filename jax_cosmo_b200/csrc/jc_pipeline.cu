@@ -123,6 +123,12 @@ extern "C" int jc_workspace_layout(const jc_plan* plan, size_t ws_bytes, jc_ws_l
 // launch (the gather records an event there and starts the peer copies of those rows): the exchange granularity is
 // then independent of the compute chunk, whose K1..K3 keep full waves.  The last slice of the batch is halved so that
 // the copy left exposed at the end of the step is short.
+// With slicing (the gather) the first compute chunk is one slice long: the first push can start after half the
+// K1..K3 time of a full chunk (the exchange needs 89 % of the step at 8 GPUs, so its start-up delay is exposed 1:1).
+static inline int64_t jc_first_chunk(int64_t cap, int64_t slice, int64_t c0) {
+  return (slice > 0 && c0 == 0 && slice < cap) ? slice : cap;
+}
+
 // The (first row, rows) slices jc_run_pipeline will launch the contraction for, in order (same rule as below).
 int jc_pipeline_slices(const jc_plan* plan, int64_t n_cosmo, size_t ws_bytes, int64_t chunk_cap, int64_t slice,
                        std::vector<std::pair<int64_t, int64_t>>* out) {
@@ -130,8 +136,11 @@ int jc_pipeline_slices(const jc_plan* plan, int64_t n_cosmo, size_t ws_bytes, in
   int st = jc_workspace_layout(plan, ws_bytes, &lo);
   if (st != JC_OK) return st;
   const int64_t cap = (chunk_cap > 0 && chunk_cap < lo.chunk) ? chunk_cap : lo.chunk;
-  for (int64_t c0 = 0; c0 < n_cosmo; c0 += cap) {
-    const int64_t chunk = (n_cosmo - c0) < cap ? (n_cosmo - c0) : cap;
+  int64_t next = 0;
+  for (int64_t c0 = 0; c0 < n_cosmo; c0 = next) {
+    const int64_t this_cap = jc_first_chunk(cap, slice, c0);
+    const int64_t chunk = (n_cosmo - c0) < this_cap ? (n_cosmo - c0) : this_cap;
+    next = c0 + chunk;
     if (slice <= 0) { out->push_back({c0, chunk}); continue; }
     const bool last_chunk = c0 + chunk >= n_cosmo;
     for (int64_t s0 = 0; s0 < chunk;) {
@@ -161,8 +170,11 @@ int jc_run_pipeline(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosm
   const size_t PL = (size_t)pl.P * pl.L;
 
   JcProf* prof = (plan->prof && plan->prof->enabled) ? plan->prof : nullptr;
-  for (int64_t c0 = 0; c0 < n_cosmo; c0 += cap) {
-    const int chunk = (int)((n_cosmo - c0) < cap ? (n_cosmo - c0) : cap);
+  int64_t c_next = 0;
+  for (int64_t c0 = 0; c0 < n_cosmo; c0 = c_next) {
+    const int64_t this_cap = jc_first_chunk(cap, slice, c0);
+    const int chunk = (int)((n_cosmo - c0) < this_cap ? (n_cosmo - c0) : this_cap);
+    c_next = c0 + chunk;
     cudaEvent_t* ev = nullptr;
     int* nl = nullptr;
     if (prof && prof->used < JC_PROF_SLOTS) { ev = prof->ev[prof->used]; nl = prof->launches[prof->used]; ++prof->used; }

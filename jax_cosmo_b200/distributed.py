@@ -10,13 +10,15 @@ Gather modes (`gather_mode`):
 
   "peer"        every rank owns a full-size `[B, P, L]` buffer mapped into all ranks (CUDA IPC); the rank computes its
                 rows straight into the final layout -- K1..K3 on chunks of `sub_chunk` cosmologies, the contraction per
-                `push_rows` cosmologies -- and a persistent pusher kernel on `push_sms` SMs stores each finished slice
-                into all peers' buffers over NVLink (st.global on the mapped peer pointers, destinations interleaved)
-                while the following slices compute (csrc/jc_gather.cu).  Only the last (halved) slice's push is
-                exposed.  Default on CUDA.
-  "peer_ce"     the same pipeline with the copy engines doing the pushes (one cudaMemcpyAsync per slice and peer): no
-                SM is taken from the FP64 kernels; fully hidden at 2 and 4 GPUs, but at 8 GPUs the ~100 medium-sized
-                copies per step only reach 58 % of the NVLink rate.
+                `push_rows` cosmologies -- and the copy engines push each finished slice into the peers' buffers over
+                NVLink while the following slices compute (csrc/jc_gather.cu): no SM is taken from the FP64 kernels.
+                With equal shards and more than two ranks the pushes of a slice run in LOCKSTEP on all ranks (a flag
+                barrier per slice by stream memory operations): free-running, eight GPUs drift into each other's
+                receivers and the ~100 copies per step reach 58 % of the link rate.  Default on CUDA.
+  "peer_sm"     the same pipeline with a persistent pusher kernel on `push_sms` reserved SMs storing each finished slice
+                to all peers (cp.async.bulk / st.global on the mapped peer pointers, destinations interleaved).  Uniform
+                traffic without any cross-rank synchronisation, but an SM moves only ~55 GB/s over NVLink, so ~16 SMs
+                are lost to the FP64 kernels; measured slower than lockstep copy engines at 2, 4 and 8 GPUs.
   "nccl"        the same sub-chunk pipeline with one grouped NCCL send/recv per sub-chunk on a side stream, received
                 straight into the final layout (the library baseline the peer path is measured against).
   "collective"  one `all_gather` after the compute (any backend; what the CPU / gloo tests exercise).
@@ -27,7 +29,7 @@ import numpy as np
 
 DEFAULT_SUB_CHUNK = 1184  # compute chunk of K1..K3: 2 x 592 = two full waves of the setup kernel (148 SMs x 4 CTAs)
 DEFAULT_PUSH_ROWS = 592   # cosmologies per contraction launch + NVLink push: 4 per persistent contraction CTA
-DEFAULT_PUSH_SMS = 12     # SMs of the pusher kernel ("peer" mode); "peer_ce" uses the copy engines instead
+DEFAULT_PUSH_SMS = 16     # SMs of the pusher kernel ("peer_sm" mode)
 
 
 def shard_bounds(n_rows, world_size, rank):
@@ -77,10 +79,10 @@ class ShardedAngularCl:
             gather_mode = "peer" if self.world > 1 else "none"
         if self.world == 1:
             gather_mode = "none"
-        if gather_mode not in ("peer", "peer_ce", "nccl", "collective", "none"):
+        if gather_mode not in ("peer", "peer_sm", "nccl", "collective", "none"):
             raise ValueError("gather_mode %r" % (gather_mode,))
         self.mode = gather_mode
-        self.push_sms = int(push_sms) if gather_mode == "peer" else 0
+        self.push_sms = int(push_sms) if gather_mode == "peer_sm" else 0
         if self.push_sms > 0:
             # the pusher kernel holds `push_sms` SMs for the whole step: size the contraction slices and the compute chunks in
             # whole waves of the remaining SMs (4 cosmologies per persistent contraction CTA, 8 per compute chunk)
@@ -93,7 +95,7 @@ class ShardedAngularCl:
         self._peer = None
         self._side = None
         shape = (self.world * self.per, self.plan.P, self.plan.L)
-        if self.mode in ("peer", "peer_ce"):
+        if self.mode in ("peer", "peer_sm"):
             self._peer = _native.PeerGather(self.plan, shape[0], self.rank, self.world, push_sms=self.push_sms)
             handles = [None] * self.world
             dist.all_gather_object(handles, self._peer.handle, group=group)
@@ -139,7 +141,7 @@ class ShardedAngularCl:
         n = shard.shape[0]
         if self.mode == "none":
             self.compute_shard(shard)
-        elif self.mode in ("peer", "peer_ce"):
+        elif self.mode in ("peer", "peer_sm"):
             self._peer.compute_and_push(shard, self.lo, self.sub_chunk, self.push_rows,
                                         equal_shards=self.n_rows % self.world == 0)
             self.barrier()

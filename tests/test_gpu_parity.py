@@ -404,7 +404,7 @@ def _nccl_worker(rank, world, port, out_dir):
         scn = sc.scenario("d", sc.PLANCK15, sc.ELL_CFG2[::10], [sc.sources(5, 2.0), sc.lenses(5, 2.0)])
         probes = sc.build_probes(scn, jcm)
         rows = sc.config5_cosmologies(37)  # ragged: 19 + 18 rows
-        for mode in ("peer", "peer_ce", "nccl", "collective"):
+        for mode in ("peer", "peer_sm", "nccl", "collective"):
             cl, (lo, hi) = angular_cl_sharded(rows, scn["ell"], probes, gather=True, gather_mode=mode, sub_chunk=7)
             np.save(os.path.join(out_dir, "g_%s_%d.npy" % (mode, rank)), cl.cpu().numpy())
         # persistent evaluator, called twice on different batches (buffer reuse, second step after the barrier)
@@ -437,7 +437,7 @@ def test_sharded_nccl_two_gpus(jc, torch_cuda, tmp_path):
     scn = sc.scenario("d", sc.PLANCK15, sc.ELL_CFG2[::10], [sc.sources(5, 2.0), sc.lenses(5, 2.0)])
     ref = jc.cl.angular_cl_batch(sc.config5_cosmologies(37), scn["ell"], sc.build_probes(scn, jc))
     for r in range(2):
-        for tag in ("peer", "peer_ce", "nccl", "collective", "again"):
+        for tag in ("peer", "peer_sm", "nccl", "collective", "again"):
             assert np.array_equal(np.load(tmp_path / ("g_%s_%d.npy" % (tag, r))), ref), (tag, r)
         assert np.array_equal(np.load(tmp_path / ("g_one_%d.npy" % r)), ref[:1]), r
 
