@@ -1,8 +1,10 @@
 """jax.ffi binding of the B200 path (north_star: XLA-FFI custom call) -- the file a jax_cosmo maintainer adds.
 
-NOT importable in this repository's image: JAX is not installed and cannot be installed (no network), so this module
-is documentation-grade code that has never run; the tested binding of the same C ABI is jax_cosmo_b200/_native.py
-(ctypes) with PyTorch owning device memory.  With JAX available:
+EXPERIMENTAL -- not importable in this repository's image: JAX is not installed and cannot be installed (no network), so
+this module has never run under JAX.  What CI does check is the C++ side it binds: integration/jc_xla_ffi.cc is compiled
+against a stand-in header, linked with libjc_b200.so and its handlers are driven through fake buffers on the GPU
+(tests/test_ffi_shim.py, which also runs this module's functions whenever `import jax` succeeds).  The tested binding of the
+same C ABI is jax_cosmo_b200/_native.py (ctypes) with PyTorch owning device memory.  With JAX available:
 
     import jax; jax.config.update("jax_enable_x64", True)
     from integration.jax_binding import angular_cl          # drop-in for jax_cosmo.angular_cl.angular_cl
@@ -30,9 +32,26 @@ for _name, _sym in (("jc_angular_cl", "JcAngularCl"), ("jc_angular_cl_jvp", "JcA
     jax.ffi.register_ffi_target(_name, jax.ffi.pycapsule(getattr(_lib, _sym)), platform="CUDA")
 
 
+# The raw jc_plan* is baked into jitted executables as an attribute: a plan must outlive every executable that may still
+# call it, so plans used through this module are pinned here for the life of the process (the 8-entry LRU of
+# _native.get_plan would otherwise free them under a cached jit).
+_PINNED_PLANS = {}
+
+
+def _leaves(cosmo):
+    """Cosmology leaves in tree_flatten order (core.py:99-108).  jax_cosmo_b200.Cosmology is a plain Python object, not a
+    registered pytree: flatten it through its own method; a jax_cosmo.Cosmology (registered) goes through jax."""
+    if hasattr(cosmo, "tree_flatten"):
+        children, _ = cosmo.tree_flatten()
+        return list(children)
+    return jax.tree_util.tree_leaves(cosmo)
+
+
 def _plan_for(cosmo_leaves, ell, probes, transfer_fn, nonlinear_fn):
     growth = 1 if len(cosmo_leaves) == 9 else 0
-    return _native.get_plan(probes, np.asarray(ell), transfer_fn, nonlinear_fn, growth=growth)
+    plan = _native.get_plan(probes, np.asarray(ell), transfer_fn, nonlinear_fn, growth=growth)
+    _PINNED_PLANS[plan._h.value] = plan
+    return plan
 
 
 def _call(rows, plan):
@@ -59,7 +78,7 @@ def _call_jvp(rows, tangents, plan):
 def angular_cl(cosmo, ell, probes, transfer_fn=None, nonlinear_fn=None):
     """Same signature and output layout [n_cls, n_ell] as jax_cosmo.angular_cl.angular_cl (angular_cl.py:49-98);
     differentiable in the cosmology leaves in both modes."""
-    leaves, treedef = jax.tree_util.tree_flatten(cosmo)
+    leaves = _leaves(cosmo)
     plan = _plan_for(leaves, ell, probes, transfer_fn, nonlinear_fn)
 
     @jax.custom_jvp
@@ -78,7 +97,7 @@ def angular_cl(cosmo, ell, probes, transfer_fn=None, nonlinear_fn=None):
 def angular_cl_rev(cosmo, ell, probes, transfer_fn=None, nonlinear_fn=None):
     """angular_cl with a reverse-mode rule (jax.grad / jax.vjp): the forward pass saves the Jacobian with respect to
     all leaves (one tangent pass per leaf), the backward pass is jc_vjp_f64."""
-    leaves, treedef = jax.tree_util.tree_flatten(cosmo)
+    leaves = _leaves(cosmo)
     plan = _plan_for(leaves, ell, probes, transfer_fn, nonlinear_fn)
     n = len(leaves)
 
