@@ -237,6 +237,7 @@ def run(args, rank, world, local):
                             "d2h_bytes_per_step": int(out_pin.numel() * 8),
                             "max_abs_diff_vs_device_path": float((out_pin[:64].to(dev) - dcl[:64]).abs().max().item())},
                     "forward_pass_ms": ms_fwd, "jvp_over_forward": (ms / steps) / ms_fwd,
+                    "jvp_group": int(_native.get_option("jvp_group")),
                     "gpu_launches": None, "roofline": None, "cpu_baseline": None, "git_head": git_head()}
             print(json.dumps(line), flush=True)
     if world > 1:

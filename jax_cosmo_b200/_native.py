@@ -31,7 +31,7 @@ SCAL_FIELDS = ["LN13KEQ", "INV13KEQ", "BETA_C", "C14_ALPHA_C", "SH_D", "LNKSILK"
 # every symbol include/jc_b200.h declares
 EXPORTS = ["jc_plan_create", "jc_plan_destroy", "jc_plan_n_tracers", "jc_plan_n_cls", "jc_plan_n_ell", "jc_plan_n_cosmo_params",
            "jc_workspace_bytes", "jc_workspace_layout", "jc_angular_cl_f64", "jc_angular_cl_host_f64",
-           "jc_workspace_bytes_jvp", "jc_angular_cl_jvp_f64", "jc_gaussian_loglike_f64", "jc_gaussian_cl_loglike_f64", "jc_fisher_f64", "jc_vjp_f64", "jc_sparse_bmm_f64", "jc_sparse_inv_f64", "jc_debug_stages_f64", "jc_grid_plan_create", "jc_grid_plan_create_probes", "jc_grid_eval_f64", "jc_grid_background_f64", "jc_a_of_chi_f64", "jc_sigmasqr_f64", "jc_nz_eval_f64",
+           "jc_workspace_bytes_jvp", "jc_workspace_bytes_jvp_group", "jc_angular_cl_jvp_f64", "jc_gaussian_loglike_f64", "jc_gaussian_cl_loglike_f64", "jc_fisher_f64", "jc_vjp_f64", "jc_sparse_bmm_f64", "jc_sparse_inv_f64", "jc_debug_stages_f64", "jc_grid_plan_create", "jc_grid_plan_create_probes", "jc_grid_eval_f64", "jc_grid_background_f64", "jc_a_of_chi_f64", "jc_sigmasqr_f64", "jc_nz_eval_f64",
            "jc_noise_f64", "jc_gaussian_cov_f64", "jc_gather_create", "jc_gather_status", "jc_gather_buffer", "jc_gather_connect_ipc",
            "jc_gather_connect_local", "jc_gather_destroy", "jc_angular_cl_gather_f64", "jc_gather_push_f64", "jc_set_option", "jc_get_option", "jc_profile_enable", "jc_profile_read",
            "jc_fp64_peak_tflops", "jc_debug_math_f64", "jc_status_string",
@@ -96,6 +96,8 @@ def load_library():
         lib.jc_angular_cl_f64.restype = C.c_int
         lib.jc_workspace_bytes_jvp.argtypes = [vp, i64, C.POINTER(C.c_size_t)]
         lib.jc_workspace_bytes_jvp.restype = C.c_int
+        lib.jc_workspace_bytes_jvp_group.argtypes = [vp, i64, i32, C.POINTER(C.c_size_t)]
+        lib.jc_workspace_bytes_jvp_group.restype = C.c_int
         lib.jc_angular_cl_jvp_f64.argtypes = [vp, vp, vp, i32, i64, vp, vp, vp, C.c_size_t, vp]
         lib.jc_angular_cl_jvp_f64.restype = C.c_int
         lib.jc_gaussian_loglike_f64.argtypes = [vp, i64, vp, vp, i64, i32, i32, i32, vp, vp, vp]
@@ -471,9 +473,10 @@ class Plan:
         self._check_rows(tangents_dev, "tangents")
         B, K = cosmo_dev.shape[0], tangents_dev.shape[0]
         need = C.c_size_t()
-        # small batches: room for B*K workspace entries lets the library run all K directions in one pass
-        entries = B * K if B * K <= 1024 else B
-        check(load_library().jc_workspace_bytes_jvp(self._h, entries, C.byref(need)), "jc_workspace_bytes_jvp")
+        if B * K <= 1024:  # small batches: room for B*K workspace entries lets the library run all K directions in one pass
+            check(load_library().jc_workspace_bytes_jvp(self._h, B * K, C.byref(need)), "jc_workspace_bytes_jvp")
+        else:  # throughput: a value plane + one plane per direction of a tangent group (4 + 3 for the 7 wCDM parameters)
+            check(load_library().jc_workspace_bytes_jvp_group(self._h, B, K, C.byref(need)), "jc_workspace_bytes_jvp_group")
         ws = torch.empty(need.value // 8, dtype=torch.float64, device=cosmo_dev.device)
         cl = torch.empty((B, self.P, self.L), dtype=torch.float64, device=cosmo_dev.device)
         dcl = torch.empty((B, K, self.P, self.L), dtype=torch.float64, device=cosmo_dev.device)
@@ -931,7 +934,8 @@ def debug_math(fn, x):
 
 
 def set_option(name, value):
-    """jc_set_option: "power_exact" (0 | 1), "contract_eps" (>= 0; read when a plan is created -- cached plans keep theirs)."""
+    """jc_set_option: "power_exact" (0 | 1), "contract_eps" (>= 0; read when a plan is created -- cached plans keep theirs),
+    "contract_kernel" (0..3), "jvp_group" (1..4 tangent directions per JVP pass)."""
     check(load_library().jc_set_option(name.encode(), float(value)), "jc_set_option(%s)" % name)
     if name == "contract_eps":
         _plan_cache.clear()

@@ -25,6 +25,7 @@
 #define JC_NHFR 256      // halofit ln R nodes (power.py:93)
 #define JC_NROMB 129     // Romberg nodes, divmax=7 (power.py:77)
 #define JC_MAX_CHUNK 4096
+#define JC_JVP_MAX_GROUP 4  // tangent directions one JVP pass can carry (DualN<4>: the setup kernel's tables fill an SM's shared memory)
 
 #define JC_C_LIGHT 299792.458      // constants.py:9
 #define JC_RH 2997.92458           // constants.py:15
@@ -174,6 +175,7 @@ struct JcDeviceGuard {
 void jc_set_cuda_error(cudaError_t e, const char* where);
 extern int g_jc_power_exact;      // jc_set_option("power_exact"): exact-formula power kernel everywhere
 extern int g_contract_cfg;        // jc_set_option("contract_kernel")
+extern int g_jc_jvp_group;        // jc_set_option("jvp_group"): tangent directions carried per JVP pass (1..JC_JVP_MAX_GROUP)
 extern double g_jc_contract_eps;  // jc_set_option("contract_eps"): support threshold of the contraction, read at plan creation
 typedef int (*jc_slice_cb)(void* ctx, int64_t first_row, int64_t rows);
 int jc_run_pipeline(const jc_plan* plan, const double* cosmo_dev, int64_t n_cosmo, double* cl_dev, void* ws_dev,
@@ -191,7 +193,7 @@ struct Ws {  // resolved workspace pointers for one chunk of cosmologies
   double* rker;    // [chunk][JC_NA_PAD][TS]   node-major radial kernels R_i(a_n)
   double* vtab;    // [chunk][513][Lpad]
   double* ellpow;  // [chunk][Lpad]  (l+1/2)^(3+n_s)
-  ptrdiff_t doff;  // JVP passes: offset (doubles) from a value to its tangent (second plane); 0 otherwise
+  ptrdiff_t doff;  // JVP passes: offset (doubles) from a value to its first tangent plane (plane k at (k + 1) * doff); 0 otherwise
 };
 
 #ifdef __CUDACC__
@@ -216,12 +218,14 @@ void jc_launch_contract_1cta(const JcDevPlan& pl, const Ws& ws, double* cl, int 
 void jc_launch_sigmasqr(const JcDevPlan& pl, const Ws& ws, const double* cosmo, int chunk, const double* R_dev, int n_R, double* out,
                         cudaStream_t s);
 void jc_launch_transfer(const JcDevPlan& pl, const Ws& ws, int chunk, double* tk, cudaStream_t s);
-// JVP (Dual) variants: same kernels instantiated on value+tangent; `tangent` = direction [8] in parameter space
+// JVP variants: the same kernels instantiated on DualN<ntan> (value + ntan tangents per workspace entry, 1 <= ntan <=
+// JC_JVP_MAX_GROUP; tangent plane k of a table at offset (k + 1) * ws.doff); `tangent` = ntan directions [ntan][ncp] in
+// parameter space per entry
 void jc_launch_setup_jvp(const JcDevPlan& pl, const double* cosmo, const double* tangent, const Ws& ws, int chunk, int kdiv,
-                         cudaStream_t s);
-int jc_launch_tracers_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s);
-void jc_launch_finish_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s);
-void jc_launch_power_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s);
+                         int ntan, cudaStream_t s);
+int jc_launch_tracers_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, int ntan, cudaStream_t s);
+void jc_launch_finish_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, int ntan, cudaStream_t s);
+void jc_launch_power_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, int ntan, cudaStream_t s);
 void jc_launch_contract_jvp(const JcDevPlan& pl, const Ws& ws, double* dcl, int64_t dcl_cosmo_stride, int chunk,
                             cudaStream_t s);
 int jc_setup_init();

@@ -50,8 +50,16 @@ extern "C" int jc_workspace_bytes_jvp(const jc_plan* plan, int64_t n_cosmo, size
   return st;
 }
 
-// Forward-mode derivatives: for every tangent direction k (a row of tangents_dev [K,8] in parameter
-// space) one pass of the Dual-instantiated kernels K1..K3 and the tangent contraction.
+// Workspace for the grouped JVP: a value plane and min(n_tangents, jvp_group) tangent planes of min(n_cosmo, JC_MAX_CHUNK) entries.
+extern "C" int jc_workspace_bytes_jvp_group(const jc_plan* plan, int64_t n_cosmo, int32_t n_tangents, size_t* bytes_out) {
+  if (n_tangents < 1) return JC_ERR_INVALID;
+  int st = jc_workspace_bytes(plan, n_cosmo, bytes_out);
+  const int g = n_tangents < g_jc_jvp_group ? n_tangents : g_jc_jvp_group;
+  if (st == JC_OK) *bytes_out *= (size_t)(1 + g);
+  return st;
+}
+
+// Forward-mode derivatives: passes of the DualN-instantiated kernels K1..K3 and one tangent contraction per direction.
 extern "C" int jc_angular_cl_jvp_f64(const jc_plan* plan, const double* cosmo_dev, const double* tangents_dev,
                                      int32_t n_tangents, int64_t n_cosmo, double* cl_dev, double* dcl_dev,
                                      void* ws_dev, size_t ws_bytes, void* stream) {
@@ -66,17 +74,17 @@ extern "C" int jc_angular_cl_jvp_f64(const jc_plan* plan, const double* cosmo_de
   Ws ws;
   resolve(lo, (double*)ws_dev, (ptrdiff_t)((lo.total + 1) & ~(int64_t)1), &ws);
   const int64_t PL = (int64_t)pl.P * pl.L;
-  if (n_tangents > 1 && n_cosmo * n_tangents <= lo.chunk) {
+  if (n_tangents > 1 && n_cosmo * n_tangents <= lo.chunk && n_cosmo * n_tangents <= 1024) {
     // Small batches (a Fisher forecast at one cosmology): all K directions of every cosmology in ONE pass over B*K workspace
     // entries (entry b*K + k = cosmology b, direction k, which is also the layout of dcl) instead of K latency-bound passes.
     // Needs a workspace for B*K entries (jc_workspace_bytes_jvp(plan, B*K)); per-entry arithmetic is the same, results are
     // bitwise those of the pass-per-direction path.  The value plane of entry b*K is C_l of cosmology b: it is contracted into the
     // dcl buffer first (same size), its rows b*K copied out to cl, then the tangent contraction overwrites dcl.
     const int entries = (int)(n_cosmo * n_tangents);
-    jc_launch_setup_jvp(pl, cosmo_dev, tangents_dev, ws, entries, n_tangents, s);
-    jc_launch_tracers_jvp(pl, ws, entries, s);
-    jc_launch_finish_jvp(pl, ws, entries, s);
-    jc_launch_power_jvp(pl, ws, entries, s);
+    jc_launch_setup_jvp(pl, cosmo_dev, tangents_dev, ws, entries, n_tangents, 1, s);
+    jc_launch_tracers_jvp(pl, ws, entries, 1, s);
+    jc_launch_finish_jvp(pl, ws, entries, 1, s);
+    jc_launch_power_jvp(pl, ws, entries, 1, s);
     if (cl_dev) {
       jc_launch_contract(pl, ws, dcl_dev, entries, s);
       JC_CUDA_TRY(cudaMemcpy2DAsync(cl_dev, (size_t)PL * sizeof(double), dcl_dev, (size_t)n_tangents * PL * sizeof(double),
@@ -86,15 +94,33 @@ extern "C" int jc_angular_cl_jvp_f64(const jc_plan* plan, const double* cosmo_de
     JC_CUDA_TRY(cudaGetLastError());
     return JC_OK;
   }
+  // Throughput path: every pass carries a GROUP of g <= jvp_group directions through one evaluation of the value (DualN<g>:
+  // the transcendentals of K1..K3 are computed once per group; 7 parameters = groups of 4 + 3).  The workspace is cut into
+  // 1 + g planes of `chunk` entries; the group shrinks when the planes would otherwise hold fewer entries than the batch
+  // needs to fill the GPU.  The tangent contraction runs per direction on (value plane, tangent plane k).
+  int group = n_tangents < g_jc_jvp_group ? n_tangents : g_jc_jvp_group;
+  const int64_t want = n_cosmo < 148 ? n_cosmo : 148;  // entries per pass that keep every SM busy
+  while (group > 1) {
+    jc_ws_layout lg;
+    if (jc_workspace_layout(plan, ws_bytes / (size_t)(1 + group), &lg) == JC_OK && lg.chunk >= want) break;
+    --group;
+  }
+  if ((st = jc_workspace_layout(plan, ws_bytes / (size_t)(1 + group), &lo)) != JC_OK) return st;
+  resolve(lo, (double*)ws_dev, (ptrdiff_t)((lo.total + 1) & ~(int64_t)1), &ws);
   for (int64_t c0 = 0; c0 < n_cosmo; c0 += lo.chunk) {
     const int chunk = (int)((n_cosmo - c0) < lo.chunk ? (n_cosmo - c0) : lo.chunk);
-    for (int k = 0; k < n_tangents; ++k) {
-      jc_launch_setup_jvp(pl, cosmo_dev + c0 * pl.ncp, tangents_dev + (size_t)k * pl.ncp, ws, chunk, 1, s);
-      jc_launch_tracers_jvp(pl, ws, chunk, s);
-      jc_launch_finish_jvp(pl, ws, chunk, s);
-      jc_launch_power_jvp(pl, ws, chunk, s);
-      if (k == 0 && cl_dev) jc_launch_contract(pl, ws, cl_dev + (size_t)c0 * PL, chunk, s);  // value plane
-      jc_launch_contract_jvp(pl, ws, dcl_dev + ((size_t)c0 * n_tangents + k) * PL, (int64_t)n_tangents * PL, chunk, s);
+    for (int k0 = 0; k0 < n_tangents; k0 += group) {
+      const int g = (n_tangents - k0) < group ? (n_tangents - k0) : group;
+      jc_launch_setup_jvp(pl, cosmo_dev + c0 * pl.ncp, tangents_dev + (size_t)k0 * pl.ncp, ws, chunk, 1, g, s);
+      jc_launch_tracers_jvp(pl, ws, chunk, g, s);
+      jc_launch_finish_jvp(pl, ws, chunk, g, s);
+      jc_launch_power_jvp(pl, ws, chunk, g, s);
+      if (k0 == 0 && cl_dev) jc_launch_contract(pl, ws, cl_dev + (size_t)c0 * PL, chunk, s);  // value plane
+      for (int j = 0; j < g; ++j) {
+        Ws wk = ws;
+        wk.doff = (ptrdiff_t)(j + 1) * ws.doff;  // the contraction pairs the value plane with tangent plane j
+        jc_launch_contract_jvp(pl, wk, dcl_dev + ((size_t)c0 * n_tangents + k0 + j) * PL, (int64_t)n_tangents * PL, chunk, s);
+      }
     }
   }
   JC_CUDA_TRY(cudaGetLastError());

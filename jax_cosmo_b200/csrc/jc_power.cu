@@ -14,7 +14,7 @@
 //   * exp/log are table driven (jc_math.cuh: 2^n T[j] p4(r), 256 entries per octave; {c_j, -ln c_j} + log1p degree 7), the tables
 //     are staged in shared memory once per CTA and the CTA strides over its cosmology's index space;
 //     sin/rcbrt/rcp and all polynomial coefficients are constant-bank DFMA operands.
-// Template on the scalar type: double (hot path) or Dual (JVP pass, jc_dual.cuh).
+// Template on the scalar type: double (hot path) or DualN<K> (JVP pass, jc_dual.cuh).
 #include <cstdlib>
 
 #include "jc_internal.cuh"
@@ -303,9 +303,11 @@ struct JcMathL {
 };
 static __constant__ JcMathL JCL = {1.4426950408889634074 * T2_EXPN, 6755399441055744.0, 6.93147180559945309417e-01 / T2_EXPN};
 
-// exp(x), |x| < 700 unless CLAMP; lane-private table: entry j of slot c at e[j * 16 + c]
+// exp(x), |x| < 700 unless CLAMP; lane-private table: entry j of slot c at e[j * 16 + c].  `e_slot_addr` is the 32-bit
+// shared-memory address of the lane's slot: table address and exponent insertion are two integer instructions each
+// (LOP3 + IMAD, SHF + LEA) instead of the seven the indexed C++ form compiled to.
 template <bool CLAMP>
-__device__ __forceinline__ double exp_lane(double x, const double* __restrict__ e_slot) {
+__device__ __forceinline__ double exp_lane(double x, unsigned e_slot_addr) {
   if (CLAMP) x = jcm_clamp_exp_arg(x);
   const double kd = fma(x, JCL.k128, JCL.magic);
   const int k = __double2loint(kd);
@@ -314,21 +316,24 @@ __device__ __forceinline__ double exp_lane(double x, const double* __restrict__ 
   double p = fma(JCT.e[1], r, JCT.e[0]);
   p = fma(p, r, JCK.one);
   p = fma(p, r, JCK.one);
-  p *= e_slot[(k & (T2_EXPN - 1)) * 16];
+  double t;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(t) : "r"(e_slot_addr + (unsigned)(k & (T2_EXPN - 1)) * 128u));
+  p *= t;
   return __hiloint2double(__double2hiint(p) + ((k >> 7) << 20), __double2loint(p));
 }
 // log(x), x >= 1 normal; lane-private table of {c_j, -ln c_j}: entry j of slot c at l[(j * 8 + c)]
-__device__ __forceinline__ double log_lane(double x, const double2* __restrict__ l_slot) {
+__device__ __forceinline__ double log_lane(double x, unsigned l_slot_addr) {
   const int hx = __double2hiint(x);
   const int e = (hx >> 20) - 1023;
-  const int j = (hx >> 13) & 127;
   const double m = __hiloint2double((hx & 0x000fffff) | 0x3ff00000, __double2loint(x));
-  const double2 cl = l_slot[j * 8];
-  const double r = fma(m, cl.x, -JCK.one);
+  double cx, cy;
+  // j = top 7 mantissa bits = (hx >> 13) & 127, entry stride 128 bytes: (hx >> 6) & 0x3f80
+  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(cx), "=d"(cy) : "r"(l_slot_addr + (((unsigned)hx >> 6) & 0x3f80u)));
+  const double r = fma(m, cx, -JCK.one);
   double p = fma(JCT.l[2], r, JCT.l[1]);
   p = fma(p, r, JCT.l[0]);
   p = fma(p * r, r, r);
-  return fma((double)e, JCK.ln2_hi, cl.y) + p;
+  return fma((double)e, JCK.ln2_hi, cy) + p;
 }
 
 template <bool NOWIG>
@@ -393,8 +398,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) jc_power_tab2_kernel(JcDevPlan 
     lpns = ws.ellpow[(size_t)c * pl.Lpad + l];
     lnl_ih = lnl * inv_h;
   }
-  const double* e_slot = e_l + (lane & 15);
-  const double2* l_slot = l_l + (lane & 7);
+  const unsigned e_slot = (unsigned)__cvta_generic_to_shared(e_l + (lane & 15));
+  const unsigned l_slot = (unsigned)__cvta_generic_to_shared(l_l + (lane & 7));
   const bool smith = pl.nonlinear == JC_PK_HALOFIT_SMITH2003;
   const bool halofit = pl.nonlinear != 0;
   double* vbase = ws.vtab + (size_t)c * JC_NA * pl.Lpad + l;
@@ -468,9 +473,6 @@ __global__ void __launch_bounds__(T2_THREADS, 1) jc_power_tab2_kernel(JcDevPlan 
   }
 }
 
-template <int NPT>
-void launch_power_tab(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s);
-
 void launch_power_tab2(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s) {
   const size_t smem = (size_t)(2 * TAB_NT + JCM_TAB_DOUBLES + T2_EXPN * 16 + 128 * 8 * 2 + 2 * T2_NF * T2_NB) * sizeof(double);
   static unsigned long long attr_done = 0;
@@ -516,64 +518,28 @@ void launch_power_cfg(const JcDevPlan& pl, const Ws& ws, int chunk, int split, c
 }  // namespace
 
 void jc_launch_power(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s) {
-  static int cfg = -1, tab_npt = 0;
-  if (cfg < 0) {  // tuning knobs
-    const char* e = getenv("JC_POWER_CFG");
-    const char* t = getenv("JC_POWER_TAB_NPT");
-    tab_npt = t ? atoi(t) : 0;
-    cfg = e ? atoi(e) : 0;
-  }
   // jc_set_option("power_exact", 1) / JC_POWER_EXACT=1: the exact-formula kernel everywhere (A/B runs, stage tests)
   if (!g_jc_power_exact && !pl.grid_mode && pl.L >= 32 && ws.doff == 0) {  // tabulated transfer function (see jc_power_tab_kernel)
+    static const int first_form = [] { const char* e = getenv("JC_POWER_TAB_NPT"); return e && atoi(e) < 0; }();  // A/B knob
     const int rows = T2_THREADS / pl.L;
-    if (tab_npt >= 0 && rows >= 1 && rows * pl.L * 10 >= T2_THREADS * 9 && pl.L <= T2_THREADS) {  // JC_POWER_TAB_NPT=-1: first form only
-      if (tab_npt == 0) { launch_power_tab2(pl, ws, chunk, s); return; }
-    }
-    switch (tab_npt) {
-      case 4: launch_power_tab<4>(pl, ws, chunk, s); break;
-      case 16: launch_power_tab<16>(pl, ws, chunk, s); break;
-      default: launch_power_tab<8>(pl, ws, chunk, s); break;
-    }
+    if (!first_form && rows >= 1 && rows * pl.L * 10 >= T2_THREADS * 9 && pl.L <= T2_THREADS) launch_power_tab2(pl, ws, chunk, s);
+    else launch_power_tab<8>(pl, ws, chunk, s);
     return;
   }
-  switch (cfg) {
-    case 1: launch_power_cfg<double, 4, 1>(pl, ws, chunk, 8, s); break;  // unconstrained registers
-    case 2: launch_power_cfg<double, 4, 3>(pl, ws, chunk, 8, s); break;  // 80 registers, 3 CTAs / SM
-    case 3: launch_power_cfg<double, 4, 2>(pl, ws, chunk, 8, s); break;  // 128 registers, 2 CTAs / SM
-    case 4: launch_power_cfg<double, 2, 3>(pl, ws, chunk, 8, s); break;
-    case 5: launch_power_cfg<double, 8, 3>(pl, ws, chunk, 8, s); break;
-    case 6: launch_power_cfg<double, 8, 4>(pl, ws, chunk, 8, s); break;   // 8 nodes per thread at 64 registers
-    case 7: launch_power_cfg<double, 8, 4>(pl, ws, chunk, 4, s); break;
-    case 8: launch_power_cfg<double, 16, 4>(pl, ws, chunk, 4, s); break;
-    case 9: launch_power_cfg<double, 4, 4>(pl, ws, chunk, 16, s); break;
-    case 10: launch_power_cfg<double, 32, 4>(pl, ws, chunk, 2, s); break;
-    case 11: launch_power_cfg<double, 32, 4>(pl, ws, chunk, 4, s); break;
-    case 12: launch_power_cfg<double, 64, 4>(pl, ws, chunk, 2, s); break;
-    case 13: launch_power_cfg<double, 16, 4>(pl, ws, chunk, 2, s); break;
-    case 14: launch_power_cfg<double, 16, 4>(pl, ws, chunk, 8, s); break;
-    case 15: launch_power_cfg<double, 4, 4>(pl, ws, chunk, 8, s); break;  // the round's earlier default: 6.34 ms
-    case 16: launch_power_cfg<double, 16, 3>(pl, ws, chunk, 8, s); break;  // 80 registers, no spills
-    case 17: launch_power_cfg<double, 16, 5>(pl, ws, chunk, 8, s); break;  // 48 registers
-    // fastest (profiles/r01_tuning.md): 16 nodes per thread (the ell-side loads and index arithmetic amortise over 16
-    // points), 64 registers, 8 CTAs per cosmology: 6.13 ms
-    default: launch_power_cfg<double, 16, 4>(pl, ws, chunk, 8, s); break;
-  }
+  // exact kernel; fastest shape of the round-1 sweep (profiles/r01_tuning.md: 17 shapes, 2..64 nodes per thread, 48..128
+  // registers): 16 nodes per thread (the ell-side loads and index arithmetic amortise over 16 points), 64 registers,
+  // 8 CTAs per cosmology: 6.13 ms per 8192 cosmologies
+  launch_power_cfg<double, 16, 4>(pl, ws, chunk, 8, s);
 }
 
-void jc_launch_power_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s) {
-  static int cfg = -1;
-  if (cfg < 0) { const char* e = getenv("JC_POWER_JVP_CFG"); cfg = e ? atoi(e) : 0; }  // tuning knob
-  switch (cfg) {
-    case 1: launch_power_cfg<Dual, 1, 2>(pl, ws, chunk, 16, s); break;
-    case 2: launch_power_cfg<Dual, 4, 2>(pl, ws, chunk, 8, s); break;
-    case 3: launch_power_cfg<Dual, 4, 1>(pl, ws, chunk, 8, s); break;
-    case 4: launch_power_cfg<Dual, 8, 2>(pl, ws, chunk, 8, s); break;
-    case 5: launch_power_cfg<Dual, 16, 2>(pl, ws, chunk, 8, s); break;
-    case 6: launch_power_cfg<Dual, 8, 3>(pl, ws, chunk, 8, s); break;
-    case 7: launch_power_cfg<Dual, 16, 3>(pl, ws, chunk, 8, s); break;
-    case 8: launch_power_cfg<Dual, 16, 4>(pl, ws, chunk, 8, s); break;
-    case 9: launch_power_cfg<Dual, 1, 1>(pl, ws, chunk, 16, s); break;  // the round's earlier default
-    // 16 nodes per thread, 3 CTAs / SM: 7-tangent batch JVP 38.6 -> 31.0 ms per 1024 cosmologies (scripts/jvp_throughput.py)
+// JVP passes: exact kernel on DualN<ntan>.  One direction: 16 nodes per thread at 3 CTAs / SM (7-tangent batch JVP
+// 38.6 -> 31.0 ms per 1024 cosmologies against one node per thread, profiles/r01_tuning.md).  Tangent groups hold
+// (1 + ntan) x the live values: fewer nodes per thread, registers up to the 255 cap.
+void jc_launch_power_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, int ntan, cudaStream_t s) {
+  switch (ntan) {
+    case 2: launch_power_cfg<DualN<2>, 8, 2>(pl, ws, chunk, 8, s); break;
+    case 3: launch_power_cfg<DualN<3>, 8, 1>(pl, ws, chunk, 8, s); break;
+    case 4: launch_power_cfg<DualN<4>, 8, 1>(pl, ws, chunk, 8, s); break;
     default: launch_power_cfg<Dual, 16, 3>(pl, ws, chunk, 8, s); break;
   }
 }

@@ -1,5 +1,5 @@
 // jc_setup.cu -- K1: per-cosmology setup kernel (background tables, EH constants, sigma8 norm, halofit).
-// Template on the scalar type: double (hot path) or Dual (value + one tangent, JVP passes).
+// Template on the scalar type: double (hot path) or DualN<K> (value + K tangents, JVP passes).
 #include "jc_internal.cuh"
 #include "jc_dual.cuh"
 
@@ -81,7 +81,7 @@ template <class T> struct SetupSmem {
 #define JC_SETUP_MINB 4  // resident CTAs per SM asked of ptxas: 64 registers (80 B spill) and 4 x 47 KB smem; 3 CTAs at 80 registers is 6 % slower
 #endif
 template <class T>
-__global__ void __launch_bounds__(256, sizeof(T) == sizeof(double) ? JC_SETUP_MINB : 2) jc_setup_kernel(JcDevPlan pl, const double* __restrict__ cosmo,
+__global__ void __launch_bounds__(256, sizeof(T) == sizeof(double) ? JC_SETUP_MINB : (sizeof(T) <= 2 * sizeof(double) ? 2 : 1)) jc_setup_kernel(JcDevPlan pl, const double* __restrict__ cosmo,
                                                        const double* __restrict__ tangent, Ws ws, int kdiv) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SetupSmem<T>& S = *reinterpret_cast<SetupSmem<T>*>(smem_raw);
@@ -96,18 +96,19 @@ __global__ void __launch_bounds__(256, sizeof(T) == sizeof(double) ? JC_SETUP_MI
   // JVP passes: workspace entry c carries cosmology c / kdiv with tangent direction c % kdiv (kdiv = 1: one direction for the whole
   // pass; kdiv = K: all K directions of every cosmology in one pass).  Forward passes: kdiv = 1, tangent = nullptr.
   const double* cp = cosmo + (size_t)(c / kdiv) * pl.ncp;
-  if constexpr (sizeof(T) != sizeof(double)) tangent += (size_t)(c % kdiv) * pl.ncp;
+  // A DualN<K> entry carries K directions: rows (c % kdiv) * K ... + K - 1 of the tangent block.
+  if constexpr (JxTangents<T>::N > 0) tangent += (size_t)(c % kdiv) * JxTangents<T>::N * pl.ncp;
   T par[JC_N_COSMO_PARAMS];
 #pragma unroll
   for (int i = 0; i < JC_N_COSMO_PARAMS; ++i) {
     par[i] = T(cp[i]);
-    if constexpr (sizeof(T) != sizeof(double)) par[i].d = tangent[i];
+    jx_seed(par[i], tangent, i, pl.ncp);
   }
   const T Oc = par[0], Ob = par[1], h = par[2], ns = par[3], s8 = par[4], Ok = par[5], w0 = par[6], wa = par[7];
   T gam = T(0.0);  // growth index (core.py:104-105), JC_GROWTH_GAMMA rows only
   if (pl.growth == JC_GROWTH_GAMMA) {
     gam = T(cp[JC_N_COSMO_PARAMS]);
-    if constexpr (sizeof(T) != sizeof(double)) gam.d = tangent[JC_N_COSMO_PARAMS];
+    jx_seed(gam, tangent, JC_N_COSMO_PARAMS, pl.ncp);
   }
   Bg<T> bg;
   bg.Om = Ob + Oc;                 // core.py:144-146
@@ -540,17 +541,36 @@ void jc_launch_transfer(const JcDevPlan& pl, const Ws& ws, int chunk, double* tk
   jc_transfer_kernel<<<dim3((pl.L + 255) / 256, chunk), 256, 0, s>>>(pl, ws, tk);
 }
 
-int jc_setup_init() {
-  JC_CUDA_TRY(cudaFuncSetAttribute(jc_setup_kernel<Dual>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)sizeof(SetupSmem<Dual>)));
+template <class T> static int setup_attr() {
+  JC_CUDA_TRY(cudaFuncSetAttribute(jc_setup_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SetupSmem<T>)));
   return JC_OK;
+}
+
+int jc_setup_init() {
+  static_assert(sizeof(SetupSmem<DualN<JC_JVP_MAX_GROUP>>) <= 227 * 1024, "setup tables of the widest tangent group must fit one SM");
+  int st = setup_attr<DualN<1>>();
+  if (st == JC_OK) st = setup_attr<DualN<2>>();
+  if (st == JC_OK) st = setup_attr<DualN<3>>();
+  if (st == JC_OK) st = setup_attr<DualN<4>>();
+  return st;
 }
 
 void jc_launch_setup(const JcDevPlan& pl, const double* cosmo, const Ws& ws, int chunk, cudaStream_t s) {
   jc_setup_kernel<double><<<chunk, 256, sizeof(SetupSmem<double>), s>>>(pl, cosmo, nullptr, ws, 1);
 }
 
+template <class T>
+static void launch_setup_t(const JcDevPlan& pl, const double* cosmo, const double* tangent, const Ws& ws, int chunk, int kdiv,
+                           cudaStream_t s) {
+  jc_setup_kernel<T><<<chunk, 256, sizeof(SetupSmem<T>), s>>>(pl, cosmo, tangent, ws, kdiv);
+}
+
 void jc_launch_setup_jvp(const JcDevPlan& pl, const double* cosmo, const double* tangent, const Ws& ws, int chunk, int kdiv,
-                         cudaStream_t s) {
-  jc_setup_kernel<Dual><<<chunk, 256, sizeof(SetupSmem<Dual>), s>>>(pl, cosmo, tangent, ws, kdiv);
+                         int ntan, cudaStream_t s) {
+  switch (ntan) {
+    case 2: launch_setup_t<DualN<2>>(pl, cosmo, tangent, ws, chunk, kdiv, s); break;
+    case 3: launch_setup_t<DualN<3>>(pl, cosmo, tangent, ws, chunk, kdiv, s); break;
+    case 4: launch_setup_t<DualN<4>>(pl, cosmo, tangent, ws, chunk, kdiv, s); break;
+    default: launch_setup_t<DualN<1>>(pl, cosmo, tangent, ws, chunk, kdiv, s); break;
+  }
 }

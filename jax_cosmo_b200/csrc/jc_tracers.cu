@@ -9,7 +9,7 @@
 //      Epilogue: WL = (q (1+z) chi 3 H0^2 Om/(2c) + NLA) (1+m)    probes.py:51,71-74,102-129,201-207
 // K2b  finish: NC = n_i(z) b_i(z) H(a)                            probes.py:77-99
 //              + delta_nz source planes and node 512 of the extended sources
-// Both are templates on the scalar type (double / Dual, see jc_dual.cuh).
+// Both are templates on the scalar type (double / DualN<K>, see jc_dual.cuh).
 #include <cstdlib>
 
 #include "jc_internal.cuh"
@@ -250,8 +250,9 @@ int launch_all_lens(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s
   int n_launch = 0;
   for (int s0 = 0; s0 < pl.n_src; ++n_launch) {
     const int rem = pl.n_src - s0;
-    if (rem >= 10) { launch_lens<T, 10, NCOS, CG>(pl, ws, chunk, s0, s); s0 += 10; }
-    else if (rem >= 8) { launch_lens<T, 8, NCOS, CG>(pl, ws, chunk, s0, s); s0 += 8; }
+    constexpr bool WIDE = sizeof(T) > 4 * sizeof(double);  // DualN<4>: 8 or 10 sources per launch would spill the accumulators
+    if (rem >= 10 && !WIDE) { launch_lens<T, 10, NCOS, CG>(pl, ws, chunk, s0, s); s0 += 10; }
+    else if (rem >= 8 && !WIDE) { launch_lens<T, 8, NCOS, CG>(pl, ws, chunk, s0, s); s0 += 8; }
     else if (rem >= 6) { launch_lens<T, 6, NCOS, CG>(pl, ws, chunk, s0, s); s0 += 6; }
     else if (rem >= 5) { launch_lens<T, 5, NCOS, CG>(pl, ws, chunk, s0, s); s0 += 5; }
     else if (rem == 4) { launch_lens<T, 4, NCOS, CG>(pl, ws, chunk, s0, s); s0 += 4; }
@@ -264,17 +265,18 @@ int launch_all_lens(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s
 
 }  // namespace
 
+// 4 cosmologies per thread, 4 cosmology groups per CTA (2 x 8 and 2 x 4 measured slower, profiles/r01_tuning.md)
 int jc_launch_tracers(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s) {
-  static int cfg = -1;
-  if (cfg < 0) { const char* e = getenv("JC_LENS_CFG"); cfg = e ? atoi(e) : 0; }  // tuning knob
-  switch (cfg) {
-    case 1: return launch_all_lens<double, 2, 8>(pl, ws, chunk, s);  // 2 cosmologies per thread, 1024-thread CTAs
-    case 2: return launch_all_lens<double, 2, 4>(pl, ws, chunk, s);
-    default: return launch_all_lens<double, 4, 4>(pl, ws, chunk, s);
-  }
+  return launch_all_lens<double, 4, 4>(pl, ws, chunk, s);
 }
-int jc_launch_tracers_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s) {
-  return launch_all_lens<Dual, 2, 4>(pl, ws, chunk, s);
+// tangent groups: one cosmology per thread (the accumulators are NS x (1 + ntan) doubles)
+int jc_launch_tracers_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, int ntan, cudaStream_t s) {
+  switch (ntan) {
+    case 2: return launch_all_lens<DualN<2>, 1, 4>(pl, ws, chunk, s);
+    case 3: return launch_all_lens<DualN<3>, 1, 4>(pl, ws, chunk, s);
+    case 4: return launch_all_lens<DualN<4>, 1, 4>(pl, ws, chunk, s);
+    default: return launch_all_lens<Dual, 2, 4>(pl, ws, chunk, s);
+  }
 }
 static int finish_threads(const JcDevPlan& pl) {  // rows x n_fin threads, at least one thread per tracer
   const int nf = pl.n_fin > 0 ? pl.n_fin : 1;
@@ -284,6 +286,11 @@ static int finish_threads(const JcDevPlan& pl) {  // rows x n_fin threads, at le
 void jc_launch_finish(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s) {
   jc_tracer_finish_kernel<double><<<chunk, finish_threads(pl), 0, s>>>(pl, ws);
 }
-void jc_launch_finish_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s) {
-  jc_tracer_finish_kernel<Dual><<<chunk, finish_threads(pl), 0, s>>>(pl, ws);
+void jc_launch_finish_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, int ntan, cudaStream_t s) {
+  switch (ntan) {
+    case 2: jc_tracer_finish_kernel<DualN<2>><<<chunk, finish_threads(pl), 0, s>>>(pl, ws); break;
+    case 3: jc_tracer_finish_kernel<DualN<3>><<<chunk, finish_threads(pl), 0, s>>>(pl, ws); break;
+    case 4: jc_tracer_finish_kernel<DualN<4>><<<chunk, finish_threads(pl), 0, s>>>(pl, ws); break;
+    default: jc_tracer_finish_kernel<Dual><<<chunk, finish_threads(pl), 0, s>>>(pl, ws); break;
+  }
 }
