@@ -1,13 +1,17 @@
 #!/bin/bash
-# usage: scripts/gpu_r2b.sh <tag> [full]  -- GPU tests, N=1 bench lines (config5 / config3 / config4 with tangent groups 1..4),
-# one ncu --set full pass over the five pipeline kernels -> ncu_current.json, launch lists
-TAG=$1; FULL=$2
+# usage: scripts/gpu_r2b.sh <tag> [final]
+#   always: GPU tests, N=1 bench line, config4 with tangent groups 4 and 1, config3, one ncu --set full pass over the five
+#           pipeline kernels -> ncu_current.json, launch list of a config4 step
+#   final:  also the CPU arm in the N=1 line, the bench line that reads the fresh ncu_current.json, the launch list of the bench
+#           command and `--impl reference`
+TAG=$1; MODE=$2
 O=gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm --format=csv > $O/${TAG}_smi.log 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a $O/${TAG}_pytest.log
 tail -6 $O/${TAG}_pytest.log
-timeout 300 python bench.py --steps 10 --warmup 3 > $O/${TAG}_bench_n1.json 2> $O/${TAG}_bench_n1.err; echo "bench n1 rc=$?"; tail -2 $O/${TAG}_bench_n1.err
-for G in 4 1 2 3; do
+CPUARM=--no-cpu-baseline; [ "$MODE" = final ] && CPUARM=
+timeout 300 python bench.py --steps 10 --warmup 3 $CPUARM > $O/${TAG}_bench_n1.json 2> $O/${TAG}_bench_n1.err; echo "bench n1 rc=$?"; tail -2 $O/${TAG}_bench_n1.err
+for G in 4 1; do
   JC_JVP_GROUP=$G timeout 300 python bench.py --workload config4 --steps 5 --warmup 3 > $O/${TAG}_config4_g$G.json 2> $O/${TAG}_config4_g$G.err; echo "config4 g$G rc=$?"
 done
 timeout 300 python bench.py --workload config3 --steps 5 --warmup 3 > $O/${TAG}_config3.json 2> $O/${TAG}_config3.err; echo "config3 rc=$?"
@@ -15,11 +19,14 @@ timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:jc_
 echo "ncu pass rc=$?"; tail -3 $O/${TAG}_ncu_pass.log
 python scripts/make_ncu_current.py $TAG 592 $O/${TAG}_pass.ncu-rep > $O/${TAG}_ncu_current.log 2>&1 && cp profiles/ncu_current.json $O/${TAG}_ncu_current.json
 tail -6 $O/${TAG}_ncu_current.log
-timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > $O/${TAG}_bench_n1_ncu.json 2> $O/${TAG}_bench_n1_ncu.err; echo "bench (with ncu_current) rc=$?"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 200 --csv --log-file $O/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --peak-tflops 36.4 > $O/${TAG}_launches_bench.log 2>&1
-echo "launch list rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches_config4.csv python bench.py --workload config4 --steps 1 --warmup 1 > $O/${TAG}_launches_config4.log 2>&1
 echo "launch list config4 rc=$?"
+if [ "$MODE" = final ]; then
+  timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_n1_ncu.json 2> $O/${TAG}_bench_n1_ncu.err; echo "bench (with ncu_current) rc=$?"
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 200 --csv --log-file $O/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --peak-tflops 36.4 > $O/${TAG}_launches_bench.log 2>&1
+  echo "launch list rc=$?"
+  timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_reference_arm.json 2> $O/${TAG}_reference_arm.err; echo "reference arm rc=$?"
+fi
 python - $TAG <<'P'
 import json,glob,sys
 tag=sys.argv[1]
