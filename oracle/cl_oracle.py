@@ -552,7 +552,9 @@ def radial_kernels(bg, tracers, z):
     c = bg.c
     a = 1.0 / (1.0 + z)
     Hz = H0 * np.sqrt(Esqr(c, a))
-    R = np.zeros((len(tracers), len(z)), dtype=np.result_type(Hz, np.float64))
+    # complex-step runs (oracle/derivatives.py): a perturbed gamma reaches R through the growth factor only, Omega_m / w0 / wa
+    # through H and chi as well
+    R = np.zeros((len(tracers), len(z)), dtype=np.result_type(Hz, bg.growth(a), bg.chi(a), np.float64))
     is_wl = np.zeros(len(tracers), dtype=bool)
     wl_idx = [i for i, t in enumerate(tracers) if t["kind"] == "wl"]
     # lensing efficiency is computed per probe in the reference; all WL tracers sharing the same

@@ -27,3 +27,17 @@ def test_complex_step_identities():
     cl, jac = od.cs_jacobian(row, ell, prob, params=("sigma8", "n_s"))
     assert np.max(np.abs(jac[0] / (2.0 * cl / row[4]) - 1.0)) < 1e-12
     assert np.all(np.isfinite(jac)) and np.abs(jac[1]).max() > 0
+
+
+def test_complex_step_gamma_growth():
+    """9-column rows (growth index gamma, core.py:104-105): a perturbed gamma reaches the tracer kernels through the growth factor
+    only (IA and inverse-growth bias), while H(z) and chi stay real -- the kernel table must still hold the imaginary part."""
+    scn = [s for s in sc.golden_scenarios() if s["name"] == "switch_gamma_growth"][0]
+    row, prob, ell = sc.cosmo_row(scn["cosmo"]), sc.flatten_spec(scn), sc.ELL_CFG2[::12]
+    assert row.shape == (9,)
+    cl, jac = od.cs_jacobian(row, ell, prob, params=("sigma8", "gamma"))
+    assert np.array_equal(cl, o.angular_cl(row, ell, prob))
+    _, jfd, _ = od.fd_jacobian(row, ell, prob, params=("gamma",))
+    scale = np.abs(jac[1]).max(axis=1, keepdims=True)
+    assert np.abs(jac[1]).max() > 0
+    assert (np.abs(jfd[0] - jac[1]) / scale).max() < 1e-6
