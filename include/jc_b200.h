@@ -233,14 +233,19 @@ int jc_angular_cl_f64(const jc_plan* plan, const double* cosmo_dev, int64_t n_co
  * directional derivative of cl[b] along it -- the derivative of the discretised program with
  * interpolation / root indices and clip branches frozen at the evaluation point.  cl_dev may be NULL.
  * cosmo_dev [B,8], tangents_dev [K,8], cl_dev [B,P,L], dcl_dev [B,K,P,L].
- * Throughput path: every pass carries a GROUP of g = min(K, jvp_group) directions through one evaluation of the value
- * (the kernels run on value + g tangents, so the exp / log / sin / reciprocals of K1..K3 are computed once per group; the
- * 7 wCDM parameters run as 4 + 3).  The workspace is cut into 1 + g planes: jc_workspace_bytes_jvp_group(plan, B, K) sizes
- * it for the full group; with less (jc_workspace_bytes_jvp() = 2 x jc_workspace_bytes() is the minimum) the group shrinks,
- * down to one direction per pass.  jc_set_option("jvp_group", 1..4) caps g (default 4).
- * Small batches: when the workspace has room for B*K <= 1024 entries (ask jc_workspace_bytes_jvp(plan, B*K)), all K
+ * Throughput path (jc_workspace_bytes_jvp_group(plan, B, K) sizes the workspace):
+ *   K1 / K2 run on value + g <= 4 tangents per pass (DualN<g> kernels: the exp / log / reciprocals are computed once per
+ *   group; the 7 wCDM parameters run as 4 + 3);
+ *   K3 for 3 <= K <= 8 directions (Eisenstein-Hu with wiggles) takes ONE reverse sweep of the (ell, node) point function and
+ *   forms every directional derivative from it with one multiply-add per input (jc_power_adj.cu); otherwise K3 runs on
+ *   DualN<g> as well;
+ *   K4: one tangent contraction per direction.
+ *   With a smaller workspace (jc_workspace_bytes_jvp() = 2 x jc_workspace_bytes() is the minimum) the tangent groups shrink,
+ *   down to one direction per pass.  jc_set_option("jvp_group", 1..4) caps g, jc_set_option("jvp_adjoint", 0) disables the
+ *   reverse sweep (A/B partners of the tests).
+ * Small batches: when the workspace has room for B*K <= 512 entries (ask jc_workspace_bytes_jvp(plan, B*K)), all K
  * directions of every cosmology run in ONE pass over B*K one-direction entries instead of latency-bound passes (a Jacobian
- * at one cosmology: 0.58 ms instead of 2.5 ms).  Group size changes the results by rounding only (<= 1e-13 relative). */
+ * at one cosmology: 0.58 ms instead of 2.5 ms).  The modes differ by rounding only (<= 1e-12 of a spectrum's largest derivative). */
 int jc_workspace_bytes_jvp(const jc_plan* plan, int64_t n_cosmo, size_t* bytes_out);
 int jc_workspace_bytes_jvp_group(const jc_plan* plan, int64_t n_cosmo, int32_t n_tangents, size_t* bytes_out);
 int jc_angular_cl_jvp_f64(const jc_plan* plan, const double* cosmo_dev, const double* tangents_dev,
@@ -441,7 +446,8 @@ int jc_debug_math_f64(int32_t fn, const double* x_dev, double* y_dev, int64_t n,
  *                           (default 1e-20; also env JC_CONTRACT_EPS);
  *   "contract_kernel" 0..3  0: persistent TMA contraction where it applies (>= 17 pair tiles), 3: the cp.async kernel
  *                           everywhere (all node stages, the reference's pair order) -- the A/B partner of the tests;
- *   "jvp_group"     1..4    tangent directions carried per pass of jc_angular_cl_jvp_f64 (default 4; also env JC_JVP_GROUP). */
+ *   "jvp_group"     1..4    tangent directions carried per pass of jc_angular_cl_jvp_f64 (default 4; also env JC_JVP_GROUP);
+ *   "jvp_adjoint"   0 | 1   1: K3 of jc_angular_cl_jvp_f64 by one reverse sweep for 3..8 directions (default 1; env JC_JVP_ADJOINT). */
 int jc_set_option(const char* name, double value);
 int jc_get_option(const char* name, double* value_out);
 

@@ -473,9 +473,9 @@ class Plan:
         self._check_rows(tangents_dev, "tangents")
         B, K = cosmo_dev.shape[0], tangents_dev.shape[0]
         need = C.c_size_t()
-        if B * K <= 1024:  # small batches: room for B*K workspace entries lets the library run all K directions in one pass
+        if B * K <= 512:  # small batches: room for B*K workspace entries lets the library run all K directions in one pass
             check(load_library().jc_workspace_bytes_jvp(self._h, B * K, C.byref(need)), "jc_workspace_bytes_jvp")
-        else:  # throughput: a value plane + one plane per direction of a tangent group (4 + 3 for the 7 wCDM parameters)
+        else:  # throughput: value plane + tangent planes of every direction (reverse-sweep K3) or of one tangent group
             check(load_library().jc_workspace_bytes_jvp_group(self._h, B, K, C.byref(need)), "jc_workspace_bytes_jvp_group")
         ws = torch.empty(need.value // 8, dtype=torch.float64, device=cosmo_dev.device)
         cl = torch.empty((B, self.P, self.L), dtype=torch.float64, device=cosmo_dev.device)

@@ -4,7 +4,7 @@ set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
 OUT="$HERE/../libjc_b200.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-SRCS="jc_plan.cu jc_setup.cu jc_tracers.cu jc_power.cu jc_contract.cu jc_pipeline.cu jc_gather.cu jc_loglike.cu jc_cl_loglike.cu jc_sparse.cu jc_api.cu"
+SRCS="jc_plan.cu jc_setup.cu jc_tracers.cu jc_power.cu jc_power_adj.cu jc_contract.cu jc_pipeline.cu jc_gather.cu jc_loglike.cu jc_cl_loglike.cu jc_sparse.cu jc_api.cu"
 mkdir -p "$HERE/build"
 pids=()
 for f in $SRCS; do

@@ -22,6 +22,7 @@ static double env_double(const char* name, double dflt) { const char* e = getenv
 int g_jc_power_exact = env_int("JC_POWER_EXACT", 0);
 double g_jc_contract_eps = env_double("JC_CONTRACT_EPS", 1e-20);
 int g_jc_jvp_group = env_int("JC_JVP_GROUP", JC_JVP_MAX_GROUP);
+int g_jc_jvp_adjoint = env_int("JC_JVP_ADJOINT", 1);
 
 extern "C" int jc_set_option(const char* name, double value) {
   if (!name) return JC_ERR_INVALID;
@@ -29,6 +30,7 @@ extern "C" int jc_set_option(const char* name, double value) {
   if (!strcmp(name, "contract_eps")) { if (!(value >= -1.0) || value > 1e-6) return JC_ERR_INVALID; g_jc_contract_eps = value; return JC_OK; }
   if (!strcmp(name, "contract_kernel")) { const int v = (int)value; if (v < 0 || v > 3) return JC_ERR_INVALID; g_contract_cfg = v; return JC_OK; }
   if (!strcmp(name, "jvp_group")) { const int v = (int)value; if (v < 1 || v > JC_JVP_MAX_GROUP) return JC_ERR_INVALID; g_jc_jvp_group = v; return JC_OK; }
+  if (!strcmp(name, "jvp_adjoint")) { g_jc_jvp_adjoint = value != 0.0; return JC_OK; }
   return JC_ERR_INVALID;
 }
 extern "C" int jc_get_option(const char* name, double* value_out) {
@@ -37,6 +39,7 @@ extern "C" int jc_get_option(const char* name, double* value_out) {
   if (!strcmp(name, "contract_eps")) { *value_out = g_jc_contract_eps; return JC_OK; }
   if (!strcmp(name, "contract_kernel")) { *value_out = g_contract_cfg < 0 ? 0 : g_contract_cfg; return JC_OK; }
   if (!strcmp(name, "jvp_group")) { *value_out = g_jc_jvp_group; return JC_OK; }
+  if (!strcmp(name, "jvp_adjoint")) { *value_out = g_jc_jvp_adjoint; return JC_OK; }
   return JC_ERR_INVALID;
 }
 extern "C" int32_t jc_abi_version(void) { return JC_ABI_VERSION; }

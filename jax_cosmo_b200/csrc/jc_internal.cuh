@@ -175,6 +175,7 @@ struct JcDeviceGuard {
 void jc_set_cuda_error(cudaError_t e, const char* where);
 extern int g_jc_power_exact;      // jc_set_option("power_exact"): exact-formula power kernel everywhere
 extern int g_contract_cfg;        // jc_set_option("contract_kernel")
+extern int g_jc_jvp_adjoint;      // jc_set_option("jvp_adjoint"): 1 = reverse sweep of the point function in K3 for >= 3 directions (default)
 extern int g_jc_jvp_group;        // jc_set_option("jvp_group"): tangent directions carried per JVP pass (1..JC_JVP_MAX_GROUP)
 extern double g_jc_contract_eps;  // jc_set_option("contract_eps"): support threshold of the contraction, read at plan creation
 typedef int (*jc_slice_cb)(void* ctx, int64_t first_row, int64_t rows);
@@ -228,6 +229,18 @@ void jc_launch_finish_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, int ntan
 void jc_launch_power_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, int ntan, cudaStream_t s);
 void jc_launch_contract_jvp(const JcDevPlan& pl, const Ws& ws, double* dcl, int64_t dcl_cosmo_stride, int chunk,
                             cudaStream_t s);
+// K3 for all directions of a Jacobian at once: value + ntan directional derivatives from one reverse sweep of the point function
+// (jc_power_adj.cu).  Direction k's tangent plane of every table sits at jc_jvp_plane(k) * ws.doff: the planes written by the
+// grouped K1 / K2 passes when group j = k / JC_JVP_MAX_GROUP runs on the workspace shifted by j * (JC_JVP_MAX_GROUP + 1) planes.
+#define JC_JVP_ADJ_MAX 8
+#define JC_JVP_FUSED_MAX 512  // B*K up to which a small batch runs as B*K one-direction entries in one (latency-bound) pass
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline int jc_jvp_plane(int k) { return (k / JC_JVP_MAX_GROUP) * (JC_JVP_MAX_GROUP + 1) + (k % JC_JVP_MAX_GROUP) + 1; }
+inline int jc_jvp_planes(int ntan) { return jc_jvp_plane(ntan - 1) + 1; }  // planes a workspace for ntan directions holds
+bool jc_power_adj_supported(const JcDevPlan& pl, int ntan);
+void jc_launch_power_adj(const JcDevPlan& pl, const Ws& ws, int chunk, int ntan, cudaStream_t s);
 int jc_setup_init();
 int jc_launch_tracers(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s);  // lensing; returns #launches
 void jc_launch_finish(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s);

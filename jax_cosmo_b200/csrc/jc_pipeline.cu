@@ -50,12 +50,16 @@ extern "C" int jc_workspace_bytes_jvp(const jc_plan* plan, int64_t n_cosmo, size
   return st;
 }
 
-// Workspace for the grouped JVP: a value plane and min(n_tangents, jvp_group) tangent planes of min(n_cosmo, JC_MAX_CHUNK) entries.
+// Workspace of the throughput path for min(n_cosmo, JC_MAX_CHUNK) entries: a value plane and the tangent planes of the mode
+// jc_angular_cl_jvp_f64 will pick (reverse-sweep K3: jc_jvp_planes(K) planes, all K directions resident; tangent groups: 1 + g).
+static bool use_adjoint(const JcDevPlan& pl, int n_tangents) {
+  return g_jc_jvp_adjoint && g_jc_jvp_group == JC_JVP_MAX_GROUP && jc_power_adj_supported(pl, n_tangents);
+}
 extern "C" int jc_workspace_bytes_jvp_group(const jc_plan* plan, int64_t n_cosmo, int32_t n_tangents, size_t* bytes_out) {
-  if (n_tangents < 1) return JC_ERR_INVALID;
-  int st = jc_workspace_bytes(plan, n_cosmo, bytes_out);
+  if (!plan || n_tangents < 1) return JC_ERR_INVALID;
+  int st = jc_workspace_bytes(plan, n_cosmo < 1024 ? n_cosmo : 1024, bytes_out);  // 1024 entries per pass fill the GPU 7 times
   const int g = n_tangents < g_jc_jvp_group ? n_tangents : g_jc_jvp_group;
-  if (st == JC_OK) *bytes_out *= (size_t)(1 + g);
+  if (st == JC_OK) *bytes_out = (*bytes_out + 16) * (size_t)(use_adjoint(plan->d, n_tangents) ? jc_jvp_planes(n_tangents) : 1 + g);
   return st;
 }
 
@@ -74,7 +78,7 @@ extern "C" int jc_angular_cl_jvp_f64(const jc_plan* plan, const double* cosmo_de
   Ws ws;
   resolve(lo, (double*)ws_dev, (ptrdiff_t)((lo.total + 1) & ~(int64_t)1), &ws);
   const int64_t PL = (int64_t)pl.P * pl.L;
-  if (n_tangents > 1 && n_cosmo * n_tangents <= lo.chunk && n_cosmo * n_tangents <= 1024) {
+  if (n_tangents > 1 && n_cosmo * n_tangents <= lo.chunk && n_cosmo * n_tangents <= JC_JVP_FUSED_MAX) {
     // Small batches (a Fisher forecast at one cosmology): all K directions of every cosmology in ONE pass over B*K workspace
     // entries (entry b*K + k = cosmology b, direction k, which is also the layout of dcl) instead of K latency-bound passes.
     // Needs a workspace for B*K entries (jc_workspace_bytes_jvp(plan, B*K)); per-entry arithmetic is the same, results are
@@ -98,8 +102,40 @@ extern "C" int jc_angular_cl_jvp_f64(const jc_plan* plan, const double* cosmo_de
   // the transcendentals of K1..K3 are computed once per group; 7 parameters = groups of 4 + 3).  The workspace is cut into
   // 1 + g planes of `chunk` entries; the group shrinks when the planes would otherwise hold fewer entries than the batch
   // needs to fill the GPU.  The tangent contraction runs per direction on (value plane, tangent plane k).
-  int group = n_tangents < g_jc_jvp_group ? n_tangents : g_jc_jvp_group;
   const int64_t want = n_cosmo < 148 ? n_cosmo : 148;  // entries per pass that keep every SM busy
+  // Reverse-sweep K3 (>= 3 directions, Eisenstein-Hu with wiggles): K1 / K2 run per group of 4 directions on the workspace shifted
+  // by 5 planes per group, so that the tangents of EVERY direction are resident; K3 then produces V and all K directional
+  // derivatives from one reverse sweep of the point function (jc_power_adj.cu) -- ~2 x the value + one multiply-add per input and
+  // direction instead of ~225 FP64 instructions per direction.
+  if (use_adjoint(pl, n_tangents)) {
+    const int planes = jc_jvp_planes(n_tangents);
+    jc_ws_layout la;
+    if (jc_workspace_layout(plan, ws_bytes / (size_t)planes, &la) == JC_OK && la.chunk >= want) {
+      const ptrdiff_t doff = (ptrdiff_t)((la.total + 1) & ~(int64_t)1);
+      resolve(la, (double*)ws_dev, doff, &ws);
+      for (int64_t c0 = 0; c0 < n_cosmo; c0 += la.chunk) {
+        const int chunk = (int)((n_cosmo - c0) < la.chunk ? (n_cosmo - c0) : la.chunk);
+        for (int k0 = 0; k0 < n_tangents; k0 += JC_JVP_MAX_GROUP) {
+          const int g = (n_tangents - k0) < JC_JVP_MAX_GROUP ? (n_tangents - k0) : JC_JVP_MAX_GROUP;
+          Ws wg;  // this group's value plane = plane jc_jvp_plane(k0) - 1 of the workspace
+          resolve(la, (double*)ws_dev + (ptrdiff_t)(jc_jvp_plane(k0) - 1) * doff, doff, &wg);
+          jc_launch_setup_jvp(pl, cosmo_dev + c0 * pl.ncp, tangents_dev + (size_t)k0 * pl.ncp, wg, chunk, 1, g, s);
+          jc_launch_tracers_jvp(pl, wg, chunk, g, s);
+          jc_launch_finish_jvp(pl, wg, chunk, g, s);
+        }
+        jc_launch_power_adj(pl, ws, chunk, n_tangents, s);
+        if (cl_dev) jc_launch_contract(pl, ws, cl_dev + (size_t)c0 * PL, chunk, s);  // value plane
+        for (int k = 0; k < n_tangents; ++k) {
+          Ws wk = ws;
+          wk.doff = (ptrdiff_t)jc_jvp_plane(k) * doff;  // the contraction pairs the value plane with direction k's plane
+          jc_launch_contract_jvp(pl, wk, dcl_dev + ((size_t)c0 * n_tangents + k) * PL, (int64_t)n_tangents * PL, chunk, s);
+        }
+      }
+      JC_CUDA_TRY(cudaGetLastError());
+      return JC_OK;
+    }
+  }
+  int group = n_tangents < g_jc_jvp_group ? n_tangents : g_jc_jvp_group;
   while (group > 1) {
     jc_ws_layout lg;
     if (jc_workspace_layout(plan, ws_bytes / (size_t)(1 + group), &lg) == JC_OK && lg.chunk >= want) break;

@@ -500,39 +500,52 @@ def test_jvp_fused_directions_bitwise(jc, torch_cuda):
     assert torch.isfinite(dcl).all() and float(dcl.abs().max()) > 0
 
 
-@pytest.mark.parametrize("n_rows,dirs", [(160, 7), (260, 5), (350, 3)])
-def test_jvp_tangent_groups(jc, torch_cuda, n_rows, dirs):
-    """Throughput path of jc_angular_cl_jvp_f64 (B*K > 1024 entries): passes carry groups of up to 4 directions on DualN<g>
-    kernels (7 = 4 + 3, 5 = 4 + 1, 3 = 3).  Held against the one-direction-per-pass mode (jvp_group = 1) and against the fused
-    small-batch mode, which the complex-step oracle pins (test_jvp_config4): the value is shared, every tangent keeps its own
-    expression, so the modes agree to rounding."""
+@pytest.mark.parametrize("n_rows,dirs,nl", [(160, 7, "halofit"), (260, 5, "halofit"), (350, 3, "linear"), (300, 2, "halofit"),
+                                            (140, 4, "smith2003")])
+def test_jvp_throughput_modes(jc, torch_cuda, n_rows, dirs, nl):
+    """Throughput path of jc_angular_cl_jvp_f64 (B*K > 512 entries).  Default: K1 / K2 on tangent groups (DualN<g>, 7 = 4 + 3) and K3
+    by ONE reverse sweep of the point function for 3..8 directions (jc_power_adj.cu).  A/B partners: tangent groups in K3 as well
+    (jvp_adjoint = 0), one direction per pass (jvp_group = 1), and the fused small-batch mode that the complex-step oracle pins
+    (test_jvp_config4).  All share the value's arithmetic; the derivatives agree to rounding (forward-mode variants 1e-12, the
+    reverse sweep -- a different summation order -- 1e-10 of a spectrum's largest derivative)."""
     torch = torch_cuda
     from jax_cosmo_b200 import _native
-    scn = sc.scenario("jg", sc.PLANCK15, sc.ELL_CFG2[::9], [sc.sources(5, 2.0, True), sc.lenses(5, 2.0, True)])
-    plan = _native.get_plan(sc.build_probes(scn, jc), scn["ell"], None, None)
+    scn = sc.scenario("jg", sc.PLANCK15, sc.ELL_CFG2[::9], [sc.sources(5, 2.0, True), sc.lenses(5, 2.0, True)],
+                      "linear" if nl == "linear" else "halofit", prescription="smith2003" if nl == "smith2003" else "takahashi2012")
+    tf, nlf = sc.build_fns(scn, jc)
+    plan = _native.get_plan(sc.build_probes(scn, jc), scn["ell"], tf, nlf)
     rows = torch.as_tensor(sc.config5_cosmologies(n_rows), device="cuda")
     cols = [0, 1, 2, 3, 4, 6, 7][:dirs]
     tang = torch.zeros((dirs, 8), dtype=torch.float64, device="cuda")
     tang[torch.arange(dirs), torch.tensor(cols)] = 1.0
     tang[dirs - 1, 0] = 0.5  # a mixed direction
-    assert n_rows * dirs > 1024
-    assert _native.get_option("jvp_group") == 4.0
-    cl, dcl = plan.angular_cl_jvp_device(rows, tang)  # grouped
+    assert n_rows * dirs > 512
+    assert _native.get_option("jvp_group") == 4.0 and _native.get_option("jvp_adjoint") == 1.0
+    cl, dcl = plan.angular_cl_jvp_device(rows, tang)  # default: reverse-sweep K3 for >= 3 directions
+    others = {}
     try:
-        _native.set_option("jvp_group", 1)
-        cl1, dcl1 = plan.angular_cl_jvp_device(rows, tang)  # one direction per pass
+        _native.set_option("jvp_adjoint", 0)
+        others["groups of 4"] = plan.angular_cl_jvp_device(rows, tang)
         _native.set_option("jvp_group", 2)
-        cl2, dcl2 = plan.angular_cl_jvp_device(rows, tang)
+        others["groups of 2"] = plan.angular_cl_jvp_device(rows, tang)
+        _native.set_option("jvp_group", 1)
+        others["one direction per pass"] = plan.angular_cl_jvp_device(rows, tang)
     finally:
         _native.set_option("jvp_group", 4)
+        _native.set_option("jvp_adjoint", 1)
     assert torch.isfinite(dcl).all() and float(dcl.abs().max()) > 0
+    cl1, dcl1 = others["one direction per pass"]
     scale = dcl1.abs().amax(dim=3, keepdim=True)
-    for other_cl, other_d in ((cl1, dcl1), (cl2, dcl2)):
-        assert float(((cl - other_cl).abs() / other_cl.abs()).max()) < 1e-13
-        assert float(((dcl - other_d).abs() / scale).max()) < 1e-12
-    clf, dclf = plan.angular_cl_jvp_device(rows[:40].contiguous(), tang)  # <= 1024 entries: fused one-direction entries
-    assert float(((cl[:40] - clf).abs() / clf.abs()).max()) < 1e-13
-    assert float(((dcl[:40] - dclf).abs() / scale[:40]).max()) < 1e-12
+    for name, (ocl, od) in others.items():
+        assert float(((ocl - cl1).abs() / cl1.abs()).max()) < 1e-13, name
+        assert float(((od - dcl1).abs() / scale).max()) < 1e-12, name
+    assert float(((cl - cl1).abs() / cl1.abs()).max()) < 1e-13
+    worst = float(((dcl - dcl1).abs() / scale).max())
+    print("reverse-sweep K3 vs forward mode, %d directions: %.2e" % (dirs, worst))
+    assert worst < (1e-10 if dirs >= 3 else 1e-12)
+    clf, dclf = plan.angular_cl_jvp_device(rows[:40].contiguous(), tang)  # <= 512 entries: fused one-direction entries
+    assert float(((cl1[:40] - clf).abs() / clf.abs()).max()) < 1e-13
+    assert float(((dcl1[:40] - dclf).abs() / scale[:40]).max()) < 1e-12
 
 
 def test_two_devices_in_one_process(jc, torch_cuda):
