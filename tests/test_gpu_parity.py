@@ -520,10 +520,12 @@ def test_jvp_throughput_modes(jc, torch_cuda, n_rows, dirs, nl):
     tang[torch.arange(dirs), torch.tensor(cols)] = 1.0
     tang[dirs - 1, 0] = 0.5  # a mixed direction
     assert n_rows * dirs > 512
-    assert _native.get_option("jvp_group") == 4.0 and _native.get_option("jvp_adjoint") == 1.0
-    cl, dcl = plan.angular_cl_jvp_device(rows, tang)  # default: reverse-sweep K3 for >= 3 directions
+    assert _native.get_option("jvp_group") == 4.0
+    adjoint_default = _native.get_option("jvp_adjoint")
     others = {}
     try:
+        _native.set_option("jvp_adjoint", 1)
+        cl, dcl = plan.angular_cl_jvp_device(rows, tang)  # reverse-sweep K3 for >= 3 directions
         _native.set_option("jvp_adjoint", 0)
         others["groups of 4"] = plan.angular_cl_jvp_device(rows, tang)
         _native.set_option("jvp_group", 2)
@@ -532,7 +534,7 @@ def test_jvp_throughput_modes(jc, torch_cuda, n_rows, dirs, nl):
         others["one direction per pass"] = plan.angular_cl_jvp_device(rows, tang)
     finally:
         _native.set_option("jvp_group", 4)
-        _native.set_option("jvp_adjoint", 1)
+        _native.set_option("jvp_adjoint", adjoint_default)
     assert torch.isfinite(dcl).all() and float(dcl.abs().max()) > 0
     cl1, dcl1 = others["one direction per pass"]
     scale = dcl1.abs().amax(dim=3, keepdim=True)
