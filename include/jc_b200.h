@@ -199,6 +199,9 @@ enum {
   JC_SCAL_OMEGA_M,
   JC_SCAL_ALPHA_GAMMA, /* no-wiggle fit  transfer.py:87-91    */
   JC_SCAL_OMH_T27,     /* Omega_m h / (tcmb/2.7)^2: q = k / (this * gamma shape), transfer.py:92-100 */
+  JC_SCAL_MOVES_R,     /* forward-mode passes only: tangent plane k holds 1 when direction k can change the tracer kernels
+                          R_i(a) (a component along Omega_c, Omega_b, Omega_k, w0, wa or gamma), 0 when dR = 0 identically
+                          (h, n_s, sigma8 reach C_ell through P(k) alone); the value plane holds 0 */
   JC_SCAL_FIELDS = 32
 };
 

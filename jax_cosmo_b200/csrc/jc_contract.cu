@@ -48,8 +48,9 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 }
 
 // One pipeline stage (KC/4 k-steps) of a warp's CNT x NT accumulator tiles.  `half` = doubles from the
-// value image [R | V] of a stage to its tangent image (JVP only).
-template <int KC, int CNT, int NT, bool JVP, int M0 = 0>
+// value image [R | V] of a stage to its tangent image (JVP only).  JVP: 0 = value, 1 = tangent (both products),
+// 2 = tangent of a direction with dR = 0 (h, n_s, sigma8: JC_SCAL_MOVES_R): (R_i R_j) . dV only.
+template <int KC, int CNT, int NT, int JVP, int M0 = 0>
 __device__ __forceinline__ void mma_stage(const double* __restrict__ Rs, const double* __restrict__ Vs,
                                           int TS, int half, int g, int tig, const int (&ti)[2], const int (&tj)[2],
                                           double (&acc)[2][NTW][2]) {
@@ -60,14 +61,16 @@ __device__ __forceinline__ void mma_stage(const double* __restrict__ Rs, const d
     double a[CNT], b[NT];
 #pragma unroll
     for (int mt = 0; mt < CNT; ++mt) a[mt] = rr[ti[M0 + mt]] * rr[tj[M0 + mt]];
+    if (JVP == 0) {
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) b[nt] = vr[nt * 8];
-    if (!JVP) {
+      for (int nt = 0; nt < NT; ++nt) b[nt] = vr[nt * 8];
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int mt = 0; mt < CNT; ++mt) dmma(acc[M0 + mt][nt][0], acc[M0 + mt][nt][1], a[mt], b[nt]);
-    } else {
+    } else if (JVP == 1) {
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) b[nt] = vr[nt * 8];
       double ad[CNT], bd[NT];
 #pragma unroll
       for (int mt = 0; mt < CNT; ++mt)
@@ -81,11 +84,18 @@ __device__ __forceinline__ void mma_stage(const double* __restrict__ Rs, const d
           dmma(acc[M0 + mt][nt][0], acc[M0 + mt][nt][1], ad[mt], b[nt]);
           dmma(acc[M0 + mt][nt][0], acc[M0 + mt][nt][1], a[mt], bd[nt]);
         }
+    } else {
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) b[nt] = vr[half + nt * 8];  // dV
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int mt = 0; mt < CNT; ++mt) dmma(acc[M0 + mt][nt][0], acc[M0 + mt][nt][1], a[mt], b[nt]);
     }
   }
 }
 
-template <int KC, int CNT, bool JVP, int M0 = 0>
+template <int KC, int CNT, int JVP, int M0 = 0>
 __device__ __forceinline__ void mma_stage_nt(int ntw, const double* Rs, const double* Vs, int TS, int half, int g,
                                              int tig, const int (&ti)[2], const int (&tj)[2],
                                              double (&acc)[2][NTW][2]) {
@@ -98,6 +108,11 @@ __device__ __forceinline__ void mma_stage_nt(int ntw, const double* Rs, const do
     case 2: mma_stage<KC, CNT, 2, JVP, M0>(Rs, Vs, TS, half, g, tig, ti, tj, acc); break;
     default: mma_stage<KC, CNT, 1, JVP, M0>(Rs, Vs, TS, half, g, tig, ti, tj, acc); break;
   }
+}
+
+// tangent kernels: does the direction staged in the tangent planes move the tracer kernels of cosmology c?  (setup kernel)
+__device__ __forceinline__ bool tangent_moves_r(const Ws& ws, int c) {
+  return ws.scal[(size_t)c * JC_SCAL_FIELDS + JC_SCAL_MOVES_R + ws.doff] != 0.0;
 }
 
 // Epilogue of the TMA kernel: tiles follow the plan's contraction order (pl.cpair_*): sorted pair q = tile * 8 + g is row
@@ -188,6 +203,7 @@ jc_contract_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64_t o
   const int mtiles = min(mtiles_all, m_lo + m_per_cta);  // this CTA owns pair tiles [m_lo, mtiles)
   const double* Rg = ws.rker + (size_t)c * JC_NA_PAD * TS;
   const double* Vg = ws.vtab + (size_t)c * JC_NA * pl.Lpad + l0;
+  const bool with_dr = JVP && tangent_moves_r(ws, c);  // CTA-uniform
 
   // fixed copy slots of this thread: piece q = tid + j*blockDim of the stage image(s) [R | V] (| [dR | dV])
   const double* slot_src[MAX_SLOTS];
@@ -259,8 +275,16 @@ jc_contract_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64_t o
       __syncthreads();  // stage kc landed; stage kc-1 (refilled below) is no longer read by anyone
       const double* Rs = smem + (size_t)(kc % STAGES) * stage_doubles;
       const double* Vs = Rs + KC * TS;
-      if (cnt == 2) mma_stage_nt<KC, 2, JVP>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
-      else if (cnt == 1) mma_stage_nt<KC, 1, JVP>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+      if (!JVP) {
+        if (cnt == 2) mma_stage_nt<KC, 2, 0>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+        else if (cnt == 1) mma_stage_nt<KC, 1, 0>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+      } else if (with_dr) {
+        if (cnt == 2) mma_stage_nt<KC, 2, 1>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+        else if (cnt == 1) mma_stage_nt<KC, 1, 1>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+      } else {
+        if (cnt == 2) mma_stage_nt<KC, 2, 2>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+        else if (cnt == 1) mma_stage_nt<KC, 1, 2>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+      }
       if (kc + STAGES - 1 < NKC) load_stage(kc + STAGES - 1);
       cp_async_commit();
     }
@@ -363,6 +387,7 @@ jc_contract_tma_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64
   int q = 0;
   int rot = blockIdx.x;
   for (int c = blockIdx.x; c < chunk; c += gridDim.x) {
+    const bool with_dr = JVP && tangent_moves_r(ws, c);
     for (int grp = 0; grp < ngroups; ++grp) {
       const int l0 = grp * NCOLS;
       const int ntw = (min(pl.L - l0, NCOLS) + 7) >> 3;
@@ -401,9 +426,19 @@ jc_contract_tma_kernel(JcDevPlan pl, Ws ws, double* __restrict__ out_base, int64
           const double* Vs = Rs + KC * TS;
           // stages outside a tile's range hold exact zeros (or values below the plan's threshold) of R_i R_j: skipped
           const bool a0 = kc >= s_lo[0] && kc <= s_hi[0], a1 = kc >= s_lo[1] && kc <= s_hi[1];
-          if (a0 && a1) mma_stage_nt<KC, 2, JVP, 0>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
-          else if (a0) mma_stage_nt<KC, 1, JVP, 0>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
-          else if (a1) mma_stage_nt<KC, 1, JVP, 1>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+          if (!JVP) {
+            if (a0 && a1) mma_stage_nt<KC, 2, 0, 0>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+            else if (a0) mma_stage_nt<KC, 1, 0, 0>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+            else if (a1) mma_stage_nt<KC, 1, 0, 1>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+          } else if (with_dr) {
+            if (a0 && a1) mma_stage_nt<KC, 2, 1, 0>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+            else if (a0) mma_stage_nt<KC, 1, 1, 0>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+            else if (a1) mma_stage_nt<KC, 1, 1, 1>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+          } else {
+            if (a0 && a1) mma_stage_nt<KC, 2, 2, 0>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+            else if (a0) mma_stage_nt<KC, 1, 2, 0>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+            else if (a1) mma_stage_nt<KC, 1, 2, 1>(ntw, Rs, Vs, TS, half, g, tig, ti, tj, acc);
+          }
           __syncwarp();
           if (lane == 0) mbar_arrive(empty + sb);
           // the lightest-loaded warp of the item (v = 15 holds one tile at most) doubles as the producer: once all 16

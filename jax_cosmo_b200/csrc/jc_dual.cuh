@@ -62,6 +62,18 @@ JCD void jx_seed(DualN<K>& x, const double* __restrict__ tangent, int i, int row
   JCD_EACH x.d[k] = tangent[(size_t)k * row_stride + i];
 }
 
+// tangent k of `flag` := 1 when direction k has a component along a parameter the tracer kernels depend on (columns Omega_c,
+// Omega_b, Omega_k, w0, wa, gamma of a cosmology row), else 0
+__device__ __forceinline__ void jx_flag_moves_r(double&, const double*, int) {}
+JCD void jx_flag_moves_r(DualN<K>& flag, const double* __restrict__ tangent, int ncp) {
+  JCD_EACH {
+    const double* t = tangent + (size_t)k * ncp;
+    bool any = t[0] != 0.0 || t[1] != 0.0 || t[5] != 0.0 || t[6] != 0.0 || t[7] != 0.0;
+    if (ncp > 8) any = any || t[8] != 0.0;
+    flag.d[k] = any ? 1.0 : 0.0;
+  }
+}
+
 // ---- elementary functions, overloaded for double and DualN ---------------------------------------------
 __device__ __forceinline__ double jx_rcp(double x) { return jcm_rcp(x); }
 JCD DualN<K> jx_rcp(DualN<K> x) {

@@ -160,6 +160,9 @@ __global__ void __launch_bounds__(256, sizeof(T) == sizeof(double) ? JC_SETUP_MI
     // no-wiggle fit (transfer.py:87-100): alpha_gamma and Omega_m h / (tcmb/2.7)^2
     S.sc[JC_SCAL_ALPHA_GAMMA] = 1.0 - 0.328 * jx_log(431.0 * w_m) * w_b / w_m + 0.38 * jx_log(22.3 * w_m) * (fb * fb);
     S.sc[JC_SCAL_OMH_T27] = bg.Om * h / T27;
+    // the tracer kernels depend on the cosmology through (Omega_m, Omega_k, w0, wa, gamma) only: a direction without a component
+    // along them has dR = 0 identically and its tangent contraction needs one product instead of two (jc_contract.cu)
+    jx_flag_moves_r(S.sc[JC_SCAL_MOVES_R], tangent, pl.ncp);
   }
 
   // ---- chi table -------------------------------------------------------------------------------

@@ -167,7 +167,7 @@ def gaussian_cl_log_likelihood_and_grad(cosmo, data, ell, probes, params=None, f
     return (float(lnl[0]), grad[0]) if hasattr(cosmo, "to_row") else (lnl, grad)
 
 
-def gaussian_cl_log_likelihood_hessian(cosmo, data, ell, probes, params=None, f_sky=0.25, rel_step=1e-4, transfer_fn=None,
+def gaussian_cl_log_likelihood_hessian(cosmo, data, ell, probes, params=None, f_sky=0.25, rel_step=1e-6, transfer_fn=None,
                                        nonlinear_fn=None):
     """Second derivatives d2 lnL / d theta_i d theta_j of the likelihood above (mean, covariance and log-determinant all functions
     of the cosmology) -- the matrix `jax.hessian(likelihood)` is asked for in the reference's notebook
@@ -175,12 +175,18 @@ def gaussian_cl_log_likelihood_hessian(cosmo, data, ell, probes, params=None, f_
 
     Built from the ANALYTIC gradient (forward-mode Jacobian x likelihood cotangent, `gaussian_cl_log_likelihood_and_grad`) by
     central differences: the 2 K displaced cosmologies theta +- h_i e_i run as ONE batch through the CUDA pipeline,
-    H[i, :] = (grad(theta + h_i e_i) - grad(theta - h_i e_i)) / (2 h_i) with h_i = rel_step * max(|theta_i|, 0.1), and the result
-    is symmetrised.  It is a numerical derivative of an exact one: truncation O(h^2), rounding ~1e-12 / h relative -- about six
-    digits at the default step -- and, unlike jax.hessian, it sees the curvature ACROSS the bracket switches of the reference's
-    piecewise-linear interpolations instead of the zero second derivative inside a bracket.  For the notebook's
-    fixed-covariance likelihood at the fiducial point the Hessian is minus the Fisher matrix, which `fisher_matrix` gives
-    exactly.  Returns (lnL, grad [K], H [K, K]) for a Cosmology or one row."""
+    H[i, :] = (grad(theta + h_i e_i) - grad(theta - h_i e_i)) / (2 h_i) with h_i = rel_step * max(|theta_i|, 0.1), symmetrised.
+
+    What it is and is not.  The reference's program is piecewise smooth in theta: the halofit root (power.py:113) is a linear
+    interpolation whose bracket switches from node to node as the cosmology moves (one switch per ~7e-5 in ln sigma8 over the 513
+    Limber nodes), and `jax.hessian` differentiates INSIDE the current brackets.  With the default step the difference window
+    (2e-6 relative) almost never contains a switch, the analytic gradient is good to ~1e-12, and the quotient reproduces that
+    within-bracket second derivative to about six digits; when a switch does fall inside the window, the two halves of the
+    quotient straddle a kink and the entry is off by the kink's share (compare two steps to detect it).  A large step
+    (rel_step ~ 1e-3) instead averages over many switches and returns the curvature of the underlying smooth function, which
+    differs from jax.hessian's by a few per cent.  For the notebook's fixed-covariance likelihood at the fiducial point the
+    Hessian is minus the Fisher matrix, which `fisher_matrix` gives exactly.
+    Returns (lnL, grad [K], H [K, K]) for a Cosmology or one row."""
     from jax_cosmo_b200.angular_cl import _PARAM_INDEX, WCDM_PARAMS, _rows
 
     rows = _rows(cosmo)
@@ -204,5 +210,6 @@ def gaussian_cl_log_likelihood_hessian(cosmo, data, ell, probes, params=None, f_
         batch[2 + 2 * i, c] -= h[i]
     lnl, grad = gaussian_cl_log_likelihood_and_grad(batch, data, ell, probes, params=params, f_sky=f_sky, transfer_fn=transfer_fn,
                                                     nonlinear_fn=nonlinear_fn)
-    H = (grad[1::2] - grad[2::2]) / (2.0 * h[:, None])
+    step = batch[1::2, cols][np.arange(K), np.arange(K)] - batch[2::2, cols][np.arange(K), np.arange(K)]  # the representable 2 h_i
+    H = (grad[1::2] - grad[2::2]) / step[:, None]
     return float(lnl[0]), grad[0], 0.5 * (H + H.T)
