@@ -22,7 +22,7 @@ static double env_double(const char* name, double dflt) { const char* e = getenv
 int g_jc_power_exact = env_int("JC_POWER_EXACT", 0);
 double g_jc_contract_eps = env_double("JC_CONTRACT_EPS", 1e-20);
 int g_jc_jvp_group = env_int("JC_JVP_GROUP", JC_JVP_MAX_GROUP);
-int g_jc_jvp_adjoint = env_int("JC_JVP_ADJOINT", 0);  // becomes the default once validated on hardware
+int g_jc_jvp_adjoint = env_int("JC_JVP_ADJOINT", 1);
 
 extern "C" int jc_set_option(const char* name, double value) {
   if (!name) return JC_ERR_INVALID;
