@@ -450,7 +450,8 @@ int jc_debug_math_f64(int32_t fn, const double* x_dev, double* y_dev, int64_t n,
  *   "contract_kernel" 0..3  0: persistent TMA contraction where it applies (>= 17 pair tiles), 3: the cp.async kernel
  *                           everywhere (all node stages, the reference's pair order) -- the A/B partner of the tests;
  *   "jvp_group"     1..4    tangent directions carried per pass of jc_angular_cl_jvp_f64 (default 4; also env JC_JVP_GROUP);
- *   "jvp_adjoint"   0 | 1   1: K3 of jc_angular_cl_jvp_f64 by one reverse sweep for 3..8 directions (default 1; env JC_JVP_ADJOINT). */
+ *   "jvp_adjoint"   0 | 1   1: K3 of jc_angular_cl_jvp_f64 by one reverse sweep for 3..8 directions (default 1; env JC_JVP_ADJOINT);
+ *   "lens_mma"      0 | 1   1: lensing-efficiency launches of >= 8 sources run on the FP64 tensor-core kernel (env JC_LENS_MMA). */
 int jc_set_option(const char* name, double value);
 int jc_get_option(const char* name, double* value_out);
 

@@ -23,6 +23,7 @@ int g_jc_power_exact = env_int("JC_POWER_EXACT", 0);
 double g_jc_contract_eps = env_double("JC_CONTRACT_EPS", 1e-20);
 int g_jc_jvp_group = env_int("JC_JVP_GROUP", JC_JVP_MAX_GROUP);
 int g_jc_jvp_adjoint = env_int("JC_JVP_ADJOINT", 1);
+int g_jc_lens_mma = env_int("JC_LENS_MMA", 0);
 
 extern "C" int jc_set_option(const char* name, double value) {
   if (!name) return JC_ERR_INVALID;
@@ -31,6 +32,7 @@ extern "C" int jc_set_option(const char* name, double value) {
   if (!strcmp(name, "contract_kernel")) { const int v = (int)value; if (v < 0 || v > 3) return JC_ERR_INVALID; g_contract_cfg = v; return JC_OK; }
   if (!strcmp(name, "jvp_group")) { const int v = (int)value; if (v < 1 || v > JC_JVP_MAX_GROUP) return JC_ERR_INVALID; g_jc_jvp_group = v; return JC_OK; }
   if (!strcmp(name, "jvp_adjoint")) { g_jc_jvp_adjoint = value != 0.0; return JC_OK; }
+  if (!strcmp(name, "lens_mma")) { g_jc_lens_mma = value != 0.0; return JC_OK; }
   return JC_ERR_INVALID;
 }
 extern "C" int jc_get_option(const char* name, double* value_out) {
@@ -40,6 +42,7 @@ extern "C" int jc_get_option(const char* name, double* value_out) {
   if (!strcmp(name, "contract_kernel")) { *value_out = g_contract_cfg < 0 ? 0 : g_contract_cfg; return JC_OK; }
   if (!strcmp(name, "jvp_group")) { *value_out = g_jc_jvp_group; return JC_OK; }
   if (!strcmp(name, "jvp_adjoint")) { *value_out = g_jc_jvp_adjoint; return JC_OK; }
+  if (!strcmp(name, "lens_mma")) { *value_out = g_jc_lens_mma; return JC_OK; }
   return JC_ERR_INVALID;
 }
 extern "C" int32_t jc_abi_version(void) { return JC_ABI_VERSION; }

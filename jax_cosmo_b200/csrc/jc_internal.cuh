@@ -175,6 +175,7 @@ struct JcDeviceGuard {
 void jc_set_cuda_error(cudaError_t e, const char* where);
 extern int g_jc_power_exact;      // jc_set_option("power_exact"): exact-formula power kernel everywhere
 extern int g_contract_cfg;        // jc_set_option("contract_kernel")
+extern int g_jc_lens_mma;         // jc_set_option("lens_mma"): K2a launches of >= 8 sources on the DMMA lens kernel
 extern int g_jc_jvp_adjoint;      // jc_set_option("jvp_adjoint"): 1 = reverse sweep of the point function in K3 for >= 3 directions (default)
 extern int g_jc_jvp_group;        // jc_set_option("jvp_group"): tangent directions carried per JVP pass (1..JC_JVP_MAX_GROUP)
 extern double g_jc_contract_eps;  // jc_set_option("contract_eps"): support threshold of the contraction, read at plan creation

@@ -174,6 +174,222 @@ jc_lens_kernel(JcDevPlan pl, Ws ws, int n_cosmo, int s0) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// K2a on the FP64 tensor-core instruction (double path, >= 8 sources per launch).
+//
+// ncu on jc_lens_kernel (profiles/r02_ncu_summary.md): FP64 pipe 44 %, issue slots 50 %, one eligible warp per scheduler -- a
+// thread spends 41 issue slots per (node, z', cosmology) item, 18 of them on the FP64 pipe: 8 for the lensing weight
+// g = max(chi' - chi_n, 0) / max(chi', 1) and 10 multiply-adds q_s += w_s g, fed by 10 weight loads.  The source sums are a
+// matrix product per node,  q[s][c] = sum_z' w[s][z'] g[z'][c]  (sources x cosmologies, z' as the k dimension), with the
+// weights independent of the cosmology.  Here a warp owns TWO nodes and 32 cosmologies: per k-step of four z' every lane
+// computes g for (z' = lane % 4, cosmology = lane / 4 + 8 q, q = 0..3) of both nodes -- exactly the B fragment of
+// mma.m8n8k4.f64 -- and loads its A-fragment element w[source = lane / 4][z' = lane % 4] of both nodes with one LDS.128; eight
+// DMMAs replace 64 DFMAs and 8 x 8 weight loads.  Sources beyond the eighth stay scalar (per-lane partial sums over the lane's
+// z' residue, reduced over the four lanes of a group at the end): a second m-tile for two rows would cost 6 x their pipe time.
+// DMMA shares the FP64 datapath, so the pipe time per item is unchanged (18 units); the issue slots fall from 41 to ~24 and a
+// lane carries 8 independent items per k-step.
+// CTA = 16 warps = 32 nodes x 32 cosmologies; the chi tables of the 32 cosmologies sit in shared memory with a row stride of
+// 258 doubles (the 8 cosmologies of a quarter-warp hit different banks); t / ix / w stream through a 3-stage cp.async ring of
+// 12 z'-rows, rows padded so that every fragment load is conflict free (units of 16 bytes: source stride 20, row stride
+// = 1 mod 8).  z' rows 257..263 of the last stage are zero-filled (w = 0, bracket 0: g finite).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int LM_NODES = 32;       // nodes per CTA (2 per warp)
+constexpr int LM_COSMO = 32;       // cosmologies per CTA (4 n-tiles)
+constexpr int LM_ZS = 12;          // z' rows per stage (3 k-steps)
+constexpr int LM_STAGES = 3;
+constexpr int LM_CHS = JC_NCHI + 2;  // chi-table row stride
+
+__device__ __forceinline__ void lens_dmma(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int NS> struct LmLayout {  // byte offsets inside one stage image
+  static constexpr int RS_S = 20 * 16;                                         // source stride: 32 nodes (256 B) + 64 B
+  static constexpr int RS_J = (NS * 20 + ((1 - NS * 20) % 8 + 8) % 8) * 16;      // z'-row stride of w: = 1 (mod 8) units
+  static constexpr int RS_T = 17 * 16, RS_IX = 5 * 16;
+  static constexpr int OFF_W = 0, OFF_T = LM_ZS * RS_J, OFF_IX = OFF_T + LM_ZS * RS_T;
+  static constexpr int STAGE = OFF_IX + LM_ZS * RS_IX;
+  static constexpr int PIECES_W = LM_ZS * NS * 16, PIECES_T = LM_ZS * 16, PIECES_IX = LM_ZS * 4;
+  static constexpr int PIECES = PIECES_W + PIECES_T + PIECES_IX;
+};
+
+template <int MT, int NX>
+__global__ void __launch_bounds__(512, 1) jc_lens_mma_kernel(JcDevPlan pl, Ws ws, int n_cosmo, int s0) {
+  constexpr int NS = 8 * MT + NX;
+  typedef LmLayout<NS> LY;
+  constexpr int NQ = LM_COSMO / 8;
+  constexpr int SLOTS = (LY::PIECES + 511) / 512;
+  constexpr int NSTAGE = (JC_NLENS + LM_ZS - 1) / LM_ZS;
+  constexpr int ROWS_LAST = JC_NLENS - (NSTAGE - 1) * LM_ZS;
+  extern __shared__ __align__(16) unsigned char lm_smem[];
+  double* s_chit = reinterpret_cast<double*>(lm_smem);                       // [LM_COSMO][LM_CHS]
+  unsigned char* s_stage = lm_smem + (size_t)LM_COSMO * LM_CHS * sizeof(double);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+  const int node0 = blockIdx.x * LM_NODES, na = node0 + 2 * warp;           // the warp's nodes: na, na + 1
+  const int cta_c0 = blockIdx.y * LM_COSMO;
+  for (int i = threadIdx.x; i < LM_COSMO * JC_NCHI; i += 512) {
+    const int c = i >> 8, k = i & 255;
+    s_chit[c * LM_CHS + k] = ws.chitab[(size_t)min(cta_c0 + c, n_cosmo - 1) * JC_NCHI + k];
+  }
+  double chin[2][NQ];  // chi at the warp's nodes for this lane's B columns (cosmology g + 8 q)
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const double* cn = node_ptr(ws, min(cta_c0 + q * 8 + g, n_cosmo - 1), JC_NODE_CHI) + na;
+    chin[0][q] = cn[0];
+    chin[1][q] = cn[1];
+  }
+  // ---- copy slots (16-byte pieces of a stage image; the global pointers advance by one stage per call) ----
+  const size_t NL = (size_t)JC_NLENS * JC_NLENS_COLS;
+  const unsigned char* slot_src[SLOTS];
+  unsigned slot_dst[SLOTS], slot_step[SLOTS];
+  unsigned valid = 0, tail_ok = 0;
+#pragma unroll
+  for (int j = 0; j < SLOTS; ++j) {
+    const int q = threadIdx.x + j * 512;
+    int r = 0;
+    slot_src[j] = nullptr; slot_dst[j] = 0; slot_step[j] = 0;
+    if (q < LY::PIECES_W) {                       // w: piece = (row r, source s, 16-byte unit u of the 32-node row)
+      r = q / (NS * 16);
+      const int s = (q - r * NS * 16) >> 4, u = q & 15;
+      slot_src[j] = (const unsigned char*)(pl.lens_nw + (size_t)(s0 + s) * NL + (size_t)r * JC_NLENS_COLS + node0) + u * 16;
+      slot_dst[j] = LY::OFF_W + r * LY::RS_J + s * LY::RS_S + u * 16;
+      slot_step[j] = LM_ZS * JC_NLENS_COLS * 8;
+    } else if (q < LY::PIECES_W + LY::PIECES_T) {
+      const int qq = q - LY::PIECES_W;
+      r = qq >> 4;
+      slot_src[j] = (const unsigned char*)(pl.lens_t + (size_t)r * JC_NLENS_COLS + node0) + (qq & 15) * 16;
+      slot_dst[j] = LY::OFF_T + r * LY::RS_T + (qq & 15) * 16;
+      slot_step[j] = LM_ZS * JC_NLENS_COLS * 8;
+    } else if (q < LY::PIECES) {
+      const int qq = q - LY::PIECES_W - LY::PIECES_T;
+      r = qq >> 2;
+      slot_src[j] = (const unsigned char*)(pl.lens_ix + (size_t)r * JC_NLENS_COLS + node0) + (qq & 3) * 16;
+      slot_dst[j] = LY::OFF_IX + r * LY::RS_IX + (qq & 3) * 16;
+      slot_step[j] = LM_ZS * JC_NLENS_COLS * 2;
+    }
+    if (q < LY::PIECES) valid |= 1u << j;
+    if (q < LY::PIECES && r < ROWS_LAST) tail_ok |= 1u << j;
+  }
+  const unsigned smem0 = (unsigned)__cvta_generic_to_shared(s_stage);
+  auto load_stage = [&](int st) {
+    const unsigned sbase = smem0 + (unsigned)(st % LM_STAGES) * LY::STAGE;
+    const bool last = st == NSTAGE - 1;
+#pragma unroll
+    for (int j = 0; j < SLOTS; ++j) {
+      if ((valid >> j) & 1) {
+        if (!last || ((tail_ok >> j) & 1))
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sbase + slot_dst[j]), "l"(slot_src[j]));
+        else  // z' rows past the rule's last node: zero weights, bracket (0, 0), t = 0
+          asm volatile("st.shared.v2.f64 [%0], {%1, %1};\n" ::"r"(sbase + slot_dst[j]), "d"(0.0));
+      }
+      slot_src[j] += slot_step[j];
+    }
+  };
+#pragma unroll
+  for (int st = 0; st < LM_STAGES - 1; ++st) {
+    load_stage(st);
+    asm volatile("cp.async.commit_group;\n" ::);
+  }
+  double acc[2][NQ][MT][2];   // D fragments: [node][n-tile][m-tile]{cosmology 2 tig, 2 tig + 1} of source g + 8 mt
+  double accx[2][NQ][NX > 0 ? NX : 1];  // scalar sources: partial sums over z' = tig (mod 4) for cosmology g + 8 q
+#pragma unroll
+  for (int nd = 0; nd < 2; ++nd)
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) acc[nd][q][mt][0] = acc[nd][q][mt][1] = 0.0;
+#pragma unroll
+      for (int x = 0; x < (NX > 0 ? NX : 1); ++x) accx[nd][q][x] = 0.0;
+    }
+  const unsigned pair_off = (unsigned)(2 * warp) * 8;  // byte offset of the warp's node pair inside a 32-node row
+  const double* chq = s_chit + g * LM_CHS;
+
+  for (int st = 0; st < NSTAGE; ++st) {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(LM_STAGES - 2));
+    __syncthreads();  // stage st landed (and its zero fill is visible); stage st - 1, refilled below, is no longer read
+    if (st + LM_STAGES - 1 < NSTAGE) load_stage(st + LM_STAGES - 1);
+    asm volatile("cp.async.commit_group;\n" ::);
+    const unsigned char* base = s_stage + (size_t)(st % LM_STAGES) * LY::STAGE;
+#pragma unroll
+    for (int ks = 0; ks < LM_ZS / 4; ++ks) {
+      const int j = ks * 4 + tig;
+      const double2 t2 = *reinterpret_cast<const double2*>(base + LY::OFF_T + j * LY::RS_T + pair_off);
+      const unsigned ix2 = *reinterpret_cast<const unsigned*>(base + LY::OFF_IX + j * LY::RS_IX + 4 * warp);
+      double2 a2[MT], wx2[NX > 0 ? NX : 1];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+        a2[mt] = *reinterpret_cast<const double2*>(base + LY::OFF_W + j * LY::RS_J + (mt * 8 + g) * LY::RS_S + pair_off);
+#pragma unroll
+      for (int x = 0; x < NX; ++x)
+        wx2[x] = *reinterpret_cast<const double2*>(base + LY::OFF_W + j * LY::RS_J + (MT * 8 + x) * LY::RS_S + pair_off);
+#pragma unroll
+      for (int nd = 0; nd < 2; ++nd) {
+        const double t = nd ? t2.y : t2.x;
+        const unsigned ix = nd ? (ix2 >> 16) : (ix2 & 0xffffu);
+        const int i0 = ix & 255, i1 = ix >> 8;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const double f0 = chq[q * 8 * LM_CHS + i0], f1 = chq[q * 8 * LM_CHS + i1];
+          const double chip = jx_clip0(f0 + (f1 - f0) * t);                                   // background.py:242
+          const double gv = jx_clip0(chip - chin[nd][q]) * jx_rcp(jx_floor1(chip));          // probes.py:49
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) lens_dmma(acc[nd][q][mt][0], acc[nd][q][mt][1], nd ? a2[mt].y : a2[mt].x, gv);
+#pragma unroll
+          for (int x = 0; x < NX; ++x) accx[nd][q][x] = fma(nd ? wx2[x].y : wx2[x].x, gv, accx[nd][q][x]);
+        }
+      }
+    }
+  }
+  // ---- epilogue: q (1+z) chi 3 H0^2 Om / (2c) (1+m) straight into R[n][t]                          probes.py:51,71-74,201-207
+#pragma unroll
+  for (int nd = 0; nd < 2; ++nd) {
+    const int n = na + nd;
+    const double zfac = (pl.lens_zmax - pl.limb_z[n]) * (1.0 + pl.limb_z[n]) * (3.0 * JC_H0 * JC_H0 / 2.0 / JC_C_LIGHT);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      // tensor-core sources: this lane holds source g + 8 mt for cosmologies 8 q + 2 tig, + 1
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int cc = cta_c0 + q * 8 + 2 * tig + h;
+        if (cc < n_cosmo) {
+          const double amp = (zfac * node_ptr(ws, cc, JC_NODE_CHI)[n]) * ws.scal[(size_t)cc * JC_SCAL_FIELDS + JC_SCAL_OMEGA_M];
+          double* row = ws.rker + ((size_t)cc * JC_NA_PAD + n) * pl.TS;
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const int tr = pl.src_tracer[s0 + mt * 8 + g];
+            row[tr] = acc[nd][q][mt][h] * amp * pl.tr_m1[tr];
+          }
+        }
+      }
+      // scalar sources: sum the four z' residues of the group; lane tig = x % 4 of group g stores source 8 MT + x
+#pragma unroll
+      for (int x = 0; x < NX; ++x) {
+        double v = accx[nd][q][x];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        const int cc = cta_c0 + q * 8 + g;
+        if (tig == (x & 3) && cc < n_cosmo) {
+          const double amp = (zfac * chin[nd][q]) * ws.scal[(size_t)cc * JC_SCAL_FIELDS + JC_SCAL_OMEGA_M];
+          const int tr = pl.src_tracer[s0 + MT * 8 + x];
+          ws.rker[((size_t)cc * JC_NA_PAD + n) * pl.TS + tr] = v * amp * pl.tr_m1[tr];
+        }
+      }
+    }
+  }
+}
+
+template <int MT, int NX>
+void launch_lens_mma(const JcDevPlan& pl, const Ws& ws, int chunk, int s0, cudaStream_t st) {
+  typedef LmLayout<8 * MT + NX> LY;
+  constexpr int smem = LM_COSMO * LM_CHS * (int)sizeof(double) + LM_STAGES * LY::STAGE;
+  static_assert(smem <= 227 * 1024, "lens stage ring + chi tables must fit one SM");
+  static unsigned long long attr_done = 0;
+  JC_ONCE_PER_DEVICE(attr_done, cudaFuncSetAttribute(jc_lens_mma_kernel<MT, NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  dim3 grid(JC_NLENS_COLS / LM_NODES, (chunk + LM_COSMO - 1) / LM_COSMO);
+  jc_lens_mma_kernel<MT, NX><<<grid, 512, smem, st>>>(pl, ws, chunk, s0);
+}
+
 template <class T>
 __global__ void __launch_bounds__(512) jc_tracer_finish_kernel(JcDevPlan pl, Ws ws) {
   // One CTA per cosmology; blockDim = rows x n_fin with every thread bound to ONE of the n_fin tracers that need all
@@ -246,9 +462,9 @@ void launch_lens(const JcDevPlan& pl, const Ws& ws, int chunk, int s0, cudaStrea
 }
 
 template <class T, int NCOS, int CG>
-int launch_all_lens(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s) {
+int launch_all_lens(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s, int first_src = 0) {
   int n_launch = 0;
-  for (int s0 = 0; s0 < pl.n_src; ++n_launch) {
+  for (int s0 = first_src; s0 < pl.n_src; ++n_launch) {
     const int rem = pl.n_src - s0;
     constexpr bool WIDE = sizeof(T) > 4 * sizeof(double);  // DualN<4>: 8 or 10 sources per launch would spill the accumulators
     if (rem >= 10 && !WIDE) { launch_lens<T, 10, NCOS, CG>(pl, ws, chunk, s0, s); s0 += 10; }
@@ -265,9 +481,19 @@ int launch_all_lens(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s
 
 }  // namespace
 
-// 4 cosmologies per thread, 4 cosmology groups per CTA (2 x 8 and 2 x 4 measured slower, profiles/r01_tuning.md)
+// Scalar kernel: 4 cosmologies per thread, 4 cosmology groups per CTA (2 x 8 and 2 x 4 measured slower, profiles/r01_tuning.md).
+// jc_set_option("lens_mma", 1): launches of >= 8 sources run on jc_lens_mma_kernel (10 / 9 / 8 sources per launch: one m-tile plus
+// up to two scalar sources; the stage ring of 16 sources would not fit beside the chi tables).
 int jc_launch_tracers(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s) {
-  return launch_all_lens<double, 4, 4>(pl, ws, chunk, s);
+  if (!g_jc_lens_mma) return launch_all_lens<double, 4, 4>(pl, ws, chunk, s);
+  int n_launch = 0, s0 = 0;
+  for (; pl.n_src - s0 >= 8; ++n_launch) {
+    const int rem = pl.n_src - s0;
+    if (rem >= 10) { launch_lens_mma<1, 2>(pl, ws, chunk, s0, s); s0 += 10; }
+    else if (rem == 9) { launch_lens_mma<1, 1>(pl, ws, chunk, s0, s); s0 += 9; }
+    else { launch_lens_mma<1, 0>(pl, ws, chunk, s0, s); s0 += 8; }
+  }
+  return n_launch + launch_all_lens<double, 4, 4>(pl, ws, chunk, s, s0);
 }
 // tangent groups: one cosmology per thread (the accumulators are NS x (1 + ntan) doubles)
 int jc_launch_tracers_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, int ntan, cudaStream_t s) {

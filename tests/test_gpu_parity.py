@@ -892,3 +892,37 @@ def test_likelihood_hessian(jc, torch_cuda):
     assert np.max(np.abs(Hf + F) / np.sqrt(np.outer(np.diag(F), np.diag(F)))) < 0.2
     with pytest.raises(ValueError):
         jc.likelihood.gaussian_cl_log_likelihood_hessian(np.stack([row, row]), data, ell, probes)
+
+
+@pytest.mark.parametrize("n_src", [8, 9, 10, 13])
+def test_lens_mma_vs_scalar_kernel(jc, torch_cuda, n_src):
+    """K2a on the FP64 tensor-core instruction (jc_lens_mma_kernel: launches of 8 / 9 / 10 sources; 13 = 10 + 3 by the scalar
+    kernel) against the scalar kernel (jc_set_option("lens_mma", 0)): same weights, same lensing-efficiency arithmetic per
+    (node, z', cosmology), the source sums in a different order -- the tracer kernels R and the spectra agree to rounding.  Ragged
+    batch (37 cosmologies: the last CTA of 32 is partly empty) and the oracle on two rows."""
+    torch = torch_cuda
+    from jax_cosmo_b200 import _native
+    scn = sc.scenario("lm", sc.PLANCK15, sc.ELL_CFG2[::11], [sc.sources(n_src, 1.0, True), sc.lenses(3, 1.0)])
+    plan, probes = _plan(jc, scn)
+    rows = sc.config5_cosmologies(37)
+    dev_rows = torch.as_tensor(rows, device="cuda")
+    default = _native.get_option("lens_mma")
+    out = {}
+    try:
+        for mode in (0, 1):
+            _native.set_option("lens_mma", mode)
+            ws = plan.workspace(37)
+            cl = plan.angular_cl_device(dev_rows, workspace=ws).clone()
+            lo = plan.workspace_layout(ws.numel() * 8)
+            rker = ws[lo.rker:lo.rker + 37 * lo.node_stride * lo.tracer_stride].clone()
+            out[mode] = (cl, rker)
+    finally:
+        _native.set_option("lens_mma", default)
+    (cl0, r0), (cl1, r1) = out[0], out[1]
+    assert torch.isfinite(r1).all()
+    scale = r0.abs().max()
+    assert float((r1 - r0).abs().max() / scale) < 1e-13
+    assert float(((cl1 - cl0).abs() / cl0.abs()).max()) < 1e-12
+    prob = sc.flatten_spec(scn)
+    for i in (0, 36):
+        assert relerr(cl1[i].cpu().numpy(), o.angular_cl(rows[i], scn["ell"], prob)) < 2e-8
