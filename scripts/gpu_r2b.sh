@@ -22,6 +22,7 @@ tail -6 $O/${TAG}_ncu_current.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches_config4.csv python bench.py --workload config4 --steps 1 --warmup 1 > $O/${TAG}_launches_config4.log 2>&1
 echo "launch list config4 rc=$?"
 if [ "$MODE" = final ]; then
+  timeout 600 python scripts/parity_sweep.py 1024 > $O/${TAG}_parity_sweep.log 2>&1; echo "parity sweep rc=$?"; tail -2 $O/${TAG}_parity_sweep.log
   timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_n1_ncu.json 2> $O/${TAG}_bench_n1_ncu.err; echo "bench (with ncu_current) rc=$?"
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 200 --csv --log-file $O/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --peak-tflops 36.4 > $O/${TAG}_launches_bench.log 2>&1
   echo "launch list rc=$?"

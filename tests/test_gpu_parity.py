@@ -902,7 +902,9 @@ def test_lens_mma_vs_scalar_kernel(jc, torch_cuda, n_src):
     batch (37 cosmologies: the last CTA of 32 is partly empty) and the oracle on two rows."""
     torch = torch_cuda
     from jax_cosmo_b200 import _native
-    scn = sc.scenario("lm", sc.PLANCK15, sc.ELL_CFG2[::11], [sc.sources(n_src, 1.0, True), sc.lenses(3, 1.0)])
+    bins = [sc.smail(1.0, 2.0, 0.25 + 0.08 * i, 1.0, shift=0.01 * (-1) ** i) for i in range(n_src)]
+    src = sc.wl(bins, ia=sc.bias("des_y1_ia", 0.5, 0.0, 0.62), m=[0.01 * (-1) ** i for i in range(n_src)])
+    scn = sc.scenario("lm", sc.PLANCK15, sc.ELL_CFG2[::11], [src, sc.lenses(5, 1.0)])
     plan, probes = _plan(jc, scn)
     rows = sc.config5_cosmologies(37)
     dev_rows = torch.as_tensor(rows, device="cuda")
