@@ -147,3 +147,45 @@ def test_sparse_to_dense(jc):
     for i in range(3):
         for j in range(2):
             assert np.array_equal(d[i * 4:(i + 1) * 4, j * 4:(j + 1) * 4], np.diag(s[i, j]))
+
+
+def test_process_options_round_trip():
+    """jc_set_option / jc_get_option (no GPU needed): defaults of the hot path, bounds, unknown names."""
+    from jax_cosmo_b200 import _native
+    assert _native.get_option("jvp_group") == 4.0       # tangent directions per forward-mode pass
+    assert _native.get_option("jvp_adjoint") == 1.0     # reverse-sweep K3 for 3..8 directions
+    assert _native.get_option("lens_mma") == 0.0        # the scalar lens kernel is the default
+    assert _native.get_option("power_exact") == 0.0 and _native.get_option("contract_eps") == 1e-20
+    try:
+        for name, good, bad in (("jvp_group", 2, 5), ("jvp_group", 1, 0), ("contract_kernel", 3, 4)):
+            _native.set_option(name, good)
+            assert _native.get_option(name) == float(good)
+            with pytest.raises(ValueError):
+                _native.set_option(name, bad)
+        _native.set_option("lens_mma", 1)
+        assert _native.get_option("lens_mma") == 1.0
+        with pytest.raises(ValueError):
+            _native.set_option("no_such_option", 1)
+        with pytest.raises(ValueError):
+            _native.get_option("no_such_option")
+    finally:
+        _native.set_option("jvp_group", 4)
+        _native.set_option("contract_kernel", 0)
+        _native.set_option("lens_mma", 0)
+
+
+def test_hessian_argument_checks(jc):
+    """likelihood.gaussian_cl_log_likelihood_hessian validates its arguments before anything touches the GPU."""
+    nz = [jc.redshift.smail_nz(1.0, 2.0, 1.0)]
+    probes = [jc.probes.WeakLensing(nz)]
+    ell = np.logspace(1, 3, 8)
+    data = np.zeros(8)
+    row = jc.Planck15().to_row()
+    with pytest.raises(ValueError, match="one cosmology"):
+        jc.likelihood.gaussian_cl_log_likelihood_hessian(np.stack([row, row]), data, ell, probes)
+    with pytest.raises(ValueError, match="unknown parameter"):
+        jc.likelihood.gaussian_cl_log_likelihood_hessian(row, data, ell, probes, params=("Omega_x",))
+    with pytest.raises(ValueError, match="unknown parameter"):
+        jc.likelihood.gaussian_cl_log_likelihood_hessian(row, data, ell, probes, params=("gamma",))  # 8-column row: no gamma
+    with pytest.raises(ValueError, match="rel_step"):
+        jc.likelihood.gaussian_cl_log_likelihood_hessian(row, data, ell, probes, rel_step=0.0)
