@@ -225,6 +225,17 @@ def run(args, rank, world, local):
             step_e2e()
         dt = max_over_ranks(time.perf_counter() - t0)
         derivs = world * B * K * P * N_ELL
+        # kernels per timed step (the throughput path of jc_angular_cl_jvp_f64 in chunks of <= 1024 cosmologies; 5 sources = one
+        # lens launch per pass) + the forward pass timed beside it: the claim `gpu_launches` makes
+        group, adjoint = int(_native.get_option("jvp_group")), int(_native.get_option("jvp_adjoint"))
+        n_chunks = -(-B // 1024)
+        if B * K <= 512:
+            launches = 4 + 2
+        elif adjoint and group == 4 and 3 <= K <= 8:
+            launches = n_chunks * (3 * -(-K // 4) + 1 + 1 + K)
+        else:
+            launches = n_chunks * (4 * -(-K // group) + 1 + K)
+        launches *= steps  # the forward pass timed beside it is outside the timed region
         if rank == 0:
             line = {"metric": "dC_ell/d theta evals/sec (cosmo x parameter x ell x pair)", "value": derivs * steps / (ms * 1e-3),
                     "unit": "dC_ell/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
@@ -237,8 +248,13 @@ def run(args, rank, world, local):
                             "d2h_bytes_per_step": int(out_pin.numel() * 8),
                             "max_abs_diff_vs_device_path": float((out_pin[:64].to(dev) - dcl[:64]).abs().max().item())},
                     "forward_pass_ms": ms_fwd, "jvp_over_forward": (ms / steps) / ms_fwd,
-                    "jvp_group": int(_native.get_option("jvp_group")),
-                    "gpu_launches": None, "roofline": None, "cpu_baseline": None, "git_head": git_head()}
+                    "jvp_group": int(_native.get_option("jvp_group")), "jvp_adjoint": int(_native.get_option("jvp_adjoint")),
+                    "gpu_launches": launches,
+                    "roofline": None,
+                    "roofline_note": "FP64-pipe bound like config 5; per-kernel times of a step: profiles/r02_final_launches_config4.csv "
+                                     "(reverse-sweep K3 39 %, tangent contractions 27 %, K1 16 %, lens 15 %), ncu of the K3 kernel: "
+                                     "profiles/r02x_ncu_power_adj_metrics.csv (36 % of the FP64 pipe)",
+                    "cpu_baseline": None, "git_head": git_head()}
             print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
