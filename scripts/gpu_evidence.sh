@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: scripts/gpu_r2b.sh <tag> [final]
+# usage: scripts/gpu_evidence.sh <tag> [final]
 #   always: GPU tests, N=1 bench line, config4 with tangent groups 4 and 1, config3, one ncu --set full pass over the five
 #           pipeline kernels -> ncu_current.json, launch list of a config4 step
 #   final:  also the CPU arm in the N=1 line, the bench line that reads the fresh ncu_current.json, the launch list of the bench

@@ -1,4 +1,5 @@
 #!/bin/bash
+# usage: scripts/gpu_jvp_adjoint.sh <tag>  -- forward-mode tests, config4 with / without the reverse-sweep K3, ncu --set full of that kernel
 TAG=$1; O=gpurun_out
 timeout 300 python -m pytest tests -m gpu -q -k "jvp" > $O/${TAG}_pytest.log 2>&1; echo rc=$? >> $O/${TAG}_pytest.log; tail -6 $O/${TAG}_pytest.log
 for A in 1 0; do
