@@ -501,7 +501,7 @@ def test_jvp_fused_directions_bitwise(jc, torch_cuda):
 
 
 @pytest.mark.parametrize("n_rows,dirs,nl", [(160, 7, "halofit"), (260, 5, "halofit"), (350, 3, "linear"), (300, 2, "halofit"),
-                                            (140, 4, "smith2003")])
+                                            (140, 4, "smith2003"), (1100, 3, "halofit")])
 def test_jvp_throughput_modes(jc, torch_cuda, n_rows, dirs, nl):
     """Throughput path of jc_angular_cl_jvp_f64 (B*K > 512 entries).  Default: K1 / K2 on tangent groups (DualN<g>, 7 = 4 + 3) and K3
     by ONE reverse sweep of the point function for 3..8 directions (jc_power_adj.cu).  A/B partners: tangent groups in K3 as well
@@ -548,6 +548,44 @@ def test_jvp_throughput_modes(jc, torch_cuda, n_rows, dirs, nl):
     clf, dclf = plan.angular_cl_jvp_device(rows[:40].contiguous(), tang)  # <= 512 entries: fused one-direction entries
     assert float(((cl1[:40] - clf).abs() / clf.abs()).max()) < 1e-13
     assert float(((dcl1[:40] - dclf).abs() / scale[:40]).max()) < 1e-12
+
+
+def test_jvp_throughput_gamma_growth_8_directions(jc, torch_cuda):
+    """9-column rows (growth index gamma) and all 8 free directions: the widest reverse-sweep instantiation (two tangent groups
+    of 4, 10 planes) against one direction per pass; the gamma direction moves the tracer kernels (IA, inverse-growth bias), so
+    its contraction keeps both products."""
+    torch = torch_cuda
+    from jax_cosmo_b200 import _native
+    scn = [s for s in sc.golden_scenarios() if s["name"] == "switch_gamma_growth"][0]
+    probes = sc.build_probes(scn, jc)
+    tf, nl = sc.build_fns(scn, jc)
+    ell = sc.ELL_CFG2[::12]
+    base = sc.cosmo_row(scn["cosmo"])
+    assert base.shape == (9,)
+    plan = _native.get_plan(probes, ell, tf, nl, growth=1)
+    rng = np.random.default_rng(11)
+    rows = np.repeat(base[None], 70, axis=0)
+    rows[:, [0, 4, 8]] *= 1.0 + 0.05 * rng.standard_normal((70, 3))
+    rows_dev = torch.as_tensor(rows, device="cuda")
+    tang = torch.zeros((8, 9), dtype=torch.float64, device="cuda")
+    tang[torch.arange(8), torch.tensor([0, 1, 2, 3, 4, 6, 7, 8])] = 1.0
+    assert 70 * 8 > 512 and _native.get_option("jvp_adjoint") == 1.0
+    cl, dcl = plan.angular_cl_jvp_device(rows_dev, tang)
+    try:
+        _native.set_option("jvp_group", 1)
+        cl1, dcl1 = plan.angular_cl_jvp_device(rows_dev, tang)
+    finally:
+        _native.set_option("jvp_group", 4)
+    scale = dcl1.abs().amax(dim=3, keepdim=True)
+    assert float(scale.min()) > 0  # every direction, gamma included, moves every spectrum
+    assert float(((cl - cl1).abs() / cl1.abs()).max()) < 1e-13
+    assert float(((dcl - dcl1).abs() / scale).max()) < 1e-10
+    # one row against the complex-step oracle (gamma and sigma8 columns)
+    from oracle import derivatives as od
+    _, jac_ref = od.cs_jacobian(rows[3], ell, sc.flatten_spec(scn), params=("sigma8", "gamma"))
+    got = dcl[3, [4, 7]].cpu().numpy()
+    ref_scale = np.abs(jac_ref).max(axis=2, keepdims=True)
+    assert (np.abs(got - jac_ref) / ref_scale).max() < 1e-9
 
 
 def test_two_devices_in_one_process(jc, torch_cuda):
