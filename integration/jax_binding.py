@@ -67,7 +67,11 @@ def _call(rows, plan):
 def _call_jvp(rows, tangents, plan):
     B, K = rows.shape[0], tangents.shape[0]
     need = ctypes.c_size_t()
-    _native.check(_native.load_library().jc_workspace_bytes_jvp(plan._h, B, ctypes.byref(need)), "jc_workspace_bytes_jvp")
+    lib = _native.load_library()
+    if B * K <= 512:  # a Jacobian at one cosmology: room for B*K one-direction entries -> one pass
+        _native.check(lib.jc_workspace_bytes_jvp(plan._h, B * K, ctypes.byref(need)), "jc_workspace_bytes_jvp")
+    else:             # batches: tangent groups in K1 / K2, one reverse sweep in K3
+        _native.check(lib.jc_workspace_bytes_jvp_group(plan._h, B, K, ctypes.byref(need)), "jc_workspace_bytes_jvp_group")
     cl, dcl, _ = jax.ffi.ffi_call(
         "jc_angular_cl_jvp",
         (jax.ShapeDtypeStruct((B, plan.P, plan.L), jnp.float64), jax.ShapeDtypeStruct((B, K, plan.P, plan.L), jnp.float64),
