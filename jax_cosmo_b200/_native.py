@@ -933,6 +933,20 @@ def debug_math(fn, x):
     return y
 
 
+_R_COLUMNS = (0, 1, 5, 6, 7, 8)  # Omega_c, Omega_b, Omega_k, w0, wa, gamma: the parameters the tracer kernels R_i(a) depend on
+
+
+def direction_order(tangents):
+    """Stable permutation of K forward-mode directions ([K, 8|9] host array) that puts those able to move the tracer kernels
+    first.  The throughput path of jc_angular_cl_jvp_f64 runs K1 / K2 per group of four directions; a LATER group made only of
+    directions along h, n_s, sigma8 (dR = 0 identically) needs no K2 pass at all.  Callers that build their tangents on the host
+    reorder them with this, call the device entry, and undo the permutation on the (host) result."""
+    t = np.atleast_2d(np.asarray(tangents, dtype=np.float64))
+    cols = [c for c in _R_COLUMNS if c < t.shape[1]]
+    moves = np.any(t[:, cols] != 0.0, axis=1)
+    return np.argsort(~moves, kind="stable")
+
+
 def set_option(name, value):
     """jc_set_option: "power_exact" (0 | 1), "contract_eps" (>= 0; read when a plan is created -- cached plans keep theirs),
     "contract_kernel" (0..3), "jvp_group" (1..4 tangent directions per JVP pass)."""

@@ -103,8 +103,12 @@ def angular_cl_jvp(cosmo, ell, probes, tangents, transfer_fn=tklib.Eisenstein_Hu
     if tang.shape[1] != rows.shape[1]:
         raise ValueError("tangents must have shape [K, %d]" % rows.shape[1])
     rows = torch.as_tensor(rows, device=dev)
-    cl, dcl = plan.angular_cl_jvp_device(rows, torch.as_tensor(tang, device=dev))
-    return _native.to_host(cl), _native.to_host(dcl)
+    order = _native.direction_order(tang)  # directions that cannot move the tracer kernels last (they may skip K2)
+    cl, dcl = plan.angular_cl_jvp_device(rows, torch.as_tensor(np.ascontiguousarray(tang[order]), device=dev))
+    dcl = _native.to_host(dcl)
+    inverse = np.empty_like(order)
+    inverse[order] = np.arange(len(order))
+    return _native.to_host(cl), (dcl if np.array_equal(order, np.arange(len(order))) else np.ascontiguousarray(dcl[:, inverse]))
 
 
 def angular_cl_jacobian(cosmo, ell, probes, params=WCDM_PARAMS, transfer_fn=tklib.Eisenstein_Hu,

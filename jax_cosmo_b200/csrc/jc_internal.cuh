@@ -225,8 +225,10 @@ void jc_launch_transfer(const JcDevPlan& pl, const Ws& ws, int chunk, double* tk
 // parameter space per entry
 void jc_launch_setup_jvp(const JcDevPlan& pl, const double* cosmo, const double* tangent, const Ws& ws, int chunk, int kdiv,
                          int ntan, cudaStream_t s);
-int jc_launch_tracers_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, int ntan, cudaStream_t s);
-void jc_launch_finish_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, int ntan, cudaStream_t s);
+// skip_static: the pass's value tables are not read by anyone (later tangent groups of the reverse-sweep path) -- the kernels
+// return at once when none of the pass's directions can move the tracer kernels (JC_SCAL_MOVES_R)
+int jc_launch_tracers_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, int ntan, cudaStream_t s, int skip_static = 0);
+void jc_launch_finish_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, int ntan, cudaStream_t s, int skip_static = 0);
 void jc_launch_power_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, int ntan, cudaStream_t s);
 void jc_launch_contract_jvp(const JcDevPlan& pl, const Ws& ws, double* dcl, int64_t dcl_cosmo_stride, int chunk,
                             cudaStream_t s);

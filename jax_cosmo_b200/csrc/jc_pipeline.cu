@@ -120,8 +120,10 @@ extern "C" int jc_angular_cl_jvp_f64(const jc_plan* plan, const double* cosmo_de
           Ws wg;  // this group's value plane = plane jc_jvp_plane(k0) - 1 of the workspace
           resolve(la, (double*)ws_dev + (ptrdiff_t)(jc_jvp_plane(k0) - 1) * doff, doff, &wg);
           jc_launch_setup_jvp(pl, cosmo_dev + c0 * pl.ncp, tangents_dev + (size_t)k0 * pl.ncp, wg, chunk, 1, g, s);
-          jc_launch_tracers_jvp(pl, wg, chunk, g, s);
-          jc_launch_finish_jvp(pl, wg, chunk, g, s);
+          // only group 0's value tables (R, chi) are read downstream: a later group whose directions all leave the tracer
+          // kernels alone (h, n_s, sigma8) has no K2 work at all -- callers that order such directions last save it
+          jc_launch_tracers_jvp(pl, wg, chunk, g, s, k0 > 0);
+          jc_launch_finish_jvp(pl, wg, chunk, g, s, k0 > 0);
         }
         jc_launch_power_adj(pl, ws, chunk, n_tangents, s);
         if (cl_dev) jc_launch_contract(pl, ws, cl_dev + (size_t)c0 * PL, chunk, s);  // value plane

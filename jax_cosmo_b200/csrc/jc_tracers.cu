@@ -22,11 +22,28 @@ constexpr int LENS_MR = 4;       // z' rows per pipeline stage
 constexpr int LENS_STAGES = 3;
 
 // NCOS: cosmologies per thread; LENS_CGROUPS: cosmology groups (of 4 warps) per CTA
+// skip_static (tangent passes whose VALUE tables nobody reads -- the second and later tangent groups of the reverse-sweep path):
+// when none of the pass's directions can move the tracer kernels (JC_SCAL_MOVES_R, same for every cosmology of a batch), dR = 0
+// identically, the tangent contraction never reads it, and the pass has nothing to produce.
+template <class T>
+__device__ __forceinline__ bool pass_is_static(const Ws& ws, int c) {
+  bool any = false;
+  if constexpr (JxTangents<T>::N > 0) {
+#pragma unroll
+    for (int k = 0; k < JxTangents<T>::N; ++k)
+      any = any || ws.scal[(size_t)c * JC_SCAL_FIELDS + JC_SCAL_MOVES_R + (ptrdiff_t)(k + 1) * ws.doff] != 0.0;
+  } else {
+    any = true;
+  }
+  return !any;
+}
+
 template <class T, int NS, int NCOS, int LENS_CGROUPS>
 __global__ void __launch_bounds__(LENS_NODES * LENS_CGROUPS)
-jc_lens_kernel(JcDevPlan pl, Ws ws, int n_cosmo, int s0) {
+jc_lens_kernel(JcDevPlan pl, Ws ws, int n_cosmo, int s0, int skip_static) {
   constexpr int CTA_COSMO = NCOS * LENS_CGROUPS;
   __shared__ T s_chit[CTA_COSMO][JC_NCHI];
+  if (skip_static && pass_is_static<T>(ws, 0)) return;  // uniform over the grid: before any barrier or copy
   const ptrdiff_t doff = ws.doff;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * LENS_NODES + (warp & 3) * 32 + lane;  // node
@@ -391,7 +408,8 @@ void launch_lens_mma(const JcDevPlan& pl, const Ws& ws, int chunk, int s0, cudaS
 }
 
 template <class T>
-__global__ void __launch_bounds__(512) jc_tracer_finish_kernel(JcDevPlan pl, Ws ws) {
+__global__ void __launch_bounds__(512) jc_tracer_finish_kernel(JcDevPlan pl, Ws ws, int skip_static) {
+  if (skip_static && pass_is_static<T>(ws, 0)) return;
   // One CTA per cosmology; blockDim = rows x n_fin with every thread bound to ONE of the n_fin tracers that need all
   // nodes (number counts, delta planes, IA-enabled sources), so the per-tracer switches are loop invariant and there is no
   // index division: ncu had 193 warp instructions per element (issue bound, 15 % FP64 pipe) with a flat (node, tracer)
@@ -451,30 +469,30 @@ __global__ void __launch_bounds__(512) jc_tracer_finish_kernel(JcDevPlan pl, Ws 
 }
 
 template <class T, int NS, int NCOS, int LENS_CGROUPS>
-void launch_lens(const JcDevPlan& pl, const Ws& ws, int chunk, int s0, cudaStream_t st) {
+void launch_lens(const JcDevPlan& pl, const Ws& ws, int chunk, int s0, cudaStream_t st, int skip_static = 0) {
   constexpr int CTA_COSMO = NCOS * LENS_CGROUPS;
   dim3 grid(JC_NLENS_COLS / LENS_NODES, (chunk + CTA_COSMO - 1) / CTA_COSMO);
   constexpr int smem = LENS_STAGES * LENS_MR * (LENS_NODES * 8 * (1 + NS) + LENS_NODES * 2);
   static unsigned long long attr_done = 0;
   JC_ONCE_PER_DEVICE(attr_done, cudaFuncSetAttribute(jc_lens_kernel<T, NS, NCOS, LENS_CGROUPS>,
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  jc_lens_kernel<T, NS, NCOS, LENS_CGROUPS><<<grid, LENS_NODES * LENS_CGROUPS, smem, st>>>(pl, ws, chunk, s0);
+  jc_lens_kernel<T, NS, NCOS, LENS_CGROUPS><<<grid, LENS_NODES * LENS_CGROUPS, smem, st>>>(pl, ws, chunk, s0, skip_static);
 }
 
 template <class T, int NCOS, int CG>
-int launch_all_lens(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s, int first_src = 0) {
+int launch_all_lens(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s, int first_src = 0, int skip_static = 0) {
   int n_launch = 0;
   for (int s0 = first_src; s0 < pl.n_src; ++n_launch) {
     const int rem = pl.n_src - s0;
     constexpr bool WIDE = sizeof(T) > 4 * sizeof(double);  // DualN<4>: 8 or 10 sources per launch would spill the accumulators
-    if (rem >= 10 && !WIDE) { launch_lens<T, 10, NCOS, CG>(pl, ws, chunk, s0, s); s0 += 10; }
-    else if (rem >= 8 && !WIDE) { launch_lens<T, 8, NCOS, CG>(pl, ws, chunk, s0, s); s0 += 8; }
-    else if (rem >= 6) { launch_lens<T, 6, NCOS, CG>(pl, ws, chunk, s0, s); s0 += 6; }
-    else if (rem >= 5) { launch_lens<T, 5, NCOS, CG>(pl, ws, chunk, s0, s); s0 += 5; }
-    else if (rem == 4) { launch_lens<T, 4, NCOS, CG>(pl, ws, chunk, s0, s); s0 += 4; }
-    else if (rem == 3) { launch_lens<T, 3, NCOS, CG>(pl, ws, chunk, s0, s); s0 += 3; }
-    else if (rem == 2) { launch_lens<T, 2, NCOS, CG>(pl, ws, chunk, s0, s); s0 += 2; }
-    else { launch_lens<T, 1, NCOS, CG>(pl, ws, chunk, s0, s); s0 += 1; }
+    if (rem >= 10 && !WIDE) { launch_lens<T, 10, NCOS, CG>(pl, ws, chunk, s0, s, skip_static); s0 += 10; }
+    else if (rem >= 8 && !WIDE) { launch_lens<T, 8, NCOS, CG>(pl, ws, chunk, s0, s, skip_static); s0 += 8; }
+    else if (rem >= 6) { launch_lens<T, 6, NCOS, CG>(pl, ws, chunk, s0, s, skip_static); s0 += 6; }
+    else if (rem >= 5) { launch_lens<T, 5, NCOS, CG>(pl, ws, chunk, s0, s, skip_static); s0 += 5; }
+    else if (rem == 4) { launch_lens<T, 4, NCOS, CG>(pl, ws, chunk, s0, s, skip_static); s0 += 4; }
+    else if (rem == 3) { launch_lens<T, 3, NCOS, CG>(pl, ws, chunk, s0, s, skip_static); s0 += 3; }
+    else if (rem == 2) { launch_lens<T, 2, NCOS, CG>(pl, ws, chunk, s0, s, skip_static); s0 += 2; }
+    else { launch_lens<T, 1, NCOS, CG>(pl, ws, chunk, s0, s, skip_static); s0 += 1; }
   }
   return n_launch;
 }
@@ -496,12 +514,12 @@ int jc_launch_tracers(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t
   return n_launch + launch_all_lens<double, 4, 4>(pl, ws, chunk, s, s0);
 }
 // tangent groups: one cosmology per thread (the accumulators are NS x (1 + ntan) doubles)
-int jc_launch_tracers_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, int ntan, cudaStream_t s) {
+int jc_launch_tracers_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, int ntan, cudaStream_t s, int skip_static) {
   switch (ntan) {
-    case 2: return launch_all_lens<DualN<2>, 1, 4>(pl, ws, chunk, s);
-    case 3: return launch_all_lens<DualN<3>, 1, 4>(pl, ws, chunk, s);
-    case 4: return launch_all_lens<DualN<4>, 1, 4>(pl, ws, chunk, s);
-    default: return launch_all_lens<Dual, 2, 4>(pl, ws, chunk, s);
+    case 2: return launch_all_lens<DualN<2>, 1, 4>(pl, ws, chunk, s, 0, skip_static);
+    case 3: return launch_all_lens<DualN<3>, 1, 4>(pl, ws, chunk, s, 0, skip_static);
+    case 4: return launch_all_lens<DualN<4>, 1, 4>(pl, ws, chunk, s, 0, skip_static);
+    default: return launch_all_lens<Dual, 2, 4>(pl, ws, chunk, s, 0, skip_static);
   }
 }
 static int finish_threads(const JcDevPlan& pl) {  // rows x n_fin threads, at least one thread per tracer
@@ -510,13 +528,13 @@ static int finish_threads(const JcDevPlan& pl) {  // rows x n_fin threads, at le
   return n < pl.T ? ((pl.T + 31) / 32) * 32 : n;
 }
 void jc_launch_finish(const JcDevPlan& pl, const Ws& ws, int chunk, cudaStream_t s) {
-  jc_tracer_finish_kernel<double><<<chunk, finish_threads(pl), 0, s>>>(pl, ws);
+  jc_tracer_finish_kernel<double><<<chunk, finish_threads(pl), 0, s>>>(pl, ws, 0);
 }
-void jc_launch_finish_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, int ntan, cudaStream_t s) {
+void jc_launch_finish_jvp(const JcDevPlan& pl, const Ws& ws, int chunk, int ntan, cudaStream_t s, int skip_static) {
   switch (ntan) {
-    case 2: jc_tracer_finish_kernel<DualN<2>><<<chunk, finish_threads(pl), 0, s>>>(pl, ws); break;
-    case 3: jc_tracer_finish_kernel<DualN<3>><<<chunk, finish_threads(pl), 0, s>>>(pl, ws); break;
-    case 4: jc_tracer_finish_kernel<DualN<4>><<<chunk, finish_threads(pl), 0, s>>>(pl, ws); break;
-    default: jc_tracer_finish_kernel<Dual><<<chunk, finish_threads(pl), 0, s>>>(pl, ws); break;
+    case 2: jc_tracer_finish_kernel<DualN<2>><<<chunk, finish_threads(pl), 0, s>>>(pl, ws, skip_static); break;
+    case 3: jc_tracer_finish_kernel<DualN<3>><<<chunk, finish_threads(pl), 0, s>>>(pl, ws, skip_static); break;
+    case 4: jc_tracer_finish_kernel<DualN<4>><<<chunk, finish_threads(pl), 0, s>>>(pl, ws, skip_static); break;
+    default: jc_tracer_finish_kernel<Dual><<<chunk, finish_threads(pl), 0, s>>>(pl, ws, skip_static); break;
   }
 }

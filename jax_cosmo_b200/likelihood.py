@@ -160,10 +160,14 @@ def gaussian_cl_log_likelihood_and_grad(cosmo, data, ell, probes, params=None, f
         if name not in _PARAM_INDEX or _PARAM_INDEX[name] >= width:
             raise ValueError("unknown parameter %r" % (name,))
         tang[k, _PARAM_INDEX[name]] = 1.0
-    cl, dcl = plan.angular_cl_jvp_device(rows_dev, torch.as_tensor(tang, device=rows_dev.device))
+    order = _native.direction_order(tang)  # directions that cannot move the tracer kernels last (they may skip K2)
+    cl, dcl = plan.angular_cl_jvp_device(rows_dev, torch.as_tensor(np.ascontiguousarray(tang[order]), device=rows_dev.device))
     lnl, cot = plan.gaussian_cl_loglike_device(cl, data_dev, f_sky, True, want_cotangent=True)
     grad = _native.vjp_device(dcl, cot)
     lnl, grad = lnl.cpu().numpy(), grad.cpu().numpy()
+    inverse = np.empty_like(order)
+    inverse[order] = np.arange(len(order))
+    grad = grad[:, inverse]
     return (float(lnl[0]), grad[0]) if hasattr(cosmo, "to_row") else (lnl, grad)
 
 

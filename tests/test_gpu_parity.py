@@ -501,7 +501,7 @@ def test_jvp_fused_directions_bitwise(jc, torch_cuda):
 
 
 @pytest.mark.parametrize("n_rows,dirs,nl", [(160, 7, "halofit"), (260, 5, "halofit"), (350, 3, "linear"), (300, 2, "halofit"),
-                                            (140, 4, "smith2003"), (1100, 3, "halofit")])
+                                            (140, 4, "smith2003"), (1100, 3, "halofit"), (161, 7, "halofit")])
 def test_jvp_throughput_modes(jc, torch_cuda, n_rows, dirs, nl):
     """Throughput path of jc_angular_cl_jvp_f64 (B*K > 512 entries).  Default: K1 / K2 on tangent groups (DualN<g>, 7 = 4 + 3) and K3
     by ONE reverse sweep of the point function for 3..8 directions (jc_power_adj.cu).  A/B partners: tangent groups in K3 as well
@@ -519,6 +519,11 @@ def test_jvp_throughput_modes(jc, torch_cuda, n_rows, dirs, nl):
     tang = torch.zeros((dirs, 8), dtype=torch.float64, device="cuda")
     tang[torch.arange(dirs), torch.tensor(cols)] = 1.0
     tang[dirs - 1, 0] = 0.5  # a mixed direction
+    if n_rows == 161:  # the order _native.direction_order produces: the second tangent group (h, n_s, sigma8) skips K2
+        tang.zero_()
+        tang[torch.arange(7), torch.tensor([0, 1, 6, 7, 2, 3, 4])] = 1.0
+        order = _native.direction_order(np.eye(8)[[0, 1, 2, 3, 4, 6, 7]])
+        assert list(np.array([0, 1, 2, 3, 4, 6, 7])[order]) == [0, 1, 6, 7, 2, 3, 4]
     assert n_rows * dirs > 512
     assert _native.get_option("jvp_group") == 4.0
     adjoint_default = _native.get_option("jvp_adjoint")

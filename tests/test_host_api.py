@@ -189,3 +189,16 @@ def test_hessian_argument_checks(jc):
         jc.likelihood.gaussian_cl_log_likelihood_hessian(row, data, ell, probes, params=("gamma",))  # 8-column row: no gamma
     with pytest.raises(ValueError, match="rel_step"):
         jc.likelihood.gaussian_cl_log_likelihood_hessian(row, data, ell, probes, rel_step=0.0)
+
+
+def test_direction_order():
+    """Forward-mode directions along h, n_s, sigma8 cannot move the tracer kernels: the host wrappers put them last (stable)."""
+    from jax_cosmo_b200 import _native
+    wcdm = np.eye(8)[[0, 1, 2, 3, 4, 6, 7]]            # Omega_c, Omega_b, h, n_s, sigma8, w0, wa
+    assert list(_native.direction_order(wcdm)) == [0, 1, 5, 6, 2, 3, 4]
+    mixed = np.zeros((3, 9))
+    mixed[0, 4] = 1.0                                   # sigma8
+    mixed[1, [2, 8]] = 1.0, 0.5                         # h + gamma/2: moves R through the growth factor
+    mixed[2, 3] = 1.0                                   # n_s
+    assert list(_native.direction_order(mixed)) == [1, 0, 2]
+    assert list(_native.direction_order(np.eye(8)[[2, 3]])) == [0, 1]
