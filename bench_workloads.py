@@ -255,7 +255,7 @@ def run(args, rank, world, local):
                     "gpu_launches": launches,
                     "roofline": None,
                     "roofline_note": "FP64-pipe bound like config 5; per-kernel times of a step: profiles/r02_final_launches_config4.csv "
-                                     "(reverse-sweep K3 39 %, tangent contractions 27 %, K1 16 %, lens 15 %), ncu of the K3 kernel: "
+                                     "(reverse-sweep K3 42 %, tangent contractions 29 %, K1 17 %, lens 9 %), ncu of the K3 kernel: "
                                      "profiles/r02x_ncu_power_adj_metrics.csv (36 % of the FP64 pipe)",
                     "cpu_baseline": None, "git_head": git_head()}
             print(json.dumps(line), flush=True)
