@@ -242,7 +242,9 @@ int jc_angular_cl_f64(const jc_plan* plan, const double* cosmo_dev, int64_t n_co
  *   K3 for 3 <= K <= 8 directions (Eisenstein-Hu with wiggles) takes ONE reverse sweep of the (ell, node) point function and
  *   forms every directional derivative from it with one multiply-add per input (jc_power_adj.cu); otherwise K3 runs on
  *   DualN<g> as well;
- *   K4: one tangent contraction per direction.
+ *   K4: one tangent contraction per direction -- two products, one for a direction that cannot move the tracer kernels
+ *   (no component along Omega_c, Omega_b, Omega_k, w0, wa, gamma: dR = 0 identically; JC_SCAL_MOVES_R).  Order such
+ *   directions LAST: in the reverse-sweep path a second tangent group made only of them skips its K2 pass as well.
  *   With a smaller workspace (jc_workspace_bytes_jvp() = 2 x jc_workspace_bytes() is the minimum) the tangent groups shrink,
  *   down to one direction per pass.  jc_set_option("jvp_group", 1..4) caps g, jc_set_option("jvp_adjoint", 0) disables the
  *   reverse sweep (A/B partners of the tests).
