@@ -11,7 +11,8 @@ import numpy as np
 from jax_cosmo_b200 import _native
 
 __all__ = ["gaussian_log_likelihood", "gaussian_log_likelihood_batch", "fisher_matrix", "gaussian_log_likelihood_grad",
-           "gaussian_cl_log_likelihood", "gaussian_cl_log_likelihood_and_grad", "gaussian_cl_log_likelihood_hessian"]
+           "gaussian_cl_log_likelihood", "gaussian_cl_log_likelihood_and_grad", "gaussian_cl_log_likelihood_hessian",
+           "gaussian_log_likelihood_hessian"]
 
 
 def gaussian_log_likelihood(data, mu, C, include_logdet=True, inverse_method="inverse"):
@@ -217,3 +218,69 @@ def gaussian_cl_log_likelihood_hessian(cosmo, data, ell, probes, params=None, f_
     step = batch[1::2, cols][np.arange(K), np.arange(K)] - batch[2::2, cols][np.arange(K), np.arange(K)]  # the representable 2 h_i
     H = (grad[1::2] - grad[2::2]) / step[:, None]
     return float(lnl[0]), grad[0], 0.5 * (H + H.T)
+
+
+def gaussian_log_likelihood_hessian(cosmo, data, C, ell, probes, params=None, rel_step=1e-6, transfer_fn=None, nonlinear_fn=None):
+    """Hessian in the cosmology of the reference notebook's likelihood (docs/notebooks/jax-cosmo-intro.ipynb:754-766 under
+    `jax.hessian`, :837-843):
+
+        lnL(theta) = -1/2 (data - mu(theta))^T C^-1 (data - mu(theta))        C fixed (stop_gradient), no log-determinant
+
+    with `C` the sparse [P, P, L] covariance and `mu = angular_cl(theta)`.  The gradient -J(theta)^T C^-1 (mu(theta) - data) is
+    analytic (forward-mode Jacobian, per-ell Cholesky kernel jc_fisher_f64 with the residual as one more right-hand side); the
+    Hessian is its central difference over ONE batch of 2 K displaced cosmologies, step small against the spacing of the
+    interpolation-bracket switches (see gaussian_cl_log_likelihood_hessian).  At the fiducial point (data = mu(theta)) the residual
+    term vanishes and the result is minus the Fisher matrix, which `fisher_matrix` gives without any differencing.
+    Returns (lnL, grad [K], H [K, K])."""
+    import torch
+
+    from jax_cosmo_b200 import power, transfer
+    from jax_cosmo_b200.angular_cl import _PARAM_INDEX, WCDM_PARAMS, _growth, _rows
+
+    rows = _rows(cosmo)
+    if rows.shape[0] != 1:
+        raise ValueError("the Hessian is evaluated at one cosmology (a Cosmology or a single row)")
+    width = rows.shape[1]
+    if params is None:
+        params = WCDM_PARAMS + (("gamma",) if width == 9 else ())
+    cols = []
+    for name in params:
+        if name not in _PARAM_INDEX or _PARAM_INDEX[name] >= width:
+            raise ValueError("unknown parameter %r" % (name,))
+        cols.append(_PARAM_INDEX[name])
+    K = len(cols)
+    if K > 15:
+        raise ValueError("at most 15 parameters (the Fisher kernel's right-hand sides)")
+    if not rel_step > 0.0:
+        raise ValueError("rel_step must be positive")
+    C = np.ascontiguousarray(np.asarray(C, dtype=np.float64))
+    if C.ndim != 3 or C.shape[0] != C.shape[1]:
+        raise ValueError("C must be a sparse [n_cls, n_cls, n_ell] covariance")
+    P, _, L = C.shape
+    data = np.ascontiguousarray(np.asarray(data, dtype=np.float64)).reshape(-1)
+    if data.size != P * L:
+        raise ValueError("data must have %d elements (n_cls * n_ell, cls-major)" % (P * L))
+    tf = transfer.Eisenstein_Hu if transfer_fn is None else transfer_fn
+    nl = power.halofit if nonlinear_fn is None else nonlinear_fn
+    plan = _native.get_plan(probes, ell, tf, nl, growth=_growth(rows))
+    if (plan.P, plan.L) != (P, L):
+        raise ValueError("covariance is [%d, %d, %d] but the probes / ell give %d spectra x %d ell" % (P, P, L, plan.P, plan.L))
+    dev = "cuda:%d" % plan.device
+    h = rel_step * np.maximum(np.abs(rows[0, cols]), 0.1)
+    batch = np.repeat(rows, 2 * K + 1, axis=0)  # row 0: theta; rows 1 + 2 i, 2 + 2 i: theta +- h_i e_i
+    for i, c in enumerate(cols):
+        batch[1 + 2 * i, c] += h[i]
+        batch[2 + 2 * i, c] -= h[i]
+    B = batch.shape[0]
+    tang = np.zeros((K, width))
+    tang[np.arange(K), cols] = 1.0
+    cl, dcl = plan.angular_cl_jvp_device(torch.as_tensor(batch, device=dev), torch.as_tensor(tang, device=dev))
+    resid = cl - torch.as_tensor(data, device=dev).reshape(1, P, L)                       # mu(theta) - data, [B, P, L]
+    aug = torch.cat([dcl, resid[:, None]], dim=1)                                         # [B, K + 1, P, L]
+    F = _native.fisher_device(aug, torch.as_tensor(C, device=dev)[None].expand(B, P, P, L).contiguous())
+    F = F.cpu().numpy()
+    grad = -F[:, :K, K]                                                                    # -J^T C^-1 r
+    lnl = -0.5 * F[0, K, K]                                                                # -1/2 r^T C^-1 r
+    step = batch[1::2, cols][np.arange(K), np.arange(K)] - batch[2::2, cols][np.arange(K), np.arange(K)]
+    H = (grad[1::2] - grad[2::2]) / step[:, None]
+    return float(lnl), grad[0], 0.5 * (H + H.T)

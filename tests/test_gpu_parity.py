@@ -971,3 +971,34 @@ def test_lens_mma_vs_scalar_kernel(jc, torch_cuda, n_src):
     prob = sc.flatten_spec(scn)
     for i in (0, 36):
         assert relerr(cl1[i].cpu().numpy(), o.angular_cl(rows[i], scn["ell"], prob)) < 2e-8
+
+
+def test_fixed_covariance_hessian_is_minus_fisher(jc, torch_cuda):
+    """likelihood.gaussian_log_likelihood_hessian: the notebook's likelihood (fixed covariance, no log-det) under jax.hessian.
+    Noise-free data at the fiducial cosmology: the residual term vanishes and -H must equal the Fisher matrix J^T C^-1 J of the
+    same Jacobian and covariance (the notebook's `F = -hessian_loglik(params)`, jax-cosmo-intro.ipynb:843); with noisy data the
+    value and the gradient must agree with the two-call forms."""
+    nz1, nz2 = sc.smail(1.0, 2.0, 1.0), sc.smail(1.0, 2.0, 0.5)
+    scn = sc.scenario("hf", sc.PLANCK15, [20.0, 50.0, 120.0, 300.0, 700.0],
+                      [sc.wl([nz1, nz2], sigma_e=[0.26, 0.3]), sc.nc([nz1, nz2], sc.bias("constant", 1.2))], f_sky=0.3)
+    probes, ell = sc.build_probes(scn, jc), np.array(scn["ell"])
+    cosmo = jc.Planck15()
+    params = ("Omega_c", "sigma8", "h", "w0")
+    mu, cov = jc.cl.gaussian_cl_covariance_and_mean(cosmo, ell, probes, f_sky=0.3, sparse=True)
+    cl0, jac = jc.cl.angular_cl_jacobian(cosmo, ell, probes, params=params)
+    F = jc.likelihood.fisher_matrix(jac, cov)
+    lnl, grad, H = jc.likelihood.gaussian_log_likelihood_hessian(cosmo, cl0.flatten(), cov, ell, probes, params=params)
+    scale = np.sqrt(np.outer(np.diag(F), np.diag(F)))
+    assert abs(lnl) < 1e-20 and np.max(np.abs(grad)) < 1e-6 * np.sqrt(np.diag(F)).max()
+    print("fixed-covariance Hessian vs -Fisher: %.2e" % np.max(np.abs(H + F) / scale))
+    assert np.max(np.abs(H + F) / scale) < 1e-5
+    rng = np.random.default_rng(9)
+    data = (cl0 * (1.0 + 0.02 * rng.standard_normal(cl0.shape))).flatten()
+    lnl, grad, H = jc.likelihood.gaussian_log_likelihood_hessian(cosmo, data, cov, ell, probes, params=params)
+    assert abs(lnl / jc.likelihood.gaussian_log_likelihood(data, mu, cov, include_logdet=False) - 1) < 1e-9
+    ref_grad = jc.likelihood.gaussian_log_likelihood_grad(data, mu, cov, jac)
+    assert np.max(np.abs(grad - ref_grad)) < 1e-9 * np.abs(ref_grad).max()
+    assert np.array_equal(H, H.T) and np.all(np.linalg.eigvalsh(-H) > 0)
+    assert np.max(np.abs(H + F) / scale) < 0.2  # the residual term is a 2 % perturbation of the data
+    with pytest.raises(ValueError):
+        jc.likelihood.gaussian_log_likelihood_hessian(cosmo, data[:-1], cov, ell, probes, params=params)
