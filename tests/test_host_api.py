@@ -189,6 +189,16 @@ def test_hessian_argument_checks(jc):
         jc.likelihood.gaussian_cl_log_likelihood_hessian(row, data, ell, probes, params=("gamma",))  # 8-column row: no gamma
     with pytest.raises(ValueError, match="rel_step"):
         jc.likelihood.gaussian_cl_log_likelihood_hessian(row, data, ell, probes, rel_step=0.0)
+    # the fixed-covariance form checks shapes before it builds a plan
+    cov = np.zeros((1, 1, 8))
+    with pytest.raises(ValueError, match="one cosmology"):
+        jc.likelihood.gaussian_log_likelihood_hessian(np.stack([row, row]), data, cov, ell, probes)
+    with pytest.raises(ValueError, match="sparse"):
+        jc.likelihood.gaussian_log_likelihood_hessian(row, data, np.zeros((8, 8)), ell, probes)
+    with pytest.raises(ValueError, match="elements"):
+        jc.likelihood.gaussian_log_likelihood_hessian(row, data[:-1], cov, ell, probes)
+    with pytest.raises(ValueError, match="unknown parameter"):
+        jc.likelihood.gaussian_log_likelihood_hessian(row, data, cov, ell, probes, params=("tau",))
 
 
 def test_direction_order():
